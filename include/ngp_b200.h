@@ -1,0 +1,180 @@
+/*
+ * ngp_b200.h - C ABI of libngp_b200.so: the B200 (sm_100a) NeRF rendering hot path of
+ * stable-dreamfusion (hash-grid encode, occupancy-grid ray marching, volume compositing,
+ * occupancy-grid update, frequency encode, fused 64-wide field MLP).
+ *
+ * This is the drop-in boundary.  Every entry point replaces one native function that the
+ * reference binds through pybind11 (file:line given per function, relative to the reference
+ * tree) and keeps its argument order and meaning.  Differences from the pybind surface:
+ *   - at::Tensor arguments become raw DEVICE pointers (the caller owns, allocates and - where
+ *     noted - zero-fills every buffer, exactly as the reference's Python wrappers do);
+ *   - a dtype code replaces AT_DISPATCH (NGP_F32 / NGP_F16);
+ *   - a trailing `stream` (a cudaStream_t passed as void*) replaces the reference's implicit
+ *     legacy default stream; kernels are launched on the CURRENT device of the calling thread;
+ *   - every function returns an int: NGP_OK (0), a negative NGP_ERR_* argument error, or a
+ *     positive cudaError_t from the launch.  Nothing is thrown, allocated or synchronised
+ *     unless stated.
+ * No torch / pybind / C++ types appear in any signature.
+ */
+#ifndef NGP_B200_H_
+#define NGP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGP_OK 0
+#define NGP_ERR_BAD_ARG (-1)     /* null pointer / inconsistent sizes */
+#define NGP_ERR_UNSUPPORTED (-2) /* D, C or dtype outside what the reference instantiates */
+#define NGP_ERR_WORKSPACE (-3)   /* workspace too small */
+
+#define NGP_F32 0
+#define NGP_F16 1
+
+/* grid-encode output / grad layouts */
+#define NGP_LAYOUT_LBC 0 /* [L, B, C] - the reference kernel's native layout (gridencoder.cu:361) */
+#define NGP_LAYOUT_BLC 1 /* [B, L*C] - what grid.py:52 permutes to; written directly (fused permute) */
+
+#define NGP_GRID_HASH 0  /* gridencoder/grid.py:14-17 */
+#define NGP_GRID_TILED 1
+
+int ngp_version(void);
+/* Human-readable text for a return code (static storage). */
+const char* ngp_error_string(int code);
+/* Name of the device the library is running on + SM count (host call, no launch). */
+int ngp_device_info(char* name, int name_len, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * gridencoder  (reference: gridencoder/src/gridencoder.h:12-13, gridencoder.cu:424-479)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Replaces grid_encode_forward (gridencoder.cu:424).  inputs f32[B,D] in [0,1]; embeddings
+ * dtype[sO,C]; offsets i32[L+1]; outputs dtype, layout per out_layout; dy_dx dtype[B,L,D,C] or
+ * NULL; S = log2(per_level_scale); H = base resolution.  D in 1..5, C in {1,2,4,8}
+ * (gridencoder.cu:354,372); dtype NGP_F32 or NGP_F16 (double is not built: NGP_ERR_UNSUPPORTED). */
+int ngp_grid_encode_forward(const float* inputs, const void* embeddings, const int* offsets, void* outputs,
+                            uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H, void* dy_dx,
+                            uint32_t gridtype, int align_corners, int dtype, int out_layout, void* stream);
+
+/* Replaces grid_encode_backward (gridencoder.cu:449).  grad dtype in grad_layout; grad_embeddings
+ * [sO,C] MUST be zero-filled by the caller (grid.py:72); its element type is grad_emb_dtype:
+ * NGP_F16 reproduces the reference's half2 atomics, NGP_F32 accumulates in fp32 (what the Python
+ * host uses: more accurate, same API-visible result after autograd's cast).  dy_dx/grad_inputs
+ * (dtype[B,L,D,C] / dtype[B,D]) may be NULL. */
+int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings, const int* offsets,
+                             void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                             uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype,
+                             int align_corners, int dtype, int grad_layout, int grad_emb_dtype, void* stream);
+
+/* Device-computed per-level (scale, resolution) exactly as gridencoder.cu:125-126 evaluates them
+ * (exp2f on the device).  scales f32[L], resolutions u32[L] are DEVICE buffers. */
+int ngp_grid_level_params(uint32_t L, float S, uint32_t H, float* scales, uint32_t* resolutions, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * raymarching  (reference: raymarching/src/raymarching.h:7-17)
+ * All floating tensors are f32 (the wrappers force-cast: raymarching.py custom_fwd(cast_inputs=float32)).
+ * ------------------------------------------------------------------------------------------ */
+
+/* raymarching.cu:148  rays_o/rays_d f32[N,3], aabb f32[6] -> nears/fars f32[N] (miss: FLT_MAX both). */
+int ngp_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                           float min_near, float* nears, float* fars, void* stream);
+/* raymarching.cu:201  coords f32[N,2] */
+int ngp_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                     void* stream);
+/* raymarching.cu:229  coords i32[N,3] -> indices i32[N] */
+int ngp_morton3D(const int* coords, uint32_t N, int* indices, void* stream);
+/* raymarching.cu:257  indices i32[N] -> coords i32[N,3] */
+int ngp_morton3D_invert(const int* indices, uint32_t N, int* coords, void* stream);
+/* raymarching.cu:292  grid f32[N*8] -> bitfield u8[N]; bit i of byte n = grid[8n+i] > thresh */
+int ngp_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream);
+
+/* raymarching.cu:482.  Outputs xyzs f32[M,3], dirs f32[M,3], deltas f32[M,2] (rows not written stay
+ * untouched: the caller zero-fills as raymarching.py:205-207 does, or relies on `rays`), rays
+ * i32[N,3] = (ray id, offset, count), counter i32[2] += (sum count, N).  Unlike the reference's
+ * nondeterministic atomic slot allocation (raymarching.cu:405-406) rows are emitted in ray order:
+ * rays[n] describes ray n and offsets are an exclusive prefix sum - one of the orders the
+ * reference itself can produce.  A ray whose offset+count > M is recorded in `rays` but writes no
+ * samples (raymarching.cu:416).  workspace: device scratch of >= ngp_march_rays_train_workspace(N)
+ * bytes. */
+int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                         float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                         const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                         int* rays, int* counter, const float* noises, void* workspace,
+                         uint64_t workspace_bytes, void* stream);
+uint64_t ngp_march_rays_train_workspace(uint32_t N);
+
+/* raymarching.cu:580 */
+int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                     const int* rays, uint32_t M, uint32_t N, float T_thresh,
+                                     float* weights_sum, float* depth, float* image, void* stream);
+/* raymarching.cu:685.  grad_sigmas f32[M], grad_rgbs f32[M,3] zero-filled by the caller
+ * (raymarching.py:283-284). */
+int ngp_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                      const float* sigmas, const float* rgbs, const float* deltas,
+                                      const int* rays, const float* weights_sum, const float* image,
+                                      uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                      float* grad_rgbs, void* stream);
+
+/* raymarching.cu:808 (inference).  Outputs are slot-major [n_alive*n_step (+pad), ...], zero-filled
+ * by the caller (raymarching.py:334-336). */
+int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t,
+                   const float* rays_o, const float* rays_d, float bound, float dt_gamma, uint32_t max_steps,
+                   uint32_t C, uint32_t H, const uint8_t* grid, const float* nears, const float* fars,
+                   float* xyzs, float* dirs, float* deltas, const float* noises, void* stream);
+/* raymarching.cu:908 (inference, in place). */
+int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* rays_alive, float* rays_t,
+                       const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                       float* depth, float* image, void* stream);
+
+/* Device-side replacement for `rays_alive = rays_alive[rays_alive >= 0]` (nerf/renderer.py:529):
+ * stable compaction of the first n_alive entries of rays_alive into out; *n_out (device i32)
+ * receives the new count.  workspace >= ngp_compact_alive_workspace(n_alive) bytes. */
+int ngp_compact_alive(const int* rays_alive, uint32_t n_alive, int* out, int* n_out, void* workspace,
+                      uint64_t workspace_bytes, void* stream);
+uint64_t ngp_compact_alive_workspace(uint32_t n_alive);
+
+/* ------------------------------------------------------------------------------------------
+ * freqencoder  (reference: freqencoder/src/freqencoder.h:7,10; freqencoder.cu:97,114)
+ * ------------------------------------------------------------------------------------------ */
+int ngp_freq_encode_forward(const float* inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
+                            float* outputs, void* stream);
+int ngp_freq_encode_backward(const float* grad, const float* outputs, uint32_t B, uint32_t D, uint32_t deg,
+                             uint32_t C, float* grad_inputs, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Occupancy-grid update  (reference: NeRFRenderer.update_extra_state, nerf/renderer.py:562-613)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Cell centres + jitter for one cascade (renderer.py:581-593): for morton-ordered cell m in
+ * [0,H^3): coords = morton3D_invert(m); xyz = (2*coords/(H-1) - 1)*cell_scale + (2*noise-1)*half_cell
+ * where the host passes cell_scale = fp32(bound_c - bound_c/H) and half_cell = fp32(bound_c/H).
+ * noise f32[H^3,3] is indexed by the LINEAR cell id x*H*H+y*H+z (the order torch.rand_like is
+ * consumed in); out xyzs f32[H^3,3] is in MORTON order so the density query result lands directly
+ * in density_grid order (renderer.py:597). */
+int ngp_occupancy_cell_points(uint32_t H, float cell_scale, float half_cell, const float* noise, float* xyzs,
+                              void* stream);
+
+/* EMA-max + mean + bitfield (renderer.py:600-607).  grid f32[n_cells] updated in place where
+ * grid >= 0: grid = max(grid*decay, tmp).  mean_out f32[1] = mean over valid cells.  bitfield
+ * u8[n_cells/8] = grid > min(mean, density_thresh).  workspace >= 16 bytes, zeroed by the call. */
+int ngp_update_density_grid(float* grid, const float* tmp_grid, uint32_t n_cells, float decay,
+                            float density_thresh, float* mean_out, uint8_t* bitfield, void* workspace,
+                            uint64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Roofline micro-benchmarks (measurement support; SURVEY 8d asks for a measured L2 peak)
+ * ------------------------------------------------------------------------------------------ */
+/* Random 4-byte gathers: each of n_threads threads performs `iters` x 8 independent loads from
+ * table u32[table_words] (table_words a power of two) and writes a checksum to sink u32[n_threads]. */
+int ngp_bench_gather4(const uint32_t* table, uint32_t table_words, uint32_t* sink, uint32_t n_threads,
+                      uint32_t iters, uint32_t seed, void* stream);
+/* Random 8-byte red.global.add.v2.f32 into table f32[table_words]. */
+int ngp_bench_red8(float* table, uint32_t table_words, uint32_t n_threads, uint32_t iters, uint32_t seed,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_B200_H_ */

@@ -1,0 +1,298 @@
+"""TEST INFRASTRUCTURE: numpy front-end of the C oracle (``ngp_oracle.c``).
+
+Each function mirrors one native entry point of the reference (same argument meaning as the
+pybind functions in gridencoder/src/gridencoder.h:12-13, raymarching/src/raymarching.h:7-17,
+freqencoder/src/freqencoder.h:7-10) but takes / returns numpy arrays on the host and allocates
+its own outputs.  Half tensors are numpy float16.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import build as _build
+
+_lib = None
+
+F32, F16 = 0, 1
+LBC, BLC = 0, 1
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(_build.build())
+        _lib.oracle_compact_alive.restype = C.c_uint32
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _dt(emb):
+    if emb.dtype == np.float16:
+        return F16
+    if emb.dtype == np.float32:
+        return F32
+    raise TypeError("embeddings must be float32 or float16")
+
+
+# ------------------------------------------------------------------ gridencoder
+def grid_level_params(L, S, H):
+    scales = np.empty(L, np.float32)
+    res = np.empty(L, np.uint32)
+    lib().oracle_grid_level_params(C.c_uint32(L), C.c_float(S), C.c_uint32(H), _p(scales), _p(res))
+    return scales, res
+
+
+def grid_encode_forward(inputs, embeddings, offsets, S, H, calc_dydx=False, gridtype=0, align_corners=False,
+                        out_layout=BLC, scale_override=None):
+    """kernel_grid (gridencoder.cu:76-223). Returns (outputs, dy_dx|None).
+    outputs: [B, L*C] for BLC, [L, B, C] for LBC, in the embeddings' dtype."""
+    inputs = _c(inputs, np.float32)
+    offsets = _c(offsets, np.int32)
+    embeddings = np.ascontiguousarray(embeddings)
+    dt = _dt(embeddings)
+    B, D = inputs.shape
+    Cc = embeddings.shape[1]
+    L = offsets.shape[0] - 1
+    out = np.empty((B, L * Cc) if out_layout == BLC else (L, B, Cc), embeddings.dtype)
+    dydx = np.empty((B, L * D * Cc), embeddings.dtype) if calc_dydx else None
+    so = None if scale_override is None else _c(scale_override, np.float32)
+    rc = lib().oracle_grid_encode_forward(_p(inputs), _p(embeddings), _p(offsets), _p(out), C.c_uint32(B), C.c_uint32(D),
+                                          C.c_uint32(Cc), C.c_uint32(L), C.c_float(S), C.c_uint32(H), _p(dydx),
+                                          C.c_uint32(gridtype), C.c_int(int(align_corners)), C.c_int(dt),
+                                          C.c_int(out_layout), _p(so))
+    if rc != 0:
+        raise RuntimeError("oracle_grid_encode_forward rc=%d" % rc)
+    return out, dydx
+
+
+def grid_encode_backward(grad, inputs, offsets, n_rows, Cc, S, H, gridtype=0, align_corners=False, grad_layout=BLC,
+                         round_addend_to_half=False, scale_override=None):
+    """kernel_grid_backward (gridencoder.cu:227-313) with exact (float64) accumulation.
+    Returns grad_embeddings float64 [n_rows, C]."""
+    inputs = _c(inputs, np.float32)
+    offsets = _c(offsets, np.int32)
+    grad = np.ascontiguousarray(grad)
+    dt = _dt(grad)
+    B, D = inputs.shape
+    L = offsets.shape[0] - 1
+    table = np.zeros((n_rows, Cc), np.float64)
+    so = None if scale_override is None else _c(scale_override, np.float32)
+    rc = lib().oracle_grid_encode_backward(_p(grad), _p(inputs), _p(offsets), _p(table), C.c_uint32(B), C.c_uint32(D),
+                                           C.c_uint32(Cc), C.c_uint32(L), C.c_float(S), C.c_uint32(H),
+                                           C.c_uint32(gridtype), C.c_int(int(align_corners)), C.c_int(dt),
+                                           C.c_int(grad_layout), C.c_int(int(round_addend_to_half)), _p(so))
+    if rc != 0:
+        raise RuntimeError("oracle_grid_encode_backward rc=%d" % rc)
+    return table
+
+
+def grid_input_backward(grad, dy_dx, B, D, Cc, L, grad_layout=BLC):
+    grad = np.ascontiguousarray(grad)
+    dy_dx = np.ascontiguousarray(dy_dx)
+    dt = _dt(grad)
+    out = np.empty((B, D), grad.dtype)
+    lib().oracle_grid_input_backward(_p(grad), _p(dy_dx), _p(out), C.c_uint32(B), C.c_uint32(D), C.c_uint32(Cc),
+                                     C.c_uint32(L), C.c_int(dt), C.c_int(grad_layout))
+    return out
+
+
+# ------------------------------------------------------------------ raymarching
+def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.2):
+    rays_o = _c(rays_o, np.float32).reshape(-1, 3)
+    rays_d = _c(rays_d, np.float32).reshape(-1, 3)
+    aabb = _c(aabb, np.float32)
+    N = rays_o.shape[0]
+    nears = np.empty(N, np.float32)
+    fars = np.empty(N, np.float32)
+    lib().oracle_near_far_from_aabb(_p(rays_o), _p(rays_d), _p(aabb), C.c_uint32(N), C.c_float(min_near), _p(nears),
+                                    _p(fars))
+    return nears, fars
+
+
+def sph_from_ray(rays_o, rays_d, radius):
+    rays_o = _c(rays_o, np.float32).reshape(-1, 3)
+    rays_d = _c(rays_d, np.float32).reshape(-1, 3)
+    N = rays_o.shape[0]
+    coords = np.empty((N, 2), np.float32)
+    lib().oracle_sph_from_ray(_p(rays_o), _p(rays_d), C.c_float(radius), C.c_uint32(N), _p(coords))
+    return coords
+
+
+def morton3D(coords):
+    coords = _c(coords, np.int32)
+    N = coords.shape[0]
+    out = np.empty(N, np.int32)
+    lib().oracle_morton3D(_p(coords), C.c_uint32(N), _p(out))
+    return out
+
+
+def morton3D_invert(indices):
+    indices = _c(indices, np.int32)
+    N = indices.shape[0]
+    out = np.empty((N, 3), np.int32)
+    lib().oracle_morton3D_invert(_p(indices), C.c_uint32(N), _p(out))
+    return out
+
+
+def packbits(grid, thresh):
+    grid = _c(grid, np.float32)
+    N = grid.size // 8
+    out = np.empty(N, np.uint8)
+    lib().oracle_packbits(_p(grid), C.c_uint32(N), C.c_float(thresh), _p(out))
+    return out
+
+
+def march_rays_train(rays_o, rays_d, bound, bitfield, Ccas, H, nears, fars, noises, dt_gamma=0.0, max_steps=1024,
+                     M=None, counter=None):
+    """kernel_march_rays_train (raymarching.cu:312-480), rows in ray order.
+    Returns xyzs[M,3], dirs[M,3], deltas[M,2], rays[N,3], counter[2]; buffers zero-filled like raymarching.py:205-207."""
+    rays_o = _c(rays_o, np.float32).reshape(-1, 3)
+    rays_d = _c(rays_d, np.float32).reshape(-1, 3)
+    bitfield = _c(bitfield, np.uint8)
+    nears = _c(nears, np.float32)
+    fars = _c(fars, np.float32)
+    noises = _c(noises, np.float32)
+    N = rays_o.shape[0]
+    if M is None:
+        M = N * max_steps
+    xyzs = np.zeros((M, 3), np.float32)
+    dirs = np.zeros((M, 3), np.float32)
+    deltas = np.zeros((M, 2), np.float32)
+    rays = np.empty((N, 3), np.int32)
+    counter = np.zeros(2, np.int32) if counter is None else _c(counter, np.int32).copy()
+    lib().oracle_march_rays_train(_p(rays_o), _p(rays_d), _p(bitfield), C.c_float(bound), C.c_float(dt_gamma),
+                                  C.c_uint32(max_steps), C.c_uint32(N), C.c_uint32(Ccas), C.c_uint32(H), C.c_uint32(M),
+                                  _p(nears), _p(fars), _p(xyzs), _p(dirs), _p(deltas), _p(rays), _p(counter), _p(noises))
+    return xyzs, dirs, deltas, rays, counter
+
+
+def composite_rays_train_forward(sigmas, rgbs, deltas, rays, T_thresh=1e-4):
+    sigmas = _c(sigmas, np.float32)
+    rgbs = _c(rgbs, np.float32)
+    deltas = _c(deltas, np.float32)
+    rays = _c(rays, np.int32)
+    M, N = sigmas.shape[0], rays.shape[0]
+    ws = np.empty(N, np.float32)
+    depth = np.empty(N, np.float32)
+    image = np.empty((N, 3), np.float32)
+    lib().oracle_composite_rays_train_forward(_p(sigmas), _p(rgbs), _p(deltas), _p(rays), C.c_uint32(M), C.c_uint32(N),
+                                              C.c_float(T_thresh), _p(ws), _p(depth), _p(image))
+    return ws, depth, image
+
+
+def composite_rays_train_backward(grad_ws, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, T_thresh=1e-4):
+    sigmas = _c(sigmas, np.float32)
+    rgbs = _c(rgbs, np.float32)
+    deltas = _c(deltas, np.float32)
+    rays = _c(rays, np.int32)
+    grad_ws = _c(grad_ws, np.float32)
+    grad_image = _c(grad_image, np.float32)
+    weights_sum = _c(weights_sum, np.float32)
+    image = _c(image, np.float32)
+    M, N = sigmas.shape[0], rays.shape[0]
+    gs = np.zeros(M, np.float32)
+    gc = np.zeros((M, 3), np.float32)
+    lib().oracle_composite_rays_train_backward(_p(grad_ws), _p(grad_image), _p(sigmas), _p(rgbs), _p(deltas), _p(rays),
+                                               _p(weights_sum), _p(image), C.c_uint32(M), C.c_uint32(N),
+                                               C.c_float(T_thresh), _p(gs), _p(gc))
+    return gs, gc
+
+
+def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, bitfield, Ccas, H, nears, fars, noises,
+               dt_gamma=0.0, max_steps=1024, align=-1):
+    rays_o = _c(rays_o, np.float32).reshape(-1, 3)
+    rays_d = _c(rays_d, np.float32).reshape(-1, 3)
+    rays_alive = _c(rays_alive, np.int32)
+    rays_t = _c(rays_t, np.float32)
+    bitfield = _c(bitfield, np.uint8)
+    nears = _c(nears, np.float32)
+    fars = _c(fars, np.float32)
+    noises = _c(noises, np.float32)
+    M = n_alive * n_step
+    if align > 0:
+        M += align - (M % align)
+    xyzs = np.zeros((M, 3), np.float32)
+    dirs = np.zeros((M, 3), np.float32)
+    deltas = np.zeros((M, 2), np.float32)
+    lib().oracle_march_rays(C.c_uint32(n_alive), C.c_uint32(n_step), _p(rays_alive), _p(rays_t), _p(rays_o), _p(rays_d),
+                            C.c_float(bound), C.c_float(dt_gamma), C.c_uint32(max_steps), C.c_uint32(Ccas), C.c_uint32(H),
+                            _p(bitfield), _p(nears), _p(fars), _p(xyzs), _p(dirs), _p(deltas), _p(noises))
+    return xyzs, dirs, deltas
+
+
+def composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image, T_thresh=1e-2):
+    """In place on copies; returns (rays_alive, rays_t, weights_sum, depth, image)."""
+    rays_alive = _c(rays_alive, np.int32).copy()
+    rays_t = _c(rays_t, np.float32).copy()
+    weights_sum = _c(weights_sum, np.float32).copy()
+    depth = _c(depth, np.float32).copy()
+    image = _c(image, np.float32).copy()
+    sigmas = _c(sigmas, np.float32)
+    rgbs = _c(rgbs, np.float32)
+    deltas = _c(deltas, np.float32)
+    lib().oracle_composite_rays(C.c_uint32(n_alive), C.c_uint32(n_step), C.c_float(T_thresh), _p(rays_alive), _p(rays_t),
+                                _p(sigmas), _p(rgbs), _p(deltas), _p(weights_sum), _p(depth), _p(image))
+    return rays_alive, rays_t, weights_sum, depth, image
+
+
+def compact_alive(rays_alive):
+    rays_alive = _c(rays_alive, np.int32)
+    out = np.empty_like(rays_alive)
+    k = lib().oracle_compact_alive(_p(rays_alive), C.c_uint32(rays_alive.shape[0]), _p(out))
+    return out[:k].copy()
+
+
+# ------------------------------------------------------------------ freqencoder
+def freq_encode_forward(inputs, degree):
+    inputs = _c(inputs, np.float32)
+    B, D = inputs.shape
+    Cc = D + D * 2 * degree
+    out = np.empty((B, Cc), np.float32)
+    lib().oracle_freq_encode_forward(_p(inputs), C.c_uint32(B), C.c_uint32(D), C.c_uint32(degree), C.c_uint32(Cc), _p(out))
+    return out
+
+
+def freq_encode_backward(grad, outputs, D, degree):
+    grad = _c(grad, np.float32)
+    outputs = _c(outputs, np.float32)
+    B, Cc = grad.shape
+    out = np.empty((B, D), np.float32)
+    lib().oracle_freq_encode_backward(_p(grad), _p(outputs), C.c_uint32(B), C.c_uint32(D), C.c_uint32(degree),
+                                      C.c_uint32(Cc), _p(out))
+    return out
+
+
+# ------------------------------------------------------------------ occupancy grid
+def occupancy_cell_points(H, cascade_bound, noise):
+    noise = _c(noise, np.float32)
+    hgs = cascade_bound / H
+    xyzs = np.empty((H ** 3, 3), np.float32)
+    lib().oracle_occupancy_cell_points(C.c_uint32(H), C.c_float(np.float32(cascade_bound - hgs)),
+                                       C.c_float(np.float32(hgs)), _p(noise), _p(xyzs))
+    return xyzs
+
+
+def update_density_grid(grid, tmp_grid, decay=0.95, density_thresh=10.0):
+    """Returns (new_grid, mean, bitfield)."""
+    grid = _c(grid, np.float32).copy()
+    tmp_grid = _c(tmp_grid, np.float32)
+    n = grid.size
+    mean = np.empty(1, np.float32)
+    bits = np.empty(n // 8, np.uint8)
+    lib().oracle_update_density_grid(_p(grid), _p(tmp_grid), C.c_uint32(n), C.c_float(decay), C.c_float(density_thresh),
+                                     _p(mean), _p(bits))
+    return grid, float(mean[0]), bits
+
+
+def f2h(x):
+    x = _c(x, np.float32)
+    out = np.empty(x.shape, np.uint16)
+    lib().oracle_f2h(_p(x), _p(out), C.c_uint64(x.size))
+    return out.view(np.float16)

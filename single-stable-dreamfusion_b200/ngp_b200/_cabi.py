@@ -1,0 +1,112 @@
+"""ctypes binding of libngp_b200.so (declared in include/ngp_b200.h).
+
+The library is the product: if it is missing or a call fails this module raises - there is no
+CPU or PyTorch fallback for any op.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libngp_b200.so")
+
+NGP_F32, NGP_F16 = 0, 1
+LAYOUT_LBC, LAYOUT_BLC = 0, 1
+
+_u32, _f32, _i32, _u64, _vp = C.c_uint32, C.c_float, C.c_int, C.c_uint64, C.c_void_p
+
+# name -> (restype, argtypes); mirrors include/ngp_b200.h one to one (tests check the export list).
+SIGNATURES = {
+    "ngp_version": (_i32, []),
+    "ngp_error_string": (C.c_char_p, [_i32]),
+    "ngp_device_info": (_i32, [C.c_char_p, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "ngp_grid_encode_forward": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _vp, _u32, _i32, _i32, _i32, _vp]),
+    "ngp_grid_encode_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _vp, _vp, _u32, _i32, _i32, _i32, _i32, _vp]),
+    "ngp_grid_level_params": (_i32, [_u32, _f32, _u32, _vp, _vp, _vp]),
+    "ngp_near_far_from_aabb": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp]),
+    "ngp_sph_from_ray": (_i32, [_vp, _vp, _f32, _u32, _vp, _vp]),
+    "ngp_morton3D": (_i32, [_vp, _u32, _vp, _vp]),
+    "ngp_morton3D_invert": (_i32, [_vp, _u32, _vp, _vp]),
+    "ngp_packbits": (_i32, [_vp, _u32, _f32, _vp, _vp]),
+    "ngp_march_rays_train": (_i32, [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "ngp_march_rays_train_workspace": (_u64, [_u32]),
+    "ngp_composite_rays_train_forward": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
+    "ngp_composite_rays_train_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp]),
+    "ngp_march_rays": (_i32, [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_composite_rays": (_i32, [_u32, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_compact_alive": (_i32, [_vp, _u32, _vp, _vp, _vp, _u64, _vp]),
+    "ngp_compact_alive_workspace": (_u64, [_u32]),
+    "ngp_freq_encode_forward": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "ngp_freq_encode_backward": (_i32, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
+    "ngp_occupancy_cell_points": (_i32, [_u32, _f32, _f32, _vp, _vp, _vp]),
+    "ngp_update_density_grid": (_i32, [_vp, _vp, _u32, _f32, _f32, _vp, _vp, _vp, _u64, _vp]),
+    "ngp_bench_gather4": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _vp]),
+    "ngp_bench_red8": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises ImportError (loudly) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libngp_b200.so is not built (expected at %s). Run `python __graft_entry__.py build` or "
+            "`python single-stable-dreamfusion_b200/ngp_b200/build.py`; there is no fallback path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library ever drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def error_string(code):
+    return load().ngp_error_string(int(code)).decode()
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed: %s (code %d)" % (what, error_string(rc), rc))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("expected a CUDA tensor (the B200 path has no CPU fallback)")
+
+
+def require_contiguous(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_contiguous():
+            raise RuntimeError("expected a contiguous tensor")
+
+
+def call(name, device, *args):
+    """Invoke an entry point with `device` current and the caller's current stream appended."""
+    lib = load()
+    with torch.cuda.device(device):
+        rc = getattr(lib, name)(*args, stream())
+    check(rc, name)
+
+
+def dtype_code(dtype):
+    if dtype == torch.float32:
+        return NGP_F32
+    if dtype == torch.float16:
+        return NGP_F16
+    raise RuntimeError("unsupported dtype %s (float32 / float16 only)" % dtype)

@@ -1,0 +1,56 @@
+// C-ABI entry points of the grid encoder; kernels live in grid_encode.cuh, one TU per input dimension.
+#include "grid_encode.cuh"
+
+using namespace ngp;
+
+extern "C" int ngp_grid_encode_forward(const float* inputs, const void* embeddings, const int* offsets, void* outputs,
+                                       uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                       void* dy_dx, uint32_t gridtype, int align_corners, int dtype, int out_layout,
+                                       void* stream) {
+    if (!inputs || !embeddings || !offsets || !outputs) return NGP_ERR_BAD_ARG;
+    if (L == 0 || L > grid::kMaxLevels || gridtype > 1) return NGP_ERR_UNSUPPORTED;
+    if (out_layout != NGP_LAYOUT_LBC && out_layout != NGP_LAYOUT_BLC) return NGP_ERR_BAD_ARG;
+    if (dtype != NGP_F32 && dtype != NGP_F16) return NGP_ERR_UNSUPPORTED;
+    if (B == 0) return NGP_OK;
+    cudaStream_t st = as_stream(stream);
+    const bool al = align_corners != 0;
+    switch (D) {  // gridencoder.cu:366-373
+        case 1: return grid::forward_for_dim<1>(inputs, embeddings, offsets, outputs, dy_dx, B, C, L, S, H, gridtype, al, dtype, out_layout, st);
+        case 2: return grid::forward_for_dim<2>(inputs, embeddings, offsets, outputs, dy_dx, B, C, L, S, H, gridtype, al, dtype, out_layout, st);
+        case 3: return grid::forward_for_dim<3>(inputs, embeddings, offsets, outputs, dy_dx, B, C, L, S, H, gridtype, al, dtype, out_layout, st);
+        case 4: return grid::forward_for_dim<4>(inputs, embeddings, offsets, outputs, dy_dx, B, C, L, S, H, gridtype, al, dtype, out_layout, st);
+        case 5: return grid::forward_for_dim<5>(inputs, embeddings, offsets, outputs, dy_dx, B, C, L, S, H, gridtype, al, dtype, out_layout, st);
+        default: return NGP_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* embeddings,
+                                        const int* offsets, void* grad_embeddings, uint32_t B, uint32_t D, uint32_t C,
+                                        uint32_t L, float S, uint32_t H, const void* dy_dx, void* grad_inputs,
+                                        uint32_t gridtype, int align_corners, int dtype, int grad_layout,
+                                        int grad_emb_dtype, void* stream) {
+    (void)embeddings;  // the reference passes the table but its backward never reads it either
+    if (!grad || !inputs || !offsets || !grad_embeddings) return NGP_ERR_BAD_ARG;
+    if (L == 0 || L > grid::kMaxLevels || gridtype > 1) return NGP_ERR_UNSUPPORTED;
+    if (grad_layout != NGP_LAYOUT_LBC && grad_layout != NGP_LAYOUT_BLC) return NGP_ERR_BAD_ARG;
+    if (dtype != NGP_F32 && dtype != NGP_F16) return NGP_ERR_UNSUPPORTED;
+    if (B == 0) return NGP_OK;
+    cudaStream_t st = as_stream(stream);
+    const bool al = align_corners != 0;
+    switch (D) {
+        case 1: return grid::backward_for_dim<1>(grad, inputs, offsets, grad_embeddings, dy_dx, grad_inputs, B, C, L, S, H, gridtype, al, dtype, grad_layout, grad_emb_dtype, st);
+        case 2: return grid::backward_for_dim<2>(grad, inputs, offsets, grad_embeddings, dy_dx, grad_inputs, B, C, L, S, H, gridtype, al, dtype, grad_layout, grad_emb_dtype, st);
+        case 3: return grid::backward_for_dim<3>(grad, inputs, offsets, grad_embeddings, dy_dx, grad_inputs, B, C, L, S, H, gridtype, al, dtype, grad_layout, grad_emb_dtype, st);
+        case 4: return grid::backward_for_dim<4>(grad, inputs, offsets, grad_embeddings, dy_dx, grad_inputs, B, C, L, S, H, gridtype, al, dtype, grad_layout, grad_emb_dtype, st);
+        case 5: return grid::backward_for_dim<5>(grad, inputs, offsets, grad_embeddings, dy_dx, grad_inputs, B, C, L, S, H, gridtype, al, dtype, grad_layout, grad_emb_dtype, st);
+        default: return NGP_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int ngp_grid_level_params(uint32_t L, float S, uint32_t H, float* scales, uint32_t* resolutions,
+                                     void* stream) {
+    if (!scales || !resolutions) return NGP_ERR_BAD_ARG;
+    if (L == 0) return NGP_OK;
+    grid::level_params_kernel<<<cdiv(L, 64), 64, 0, as_stream(stream)>>>(L, S, H, scales, resolutions);
+    return launch_status();
+}

@@ -1,0 +1,542 @@
+// Multi-resolution hash / tiled grid encoding, forward + backward, for sm_100a.
+//
+// Behavioural contract: gridencoder/src/gridencoder.cu of the reference (kernel_grid :76-223,
+// kernel_grid_backward :227-313, kernel_input_backward :317-342, get_grid_index :54-72,
+// fast_hash :35-51).  The floating-point expression shapes below (which products feed which
+// adds, where a value is rounded to half) are kept identical to the reference so that fp32 AND
+// fp16 results are bit-equal to it; the parallel decomposition is not the reference's:
+//
+//   * one thread owns (point, LPT consecutive levels) and keeps the whole row of features in
+//     registers; inputs are read once per LPT levels instead of once per level, and the result is
+//     stored straight into the [B, L*C] layout the Python side wants (the reference writes
+//     [L,B,C] and then pays a full permute copy, grid.py:52,70);
+//   * feature rows are fetched with ONE vector load per corner (half2 for C=2) from the
+//     L2/L1-resident table instead of C scalar 2-byte loads;
+//   * the backward scatters whole rows with one red.global.add.v2/v4.f32 per corner into an fp32
+//     gradient table (no fp16 accumulation), or - for strict drop-in use through the C ABI - with
+//     half2 atomics like the reference.
+#pragma once
+#include "common.cuh"
+
+namespace ngp {
+namespace grid {
+
+constexpr uint32_t kMaxLevels = 64;
+
+struct LevelParams {
+    float scale;
+    uint32_t resolution;
+    uint32_t hashmap_size;
+    uint32_t offset;  // in rows
+};
+
+// gridencoder.cu:124-126 - evaluated on the device, with the reference's operand order.
+NGP_DEVINL LevelParams make_level(const int* __restrict__ offsets, uint32_t level, float S, uint32_t H) {
+    LevelParams p;
+    p.offset = (uint32_t)offsets[level];
+    p.hashmap_size = (uint32_t)offsets[level + 1] - (uint32_t)offsets[level];
+    p.scale = exp2f(level * S) * H - 1.0f;
+    p.resolution = (uint32_t)ceil(p.scale) + 1;
+    return p;
+}
+
+template <uint32_t D>
+NGP_DEVINL uint32_t spatial_hash(const uint32_t (&p)[D]) {
+    // gridencoder.cu:42 - the instant-ngp primes; 1 for the first axis keeps x-neighbours adjacent.
+    constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+    uint32_t h = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) h ^= p[d] * primes[d];
+    return h;
+}
+
+// Row index of a lattice point inside one level (gridencoder.cu:54-72, without the *C + ch).
+// Dense while the running stride fits the level's table; the stride loop stops at the first
+// axis whose stride exceeds the table (so a 'tiled' level silently drops the remaining axes).
+template <uint32_t D>
+NGP_DEVINL uint32_t lattice_row(uint32_t gridtype, bool align_corners, uint32_t hashmap_size, uint32_t resolution,
+                                const uint32_t (&p)[D]) {
+    uint32_t stride = 1, index = 0;
+    bool open = true;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        open = open && (stride <= hashmap_size);
+        if (open) {
+            index += p[d] * stride;
+            stride *= align_corners ? resolution : (resolution + 1);
+        }
+    }
+    if (gridtype == NGP_GRID_HASH && stride > hashmap_size) index = spatial_hash<D>(p);
+    return index % hashmap_size;
+}
+
+// ---- element-type plumbing ----------------------------------------------------------------------
+template <typename T> struct ElemOps;
+template <> struct ElemOps<float> {
+    static NGP_DEVINL float to_f(float v) { return v; }
+    static NGP_DEVINL float round(float v) { return v; }
+};
+template <> struct ElemOps<__half> {
+    static NGP_DEVINL float to_f(__half v) { return __half2float(v); }
+    static NGP_DEVINL float round(float v) { return __half2float(__float2half_rn(v)); }
+};
+
+// Load one row of C features as floats with a single (or, for 32 bytes, two) vector load.
+template <typename T, uint32_t C>
+NGP_DEVINL void load_row(const T* __restrict__ p, float (&out)[C]) {
+    constexpr uint32_t BYTES = sizeof(T) * C;
+    if constexpr (BYTES == 2) {
+        unsigned short raw = __ldg(reinterpret_cast<const unsigned short*>(p));
+        out[0] = __half2float(__ushort_as_half(raw));
+    } else if constexpr (BYTES == 4) {
+        unsigned int raw = __ldg(reinterpret_cast<const unsigned int*>(p));
+        if constexpr (sizeof(T) == 4) {
+            out[0] = __uint_as_float(raw);
+        } else {
+            float2 f = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+            out[0] = f.x; out[1] = f.y;
+        }
+    } else if constexpr (BYTES == 8) {
+        uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
+        if constexpr (sizeof(T) == 4) {
+            out[0] = __uint_as_float(raw.x); out[1] = __uint_as_float(raw.y);
+        } else {
+            float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+            out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
+        }
+    } else if constexpr (BYTES == 16) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+        const unsigned int w[4] = {raw.x, raw.y, raw.z, raw.w};
+        if constexpr (sizeof(T) == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[i] = __uint_as_float(w[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                out[2 * i] = a.x; out[2 * i + 1] = a.y;
+            }
+        }
+    } else {  // 32 bytes: fp32, C = 8
+        static_assert(BYTES == 32 && sizeof(T) == 4, "unexpected row size");
+        uint4 r0 = __ldg(reinterpret_cast<const uint4*>(p));
+        uint4 r1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        out[0] = __uint_as_float(r0.x); out[1] = __uint_as_float(r0.y);
+        out[2] = __uint_as_float(r0.z); out[3] = __uint_as_float(r0.w);
+        out[4] = __uint_as_float(r1.x); out[5] = __uint_as_float(r1.y);
+        out[6] = __uint_as_float(r1.z); out[7] = __uint_as_float(r1.w);
+    }
+}
+
+template <typename T, uint32_t C>
+NGP_DEVINL void store_row(T* p, const float (&v)[C]) {
+    if constexpr (sizeof(T) == 4) {
+        if constexpr (C == 1) {
+            p[0] = v[0];
+        } else if constexpr (C == 2) {
+            *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+        } else {
+#pragma unroll
+            for (uint32_t i = 0; i < C; i += 4)
+                *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+    } else {
+        if constexpr (C == 1) {
+            p[0] = __float2half_rn(v[0]);
+        } else if constexpr (C == 2) {
+            *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v[0], v[1]);
+        } else if constexpr (C == 4) {
+            __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+            uint2 raw;
+            raw.x = *reinterpret_cast<unsigned int*>(&a); raw.y = *reinterpret_cast<unsigned int*>(&b);
+            *reinterpret_cast<uint2*>(p) = raw;
+        } else {
+            __half2 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            uint4 raw;
+            raw.x = *reinterpret_cast<unsigned int*>(&h[0]); raw.y = *reinterpret_cast<unsigned int*>(&h[1]);
+            raw.z = *reinterpret_cast<unsigned int*>(&h[2]); raw.w = *reinterpret_cast<unsigned int*>(&h[3]);
+            *reinterpret_cast<uint4*>(p) = raw;
+        }
+    }
+}
+
+// Fractional position + base lattice point for one level (gridencoder.cu:132-137).
+template <uint32_t D>
+NGP_DEVINL void locate(const float (&x)[D], float scale, bool align_corners, float (&frac)[D], uint32_t (&base)[D]) {
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        float pos = x[d] * scale + (align_corners ? 0.0f : 0.5f);
+        base[d] = floorf(pos);
+        frac[d] = pos - (float)base[d];
+    }
+}
+
+template <uint32_t D>
+NGP_DEVINL bool out_of_unit_cube(const float (&x)[D]) {
+    bool oob = false;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) oob = oob || (x[d] < 0 || x[d] > 1);
+    return oob;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Forward
+// -------------------------------------------------------------------------------------------------
+template <typename T, uint32_t D, uint32_t C, uint32_t LPT, bool OUT_BLC, bool WITH_DYDX>
+__global__ void __launch_bounds__(256) encode_forward_kernel(
+    const float* __restrict__ inputs, const T* __restrict__ table, const int* __restrict__ offsets,
+    T* __restrict__ outputs, T* __restrict__ dy_dx, uint32_t B, uint32_t L, float S, uint32_t H,
+    uint32_t gridtype, bool align_corners) {
+    __shared__ LevelParams s_levels[kMaxLevels];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_level(offsets, l, S, H);
+    __syncthreads();
+
+    const uint32_t groups = (L + LPT - 1) / LPT;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = (uint32_t)(tid / groups);
+    const uint32_t g = (uint32_t)(tid - (uint64_t)b * groups);
+    if (b >= B) return;
+
+    float x[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(inputs + (size_t)b * D + d);
+    const bool oob = out_of_unit_cube<D>(x);
+
+#pragma unroll
+    for (uint32_t li = 0; li < LPT; ++li) {
+        const uint32_t level = g * LPT + li;
+        if (level >= L) break;
+        T* out = OUT_BLC ? outputs + ((size_t)b * L + level) * C : outputs + ((size_t)level * B + b) * C;
+        T* dout = WITH_DYDX ? dy_dx + ((size_t)b * L + level) * D * C : nullptr;
+        float acc[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) acc[c] = 0.f;
+
+        if (oob) {  // gridencoder.cu:106-122
+            store_row<T, C>(out, acc);
+            if (WITH_DYDX) {
+#pragma unroll
+                for (uint32_t d = 0; d < D; ++d) store_row<T, C>(dout + d * C, acc);
+            }
+            continue;
+        }
+
+        const LevelParams lp = s_levels[level];
+        const T* __restrict__ tbl = table + (size_t)lp.offset * C;
+        float frac[D];
+        uint32_t base[D];
+        locate<D>(x, lp.scale, align_corners, frac, base);
+
+        // Issue all 2^D row gathers first (independent loads in flight), then blend.
+        float rows[1u << D][C];
+        float wts[1u << D];
+#pragma unroll
+        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+            float w = 1;
+            uint32_t p[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                if ((corner & (1u << d)) == 0) { w *= 1 - frac[d]; p[d] = base[d]; }
+                else                           { w *= frac[d];     p[d] = base[d] + 1; }
+            }
+            wts[corner] = w;
+            const uint32_t row = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
+            load_row<T, C>(tbl + (size_t)row * C, rows[corner]);
+        }
+#pragma unroll
+        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) {
+                if constexpr (sizeof(T) == 4) {
+                    acc[c] += wts[corner] * rows[corner][c];  // contracts to one FFMA, as in the reference
+                } else {
+                    // c10::Half semantics of `results[ch] += w * grid[..]` (gridencoder.cu:165): the float
+                    // product is rounded to half, then the half+half sum is rounded again.
+                    const float prod = ElemOps<T>::round(wts[corner] * rows[corner][c]);
+                    acc[c] = ElemOps<T>::round(acc[c] + prod);
+                }
+            }
+        }
+        store_row<T, C>(out, acc);
+
+        if (WITH_DYDX) {  // gridencoder.cu:179-222
+#pragma unroll
+            for (uint32_t gd = 0; gd < D; ++gd) {
+                float gacc[C];
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) gacc[c] = 0.f;
+#pragma unroll
+                for (uint32_t corner = 0; corner < (1u << (D - 1)); ++corner) {
+                    float w = lp.scale;
+                    uint32_t p[D];
+#pragma unroll
+                    for (uint32_t nd = 0; nd < D - 1; ++nd) {
+                        const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
+                        if ((corner & (1u << nd)) == 0) { w *= 1 - frac[d]; p[d] = base[d]; }
+                        else                            { w *= frac[d];     p[d] = base[d] + 1; }
+                    }
+                    p[gd] = base[gd];
+                    const uint32_t left = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
+                    p[gd] = base[gd] + 1;
+                    const uint32_t right = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
+                    float lo[C], hi[C];
+                    load_row<T, C>(tbl + (size_t)left * C, lo);
+                    load_row<T, C>(tbl + (size_t)right * C, hi);
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c) {
+                        if constexpr (sizeof(T) == 4) {
+                            gacc[c] += w * (hi[c] - lo[c]);
+                        } else {
+                            const float diff = ElemOps<T>::round(hi[c] - lo[c]);
+                            const float prod = ElemOps<T>::round(w * diff);
+                            gacc[c] = ElemOps<T>::round(gacc[c] + prod);
+                        }
+                    }
+                }
+                store_row<T, C>(dout + gd * C, gacc);
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Backward: scatter-add of w * grad rows into the gradient table.
+//   GT = float : fp32 table, one red.global.add (v2/v4 where C allows) per corner.
+//   GT = __half: reference-compatible half2 atomics (gridencoder.cu:298-304); needs even C.
+// -------------------------------------------------------------------------------------------------
+template <typename GT, uint32_t C>
+NGP_DEVINL void scatter_row(GT* dst, float w, const float (&g)[C]) {
+    if constexpr (sizeof(GT) == 4) {
+        if constexpr (C == 1) {
+            red_add_f32(dst, w * g[0]);
+        } else if constexpr (C == 2) {
+            red_add_f32x2(dst, w * g[0], w * g[1]);
+        } else {
+#pragma unroll
+            for (uint32_t c = 0; c < C; c += 4) red_add_f32x4(dst + c, w * g[c], w * g[c + 1], w * g[c + 2], w * g[c + 3]);
+        }
+    } else {
+        static_assert(C % 2 == 0, "half gradient tables need an even feature count");
+#pragma unroll
+        for (uint32_t c = 0; c < C; c += 2) {
+            __half2 v = __halves2half2(__float2half_rn(w * g[c]), __float2half_rn(w * g[c + 1]));
+            atomicAdd(reinterpret_cast<__half2*>(dst + c), v);
+        }
+    }
+}
+
+template <typename T, typename GT, uint32_t D, uint32_t C, uint32_t LPT, bool GRAD_BLC>
+__global__ void __launch_bounds__(256) encode_backward_kernel(
+    const T* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
+    GT* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+    bool align_corners) {
+    __shared__ LevelParams s_levels[kMaxLevels];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_level(offsets, l, S, H);
+    __syncthreads();
+
+    const uint32_t groups = (L + LPT - 1) / LPT;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = (uint32_t)(tid / groups);
+    const uint32_t g = (uint32_t)(tid - (uint64_t)b * groups);
+    if (b >= B) return;
+
+    float x[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(inputs + (size_t)b * D + d);
+    if (out_of_unit_cube<D>(x)) return;  // gridencoder.cu:253-258
+
+#pragma unroll
+    for (uint32_t li = 0; li < LPT; ++li) {
+        const uint32_t level = g * LPT + li;
+        if (level >= L) break;
+        const LevelParams lp = s_levels[level];
+        const T* gsrc = GRAD_BLC ? grad + ((size_t)b * L + level) * C : grad + ((size_t)level * B + b) * C;
+        float gr[C];
+        load_row<T, C>(gsrc, gr);
+
+        float frac[D];
+        uint32_t base[D];
+        locate<D>(x, lp.scale, align_corners, frac, base);
+        GT* tbl = grad_table + (size_t)lp.offset * C;
+#pragma unroll
+        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+            float w = 1;
+            uint32_t p[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                if ((corner & (1u << d)) == 0) { w *= 1 - frac[d]; p[d] = base[d]; }
+                else                           { w *= frac[d];     p[d] = base[d] + 1; }
+            }
+            const uint32_t row = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
+            scatter_row<GT, C>(tbl + (size_t)row * C, w, gr);
+        }
+    }
+}
+
+// grad_inputs[b,d] = sum_{l,c} grad[l,b,c] * dy_dx[b,l,d,c]   (gridencoder.cu:317-342).  In half mode the
+// reference's running sum AND each product are at::Half, i.e. rounded to half after every operation.
+template <typename T, uint32_t D, uint32_t C, bool GRAD_BLC>
+__global__ void __launch_bounds__(256) input_backward_kernel(const T* __restrict__ grad, const T* __restrict__ dy_dx,
+                                                             T* __restrict__ grad_inputs, uint32_t B, uint32_t L) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)B * D) return;
+    const uint32_t b = (uint32_t)(t / D), d = (uint32_t)(t - (uint64_t)b * D);
+    float acc = 0.f;
+    for (uint32_t l = 0; l < L; ++l) {
+        const T* gsrc = GRAD_BLC ? grad + ((size_t)b * L + l) * C : grad + ((size_t)l * B + b) * C;
+        const T* jsrc = dy_dx + (((size_t)b * L + l) * D + d) * C;
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) {
+            const float gv = ElemOps<T>::to_f(gsrc[c]), jv = ElemOps<T>::to_f(jsrc[c]);
+            if constexpr (sizeof(T) == 4) {
+                acc += gv * jv;
+            } else {
+                acc = ElemOps<T>::round(acc + ElemOps<T>::round(gv * jv));
+            }
+        }
+    }
+    if constexpr (sizeof(T) == 4) grad_inputs[t] = acc; else grad_inputs[t] = __float2half_rn(acc);
+}
+
+static __global__ void level_params_kernel(uint32_t L, float S, uint32_t H, float* scales, uint32_t* resolutions) {
+    const uint32_t level = blockIdx.x * blockDim.x + threadIdx.x;
+    if (level >= L) return;
+    const float scale = exp2f(level * S) * H - 1.0f;
+    scales[level] = scale;
+    resolutions[level] = (uint32_t)ceil(scale) + 1;
+}
+
+// ---- host-side dispatch -------------------------------------------------------------------------
+// Levels per thread: 4 keeps 16-byte (C=2, half) output stores and 32 gathers in flight per thread
+// while giving 4x more threads than a thread-per-point mapping (matters for the ~3e5-sample
+// batches of a 64x64 training view).
+template <uint32_t C> struct Lpt { static constexpr uint32_t value = (C <= 2) ? 4 : (C == 4 ? 2 : 1); };
+
+template <typename T, uint32_t D, uint32_t C>
+int forward_dispatch(const float* inputs, const T* table, const int* offsets, T* outputs, T* dy_dx, uint32_t B,
+                     uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align, int layout, cudaStream_t st) {
+    constexpr uint32_t LPT = Lpt<C>::value;
+    const uint32_t groups = (L + LPT - 1) / LPT;
+    const uint64_t threads = (uint64_t)B * groups;
+    const dim3 grid((unsigned)((threads + 255) / 256)), block(256);
+    const bool blc = layout == NGP_LAYOUT_BLC;
+#define NGP_FWD(OUT_BLC, DYDX)                                                                              \
+    encode_forward_kernel<T, D, C, LPT, OUT_BLC, DYDX><<<grid, block, 0, st>>>(inputs, table, offsets, outputs, dy_dx, \
+                                                                            B, L, S, H, gridtype, align)
+    if (dy_dx) { if (blc) NGP_FWD(true, true); else NGP_FWD(false, true); }
+    else       { if (blc) NGP_FWD(true, false); else NGP_FWD(false, false); }
+#undef NGP_FWD
+    return launch_status();
+}
+
+template <typename T, uint32_t D>
+int forward_dispatch_c(const float* inputs, const void* table, const int* offsets, void* outputs, void* dy_dx,
+                       uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align,
+                       int layout, cudaStream_t st) {
+    const T* t = static_cast<const T*>(table);
+    T* o = static_cast<T*>(outputs);
+    T* j = static_cast<T*>(dy_dx);
+    switch (C) {
+        case 1: return forward_dispatch<T, D, 1>(inputs, t, offsets, o, j, B, L, S, H, gridtype, align, layout, st);
+        case 2: return forward_dispatch<T, D, 2>(inputs, t, offsets, o, j, B, L, S, H, gridtype, align, layout, st);
+        case 4: return forward_dispatch<T, D, 4>(inputs, t, offsets, o, j, B, L, S, H, gridtype, align, layout, st);
+        case 8: return forward_dispatch<T, D, 8>(inputs, t, offsets, o, j, B, L, S, H, gridtype, align, layout, st);
+        default: return NGP_ERR_UNSUPPORTED;  // gridencoder.cu:354
+    }
+}
+
+template <typename T, typename GT, uint32_t D, uint32_t C>
+int backward_launch(const T* grad, const float* inputs, const int* offsets, GT* grad_table, const T* dy_dx,
+                    T* grad_inputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align,
+                    int layout, cudaStream_t st) {
+    constexpr uint32_t LPT = Lpt<C>::value;
+    const uint32_t groups = (L + LPT - 1) / LPT;
+    const uint64_t threads = (uint64_t)B * groups;
+    const dim3 grid((unsigned)((threads + 255) / 256)), block(256);
+    const bool blc = layout == NGP_LAYOUT_BLC;
+    if (blc) encode_backward_kernel<T, GT, D, C, LPT, true><<<grid, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align);
+    else     encode_backward_kernel<T, GT, D, C, LPT, false><<<grid, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align);
+    int rc = launch_status();
+    if (rc != NGP_OK) return rc;
+    if (dy_dx && grad_inputs) {
+        const dim3 g2((unsigned)(((uint64_t)B * D + 255) / 256));
+        if (blc) input_backward_kernel<T, D, C, true><<<g2, block, 0, st>>>(grad, dy_dx, grad_inputs, B, L);
+        else     input_backward_kernel<T, D, C, false><<<g2, block, 0, st>>>(grad, dy_dx, grad_inputs, B, L);
+        rc = launch_status();
+    }
+    return rc;
+}
+
+template <typename T, uint32_t D, uint32_t C>
+int backward_dispatch_gt(const T* grad, const float* inputs, const int* offsets, void* grad_table, const T* dy_dx,
+                         T* grad_inputs, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align,
+                         int layout, int gt, cudaStream_t st) {
+    if (gt == NGP_F32)
+        return backward_launch<T, float, D, C>(grad, inputs, offsets, static_cast<float*>(grad_table), dy_dx, grad_inputs, B, L, S, H, gridtype, align, layout, st);
+    if constexpr (C % 2 == 0) {
+        if (gt == NGP_F16)
+            return backward_launch<T, __half, D, C>(grad, inputs, offsets, static_cast<__half*>(grad_table), dy_dx, grad_inputs, B, L, S, H, gridtype, align, layout, st);
+    }
+    return NGP_ERR_UNSUPPORTED;  // half table with C == 1: the reference's path is a body-less stub (gridencoder.cu:22-26)
+}
+
+template <typename T, uint32_t D>
+int backward_dispatch_c(const void* grad, const float* inputs, const int* offsets, void* grad_table, const void* dy_dx,
+                        void* grad_inputs, uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                        bool align, int layout, int gt, cudaStream_t st) {
+    const T* g = static_cast<const T*>(grad);
+    const T* j = static_cast<const T*>(dy_dx);
+    T* gi = static_cast<T*>(grad_inputs);
+    switch (C) {
+        case 1: return backward_dispatch_gt<T, D, 1>(g, inputs, offsets, grad_table, j, gi, B, L, S, H, gridtype, align, layout, gt, st);
+        case 2: return backward_dispatch_gt<T, D, 2>(g, inputs, offsets, grad_table, j, gi, B, L, S, H, gridtype, align, layout, gt, st);
+        case 4: return backward_dispatch_gt<T, D, 4>(g, inputs, offsets, grad_table, j, gi, B, L, S, H, gridtype, align, layout, gt, st);
+        case 8: return backward_dispatch_gt<T, D, 8>(g, inputs, offsets, grad_table, j, gi, B, L, S, H, gridtype, align, layout, gt, st);
+        default: return NGP_ERR_UNSUPPORTED;
+    }
+}
+
+
+// Per-dimension entry points: each D is instantiated in its own translation unit
+// (grid_encode_d<D>.cu) so the 2 dtypes x 4 feature widths x layouts compile in parallel.
+template <uint32_t D>
+int forward_for_dim(const float* inputs, const void* table, const int* offsets, void* outputs, void* dy_dx, uint32_t B,
+                    uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align, int dtype, int layout,
+                    cudaStream_t st);
+template <uint32_t D>
+int backward_for_dim(const void* grad, const float* inputs, const int* offsets, void* grad_table, const void* dy_dx,
+                     void* grad_inputs, uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+                     bool align, int dtype, int layout, int gt, cudaStream_t st);
+
+#define NGP_GRID_INSTANTIATE_DIM(DIM)                                                                                  \
+    template <>                                                                                                        \
+    int forward_for_dim<DIM>(const float* inputs, const void* table, const int* offsets, void* outputs, void* dy_dx,   \
+                             uint32_t B, uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align,   \
+                             int dtype, int layout, cudaStream_t st) {                                                 \
+        if (dtype == NGP_F32)                                                                                          \
+            return forward_dispatch_c<float, DIM>(inputs, table, offsets, outputs, dy_dx, B, C, L, S, H, gridtype,     \
+                                                  align, layout, st);                                                  \
+        if (dtype == NGP_F16)                                                                                          \
+            return forward_dispatch_c<__half, DIM>(inputs, table, offsets, outputs, dy_dx, B, C, L, S, H, gridtype,    \
+                                                   align, layout, st);                                                 \
+        return NGP_ERR_UNSUPPORTED;                                                                                    \
+    }                                                                                                                  \
+    template <>                                                                                                        \
+    int backward_for_dim<DIM>(const void* grad, const float* inputs, const int* offsets, void* grad_table,             \
+                              const void* dy_dx, void* grad_inputs, uint32_t B, uint32_t C, uint32_t L, float S,       \
+                              uint32_t H, uint32_t gridtype, bool align, int dtype, int layout, int gt,                \
+                              cudaStream_t st) {                                                                       \
+        if (dtype == NGP_F32)                                                                                          \
+            return backward_dispatch_c<float, DIM>(grad, inputs, offsets, grad_table, dy_dx, grad_inputs, B, C, L, S,  \
+                                                   H, gridtype, align, layout, gt, st);                                \
+        if (dtype == NGP_F16)                                                                                          \
+            return backward_dispatch_c<__half, DIM>(grad, inputs, offsets, grad_table, dy_dx, grad_inputs, B, C, L, S, \
+                                                    H, gridtype, align, layout, gt, st);                               \
+        return NGP_ERR_UNSUPPORTED;                                                                                    \
+    }
+
+}  // namespace grid
+}  // namespace ngp

@@ -1,0 +1,7 @@
+// Instantiates the grid-encoding kernels for input dimension D = 2 (see grid_encode.cuh).
+#include "grid_encode.cuh"
+namespace ngp {
+namespace grid {
+NGP_GRID_INSTANTIATE_DIM(2)
+}  // namespace grid
+}  // namespace ngp

@@ -1,0 +1,704 @@
+// Occupancy-grid ray marching and volume compositing for sm_100a.
+//
+// Behavioural contract: raymarching/src/raymarching.cu of the reference.  Sample positions, step
+// sizes, per-ray counts and bitfields must be BIT-EXACT with it, so every floating-point
+// expression that decides a sample keeps the reference's operand order (cited inline); the
+// parallel structure is new:
+//   * training march = count pass -> block-wide exclusive scan in ray order -> write pass, which
+//     replaces the reference's two global atomics per ray (raymarching.cu:405-406) and makes the
+//     sample layout deterministic (ray n owns rows [offset_n, offset_n + count_n));
+//   * compositing runs one WARP per ray: 32 samples per step, alpha/exp evaluated in parallel, the
+//     transmittance chain rebuilt with warp shuffles in the reference's multiplication order (so
+//     the early-termination decision is the reference's), colour/weight sums by warp reduction.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace ngp {
+namespace march {
+
+NGP_DEVINL float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }  // raymarching.cu:34
+
+// 10-bit-per-axis Morton interleave (raymarching.cu:56-71): the classic magic-multiply spread.
+NGP_DEVINL uint32_t spread3(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+NGP_DEVINL uint32_t morton_encode(uint32_t x, uint32_t y, uint32_t z) {
+    return spread3(x) | (spread3(y) << 1) | (spread3(z) << 2);
+}
+NGP_DEVINL uint32_t compact3(uint32_t x) {  // raymarching.cu:73-81
+    x &= 0x49249249u;
+    x = (x | (x >> 2)) & 0xc30c30c3u;
+    x = (x | (x >> 4)) & 0x0f00f00fu;
+    x = (x | (x >> 8)) & 0xff0000ffu;
+    x = (x | (x >> 16)) & 0x0000ffffu;
+    return x;
+}
+
+// Cascade level of a position / of a step size (raymarching.cu:42-54).  frexpf exponent, clamped.
+NGP_DEVINL int level_from_pos(float x, float y, float z, float n_cascades) {
+    const float mx = fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z)));
+    int e;
+    frexpf(mx, &e);
+    return (int)fminf(n_cascades - 1, fmaxf(0.f, (float)e));
+}
+NGP_DEVINL int level_from_dt(float dt, float H, float n_cascades) {
+    const float mx = (dt * H) * 0.5f;  // the reference's `* 0.5` is a double multiply by a power of two: exact
+    int e;
+    frexpf(mx, &e);
+    return (int)fminf(n_cascades - 1, fmaxf(0.f, (float)e));
+}
+
+struct MarchParams {
+    const uint8_t* __restrict__ grid;
+    float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Cf, Hm1;
+};
+
+NGP_DEVINL MarchParams make_params(const uint8_t* grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
+                                   uint32_t H) {
+    MarchParams p;
+    p.grid = grid;
+    p.bound = bound;
+    p.dt_gamma = dt_gamma;
+    p.dt_min = 2 * 1.7320508075688772f / max_steps;            // raymarching.cu:345
+    p.dt_max = 2 * 1.7320508075688772f * (1 << (C - 1)) / H;   // raymarching.cu:346
+    p.rH = 1 / (float)H;
+    p.H3 = H * H * H;                                          // uint32 product converted to float (:339)
+    p.Hf = (float)H;
+    p.Cf = (float)C;
+    p.Hm1 = (float)(H - 1);
+    return p;
+}
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, rdx, rdy, rdz;
+};
+NGP_DEVINL Ray load_ray(const float* __restrict__ rays_o, const float* __restrict__ rays_d, uint32_t n) {
+    Ray r;
+    r.ox = rays_o[n * 3 + 0]; r.oy = rays_o[n * 3 + 1]; r.oz = rays_o[n * 3 + 2];
+    r.dx = rays_d[n * 3 + 0]; r.dy = rays_d[n * 3 + 1]; r.dz = rays_d[n * 3 + 2];
+    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;  // IEEE division: this TU is never built with fast-math
+    return r;
+}
+
+// One lattice point of the marcher (raymarching.cu:360-399): classify the cell under t, and
+// either report an occupied sample (returns true; x,y,z,dt valid) or advance t past the empty cell.
+NGP_DEVINL bool probe(const MarchParams& p, const Ray& r, float& t, float& x, float& y, float& z, float& dt) {
+    x = clampf(r.ox + t * r.dx, -p.bound, p.bound);
+    y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
+    z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
+    dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+
+    const int level = max(level_from_pos(x, y, z, p.Cf), level_from_dt(dt, p.Hf, p.Cf));
+    const float mip_bound = fminf(scalbnf(1.0f, level), p.bound);
+    const float mip_rbound = 1 / mip_bound;
+
+    // `0.5 * (x*rb + 1) * H` is evaluated in double by the reference; both factors are exactly
+    // representable so the float product below rounds to the same value (DESIGN.md "marcher").
+    const int nx = (int)clampf(__fmul_rn(0.5f * (x * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
+    const int ny = (int)clampf(__fmul_rn(0.5f * (y * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
+    const int nz = (int)clampf(__fmul_rn(0.5f * (z * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
+
+    const uint32_t index = level * p.H3 + morton_encode(nx, ny, nz);  // float arithmetic, as in :378
+    const bool occ = p.grid[index / 8] & (1 << (index % 8));
+    if (occ) return true;
+
+    // distance to the far face of this cell along each axis (:390-394), then step the fixed
+    // t-lattice until it has been crossed (:396-398).
+    const float tx = (((nx + 0.5f + 0.5f * copysignf(1.0f, r.dx)) * p.rH * 2 - 1) * mip_bound - x) * r.rdx;
+    const float ty = (((ny + 0.5f + 0.5f * copysignf(1.0f, r.dy)) * p.rH * 2 - 1) * mip_bound - y) * r.rdy;
+    const float tz = (((nz + 0.5f + 0.5f * copysignf(1.0f, r.dz)) * p.rH * 2 - 1) * mip_bound - z) * r.rdz;
+    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+    do {
+        t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+    } while (t < tt);
+    return false;
+}
+
+// -------------------------------------------------------------------------------------------------
+// utils
+// -------------------------------------------------------------------------------------------------
+__global__ void near_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                const float* __restrict__ aabb, uint32_t N, float min_near, float* nears,
+                                float* fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const Ray r = load_ray(rays_o, rays_d, n);
+    // slab test, axis by axis (raymarching.cu:113-141)
+    float lo = (aabb[0] - r.ox) * r.rdx, hi = (aabb[3] - r.ox) * r.rdx;
+    if (lo > hi) { float s = lo; lo = hi; hi = s; }
+    float lo_y = (aabb[1] - r.oy) * r.rdy, hi_y = (aabb[4] - r.oy) * r.rdy;
+    if (lo_y > hi_y) { float s = lo_y; lo_y = hi_y; hi_y = s; }
+    bool miss = (lo > hi_y || lo_y > hi);
+    if (!miss) {
+        if (lo_y > lo) lo = lo_y;
+        if (hi_y < hi) hi = hi_y;
+        float lo_z = (aabb[2] - r.oz) * r.rdz, hi_z = (aabb[5] - r.oz) * r.rdz;
+        if (lo_z > hi_z) { float s = lo_z; lo_z = hi_z; hi_z = s; }
+        miss = (lo > hi_z || lo_z > hi);
+        if (!miss) {
+            if (lo_z > lo) lo = lo_z;
+            if (hi_z < hi) hi = hi_z;
+            if (lo < min_near) lo = min_near;
+        }
+    }
+    nears[n] = miss ? FLT_MAX : lo;
+    fars[n] = miss ? FLT_MAX : hi;
+}
+
+__global__ void sph_from_ray_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
+                                    uint32_t N, float* coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float ox = rays_o[n * 3], oy = rays_o[n * 3 + 1], oz = rays_o[n * 3 + 2];
+    const float dx = rays_d[n * 3], dy = rays_d[n * 3 + 1], dz = rays_d[n * 3 + 2];
+    // |o + t d| = radius, larger root (raymarching.cu:184-188)
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float Bh = ox * dx + oy * dy + oz * dz;
+    const float Cq = ox * ox + oy * oy + oz * oz - radius * radius;
+    const float t = (-Bh + sqrtf(Bh * Bh - A * Cq)) / A;
+    const float x = ox + t * dx, y = oy + t * dy, z = oz + t * dz;
+    const float theta = atan2f(sqrtf(x * x + z * z), y);
+    const float phi = atan2f(z, x);
+    const float inv_pi = 0.3183098861837907f;
+    coords[n * 2] = 2 * theta * inv_pi - 1;
+    coords[n * 2 + 1] = phi * inv_pi;
+}
+
+__global__ void morton_kernel(const int* __restrict__ coords, uint32_t N, int* indices) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    indices[n] = (int)morton_encode(coords[n * 3], coords[n * 3 + 1], coords[n * 3 + 2]);
+}
+__global__ void morton_invert_kernel(const int* __restrict__ indices, uint32_t N, int* coords) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int m = indices[n];
+    coords[n * 3 + 0] = (int)compact3(m >> 0);
+    coords[n * 3 + 1] = (int)compact3(m >> 1);
+    coords[n * 3 + 2] = (int)compact3(m >> 2);
+}
+
+// One thread packs one byte from two 16-byte loads (raymarching.cu:268-289).
+__global__ void packbits_kernel(const float* __restrict__ grid, uint32_t N, float thresh, uint8_t* bitfield) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(grid) + 2 * (size_t)n);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(grid) + 2 * (size_t)n + 1);
+    uint32_t bits = 0;
+    bits |= (a.x > thresh) ? 1u : 0u;   bits |= (a.y > thresh) ? 2u : 0u;
+    bits |= (a.z > thresh) ? 4u : 0u;   bits |= (a.w > thresh) ? 8u : 0u;
+    bits |= (b.x > thresh) ? 16u : 0u;  bits |= (b.y > thresh) ? 32u : 0u;
+    bits |= (b.z > thresh) ? 64u : 0u;  bits |= (b.w > thresh) ? 128u : 0u;
+    bitfield[n] = (uint8_t)bits;
+}
+
+// -------------------------------------------------------------------------------------------------
+// training march
+// -------------------------------------------------------------------------------------------------
+NGP_DEVINL float perturbed_start(const MarchParams& p, float near, float noise) {
+    float t0 = near;
+    t0 += clampf(t0 * p.dt_gamma, p.dt_min, p.dt_max) * noise;  // raymarching.cu:351
+    return t0;
+}
+
+__global__ void __launch_bounds__(128) march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                          const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                                          const float* __restrict__ nears, const float* __restrict__ fars,
+                                                          const float* __restrict__ noises, int* __restrict__ counts) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, n);
+    const float far = fars[n];
+    float t = perturbed_start(p, nears[n], noises[n]);
+    uint32_t steps = 0;
+    float x, y, z, dt;
+    while (t < far && steps < max_steps) {
+        if (probe(p, r, t, x, y, z, dt)) { ++steps; t += dt; }
+    }
+    counts[n] = (int)steps;
+}
+
+// Single-CTA exclusive scan of the per-ray counts, in ray order.  Writes the (id, offset, count)
+// rows (row n <-> ray n; offsets start at the incoming counter[0], as the reference's atomicAdd
+// would) and bumps the two counters the way the reference's atomics do in aggregate.
+__global__ void __launch_bounds__(1024) march_scan_kernel(const int* __restrict__ counts, uint32_t N, int* __restrict__ rays,
+                                                          int* __restrict__ counter) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = counter[0];
+    __syncthreads();
+    for (uint32_t base = 0; base < N; base += blockDim.x) {
+        const uint32_t n = base + threadIdx.x;
+        const int c = n < N ? counts[n] : 0;
+        int incl = warp_incl_scan_i(c, lane);
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+            w = warp_incl_scan_i(w, lane);
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int offset = carry + (warp ? s_warp[warp - 1] : 0) + incl - c;
+        if (n < N) {
+            rays[(size_t)n * 3 + 0] = (int)n;
+            rays[(size_t)n * 3 + 1] = offset;
+            rays[(size_t)n * 3 + 2] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        counter[0] = s_carry;
+        counter[1] += (int)N;
+    }
+}
+
+__global__ void __launch_bounds__(128) march_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                          const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                                          const float* __restrict__ nears, const float* __restrict__ fars,
+                                                          const float* __restrict__ noises, const int* __restrict__ counts,
+                                                          const int* __restrict__ rays, float* __restrict__ xyzs,
+                                                          float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t num_steps = (uint32_t)counts[n];
+    if (num_steps == 0) return;
+    const uint32_t offset = (uint32_t)rays[(size_t)n * 3 + 1];
+    if (offset + num_steps > M) return;  // raymarching.cu:416
+
+    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, n);
+    const float far = fars[n];
+    float t = perturbed_start(p, nears[n], noises[n]);
+    float last_t = t;
+    float* px = xyzs + (size_t)offset * 3;
+    float* pd = dirs + (size_t)offset * 3;
+    float* pl = deltas + (size_t)offset * 2;
+    uint32_t step = 0;
+    float x, y, z, dt;
+    while (t < far && step < num_steps) {
+        if (probe(p, r, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t += dt;
+            pl[0] = dt;
+            pl[1] = t - last_t;  // raymarching.cu:461
+            last_t = t;
+            px += 3; pd += 3; pl += 2;
+            ++step;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// training composite: one warp per ray
+// -------------------------------------------------------------------------------------------------
+struct RaySpan { uint32_t id, offset, count; bool live; };
+NGP_DEVINL RaySpan load_span(const int* __restrict__ rays, uint32_t n, uint32_t M) {
+    RaySpan s;
+    s.id = (uint32_t)rays[n * 3]; s.offset = (uint32_t)rays[n * 3 + 1]; s.count = (uint32_t)rays[n * 3 + 2];
+    s.live = !(s.count == 0 || s.offset + s.count > M);  // raymarching.cu:521
+    return s;
+}
+
+// For the 32 samples [base, base+32) of one ray: per-lane transmittance BEFORE the sample, rebuilt in
+// the reference's left-to-right multiplication order (T *= 1 - alpha, raymarching.cu:554), and the
+// running depth parameter t (t += deltas[1], :549).  Returns the lane's own (1 - alpha).
+NGP_DEVINL void serial_prefix(float om, float d1, int lane, float T_in, float t_in, float& T_before, float& t_incl) {
+    float T = T_in, tt = t_in;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float om_j = __shfl_sync(0xffffffffu, om, j);
+        const float d_j = __shfl_sync(0xffffffffu, d1, j);
+        if (j < lane) T *= om_j;
+        if (j <= lane) tt += d_j;
+    }
+    T_before = T;
+    t_incl = tt;
+}
+
+__global__ void __launch_bounds__(256) composite_train_fwd_kernel(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                                  const float* __restrict__ deltas, const int* __restrict__ rays,
+                                                                  uint32_t M, uint32_t N, float T_thresh, float* weights_sum,
+                                                                  float* depth, float* image) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const RaySpan s = load_span(rays, n, M);
+    float r = 0, g = 0, b = 0, ws = 0, d = 0;
+    if (s.live) {
+        float T_carry = 1.0f, t_carry = 0.f;
+        for (uint32_t base = 0; base < s.count; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < s.count;
+            float om = 1.0f, d1 = 0.f, alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            if (valid) {
+                const size_t m = (size_t)s.offset + i;
+                const float sigma = __ldg(sigmas + m);
+                const float2 dl = __ldg(reinterpret_cast<const float2*>(deltas) + m);
+                alpha = 1.0f - __expf(-sigma * dl.x);  // raymarching.cu:542
+                om = 1.0f - alpha;
+                d1 = dl.y;
+                cr = __ldg(rgbs + m * 3); cg = __ldg(rgbs + m * 3 + 1); cb = __ldg(rgbs + m * 3 + 2);
+            }
+            float T_before, t_incl;
+            serial_prefix(om, d1, lane, T_carry, t_carry, T_before, t_incl);
+            const float T_after = T_before * om;
+            // first sample after which the ray is opaque enough (:557): it is still accumulated
+            const unsigned stop_mask = __ballot_sync(0xffffffffu, valid && (T_after < T_thresh));
+            const int stop_lane = stop_mask ? (__ffs(stop_mask) - 1) : 31;
+            if (valid && lane <= stop_lane) {
+                const float w = alpha * T_before;
+                r += w * cr; g += w * cg; b += w * cb;
+                d += w * t_incl;
+                ws += w;
+            }
+            if (stop_mask) break;
+            T_carry = __shfl_sync(0xffffffffu, T_after, 31);
+            t_carry = __shfl_sync(0xffffffffu, t_incl, 31);
+        }
+        r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
+    }
+    if (lane == 0) {
+        weights_sum[s.id] = ws;
+        depth[s.id] = d;
+        image[s.id * 3] = r; image[s.id * 3 + 1] = g; image[s.id * 3 + 2] = b;
+    }
+}
+
+NGP_DEVINL float warp_incl_scan_f(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// raymarching.cu:602-682.  ZERO_TAIL additionally writes zeros for the samples of a live ray that lie
+// behind the early-termination point, so the caller need not pre-zero rows owned by live rays.
+template <bool ZERO_TAIL>
+__global__ void __launch_bounds__(256) composite_train_bwd_kernel(
+    const float* __restrict__ grad_ws, const float* __restrict__ grad_image, const float* __restrict__ sigmas,
+    const float* __restrict__ rgbs, const float* __restrict__ deltas, const int* __restrict__ rays,
+    const float* __restrict__ weights_sum, const float* __restrict__ image, uint32_t M, uint32_t N, float T_thresh,
+    float* __restrict__ grad_sigmas, float* __restrict__ grad_rgbs) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const RaySpan s = load_span(rays, n, M);
+    if (!s.live) return;
+    const float gi0 = grad_image[s.id * 3], gi1 = grad_image[s.id * 3 + 1], gi2 = grad_image[s.id * 3 + 2];
+    const float gws = grad_ws[s.id];
+    const float r_final = image[s.id * 3], g_final = image[s.id * 3 + 1], b_final = image[s.id * 3 + 2];
+    const float ws_final = weights_sum[s.id];
+
+    float T_carry = 1.0f, r_carry = 0.f, g_carry = 0.f, b_carry = 0.f;
+    bool stopped = false;
+    for (uint32_t base = 0; base < s.count; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < s.count;
+        const size_t m = (size_t)s.offset + i;
+        if (stopped) {  // warp-uniform
+            if (ZERO_TAIL && valid) {
+                grad_sigmas[m] = 0.f;
+                grad_rgbs[m * 3] = 0.f; grad_rgbs[m * 3 + 1] = 0.f; grad_rgbs[m * 3 + 2] = 0.f;
+            }
+            continue;
+        }
+        float om = 1.0f, alpha = 0.f, d0 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (valid) {
+            const float sigma = __ldg(sigmas + m);
+            d0 = __ldg(deltas + m * 2);
+            alpha = 1.0f - __expf(-sigma * d0);
+            om = 1.0f - alpha;
+            cr = __ldg(rgbs + m * 3); cg = __ldg(rgbs + m * 3 + 1); cb = __ldg(rgbs + m * 3 + 2);
+        }
+        float T_before, unused_t;
+        serial_prefix(om, 0.f, lane, T_carry, 0.f, T_before, unused_t);
+        const float T_after = T_before * om;
+        const unsigned stop_mask = __ballot_sync(0xffffffffu, valid && (T_after < T_thresh));
+        const int stop_lane = stop_mask ? (__ffs(stop_mask) - 1) : 31;
+        const bool active = valid && lane <= stop_lane;
+        const float w = active ? alpha * T_before : 0.f;
+        // running colour INCLUDING this sample (:648-650)
+        const float r_run = r_carry + warp_incl_scan_f(w * cr, lane);
+        const float g_run = g_carry + warp_incl_scan_f(w * cg, lane);
+        const float b_run = b_carry + warp_incl_scan_f(w * cb, lane);
+        if (active) {
+            grad_rgbs[m * 3] = gi0 * w; grad_rgbs[m * 3 + 1] = gi1 * w; grad_rgbs[m * 3 + 2] = gi2 * w;
+            grad_sigmas[m] = d0 * (gi0 * (T_after * cr - (r_final - r_run)) + gi1 * (T_after * cg - (g_final - g_run)) +
+                                   gi2 * (T_after * cb - (b_final - b_run)) + gws * (1 - ws_final));
+        } else if (ZERO_TAIL && valid) {
+            grad_sigmas[m] = 0.f;
+            grad_rgbs[m * 3] = 0.f; grad_rgbs[m * 3 + 1] = 0.f; grad_rgbs[m * 3 + 2] = 0.f;
+        }
+        if (stop_mask) { stopped = true; continue; }
+        T_carry = __shfl_sync(0xffffffffu, T_after, 31);
+        r_carry = __shfl_sync(0xffffffffu, r_run, 31);
+        g_carry = __shfl_sync(0xffffffffu, g_run, 31);
+        b_carry = __shfl_sync(0xffffffffu, b_run, 31);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// inference march / composite (raymarching.cu:701-905): few steps per call, one thread per ray
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) march_infer_kernel(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive,
+                                                          const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d, float bound, float dt_gamma,
+                                                          uint32_t max_steps, uint32_t C, uint32_t H,
+                                                          const uint8_t* __restrict__ grid, const float* __restrict__ nears,
+                                                          const float* __restrict__ fars, float* __restrict__ xyzs,
+                                                          float* __restrict__ dirs, float* __restrict__ deltas,
+                                                          const float* __restrict__ noises) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int id = rays_alive[n];
+    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, (uint32_t)id);
+    const float far = fars[id];
+    float t = rays_t[id];
+    t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * noises[n];  // raymarching.cu:746
+    float last_t = t;
+    float* px = xyzs + (size_t)n * n_step * 3;
+    float* pd = dirs + (size_t)n * n_step * 3;
+    float* pl = deltas + (size_t)n * n_step * 2;
+    uint32_t step = 0;
+    float x, y, z, dt;
+    while (t < far && step < n_step) {
+        if (probe(p, r, t, x, y, z, dt)) {
+            px[0] = x; px[1] = y; px[2] = z;
+            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            t += dt;
+            pl[0] = dt;
+            pl[1] = t - last_t;
+            last_t = t;
+            px += 3; pd += 3; pl += 2;
+            ++step;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) composite_infer_kernel(uint32_t n_alive, uint32_t n_step, float T_thresh, int* rays_alive,
+                                                              float* rays_t, const float* __restrict__ sigmas,
+                                                              const float* __restrict__ rgbs, const float* __restrict__ deltas,
+                                                              float* weights_sum, float* depth, float* image) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int id = rays_alive[n];
+    const float* ps = sigmas + (size_t)n * n_step;
+    const float* pc = rgbs + (size_t)n * n_step * 3;
+    const float* pl = deltas + (size_t)n * n_step * 2;
+    float t = rays_t[id];
+    float wsum = weights_sum[id], d = depth[id];
+    float r = image[id * 3], g = image[id * 3 + 1], b = image[id * 3 + 2];
+    uint32_t step = 0;
+    while (step < n_step) {
+        if (pl[0] == 0) break;  // unused slot: the marcher ran out of ray (raymarching.cu:858)
+        const float alpha = 1.0f - __expf(-ps[0] * pl[0]);
+        const float T = 1 - wsum;  // transmittance from the running alpha sum (:868)
+        const float w = alpha * T;
+        wsum += w;
+        t += pl[1];
+        d += w * t;
+        r += w * pc[0]; g += w * pc[1]; b += w * pc[2];
+        if (T < T_thresh) break;
+        ++ps; pc += 3; pl += 2; ++step;
+    }
+    if (step < n_step) rays_alive[n] = -1; else rays_t[id] = t;  // :894-898
+    weights_sum[id] = wsum;
+    depth[id] = d;
+    image[id * 3] = r; image[id * 3 + 1] = g; image[id * 3 + 2] = b;
+}
+
+// -------------------------------------------------------------------------------------------------
+// stable compaction of alive rays (device-side replacement for the boolean-mask indexing)
+// -------------------------------------------------------------------------------------------------
+constexpr int kCompactBlock = 1024;
+__global__ void __launch_bounds__(kCompactBlock) compact_count_kernel(const int* __restrict__ rays_alive, uint32_t n,
+                                                                      int* __restrict__ block_counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int keep = (i < n && rays_alive[i] >= 0) ? 1 : 0;
+    const int total = __syncthreads_count(keep);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kCompactBlock) compact_scatter_kernel(const int* __restrict__ rays_alive, uint32_t n,
+                                                                        const int* __restrict__ block_counts, int* __restrict__ out,
+                                                                        int* __restrict__ n_out) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // prefix of the preceding blocks' counts (grid is small: <= n/1024 entries)
+    int part = 0;
+    for (uint32_t j = threadIdx.x; j < blockIdx.x; j += blockDim.x) part += block_counts[j];
+    part = warp_sum_i(part);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_warp[lane];
+        v = warp_sum_i(v);
+        if (lane == 0) s_base = v;
+    }
+    __syncthreads();
+    const int base = s_base;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = i < n ? rays_alive[i] : -1;
+    const int keep = v >= 0 ? 1 : 0;
+    const int incl = warp_incl_scan_i(keep, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        w = warp_incl_scan_i(w, lane);
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int pos = base + (warp ? s_warp[warp - 1] : 0) + incl - keep;
+    if (keep) out[pos] = v;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) *n_out = base + s_warp[31];
+}
+
+}  // namespace march
+}  // namespace ngp
+
+using namespace ngp;
+
+extern "C" int ngp_near_far_from_aabb(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N,
+                                      float min_near, float* nears, float* fars, void* stream) {
+    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NGP_ERR_BAD_ARG;
+    if (N == 0) return NGP_OK;
+    march::near_far_kernel<<<cdiv(N, 128), 128, 0, as_stream(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears, fars);
+    return launch_status();
+}
+
+extern "C" int ngp_sph_from_ray(const float* rays_o, const float* rays_d, float radius, uint32_t N, float* coords,
+                                void* stream) {
+    if (!rays_o || !rays_d || !coords) return NGP_ERR_BAD_ARG;
+    if (N == 0) return NGP_OK;
+    march::sph_from_ray_kernel<<<cdiv(N, 128), 128, 0, as_stream(stream)>>>(rays_o, rays_d, radius, N, coords);
+    return launch_status();
+}
+
+extern "C" int ngp_morton3D(const int* coords, uint32_t N, int* indices, void* stream) {
+    if (!coords || !indices) return NGP_ERR_BAD_ARG;
+    if (N == 0) return NGP_OK;
+    march::morton_kernel<<<cdiv(N, 256), 256, 0, as_stream(stream)>>>(coords, N, indices);
+    return launch_status();
+}
+
+extern "C" int ngp_morton3D_invert(const int* indices, uint32_t N, int* coords, void* stream) {
+    if (!coords || !indices) return NGP_ERR_BAD_ARG;
+    if (N == 0) return NGP_OK;
+    march::morton_invert_kernel<<<cdiv(N, 256), 256, 0, as_stream(stream)>>>(indices, N, coords);
+    return launch_status();
+}
+
+extern "C" int ngp_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* bitfield, void* stream) {
+    if (!grid || !bitfield) return NGP_ERR_BAD_ARG;
+    if (N == 0) return NGP_OK;
+    march::packbits_kernel<<<cdiv(N, 256), 256, 0, as_stream(stream)>>>(grid, N, density_thresh, bitfield);
+    return launch_status();
+}
+
+extern "C" uint64_t ngp_march_rays_train_workspace(uint32_t N) { return (uint64_t)N * sizeof(int) + 16; }
+
+extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                    float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                    const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                    int* rays, int* counter, const float* noises, void* workspace,
+                                    uint64_t workspace_bytes, void* stream) {
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !dirs || !deltas || !rays || !counter || !noises)
+        return NGP_ERR_BAD_ARG;
+    if (C == 0 || H == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
+    if (!workspace || workspace_bytes < ngp_march_rays_train_workspace(N)) return NGP_ERR_WORKSPACE;
+    if (N == 0) return NGP_OK;
+    cudaStream_t st = as_stream(stream);
+    int* counts = static_cast<int*>(workspace);
+    march::march_count_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
+                                                            fars, noises, counts);
+    march::march_scan_kernel<<<1, 1024, 0, st>>>(counts, N, rays, counter);
+    march::march_write_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
+                                                            fars, noises, counts, rays, xyzs, dirs, deltas);
+    return launch_status();
+}
+
+extern "C" int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,
+                                                const int* rays, uint32_t M, uint32_t N, float T_thresh,
+                                                float* weights_sum, float* depth, float* image, void* stream) {
+    if (!sigmas || !rgbs || !deltas || !rays || !weights_sum || !depth || !image) return NGP_ERR_BAD_ARG;
+    if (N == 0) return NGP_OK;
+    march::composite_train_fwd_kernel<<<cdiv((uint64_t)N * 32, 256), 256, 0, as_stream(stream)>>>(
+        sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image);
+    return launch_status();
+}
+
+extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, const float* grad_image,
+                                                 const float* sigmas, const float* rgbs, const float* deltas,
+                                                 const int* rays, const float* weights_sum, const float* image,
+                                                 uint32_t M, uint32_t N, float T_thresh, float* grad_sigmas,
+                                                 float* grad_rgbs, void* stream) {
+    if (!grad_weights_sum || !grad_image || !sigmas || !rgbs || !deltas || !rays || !weights_sum || !image ||
+        !grad_sigmas || !grad_rgbs)
+        return NGP_ERR_BAD_ARG;
+    if (N == 0) return NGP_OK;
+    march::composite_train_bwd_kernel<true><<<cdiv((uint64_t)N * 32, 256), 256, 0, as_stream(stream)>>>(
+        grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas,
+        grad_rgbs);
+    return launch_status();
+}
+
+extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays_alive, const float* rays_t,
+                              const float* rays_o, const float* rays_d, float bound, float dt_gamma,
+                              uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, const float* nears,
+                              const float* fars, float* xyzs, float* dirs, float* deltas, const float* noises,
+                              void* stream) {
+    if (!rays_alive || !rays_t || !rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !dirs || !deltas || !noises)
+        return NGP_ERR_BAD_ARG;
+    if (C == 0 || H == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
+    if (n_alive == 0 || n_step == 0) return NGP_OK;
+    march::march_infer_kernel<<<cdiv(n_alive, 128), 128, 0, as_stream(stream)>>>(
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs,
+        deltas, noises);
+    return launch_status();
+}
+
+extern "C" int ngp_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int* rays_alive, float* rays_t,
+                                  const float* sigmas, const float* rgbs, const float* deltas, float* weights_sum,
+                                  float* depth, float* image, void* stream) {
+    if (!rays_alive || !rays_t || !sigmas || !rgbs || !deltas || !weights_sum || !depth || !image) return NGP_ERR_BAD_ARG;
+    if (n_alive == 0) return NGP_OK;
+    march::composite_infer_kernel<<<cdiv(n_alive, 128), 128, 0, as_stream(stream)>>>(
+        n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth, image);
+    return launch_status();
+}
+
+extern "C" uint64_t ngp_compact_alive_workspace(uint32_t n_alive) {
+    return (uint64_t)cdiv(n_alive > 0 ? n_alive : 1, march::kCompactBlock) * sizeof(int);
+}
+
+extern "C" int ngp_compact_alive(const int* rays_alive, uint32_t n_alive, int* out, int* n_out, void* workspace,
+                                 uint64_t workspace_bytes, void* stream) {
+    if (!rays_alive || !out || !n_out) return NGP_ERR_BAD_ARG;
+    cudaStream_t st = as_stream(stream);
+    if (n_alive == 0) { cudaMemsetAsync(n_out, 0, sizeof(int), st); return launch_status(); }
+    if (!workspace || workspace_bytes < ngp_compact_alive_workspace(n_alive)) return NGP_ERR_WORKSPACE;
+    const int blocks = cdiv(n_alive, march::kCompactBlock);
+    int* block_counts = static_cast<int*>(workspace);
+    march::compact_count_kernel<<<blocks, march::kCompactBlock, 0, st>>>(rays_alive, n_alive, block_counts);
+    march::compact_scatter_kernel<<<blocks, march::kCompactBlock, 0, st>>>(rays_alive, n_alive, block_counts, out, n_out);
+    return launch_status();
+}

@@ -1,0 +1,237 @@
+"""``NeRFRenderer`` - host-side mirror of the reference's cuda-ray renderer (nerf/renderer.py:64-653).
+
+The contract of ``run_cuda`` / ``update_extra_state`` / ``render`` is the reference's: same
+arguments (including the swallowed ``**kwargs`` the Trainer splats in, nerf/utils.py:363), same
+``results`` dict, same registered buffers (``aabb_train``, ``aabb_infer``, ``density_grid``,
+``density_bitfield``, ``step_counter``) so reference checkpoints load, same side effects on
+``local_step`` / ``step_counter``.  The plumbing underneath is new:
+
+* the occupancy update builds its query points directly in Morton order and does EMA-max, mean and
+  bit packing on the device without a host round trip (``mean_density`` / ``mean_count`` are read
+  back lazily, only if somebody asks for the python value);
+* the inference loop compacts alive rays with a device kernel instead of boolean-mask indexing.
+
+``export_mesh`` (offline marching cubes + UV unwrap) is outside the hot path and not provided.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+import raymarching
+from . import _cabi
+
+
+def safe_normalize(x, eps=1e-20):
+    return x / torch.sqrt(torch.clamp(torch.sum(x * x, -1, keepdim=True), min=eps))
+
+
+class _LazyScalar:
+    """A device scalar whose python value is fetched (one sync) only on first use."""
+
+    def __init__(self, tensor=None, value=None, fn=None):
+        self.tensor, self.value, self.fn = tensor, value, fn
+
+    def get(self):
+        if self.value is None:
+            v = self.tensor.item() if self.tensor is not None else 0
+            self.value = self.fn(v) if self.fn is not None else v
+        return self.value
+
+
+class NeRFRenderer(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.bound = opt.bound
+        self.cascade = 1 + math.ceil(math.log2(opt.bound))
+        self.grid_size = 128
+        self.cuda_ray = opt.cuda_ray
+        self.min_near = opt.min_near
+        self.density_thresh = opt.density_thresh
+        self.bg_radius = opt.bg_radius
+
+        # (xmin, ymin, zmin, xmax, ymax, zmax); only used to clip rays - hashing uses the cubic bound
+        aabb_train = torch.FloatTensor([-opt.bound, -opt.bound, -opt.bound, opt.bound, opt.bound, opt.bound])
+        self.register_buffer('aabb_train', aabb_train)
+        self.register_buffer('aabb_infer', aabb_train.clone())
+
+        if self.cuda_ray:
+            self.register_buffer('density_grid', torch.zeros([self.cascade, self.grid_size ** 3]))
+            self.register_buffer('density_bitfield',
+                                 torch.zeros(self.cascade * self.grid_size ** 3 // 8, dtype=torch.uint8))
+            self._mean_density = _LazyScalar(value=0)
+            self.iter_density = 0
+            self.register_buffer('step_counter', torch.zeros(16, 2, dtype=torch.int32))  # 16 steps averaged
+            self._mean_count = _LazyScalar(value=0)
+            self.local_step = 0
+
+    # python-visible scalars of the reference (renderer.py:91,96), fetched lazily from the device
+    @property
+    def mean_density(self):
+        return self._mean_density.get()
+
+    @mean_density.setter
+    def mean_density(self, v):
+        self._mean_density = _LazyScalar(value=v)
+
+    @property
+    def mean_count(self):
+        return self._mean_count.get()
+
+    @mean_count.setter
+    def mean_count(self, v):
+        self._mean_count = _LazyScalar(value=v)
+
+    def forward(self, x, d):
+        raise NotImplementedError()
+
+    def density(self, x):
+        raise NotImplementedError()
+
+    def color(self, x, d, mask=None, **kwargs):
+        raise NotImplementedError()
+
+    def reset_extra_state(self):
+        if not self.cuda_ray:
+            return
+        self.density_grid.zero_()
+        self.mean_density = 0
+        self.iter_density = 0
+        self.step_counter.zero_()
+        self.mean_count = 0
+        self.local_step = 0
+
+    def export_mesh(self, *args, **kwargs):
+        raise NotImplementedError("export_mesh (offline mesh extraction) is outside the B200 hot path")
+
+    def run(self, *args, **kwargs):
+        raise NotImplementedError(
+            "the pure-PyTorch sampler (nerf/renderer.py:301) is not part of the B200 hot path; construct the model "
+            "with opt.cuda_ray=True")
+
+    # --------------------------------------------------------------------------------------------
+    def run_cuda(self, rays_o, rays_d, dt_gamma=0, light_d=None, ambient_ratio=1.0, shading='albedo', bg_color=None,
+                 perturb=False, force_all_rays=False, max_steps=1024, T_thresh=1e-4, **kwargs):
+        # rays_o, rays_d: [B, N, 3] -> image [B, N, 3], depth [B, N], weights_sum [B, N], mask [B, N]
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3)
+        rays_d = rays_d.contiguous().view(-1, 3)
+        N = rays_o.shape[0]
+        device = rays_o.device
+
+        # NOTE the reference passes no min_near here, so the wrapper default 0.2 applies (renderer.py:458)
+        nears, fars = raymarching.near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer)
+
+        if light_d is None:
+            # light roughly from the camera side so the visible face is lit (renderer.py:461-464)
+            light_d = safe_normalize(rays_o[0] + torch.randn(3, device=device, dtype=torch.float))
+
+        results = {}
+
+        if self.training:
+            counter = self.step_counter[self.local_step % 16]
+            counter.zero_()
+            self.local_step += 1
+
+            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                self.mean_count if not force_all_rays else -1, perturb, 128, force_all_rays, dt_gamma, max_steps)
+
+            sigmas, rgbs, normals = self(xyzs, dirs, light_d, ratio=ambient_ratio, shading=shading)
+
+            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+
+            if normals is not None:
+                # orientation + smoothness regularisers (renderer.py:485-494)
+                weights = 1 - torch.exp(-sigmas)
+                loss_orient = weights.detach() * (normals * dirs).sum(-1).clamp(min=0) ** 2
+                results['loss_orient'] = loss_orient.mean()
+                normals_perturb = self.normal(xyzs + torch.randn_like(xyzs) * 1e-2)
+                results['loss_smooth'] = (normals - normals_perturb).abs().mean()
+        else:
+            dtype = torch.float32
+            weights_sum = torch.zeros(N, dtype=dtype, device=device)
+            depth = torch.zeros(N, dtype=dtype, device=device)
+            image = torch.zeros(N, 3, dtype=dtype, device=device)
+
+            n_alive = N
+            rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
+            rays_t = nears.clone()
+
+            step = 0
+            while step < max_steps and n_alive > 0:
+                # more steps per launch as rays die off (renderer.py:521)
+                n_step = max(min(N // n_alive, 8), 1)
+                xyzs, dirs, deltas = raymarching.march_rays(
+                    n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, self.density_bitfield, self.cascade,
+                    self.grid_size, nears, fars, 128, perturb if step == 0 else False, dt_gamma, max_steps)
+                sigmas, rgbs, normals = self(xyzs, dirs, light_d, ratio=ambient_ratio, shading=shading)
+                raymarching.composite_rays(n_alive, n_step, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth,
+                                           image, T_thresh)
+                rays_alive, n_out = raymarching.compact_alive(rays_alive, n_alive)
+                n_alive = int(n_out.item())  # the loop shape is data dependent (one 4-byte D2H per iteration)
+                step += n_step
+
+        if self.bg_radius > 0:
+            bg_color = self.background(rays_d)  # [N, 3]
+        elif bg_color is None:
+            bg_color = 1
+
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        image = image.view(*prefix, 3)
+
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)  # NaN for rays that miss the box, as the reference
+        depth = depth.view(*prefix)
+        weights_sum = weights_sum.reshape(*prefix)
+        mask = (nears < fars).reshape(*prefix)
+
+        results['image'] = image
+        results['depth'] = depth
+        results['weights_sum'] = weights_sum
+        results['mask'] = mask
+        return results
+
+    # --------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def update_extra_state(self, decay=0.95, S=128, noise=None):
+        """Occupancy-grid refresh (renderer.py:562-613).  `noise` ([cascade, H^3, 3] uniform in [0,1), indexed by
+        the linear cell id) can be injected for reproducible comparisons; by default it is drawn with
+        torch.rand exactly where the reference draws its jitter (one rand per cascade, same shape)."""
+        if not self.cuda_ray:
+            return
+        H = self.grid_size
+        device = self.density_bitfield.device
+        n_cells = H ** 3
+        tmp_grid = torch.empty_like(self.density_grid)
+
+        for cas in range(self.cascade):
+            bound = min(2 ** cas, self.bound)
+            half_cell = bound / H
+            u = torch.rand(n_cells, 3, device=device) if noise is None else noise[cas].to(device, torch.float32).contiguous()
+            xyzs = torch.empty(n_cells, 3, device=device, dtype=torch.float32)
+            _cabi.call("ngp_occupancy_cell_points", device, H, float(bound - half_cell), float(half_cell), _cabi.ptr(u),
+                       _cabi.ptr(xyzs))
+            # Morton-ordered queries: the densities land in density_grid order, no index scatter needed
+            tmp_grid[cas] = self.density(xyzs)['sigma'].reshape(-1).detach().float()
+
+        mean = torch.empty(1, device=device, dtype=torch.float32)
+        ws = torch.empty(16, device=device, dtype=torch.uint8)
+        _cabi.call("ngp_update_density_grid", device, _cabi.ptr(self.density_grid), _cabi.ptr(tmp_grid),
+                   self.cascade * n_cells, float(decay), float(self.density_thresh), _cabi.ptr(mean),
+                   _cabi.ptr(self.density_bitfield), _cabi.ptr(ws), ws.numel())
+        self._mean_density = _LazyScalar(tensor=mean)
+        self.iter_density += 1
+
+        # mean sample count of the last (up to 16) steps (renderer.py:610-613)
+        total_step = min(16, self.local_step)
+        if total_step > 0:
+            s = self.step_counter[:total_step, 0].sum()
+            self._mean_count = _LazyScalar(tensor=s, fn=lambda v, n=total_step: int(v / n))
+        self.local_step = 0
+
+    def render(self, rays_o, rays_d, staged=False, max_ray_batch=4096, **kwargs):
+        # rays_o, rays_d: [B, N, 3]; never staged in cuda_ray mode (renderer.py:630-652)
+        if not self.cuda_ray:
+            return self.run(rays_o, rays_d, **kwargs)
+        return self.run_cuda(rays_o, rays_d, **kwargs)
