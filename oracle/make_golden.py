@@ -30,6 +30,15 @@ def main(out_path):
     T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     out = {}
 
+    # ---- per-level scales exp2f(l*S)*H-1 as the DEVICE evaluates them (gridencoder.cu:125; MUFU.EX2 != libm) ----
+    c0 = util.golden_grid_case(0, "f32")
+    sys.path.insert(0, os.path.join(ROOT, "single-stable-dreamfusion_b200"))
+    from ngp_b200 import _cabi
+    sc = torch.empty(16, device=dev)
+    rs = torch.empty(16, dtype=torch.int32, device=dev)
+    _cabi.call("ngp_grid_level_params", dev, 16, float(c0["S"]), 16, _cabi.ptr(sc), _cabi.ptr(rs))
+    out["grid_scales"] = sc.cpu().numpy()
+
     # ---- grid encoder: forward (+dy_dx) and backward, fp32 and fp16, hash and tiled -----------------
     for gridtype in (0, 1):
         for dt in ("f32", "f16"):
@@ -44,7 +53,7 @@ def main(out_path):
             rows = np.random.default_rng(5).integers(0, ge.shape[0], 4096)
             out[key + "gemb_rows"] = ge[rows]
             out[key + "gemb_l1"] = np.array([np.abs(ge.astype(np.float64)).sum()])
-            out[key + "ginp"] = gi.float().cpu().numpy()
+            out[key + "ginp"] = gi.cpu().numpy()
 
     # ---- raymarching ------------------------------------------------------------------------------------
     for name, kw in (("m1", {}), ("m2", dict(cascade=2, bound=2.0, dt_gamma=1.0 / 128, max_steps=128, seed=21))):

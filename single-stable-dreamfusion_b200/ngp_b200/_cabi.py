@@ -96,11 +96,28 @@ def require_contiguous(*tensors):
             raise RuntimeError("expected a contiguous tensor")
 
 
+# kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
+KERNELS_PER_CALL = {"ngp_march_rays_train": 3, "ngp_update_density_grid": 2, "ngp_compact_alive": 2}
+LAUNCHES = 0       # running count of our kernels launched through this module
+PROFILE = None     # optional {entry point name: [(start_event, end_event), ...]} filled while set (bench.py)
+
+
 def call(name, device, *args):
     """Invoke an entry point with `device` current and the caller's current stream appended."""
+    global LAUNCHES
     lib = load()
     with torch.cuda.device(device):
-        rc = getattr(lib, name)(*args, stream())
+        prof = PROFILE.get(name) if PROFILE is not None else None
+        if prof is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = getattr(lib, name)(*args, stream())
+            e1.record()
+            prof.append((e0, e1))
+        else:
+            rc = getattr(lib, name)(*args, stream())
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
 
 
