@@ -68,6 +68,10 @@ int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* 
                              uint32_t H, const void* dy_dx, void* grad_inputs, uint32_t gridtype,
                              int align_corners, int dtype, int grad_layout, int grad_emb_dtype, void* stream);
 
+/* Tuning / test switches.  option 0: value != 0 disables the warp-aggregated scatter of the backward (every
+ * sample then issues its own atomics, like the reference). */
+int ngp_grid_set_option(int option, int value);
+
 /* Device-computed per-level (scale, resolution) exactly as gridencoder.cu:125-126 evaluates them
  * (exp2f on the device).  scales f32[L], resolutions u32[L] are DEVICE buffers. */
 int ngp_grid_level_params(uint32_t L, float S, uint32_t H, float* scales, uint32_t* resolutions, void* stream);
@@ -173,6 +177,12 @@ int ngp_bench_gather4(const uint32_t* table, uint32_t table_words, uint32_t* sin
 /* Random 8-byte red.global.add.v2.f32 into table f32[table_words]. */
 int ngp_bench_red8(float* table, uint32_t table_words, uint32_t n_threads, uint32_t iters, uint32_t seed,
                    void* stream);
+
+/* Hardware self-test of the hand-written tcgen05 path (one CTA, one small fp16 GEMM with fp32 accumulate):
+ * mode 0: D[128,N] = A[128,K] B[N,K]^T ; mode 1: D[M,N] = A[128,M]^T B[128,N] (M in {64,128}) ;
+ * mode 2: D[128,N] = A[128,K] B[K,N].  A, B row-major fp16, D row-major fp32, N,K multiples of 16 <= 128. */
+int ngp_tc_selftest(int mode, const void* A, const void* B, float* D, uint32_t M, uint32_t N, uint32_t K,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@ SIGNATURES = {
     "ngp_device_info": (_i32, [C.c_char_p, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "ngp_grid_encode_forward": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _vp, _u32, _i32, _i32, _i32, _vp]),
     "ngp_grid_encode_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _vp, _vp, _u32, _i32, _i32, _i32, _i32, _vp]),
+    "ngp_grid_set_option": (_i32, [_i32, _i32]),
     "ngp_grid_level_params": (_i32, [_u32, _f32, _u32, _vp, _vp, _vp]),
     "ngp_near_far_from_aabb": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp]),
     "ngp_sph_from_ray": (_i32, [_vp, _vp, _f32, _u32, _vp, _vp]),
@@ -43,6 +44,7 @@ SIGNATURES = {
     "ngp_update_density_grid": (_i32, [_vp, _vp, _u32, _f32, _f32, _vp, _vp, _vp, _u64, _vp]),
     "ngp_bench_gather4": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _vp]),
     "ngp_bench_red8": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp]),
+    "ngp_tc_selftest": (_i32, [_i32, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
 }
 
 _lib = None

@@ -3,6 +3,13 @@
 
 using namespace ngp;
 
+namespace ngp { namespace grid { bool g_disable_warpagg = false; } }
+
+extern "C" int ngp_grid_set_option(int option, int value) {
+    if (option == 0) { grid::g_disable_warpagg = (value != 0); return NGP_OK; }
+    return NGP_ERR_BAD_ARG;
+}
+
 extern "C" int ngp_grid_encode_forward(const float* inputs, const void* embeddings, const int* offsets, void* outputs,
                                        uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
                                        void* dy_dx, uint32_t gridtype, int align_corners, int dtype, int out_layout,

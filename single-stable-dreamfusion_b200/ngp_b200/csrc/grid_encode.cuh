@@ -23,6 +23,9 @@ namespace grid {
 
 constexpr uint32_t kMaxLevels = 64;
 
+// test / profiling switch (ngp_grid_set_option): force the per-sample scatter kernel
+extern bool g_disable_warpagg;
+
 struct LevelParams {
     float scale;
     uint32_t resolution;
@@ -376,6 +379,103 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Backward, warp-aggregated (D = 3, fp32 table, [B, L*C] gradients): one thread per sample, one warp per 32
+// CONSECUTIVE samples.  Marched samples arrive in ray order, so at coarse levels long runs of neighbouring
+// lanes fall into the same grid cell and would hit the same 8 table rows.  Per level the warp finds those
+// runs (cell key compared with the previous lane), sums the 8 corner contributions of each run with a
+// segmented shuffle reduction, and only the first lane of a run issues the 8 red.global.add - instead of
+// every sample issuing its own atomics (gridencoder.cu:298-310).  The SM issues reds at ~1.3 cycles per
+// active LANE, so fewer active lanes is a direct speed-up; levels whose cells are finer than the sample
+// spacing have runs of length 1 and pay only two shuffles and a ballot.
+// -------------------------------------------------------------------------------------------------
+template <typename T, uint32_t C>
+__global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
+    const T* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
+    float* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+    bool align_corners) {
+    constexpr uint32_t D = 3;
+    __shared__ LevelParams s_levels[kMaxLevels];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_level(offsets, l, S, H);
+    __syncthreads();
+
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    // whole warps stay alive (shuffles below); out-of-range / out-of-cube samples just contribute nothing
+    if ((b & ~31u) >= B) return;
+    bool valid = b < B;
+    float x[D] = {0.f, 0.f, 0.f};
+    if (valid) {
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(inputs + (size_t)b * D + d);
+        valid = !out_of_unit_cube<D>(x);  // gridencoder.cu:253-258
+    }
+
+    for (uint32_t level = 0; level < L; ++level) {
+        const LevelParams lp = s_levels[level];
+        float frac[D];
+        uint32_t base[D];
+        locate<D>(x, lp.scale, align_corners, frac, base);
+
+        float g[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) g[c] = 0.f;
+        if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
+
+        // run detection: same cell as the previous lane (both valid)
+        const uint32_t kxy = valid ? (base[0] | (base[1] << 16)) : 0xffffffffu;
+        const uint32_t kz = valid ? base[2] : (0x80000000u | lane);
+        const uint32_t pxy = __shfl_up_sync(0xffffffffu, kxy, 1);
+        const uint32_t pz = __shfl_up_sync(0xffffffffu, kz, 1);
+        const bool head = (lane == 0) || !valid || (pxy != kxy) || (pz != kz);
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        // last lane of my run = (next head above me) - 1
+        const uint32_t above = (lane == 31) ? 0u : (heads >> (lane + 1));
+        const uint32_t run_end = above ? (lane + (uint32_t)__ffs(above) - 1u) : 31u;
+        // longest run in the warp bounds the number of reduction steps (warp-uniform)
+        const uint32_t my_len = head ? (run_end - lane + 1u) : 0u;
+        const uint32_t max_len = __reduce_max_sync(0xffffffffu, my_len);
+
+        float v[1u << D][C];
+#pragma unroll
+        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+            float w = 1;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) w *= (corner & (1u << d)) ? frac[d] : 1 - frac[d];
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) v[corner][c] = w * g[c];
+        }
+        for (uint32_t off = 1; off < max_len; off <<= 1) {
+            const bool take = (lane + off) <= run_end;
+#pragma unroll
+            for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) {
+                    const float o = __shfl_down_sync(0xffffffffu, v[corner][c], off);
+                    if (take) v[corner][c] += o;
+                }
+            }
+        }
+        if (head && valid) {
+            float* tbl = grad_table + (size_t)lp.offset * C;
+#pragma unroll
+            for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+                uint32_t p[D];
+#pragma unroll
+                for (uint32_t d = 0; d < D; ++d) p[d] = base[d] + ((corner >> d) & 1u);
+                const uint32_t row = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
+                float* dst = tbl + (size_t)row * C;
+                if constexpr (C == 1) red_add_f32(dst, v[corner][0]);
+                else if constexpr (C == 2) red_add_f32x2(dst, v[corner][0], v[corner][1]);
+                else {
+#pragma unroll
+                    for (uint32_t c = 0; c < C; c += 4) red_add_f32x4(dst + c, v[corner][c], v[corner][c + 1], v[corner][c + 2], v[corner][c + 3]);
+                }
+            }
+        }
+    }
+}
+
 // grad_inputs[b,d] = sum_{l,c} grad[l,b,c] * dy_dx[b,l,d,c]   (gridencoder.cu:317-342).  In half mode the
 // reference's running sum AND each product are at::Half, i.e. rounded to half after every operation.
 template <typename T, uint32_t D, uint32_t C, bool GRAD_BLC>
@@ -457,8 +557,19 @@ int backward_launch(const T* grad, const float* inputs, const int* offsets, GT* 
     const uint64_t threads = (uint64_t)B * groups;
     const dim3 grid((unsigned)((threads + 255) / 256)), block(256);
     const bool blc = layout == NGP_LAYOUT_BLC;
-    if (blc) encode_backward_kernel<T, GT, D, C, LPT, true><<<grid, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align);
-    else     encode_backward_kernel<T, GT, D, C, LPT, false><<<grid, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align);
+    bool launched = false;
+    if constexpr (D == 3 && sizeof(GT) == 4 && C <= 2) {
+        // hot path: ray-ordered samples, fp32 table -> warp-aggregated scatter
+        if (blc && !g_disable_warpagg) {
+            const dim3 g1((unsigned)(((uint64_t)B + 255) / 256));
+            encode_backward_warpagg_kernel<T, C><<<g1, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align);
+            launched = true;
+        }
+    }
+    if (!launched) {
+        if (blc) encode_backward_kernel<T, GT, D, C, LPT, true><<<grid, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align);
+        else     encode_backward_kernel<T, GT, D, C, LPT, false><<<grid, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align);
+    }
     int rc = launch_status();
     if (rc != NGP_OK) return rc;
     if (dy_dx && grad_inputs) {

@@ -502,3 +502,37 @@ def test_occupancy_update_vs_oracle():
     gt[valid] = torch.maximum(gt[valid] * 0.95, T(tmp)[valid])
     assert torch.equal(gt, g_t)
     assert abs(gt[valid].mean().item() - mean.item()) < 1e-5 * mean.item()
+
+
+def test_grid_backward_warp_aggregated_on_ray_ordered_samples():
+    """Marched samples are ray ordered: neighbouring lanes share coarse cells, which the warp-aggregated scatter
+    collapses.  Same result as the per-sample scatter and as the oracle's exact sum."""
+    c = cabi()
+    case = MARCH_CASES[0]
+    rays_o, rays_d, bits, nears, fars, noises = _march_setup(case, seed=5)
+    ox, _, _, _, ocounter = O.march_rays_train(rays_o, rays_d, 1.0, bits, 1, 128, nears, fars, noises, 0.0, 1024)
+    total = int(ocounter[0])
+    x01 = ((ox[:total] + 1) / 2).astype(np.float32)
+    x01[7] = [1.5, 0.5, 0.5]                        # an out-of-range sample inside a run
+    rng = np.random.default_rng(0)
+    offs, S = util.make_offsets(log2_hashmap_size=16)
+    dev_sc, _ = device_scales(16, np.float32(S), 16)
+    for dtype in (np.float16, np.float32):
+        g = rng.standard_normal((total, 32)).astype(dtype)
+        truth = O.grid_encode_backward(g, x01, offs, offs[-1], 2, np.float32(S), 16, gridtype=1, scale_override=dev_sc)
+        ge_agg, _ = my_grid_backward(T(g), T(x01), T(offs), int(offs[-1]), 2, np.float32(S), 16, 1)
+        c.load().ngp_grid_set_option(0, 1)
+        try:
+            ge_plain, _ = my_grid_backward(T(g), T(x01), T(offs), int(offs[-1]), 2, np.float32(S), 16, 1)
+        finally:
+            c.load().ngp_grid_set_option(0, 0)
+        assert util.rel_l2(N_(ge_agg), truth) < 1e-6
+        assert util.rel_l2(N_(ge_plain), truth) < 1e-6
+    # hashed table, partial last warp
+    offs, S = util.make_offsets(log2_hashmap_size=19)
+    n = total - 13
+    g = rng.standard_normal((n, 32)).astype(np.float16)
+    dev_sc, _ = device_scales(16, np.float32(S), 16)
+    truth = O.grid_encode_backward(g, x01[:n], offs, offs[-1], 2, np.float32(S), 16, gridtype=0, scale_override=dev_sc)
+    ge, _ = my_grid_backward(T(g), T(x01[:n]), T(offs), int(offs[-1]), 2, np.float32(S), 16, 0)
+    assert util.rel_l2(N_(ge), truth) < 1e-6
