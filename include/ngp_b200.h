@@ -168,6 +168,32 @@ int ngp_update_density_grid(float* grid, const float* tmp_grid, uint32_t n_cells
                             uint64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused field network  (reference: NeRFNetwork.common_forward, nerf/network_grid.py:76-87, under fp16
+ * autocast: GridEncoder -> Linear(32,64)+ReLU -> Linear(64,64)+ReLU -> Linear(64,4) -> trunc_exp / sigmoid;
+ * activation.py:4-17).  The three GEMMs run on tcgen05 tensor cores inside one kernel per direction.
+ * Only the reference's own shape is built: L=16 levels x C=2 features, D=3, hidden 64, 4 outputs
+ * (anything else: NGP_ERR_UNSUPPORTED - the host then uses the unfused ops).
+ * ------------------------------------------------------------------------------------------ */
+
+/* xyzs f32[M,3] in [-bound,bound]; table f16[rows,2]; w1..w3 and b1..b3 are the fp16 casts of the nn.Linear weights
+ * ([out,in] row-major) and biases; count_ptr (optional, device i32) limits the rows actually processed.
+ * Outputs: sigma f32[M]; rgb f32[M,3] (the fp16-rounded sigmoid, widened).  enc_save f16[M,32], h1_save /
+ * h2_save f16[M,64] are optional (NULL for inference) and feed ngp_field_backward. */
+int ngp_field_forward(const float* xyzs, uint32_t M, const int* count_ptr, const void* table, const int* offsets,
+                      uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, int align_corners, float bound,
+                      const void* w1, const void* b1, const void* w2, const void* b2, const void* w3, const void* b3,
+                      uint32_t hidden, uint32_t out_dim, float* sigma, float* rgb, void* enc_save, void* h1_save,
+                      void* h2_save, void* stream);
+
+/* Backward of the MLP part: from d_sigma f32[M], d_rgb f32[M,3] (+ the forward outputs and saves) to
+ * d_enc f16[M,32] (gradient wrt the grid encoding - feed it to ngp_grid_encode_backward) and the fp32 weight /
+ * bias gradients gw1[64,32] gb1[64] gw2[64,64] gb2[64] gw3[4,64] gb3[4], which are ACCUMULATED (+=). */
+int ngp_field_backward(uint32_t M, const int* count_ptr, const void* w1, const void* w2, const void* w3,
+                       uint32_t hidden, uint32_t out_dim, const float* d_sigma, const float* d_rgb, const float* sigma,
+                       const float* rgb, const void* enc_save, const void* h1_save, const void* h2_save, void* d_enc,
+                       float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Roofline micro-benchmarks (measurement support; SURVEY 8d asks for a measured L2 peak)
  * ------------------------------------------------------------------------------------------ */
 /* Random 4-byte gathers: each of n_threads threads performs `iters` x 8 independent loads from

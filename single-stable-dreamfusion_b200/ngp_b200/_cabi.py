@@ -44,6 +44,10 @@ SIGNATURES = {
     "ngp_update_density_grid": (_i32, [_vp, _vp, _u32, _f32, _f32, _vp, _vp, _vp, _u64, _vp]),
     "ngp_bench_gather4": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _vp]),
     "ngp_bench_red8": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp]),
+    "ngp_field_forward": (_i32, [_vp, _u32, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_field_backward": (_i32, [_u32, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _vp]),
     "ngp_tc_selftest": (_i32, [_i32, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
 }
 

@@ -10,6 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import field as _field
 from .activation import trunc_exp
 from .encoding import get_encoder
 from .renderer import NeRFRenderer, safe_normalize
@@ -54,8 +55,12 @@ class NeRFNetwork(NeRFRenderer):
         d = (x ** 2).sum(-1)
         return 5 * torch.exp(-d / (2 * 0.2 ** 2))
 
+    fused = True  # use the fused tcgen05 field kernels when the shapes / autocast state allow it
+
     def common_forward(self, x):
         # x: [N, 3] in [-bound, bound] -> sigma [N] (fp32), albedo [N, 3]
+        if self.fused and _field.can_fuse(x, self.encoder, self.sigma_net):
+            return _field.fused_field(x, self.encoder, self.sigma_net, self.bound)
         h = self.encoder(x, bound=self.bound)
         h = self.sigma_net(h)
         sigma = trunc_exp(h[..., 0] + self.gaussian(x))

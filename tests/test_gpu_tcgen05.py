@@ -43,3 +43,79 @@ def test_umma_data_gradient_shape(N, K):
     D = _selftest(2, A, B, 128, N, K)
     want = A.float() @ B.float()
     assert torch.allclose(D, want, rtol=1e-3, atol=2e-3), (D - want).abs().max().item()
+
+
+def _field_models():
+    import argparse
+    from ngp_b200.network_grid import NeRFNetwork
+    opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)
+    torch.manual_seed(0)
+    m = NeRFNetwork(opt).to(DEV)
+    with torch.no_grad():
+        m.encoder.embeddings.uniform_(-0.5, 0.5)
+    return m
+
+
+@pytest.mark.parametrize("M", [1, 127, 128, 5000, 300001])
+def test_fused_field_forward_matches_unfused(M):
+    m = _field_models()
+    g = torch.Generator(device=DEV).manual_seed(M)
+    x = (torch.rand(M, 3, device=DEV, generator=g) * 2 - 1) * 0.9
+    if M > 10:
+        x[3] = torch.tensor([1.0, -1.0, 0.3], device=DEV)      # on the boundary
+        x[4] = 0.0                                             # blob centre: sigma ~ e^5
+    with torch.no_grad(), torch.autocast("cuda", torch.float16):
+        m.fused = True
+        s1, a1 = m.common_forward(x)
+        m.fused = False
+        s0, a0 = m.common_forward(x)
+    assert s1.dtype == torch.float32 and s1.shape == (M,) and a1.shape == (M, 3)
+    # three chained fp16 GEMMs: tensor-core summation order differs from cuBLAS by <~1 half-ulp per layer
+    assert torch.allclose(s1, s0.float(), rtol=4e-3, atol=1e-6), ((s1 - s0).abs() / s0.abs()).max().item()
+    assert torch.allclose(a1, a0.float(), rtol=0, atol=2e-3), (a1 - a0.float()).abs().max().item()
+    assert ((s1 - s0).abs() / s0.abs()).mean().item() < 5e-4
+
+
+def test_fused_field_backward_matches_unfused():
+    m = _field_models()
+    M = 70000
+    g = torch.Generator(device=DEV).manual_seed(3)
+    x = (torch.rand(M, 3, device=DEV, generator=g) * 2 - 1) * 0.9
+    gs = torch.randn(M, device=DEV, generator=g) * 0.1
+    ga = torch.randn(M, 3, device=DEV, generator=g)
+    grads = {}
+    for fused in (True, False):
+        m.fused = fused
+        m.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", torch.float16):
+            s, a = m.common_forward(x)
+            (s * gs).sum().add((a.float() * ga).sum()).backward()
+        grads[fused] = {n: p.grad.detach().clone() for n, p in m.named_parameters() if p.grad is not None}
+    assert set(grads[True]) == set(grads[False])
+    assert "encoder.embeddings" in grads[True] and "sigma_net.net.0.weight" in grads[True]
+    for n in grads[True]:
+        a, b = grads[True][n].float(), grads[False][n].float()
+        rel = ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+        assert rel < 1e-2, (n, rel)        # the unfused path rounds every weight gradient / activation grad to fp16
+
+
+def test_fused_field_matches_fp64_reference_better_than_tolerance():
+    """Against an fp64 evaluation of the same fp16-quantised network the fused kernel is within fp16 noise."""
+    m = _field_models()
+    M = 4096
+    x = (torch.rand(M, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(9)) * 2 - 1) * 0.9
+    with torch.no_grad(), torch.autocast("cuda", torch.float16):
+        m.fused = True
+        s1, a1 = m.common_forward(x)
+        enc = m.encoder(x, bound=1).double()
+    with torch.no_grad():
+        W = [l.weight.half().double() for l in m.sigma_net.net]
+        B = [l.bias.half().double() for l in m.sigma_net.net]
+        h = torch.relu(enc @ W[0].T + B[0]).half().double()
+        h = torch.relu(h @ W[1].T + B[1]).half().double()
+        o = (h @ W[2].T + B[2]).half().double()
+        blob = 5 * torch.exp(-(x.double() ** 2).sum(-1) / 0.08)
+        s_ref = torch.exp(o[:, 0] + blob)
+        a_ref = torch.sigmoid(o[:, 1:])
+    assert ((s1.double() - s_ref).abs() / s_ref).max().item() < 4e-3
+    assert (a1.double() - a_ref).abs().max().item() < 1.5e-3
