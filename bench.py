@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's CUDA extensions")
     ap.add_argument("--cpu-sample-steps", type=int, default=3)
+    ap.add_argument("--no-graph", action="store_true", help="run the train step eagerly instead of as one CUDA graph")
+    ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
     return ap.parse_args()
 
 
@@ -153,50 +155,6 @@ def build_model(device):
     return model
 
 
-def entropy_loss(ws, lam=1e-4):
-    import torch
-    alphas = ws.clamp(1e-5, 1 - 1e-5)
-    return lam * (-alphas * torch.log2(alphas) - (1 - alphas) * torch.log2(1 - alphas)).mean()
-
-
-class TrainStep:
-    """The reference Trainer's call pattern (nerf/utils.py:337-403, 696-713) around the B200 renderer."""
-
-    def __init__(self, model, device, world_size):
-        import torch
-        from ngp_b200.parallel import FlatGradBucket
-        self.model, self.device, self.world = model, device, world_size
-        self.opt = torch.optim.Adam(model.get_params(1e-3), betas=(0.9, 0.99), eps=1e-15)
-        self.scaler = torch.amp.GradScaler("cuda")
-        self.bucket = FlatGradBucket(list(model.parameters()), device)
-        self.global_step = 0
-        self.n_updates = 0
-
-    def __call__(self, rays_o, rays_d, G):
-        import torch
-        model = self.model
-        if self.global_step % 16 == 0:
-            with torch.autocast("cuda", torch.float16):
-                model.update_extra_state()
-            self.n_updates += 1
-        self.global_step += 1
-        self.bucket.zero()
-        self.bucket.attach()
-        B = rays_o.shape[0]
-        with torch.autocast("cuda", torch.float16):
-            out = model.render(rays_o, rays_d, staged=False, perturb=True, bg_color=None, ambient_ratio=1.0,
-                               shading="albedo", force_all_rays=True, max_steps=MAX_STEPS, dt_gamma=0)
-            pred_rgb = out["image"].reshape(B, H, W, 3).permute(0, 3, 1, 2).contiguous()
-            # synthetic SDS: the guidance back-propagates a given gradient through the NeRF graph (nerf/sd.py:115)
-            pred_rgb.backward(gradient=G, retain_graph=True)
-            loss = entropy_loss(out["weights_sum"].reshape(B, 1, H, W))
-        self.scaler.scale(loss).backward()
-        self.bucket.all_reduce(average=True)
-        self.scaler.step(self.opt)
-        self.scaler.update()
-        return loss
-
-
 def measure_l2_peaks(device):
     """Chip ceilings for the encoder's access shapes: random 4-byte gathers / 8-byte red.add over a 24 MB
     (L2-resident) table.  Returns (gathers/s, reds/s)."""
@@ -246,8 +204,9 @@ def run_b200_arm(args):
     rd_all = rd_all.view(n_pool, args.views, H * W, 3)
     g_host = (torch.randn(n_pool, args.views, 3, H, W, generator=torch.Generator().manual_seed(2)) * 1e-2).pin_memory()
 
+    from ngp_b200.trainer import TrainStep
     model = build_model(device)
-    step_fn = TrainStep(model, device, world)
+    step_fn = TrainStep(model, H, W, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world)
 
     def host_batch(i):
         k = i % n_pool
@@ -262,7 +221,7 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sample_acc = torch.zeros(1, dtype=torch.int64, device=device)
+    sample_acc = step_fn.samples
 
     def run_steps(n, e2e, start_index):
         for s in range(n):
@@ -272,7 +231,6 @@ def run_b200_arm(args):
             else:
                 ro, rd, G = dev_pool[i % n_pool]
             loss = step_fn(ro, rd, G)
-            sample_acc.add_(model.step_counter[(model.local_step - 1) % 16, 0].long())
             if e2e:
                 loss.item()  # device -> host read of the step's result
 
@@ -284,7 +242,6 @@ def run_b200_arm(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    _cabi.PROFILE = {"ngp_grid_encode_forward": [], "ngp_grid_encode_backward": []}
     sample_acc.zero_()
     updates0 = step_fn.n_updates
     launches0 = _cabi.LAUNCHES
@@ -297,13 +254,7 @@ def run_b200_arm(args):
     ms = e0.elapsed_time(e1)
     launches = _cabi.LAUNCHES - launches0
     n_updates = step_fn.n_updates - updates0
-    prof = _cabi.PROFILE
-    _cabi.PROFILE = None
     samples = int(sample_acc.item())
-    kern = {}
-    for name, evs in prof.items():
-        tot = sum(a.elapsed_time(b) for a, b in evs)
-        kern[name] = (tot, len(evs))
 
     # ---- timed: end to end (pinned host inputs, H2D inside, loss read back) -----------------------------
     sample_acc.zero_()
@@ -316,6 +267,33 @@ def run_b200_arm(args):
     ms_e2e = f0.elapsed_time(f1)
     samples_e2e = int(sample_acc.item())
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- per-kernel durations for the roofline: a few EAGER steps with CUDA events around our entry points ----
+    # (events cannot be recorded inside a graph replay; same kernels, same data shapes, same stream)
+    kern = {}
+    prof_samples = 0
+    if True:  # every rank runs the same eager steps (they contain the gradient all-reduce); rank 0 reports
+        was_graph = step_fn.use_graph
+        step_fn.use_graph = False
+        names = ["ngp_grid_scatter_samples", "ngp_grid_encode_backward", "ngp_field_forward", "ngp_field_backward",
+                 "ngp_march_rays_train", "ngp_composite_rays_train_forward", "ngp_composite_rays_train_backward",
+                 "ngp_grid_encode_forward"]
+        step_fn.global_step = 1  # keep the occupancy refresh out of the profiled steps
+        run_steps(2, False, 3000)
+        torch.cuda.synchronize()
+        _cabi.PROFILE = {n: [] for n in names}
+        sample_acc.zero_()
+        run_steps(args.profile_steps, False, 3100)
+        torch.cuda.synchronize()
+        prof = _cabi.PROFILE
+        _cabi.PROFILE = None
+        prof_samples = int(sample_acc.item())
+        for name, evs in prof.items():
+            if evs:
+                kern[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+        step_fn.use_graph = was_graph
+    if world > 1:
+        dist.barrier()
 
     # ---- reduce over ranks: time = max, samples = sum ------------------------------------------------------
     stats = torch.tensor([ms, ms_e2e, float(samples), float(samples_e2e)], dtype=torch.float64, device=device)
@@ -336,20 +314,29 @@ def run_b200_arm(args):
             os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         dom = max(kern, key=lambda k: kern[k][0])
         tot_ms, n_calls = kern[dom]
-        # algorithmic L2 bytes per encoded point: 16 levels x 8 corners x 4 B (SURVEY 8d / BASELINE.md 4)
-        # (rank 0's launches: its share of the marched samples, padded to 128, plus the 128^3 occupancy queries)
-        local_points = samples / world + (2097152 * n_updates if "forward" in dom else 0)
-        achieved = 512.0 * local_points / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
-        peak = (gathers_s if "forward" in dom else reds_s) * 4 / 1e9
+        per_launch_ms = tot_ms / max(n_calls, 1)
+        # algorithmic L2 bytes per encoded point: 16 levels x 8 corners x 4 B (SURVEY 8d / BASELINE.md 4); the profiled
+        # eager steps processed prof_samples points in total, one forward and two backward launches per step
+        launches_per_step = n_calls / max(args.profile_steps, 1)
+        points_per_launch = prof_samples / max(args.profile_steps, 1)
+        is_gather = dom in ("ngp_field_forward", "ngp_grid_encode_forward")
+        is_scatter = dom in ("ngp_grid_scatter_samples", "ngp_grid_encode_backward")
+        achieved = 512.0 * points_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        peak = (gathers_s if is_gather else reds_s) * 4 / 1e9
+        step_kernel_ms = sum(v[0] for v in kern.values()) / max(args.profile_steps, 1)
         roofline = {
             "bound": "l2", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if peak else None, "traffic": None,
-            "avg_launch_ms": tot_ms / max(n_calls, 1), "launches": n_calls,
-            "share_of_step": tot_ms / ms,
+            "frac": achieved / peak if (peak and (is_gather or is_scatter)) else None, "traffic": None,
+            "avg_launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
+            "share_of_step": (tot_ms / max(args.profile_steps, 1)) / (ms / args.steps),
+            "how": "CUDA events around the entry point over %d eager (non-graph) steps after the timed region; "
+                   "algorithmic bytes = 512 B x marched samples of the launch" % args.profile_steps,
             "peak_source": "measured in this run: random 4-B gathers / 8-B red.add over a 32 MB L2-resident table "
                            "(ngp_bench_gather4 / ngp_bench_red8), counted at 4 algorithmic bytes per access",
+            "l2_gather_peak_gbs": gathers_s * 4 / 1e9, "l2_red_peak_gbs": reds_s * 4 / 1e9,
             "hbm_peak_gbs": peaks.get("hbm_gbs"),
-            "other_kernels_ms": {k: v[0] for k, v in kern.items()},
+            "kernels_ms_per_step": {k: v[0] / max(args.profile_steps, 1) for k, v in kern.items()},
+            "our_kernels_ms_per_step": step_kernel_ms,
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -361,7 +348,7 @@ def run_b200_arm(args):
                             "synthetic SDS grad + entropy backward, grad all-reduce, Adam + GradScaler, occupancy "
                             "update every 16 steps" % (args.views, world),
                 "views_per_step": args.views, "rays_per_step": args.views * H * W,
-                "samples_per_step": samples / args.steps, "timing": "inputs (3.5 MB/step) and the 7 MB table are "
+                "samples_per_step": samples / args.steps, "cuda_graph": not args.no_graph, "timing": "inputs (3.5 MB/step) and the 7 MB table are "
                 "smaller than L2 by nature of the workload; each step runs on a different view batch (64-batch pool), "
                 "the 134+ MB/step of sample buffers exceed L2",
             },

@@ -107,6 +107,7 @@ int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t
                          const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                          int* rays, int* counter, const float* noises, void* workspace,
                          uint64_t workspace_bytes, void* stream);
+/* (dirs may be NULL: the albedo-shaded training path never reads the per-sample directions.) */
 uint64_t ngp_march_rays_train_workspace(uint32_t N);
 
 /* raymarching.cu:580 */
@@ -192,6 +193,14 @@ int ngp_field_backward(uint32_t M, const int* count_ptr, const void* w1, const v
                        uint32_t hidden, uint32_t out_dim, const float* d_sigma, const float* d_rgb, const float* sigma,
                        const float* rgb, const void* enc_save, const void* h1_save, const void* h2_save, void* d_enc,
                        float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3, void* stream);
+
+/* Table-gradient scatter for the sync-free training path: like ngp_grid_encode_backward for D=3, C=2, fp16
+ * [M, L*C] gradients and an fp32 table, but (a) only the first *count_ptr rows (device i32, may be NULL) of the
+ * M_cap-row buffers are processed and (b) positions are world coordinates in [-bound, bound], mapped to [0,1]
+ * inside the kernel as GridEncoder.forward does (grid.py:142).  grad_table is accumulated into (+=). */
+int ngp_grid_scatter_samples(const void* d_enc, const float* xyzs, float bound, const int* count_ptr, uint32_t M_cap,
+                             const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
+                             int align_corners, float* grad_table, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Roofline micro-benchmarks (measurement support; SURVEY 8d asks for a measured L2 peak)

@@ -20,21 +20,10 @@ from ngp_b200 import _cabi
 
 _gridtype_to_id = {'hash': 0, 'tiled': 1}
 
-# (data_ptr, version, dtype) -> half copy; one entry per embedding parameter object
-_half_cache = {}
-
 
 def _half_table(embeddings):
-    key = id(embeddings)
-    ver = (embeddings.data_ptr(), embeddings._version, tuple(embeddings.shape))
-    hit = _half_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    half = embeddings.detach().to(torch.half)
-    if len(_half_cache) > 64:
-        _half_cache.clear()
-    _half_cache[key] = (ver, half)
-    return half
+    from ngp_b200.field import cached_half
+    return cached_half(embeddings)
 
 
 class _grid_encode(Function):

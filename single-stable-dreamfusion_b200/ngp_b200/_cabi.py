@@ -48,6 +48,7 @@ SIGNATURES = {
                                  _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ngp_field_backward": (_i32, [_u32, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp]),
+    "ngp_grid_scatter_samples": (_i32, [_vp, _vp, _f32, _vp, _u32, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _vp, _vp]),
     "ngp_tc_selftest": (_i32, [_i32, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
 }
 

@@ -61,3 +61,16 @@ extern "C" int ngp_grid_level_params(uint32_t L, float S, uint32_t H, float* sca
     grid::level_params_kernel<<<cdiv(L, 64), 64, 0, as_stream(stream)>>>(L, S, H, scales, resolutions);
     return launch_status();
 }
+
+// Sync-free training path: scatter the MLP's encoding gradients of the first *count_ptr samples.
+extern "C" int ngp_grid_scatter_samples(const void* d_enc, const float* xyzs, float bound, const int* count_ptr, uint32_t M_cap,
+                                        const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
+                                        int align_corners, float* grad_table, void* stream) {
+    if (!d_enc || !xyzs || !offsets || !grad_table) return NGP_ERR_BAD_ARG;
+    if (L == 0 || L > grid::kMaxLevels || gridtype > 1 || C != 2) return NGP_ERR_UNSUPPORTED;
+    if (M_cap == 0) return NGP_OK;
+    const int blocks = min(cdiv(M_cap, 256), num_sms() * 16);
+    grid::encode_backward_warpagg_kernel<__half, 2><<<blocks, 256, 0, as_stream(stream)>>>(
+        static_cast<const __half*>(d_enc), xyzs, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners != 0, count_ptr, bound);
+    return launch_status();
+}

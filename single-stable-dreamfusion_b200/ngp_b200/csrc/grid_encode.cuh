@@ -392,22 +392,28 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
 template <typename T, uint32_t C>
 __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
     const T* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
-    float* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-    bool align_corners) {
+    float* __restrict__ grad_table, uint32_t B_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype,
+    bool align_corners, const int* __restrict__ count_ptr, float bound) {
     constexpr uint32_t D = 3;
     __shared__ LevelParams s_levels[kMaxLevels];
     for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_level(offsets, l, S, H);
     __syncthreads();
 
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    // optional device-side row count (sync-free training path) and optional [-bound, bound] -> [0, 1] mapping
+    const uint32_t B = count_ptr ? min((uint32_t)max(*count_ptr, 0), B_cap) : B_cap;
+    const float inv_2b = bound > 0.f ? __fdiv_rn(1.0f, 2 * bound) : 1.0f;
     const uint32_t lane = threadIdx.x & 31;
+
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; (b & ~31u) < B; b += gridDim.x * blockDim.x) {
     // whole warps stay alive (shuffles below); out-of-range / out-of-cube samples just contribute nothing
-    if ((b & ~31u) >= B) return;
     bool valid = b < B;
     float x[D] = {0.f, 0.f, 0.f};
     if (valid) {
 #pragma unroll
-        for (uint32_t d = 0; d < D; ++d) x[d] = __ldg(inputs + (size_t)b * D + d);
+        for (uint32_t d = 0; d < D; ++d) {
+            x[d] = __ldg(inputs + (size_t)b * D + d);
+            if (bound > 0.f) x[d] = __fmul_rn(__fadd_rn(x[d], bound), inv_2b);  // GridEncoder.forward's mapping (grid.py:142)
+        }
         valid = !out_of_unit_cube<D>(x);  // gridencoder.cu:253-258
     }
 
@@ -474,6 +480,7 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
             }
         }
     }
+  }
 }
 
 // grad_inputs[b,d] = sum_{l,c} grad[l,b,c] * dy_dx[b,l,d,c]   (gridencoder.cu:317-342).  In half mode the
@@ -562,7 +569,7 @@ int backward_launch(const T* grad, const float* inputs, const int* offsets, GT* 
         // hot path: ray-ordered samples, fp32 table -> warp-aggregated scatter
         if (blc && !g_disable_warpagg) {
             const dim3 g1((unsigned)(((uint64_t)B + 255) / 256));
-            encode_backward_warpagg_kernel<T, C><<<g1, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align);
+            encode_backward_warpagg_kernel<T, C><<<g1, block, 0, st>>>(grad, inputs, offsets, grad_table, B, L, S, H, gridtype, align, nullptr, 0.f);
             launched = true;
         }
     }

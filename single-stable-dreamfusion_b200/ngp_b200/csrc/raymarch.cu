@@ -284,19 +284,19 @@ __global__ void __launch_bounds__(128) march_write_kernel(const float* __restric
     float t = perturbed_start(p, nears[n], noises[n]);
     float last_t = t;
     float* px = xyzs + (size_t)offset * 3;
-    float* pd = dirs + (size_t)offset * 3;
+    float* pd = dirs ? dirs + (size_t)offset * 3 : nullptr;  // dirs may be omitted (albedo shading never reads them)
     float* pl = deltas + (size_t)offset * 2;
     uint32_t step = 0;
     float x, y, z, dt;
     while (t < far && step < num_steps) {
         if (probe(p, r, t, x, y, z, dt)) {
             px[0] = x; px[1] = y; px[2] = z;
-            pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz;
+            if (pd) { pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz; pd += 3; }
             t += dt;
             pl[0] = dt;
             pl[1] = t - last_t;  // raymarching.cu:461
             last_t = t;
-            px += 3; pd += 3; pl += 2;
+            px += 3; pl += 2;
             ++step;
         }
     }
@@ -621,7 +621,7 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
                                     const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                                     int* rays, int* counter, const float* noises, void* workspace,
                                     uint64_t workspace_bytes, void* stream) {
-    if (!rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !dirs || !deltas || !rays || !counter || !noises)
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !deltas || !rays || !counter || !noises)
         return NGP_ERR_BAD_ARG;
     if (C == 0 || H == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
     if (!workspace || workspace_bytes < ngp_march_rays_train_workspace(N)) return NGP_ERR_WORKSPACE;

@@ -13,14 +13,22 @@ from torch.autograd import Function
 from . import _cabi
 
 _half_cache = {}
+_cache_epoch = [0]
+
+
+def invalidate_half_cache():
+    """Forget every cached fp16 copy (call after parameters were updated behind autograd's back, e.g. by a
+    CUDA-graph replay of the optimizer step)."""
+    _cache_epoch[0] += 1
 
 
 def cached_half(t):
     """fp16 copy of a parameter, refreshed only when the parameter changes (autocast re-casts per forward)."""
     key = id(t)
-    ver = (t.data_ptr(), t._version, tuple(t.shape))
+    ver = (t.data_ptr(), t._version, tuple(t.shape), _cache_epoch[0])
     hit = _half_cache.get(key)
-    if hit is not None and hit[0] == ver:
+    # while a CUDA graph is being captured the cast must become part of the graph (replays do not bump _version)
+    if hit is not None and hit[0] == ver and not torch.cuda.is_current_stream_capturing():
         return hit[1]
     h = t.detach().to(torch.half).contiguous()
     if len(_half_cache) > 256:

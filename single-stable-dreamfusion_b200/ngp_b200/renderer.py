@@ -105,6 +105,18 @@ class NeRFRenderer(nn.Module):
     def export_mesh(self, *args, **kwargs):
         raise NotImplementedError("export_mesh (offline mesh extraction) is outside the B200 hot path")
 
+    fused_train = True  # take the sync-free fused training render when the field has the reference's shape
+
+    def _fused_training_path(self, rays_o):
+        if not self.fused_train or not getattr(self, "fused", False):
+            return False
+        from . import field as _field
+        enc, net = getattr(self, "encoder", None), getattr(self, "sigma_net", None)
+        if enc is None or net is None:
+            return False
+        probe = rays_o.detach().view(-1, 3)
+        return _field.can_fuse(probe, enc, net)
+
     def run(self, *args, **kwargs):
         raise NotImplementedError(
             "the pure-PyTorch sampler (nerf/renderer.py:301) is not part of the B200 hot path; construct the model "
@@ -131,16 +143,29 @@ class NeRFRenderer(nn.Module):
 
         if self.training:
             counter = self.step_counter[self.local_step % 16]
-            counter.zero_()
             self.local_step += 1
+            normals = None
 
-            xyzs, dirs, deltas, rays = raymarching.march_rays_train(
-                rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
-                self.mean_count if not force_all_rays else -1, perturb, 128, force_all_rays, dt_gamma, max_steps)
+            if shading == 'albedo' and self._fused_training_path(rays_o):
+                # sync-free path: fixed-capacity buffers + device-side sample count (render_train.py); draws the
+                # same torch.rand(N) the reference's wrapper draws (raymarching.py:213-216)
+                from .render_train import render_train
+                if perturb:
+                    noises = torch.rand(N, dtype=torch.float32, device=device)
+                else:
+                    noises = torch.zeros(N, dtype=torch.float32, device=device)
+                weights_sum, depth, image = render_train(self, rays_o.float(), rays_d.float(), nears, fars, noises,
+                                                         dt_gamma, max_steps, T_thresh)
+                counter.copy_(self._train_ws.counter)
+            else:
+                counter.zero_()
+                xyzs, dirs, deltas, rays = raymarching.march_rays_train(
+                    rays_o, rays_d, self.bound, self.density_bitfield, self.cascade, self.grid_size, nears, fars, counter,
+                    self.mean_count if not force_all_rays else -1, perturb, 128, force_all_rays, dt_gamma, max_steps)
 
-            sigmas, rgbs, normals = self(xyzs, dirs, light_d, ratio=ambient_ratio, shading=shading)
+                sigmas, rgbs, normals = self(xyzs, dirs, light_d, ratio=ambient_ratio, shading=shading)
 
-            weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
+                weights_sum, depth, image = raymarching.composite_rays_train(sigmas, rgbs, deltas, rays, T_thresh)
 
             if normals is not None:
                 # orientation + smoothness regularisers (renderer.py:485-494)
