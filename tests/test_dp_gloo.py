@@ -1,0 +1,70 @@
+"""CPU tests (world_size 2, gloo): the data-parallel host logic - view sharding and the flat gradient bucket whose
+single all-reduce replaces the per-parameter reductions DDP would do."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn as nn
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ngp_b200.parallel import FlatGradBucket, shard_views
+        torch.manual_seed(0)                       # identical replicas
+        net = nn.Sequential(nn.Linear(6, 5), nn.ReLU(), nn.Linear(5, 3))
+        table = nn.Parameter(torch.randn(40, 2))
+        params = [table] + list(net.parameters())
+        bucket = FlatGradBucket(params, torch.device("cpu"), extra=1)
+        assert bucket.numel == sum(p.numel() for p in params) and bucket.flat.numel() == bucket.numel + 1
+        # every rank owns a contiguous share of 8 "views"
+        g = torch.Generator().manual_seed(1)
+        views = torch.randn(8, 16, 6, generator=g)
+        idx = torch.randint(0, 40, (8, 16), generator=g)
+        first, count = shard_views(8, rank, world)
+        bucket.zero()
+        bucket.attach()
+        x, ii = views[first:first + count].reshape(-1, 6), idx[first:first + count].reshape(-1)
+        loss = (net(x) * table[ii].sum(-1, keepdim=True)).sum()
+        loss.backward()
+        assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in params)   # autograd wrote into the bucket
+        bucket.extra[0] = float(count)                      # piggy-backed scalar (e.g. a sample count)
+        bucket.all_reduce(average=False)
+        # single-process ground truth over all 8 views
+        torch.manual_seed(0)
+        net2 = nn.Sequential(nn.Linear(6, 5), nn.ReLU(), nn.Linear(5, 3))
+        table2 = nn.Parameter(table.detach().clone())
+        (net2(views.reshape(-1, 6)) * table2[idx.reshape(-1)].sum(-1, keepdim=True)).sum().backward()
+        want = torch.cat([table2.grad.reshape(-1)] + [p.grad.reshape(-1) for p in net2.parameters()])
+        ok = torch.allclose(bucket.flat[:bucket.numel], want, rtol=1e-5, atol=1e-6) and bucket.extra[0].item() == 8.0
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_views_partitions_evenly():
+    from ngp_b200.parallel import shard_views
+    for n, w in [(8, 1), (8, 2), (8, 4), (8, 8), (7, 2), (3, 4)]:
+        spans = [shard_views(n, r, w) for r in range(w)]
+        assert sum(c for _, c in spans) == n
+        assert spans[0][0] == 0 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_flat_bucket_allreduce_equals_single_process_gradient():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
