@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's CUDA extensions")
     ap.add_argument("--cpu-sample-steps", type=int, default=3)
+    ap.add_argument("--lr", type=float, default=1e-5)
     ap.add_argument("--no-graph", action="store_true", help="run the train step eagerly instead of as one CUDA graph")
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
     return ap.parse_args()
@@ -206,7 +207,9 @@ def run_b200_arm(args):
 
     from ngp_b200.trainer import TrainStep
     model = build_model(device)
-    step_fn = TrainStep(model, H, W, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world)
+    # lr: the optimizer step runs in full, but a small step keeps the synthetic (random-gradient) scene at its
+    # random-init occupancy so that every timed pass sees the same ~3.4 M samples per step
+    step_fn = TrainStep(model, H, W, lr=args.lr, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world)
 
     def host_batch(i):
         k = i % n_pool
@@ -348,7 +351,7 @@ def run_b200_arm(args):
                             "synthetic SDS grad + entropy backward, grad all-reduce, Adam + GradScaler, occupancy "
                             "update every 16 steps" % (args.views, world),
                 "views_per_step": args.views, "rays_per_step": args.views * H * W,
-                "samples_per_step": samples / args.steps, "cuda_graph": not args.no_graph, "timing": "inputs (3.5 MB/step) and the 7 MB table are "
+                "samples_per_step": samples / args.steps, "cuda_graph": not args.no_graph, "lr": args.lr, "timing": "inputs (3.5 MB/step) and the 7 MB table are "
                 "smaller than L2 by nature of the workload; each step runs on a different view batch (64-batch pool), "
                 "the 134+ MB/step of sample buffers exceed L2",
             },
@@ -366,9 +369,13 @@ def run_b200_arm(args):
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"error": repr(e)}
         if not args.no_ref_cuda:
-            try:
-                from oracle import ref_pipeline
-                line["ref_cuda_ext"] = ref_pipeline.time_reference_train_step(device, views=1, steps=20, warmup=5)
+            try:  # the reference's own CUDA extensions, in a fresh process on the same GPU (see oracle/ref_pipeline.py)
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(local_rank))
+                out = subprocess.run([sys.executable, "-m", "oracle.ref_pipeline", "20", "5"], cwd=ROOT, env=env,
+                                     capture_output=True, text=True, timeout=600)
+                tag = [l for l in out.stdout.splitlines() if l.startswith("REF_PIPELINE_JSON ")]
+                line["ref_cuda_ext"] = json.loads(tag[-1][len("REF_PIPELINE_JSON "):]) if tag else {
+                    "unavailable": (out.stderr or out.stdout)[-300:]}
             except Exception as e:
                 line["ref_cuda_ext"] = {"unavailable": repr(e)[:200]}
         emit(line)

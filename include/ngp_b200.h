@@ -109,6 +109,9 @@ int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t
                          uint64_t workspace_bytes, void* stream);
 /* (dirs may be NULL: the albedo-shaded training path never reads the per-sample directions.) */
 uint64_t ngp_march_rays_train_workspace(uint32_t N);
+/* option 0: value != 0 selects the one-thread-per-ray kernels (the reference's decomposition) instead of the
+ * default warp-per-ray walk; results are bit-identical. */
+int ngp_march_set_option(int option, int value);
 
 /* raymarching.cu:580 */
 int ngp_composite_rays_train_forward(const float* sigmas, const float* rgbs, const float* deltas,

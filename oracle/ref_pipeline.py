@@ -289,3 +289,14 @@ def time_reference_train_step(device, views=1, steps=20, warmup=5, Hh=64, Ww=64,
             "samples_per_step": samples / steps, "steps": steps,
             "what": "reference CUDA extensions (gridencoder/raymarching/freqencoder rebuilt unmodified for sm_100) "
                     "+ the reference's host call pattern, same -O train step, 1 GPU"}
+
+
+if __name__ == "__main__":
+    # run in a fresh process (own CUDA context / caching allocator): the reference empties the allocator cache every
+    # step (raymarching.py:231), which must not be charged for another workload's cached blocks
+    import json
+    import sys
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    warm = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    res = time_reference_train_step(torch.device("cuda", 0), views=1, steps=steps, warmup=warm)
+    print("REF_PIPELINE_JSON " + json.dumps(res), flush=True)

@@ -64,6 +64,9 @@ NGP_DEVINL uint32_t encode_level(const float (&x01)[3], bool oob, const GridDesc
         uint32_t base[3];
         grid::locate<3>(x01, lp.scale, gd.align_corners != 0, frac, base);
         float rows[8][2], wts[8];
+        // levels that ignore trailing axes (tiled, resolution >= 256: z) have only 4 distinct rows per cell
+        const uint32_t axes_used = grid::level_axes_used<3>(gd.gridtype, gd.align_corners != 0, lp.hashmap_size, lp.resolution);
+        const uint32_t distinct = 1u << axes_used;
 #pragma unroll
         for (uint32_t corner = 0; corner < 8; ++corner) {
             float w = 1;
@@ -74,9 +77,12 @@ NGP_DEVINL uint32_t encode_level(const float (&x01)[3], bool oob, const GridDesc
                 else                           { w *= frac[d];     p[d] = base[d] + 1; }
             }
             wts[corner] = w;
-            const uint32_t row = grid::lattice_row<3>(gd.gridtype, gd.align_corners != 0, lp.hashmap_size, lp.resolution, p);
-            grid::load_row<__half, 2>(tbl + (size_t)row * 2, rows[corner]);
+            if (corner < distinct) {
+                const uint32_t row = grid::lattice_row<3>(gd.gridtype, gd.align_corners != 0, lp.hashmap_size, lp.resolution, p);
+                grid::load_row<__half, 2>(tbl + (size_t)row * 2, rows[corner]);
+            }
         }
+        grid::replicate_rows<3, 2>(rows, axes_used);
 #pragma unroll
         for (uint32_t corner = 0; corner < 8; ++corner) {
 #pragma unroll

@@ -73,6 +73,56 @@ NGP_DEVINL uint32_t lattice_row(uint32_t gridtype, bool align_corners, uint32_t 
     return index % hashmap_size;
 }
 
+// How many leading axes actually enter a level's row index.  The stride loop of lattice_row stops at the first axis
+// whose stride exceeds the table, so a 'tiled' level (or any level that is not hashed) can ignore trailing axes:
+// with 2^16 rows the reference's field drops z for every resolution >= 256 (gridencoder.cu:60-63).  Corners that
+// differ only in ignored axes address the SAME row - the kernels below fetch / update such rows once.
+template <uint32_t D>
+NGP_DEVINL uint32_t level_axes_used(uint32_t gridtype, bool align_corners, uint32_t hashmap_size, uint32_t resolution) {
+    uint32_t stride = 1, used = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        if (stride <= hashmap_size && used == d) {
+            ++used;
+            stride *= align_corners ? resolution : (resolution + 1);
+        }
+    }
+    if (gridtype == NGP_GRID_HASH && stride > hashmap_size) return D;  // hashed: every axis is mixed in
+    return used;
+}
+
+// Static-index helpers for the above (dynamic indexing would push the per-corner arrays to local memory).
+template <uint32_t D, uint32_t C, uint32_t U>
+NGP_DEVINL void replicate_rows_static(float (&rows)[1u << D][C]) {
+#pragma unroll
+    for (uint32_t corner = (1u << U); corner < (1u << D); ++corner) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) rows[corner][c] = rows[corner & ((1u << U) - 1)][c];
+    }
+}
+template <uint32_t D, uint32_t C>
+NGP_DEVINL void replicate_rows(float (&rows)[1u << D][C], uint32_t axes_used) {
+    if constexpr (D >= 2) { if (axes_used == 1) { replicate_rows_static<D, C, 1>(rows); return; } }
+    if constexpr (D >= 3) { if (axes_used == 2) { replicate_rows_static<D, C, 2>(rows); return; } }
+    if constexpr (D >= 4) { if (axes_used == 3) { replicate_rows_static<D, C, 3>(rows); return; } }
+    if constexpr (D >= 5) { if (axes_used == 4) { replicate_rows_static<D, C, 4>(rows); return; } }
+}
+template <uint32_t D, uint32_t C, uint32_t U>
+NGP_DEVINL void fold_rows_static(float (&v)[1u << D][C]) {
+#pragma unroll
+    for (uint32_t corner = (1u << U); corner < (1u << D); ++corner) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) v[corner & ((1u << U) - 1)][c] += v[corner][c];
+    }
+}
+template <uint32_t D, uint32_t C>
+NGP_DEVINL void fold_rows(float (&v)[1u << D][C], uint32_t axes_used) {
+    if constexpr (D >= 2) { if (axes_used == 1) { fold_rows_static<D, C, 1>(v); return; } }
+    if constexpr (D >= 3) { if (axes_used == 2) { fold_rows_static<D, C, 2>(v); return; } }
+    if constexpr (D >= 4) { if (axes_used == 3) { fold_rows_static<D, C, 3>(v); return; } }
+    if constexpr (D >= 5) { if (axes_used == 4) { fold_rows_static<D, C, 4>(v); return; } }
+}
+
 // ---- element-type plumbing ----------------------------------------------------------------------
 template <typename T> struct ElemOps;
 template <> struct ElemOps<float> {
@@ -233,9 +283,12 @@ __global__ void __launch_bounds__(256) encode_forward_kernel(
         uint32_t base[D];
         locate<D>(x, lp.scale, align_corners, frac, base);
 
-        // Issue all 2^D row gathers first (independent loads in flight), then blend.
+        // Issue all 2^D row gathers first (independent loads in flight), then blend.  Corners that differ only in an
+        // axis the level ignores share a row: it is fetched once and reused (same values, same arithmetic).
         float rows[1u << D][C];
         float wts[1u << D];
+        const uint32_t axes_used = level_axes_used<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution);
+        const uint32_t distinct = 1u << axes_used;
 #pragma unroll
         for (uint32_t corner = 0; corner < (1u << D); ++corner) {
             float w = 1;
@@ -246,9 +299,12 @@ __global__ void __launch_bounds__(256) encode_forward_kernel(
                 else                           { w *= frac[d];     p[d] = base[d] + 1; }
             }
             wts[corner] = w;
-            const uint32_t row = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
-            load_row<T, C>(tbl + (size_t)row * C, rows[corner]);
+            if (corner < distinct) {
+                const uint32_t row = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
+                load_row<T, C>(tbl + (size_t)row * C, rows[corner]);
+            }
         }
+        replicate_rows<D, C>(rows, axes_used);
 #pragma unroll
         for (uint32_t corner = 0; corner < (1u << D); ++corner) {
 #pragma unroll
@@ -451,14 +507,20 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
 #pragma unroll
             for (uint32_t c = 0; c < C; ++c) v[corner][c] = w * g[c];
         }
+        // corners that differ only in an axis this level ignores hit the same row: fold them first (warp-uniform)
+        const uint32_t axes_used = level_axes_used<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution);
+        const uint32_t distinct = 1u << axes_used;
+        fold_rows<D, C>(v, axes_used);
         for (uint32_t off = 1; off < max_len; off <<= 1) {
             const bool take = (lane + off) <= run_end;
 #pragma unroll
             for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+                if (corner < distinct) {
 #pragma unroll
-                for (uint32_t c = 0; c < C; ++c) {
-                    const float o = __shfl_down_sync(0xffffffffu, v[corner][c], off);
-                    if (take) v[corner][c] += o;
+                    for (uint32_t c = 0; c < C; ++c) {
+                        const float o = __shfl_down_sync(0xffffffffu, v[corner][c], off);
+                        if (take) v[corner][c] += o;
+                    }
                 }
             }
         }
@@ -466,6 +528,7 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
             float* tbl = grad_table + (size_t)lp.offset * C;
 #pragma unroll
             for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+                if (corner >= distinct) continue;
                 uint32_t p[D];
 #pragma unroll
                 for (uint32_t d = 0; d < D; ++d) p[d] = base[d] + ((corner >> d) & 1u);

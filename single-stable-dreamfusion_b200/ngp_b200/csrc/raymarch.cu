@@ -17,6 +17,9 @@
 namespace ngp {
 namespace march {
 
+// test / profiling switch (ngp_march_set_option 0): 1 = the reference's decomposition, one thread per ray
+bool g_thread_per_ray = false;
+
 NGP_DEVINL float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }  // raymarching.cu:34
 
 // 10-bit-per-axis Morton interleave (raymarching.cu:56-71): the classic magic-multiply spread.
@@ -85,38 +88,150 @@ NGP_DEVINL Ray load_ray(const float* __restrict__ rays_o, const float* __restric
     return r;
 }
 
-// One lattice point of the marcher (raymarching.cu:360-399): classify the cell under t, and
-// either report an occupied sample (returns true; x,y,z,dt valid) or advance t past the empty cell.
-NGP_DEVINL bool probe(const MarchParams& p, const Ray& r, float& t, float& x, float& y, float& z, float& dt) {
-    x = clampf(r.ox + t * r.dx, -p.bound, p.bound);
-    y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
-    z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
-    dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
+// Cell under parameter t (raymarching.cu:360-379): sample position, step size, cascade and occupancy bit.
+struct Cell {
+    float x, y, z, dt, mip_bound;
+    int nx, ny, nz;
+    bool occ;
+};
+NGP_DEVINL Cell classify(const MarchParams& p, const Ray& r, float t) {
+    Cell c;
+    c.x = clampf(r.ox + t * r.dx, -p.bound, p.bound);
+    c.y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
+    c.z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
+    c.dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
 
-    const int level = max(level_from_pos(x, y, z, p.Cf), level_from_dt(dt, p.Hf, p.Cf));
-    const float mip_bound = fminf(scalbnf(1.0f, level), p.bound);
-    const float mip_rbound = 1 / mip_bound;
+    const int level = max(level_from_pos(c.x, c.y, c.z, p.Cf), level_from_dt(c.dt, p.Hf, p.Cf));
+    c.mip_bound = fminf(scalbnf(1.0f, level), p.bound);
+    const float mip_rbound = 1 / c.mip_bound;
 
     // `0.5 * (x*rb + 1) * H` is evaluated in double by the reference; both factors are exactly
     // representable so the float product below rounds to the same value (DESIGN.md "marcher").
-    const int nx = (int)clampf(__fmul_rn(0.5f * (x * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
-    const int ny = (int)clampf(__fmul_rn(0.5f * (y * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
-    const int nz = (int)clampf(__fmul_rn(0.5f * (z * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
+    c.nx = (int)clampf(__fmul_rn(0.5f * (c.x * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
+    c.ny = (int)clampf(__fmul_rn(0.5f * (c.y * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
+    c.nz = (int)clampf(__fmul_rn(0.5f * (c.z * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
 
-    const uint32_t index = level * p.H3 + morton_encode(nx, ny, nz);  // float arithmetic, as in :378
-    const bool occ = p.grid[index / 8] & (1 << (index % 8));
-    if (occ) return true;
+    const uint32_t index = level * p.H3 + morton_encode(c.nx, c.ny, c.nz);  // float arithmetic, as in :378
+    c.occ = p.grid[index / 8] & (1 << (index % 8));
+    return c;
+}
+// Parameter at which the ray leaves the (empty) cell (raymarching.cu:390-394).
+NGP_DEVINL float cell_exit(const MarchParams& p, const Ray& r, const Cell& c, float t) {
+    const float tx = (((c.nx + 0.5f + 0.5f * copysignf(1.0f, r.dx)) * p.rH * 2 - 1) * c.mip_bound - c.x) * r.rdx;
+    const float ty = (((c.ny + 0.5f + 0.5f * copysignf(1.0f, r.dy)) * p.rH * 2 - 1) * c.mip_bound - c.y) * r.rdy;
+    const float tz = (((c.nz + 0.5f + 0.5f * copysignf(1.0f, r.dz)) * p.rH * 2 - 1) * c.mip_bound - c.z) * r.rdz;
+    return t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+}
 
-    // distance to the far face of this cell along each axis (:390-394), then step the fixed
-    // t-lattice until it has been crossed (:396-398).
-    const float tx = (((nx + 0.5f + 0.5f * copysignf(1.0f, r.dx)) * p.rH * 2 - 1) * mip_bound - x) * r.rdx;
-    const float ty = (((ny + 0.5f + 0.5f * copysignf(1.0f, r.dy)) * p.rH * 2 - 1) * mip_bound - y) * r.rdy;
-    const float tz = (((nz + 0.5f + 0.5f * copysignf(1.0f, r.dz)) * p.rH * 2 - 1) * mip_bound - z) * r.rdz;
-    const float tt = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
+// One iteration of the reference's serial loop (raymarching.cu:360-399): either report an occupied sample
+// (returns true; x,y,z,dt valid) or step the fixed t-lattice until the empty cell has been crossed (:396-398).
+NGP_DEVINL bool probe(const MarchParams& p, const Ray& r, float& t, float& x, float& y, float& z, float& dt) {
+    const Cell c = classify(p, r, t);
+    x = c.x; y = c.y; z = c.z; dt = c.dt;
+    if (c.occ) return true;
+    const float tt = cell_exit(p, r, c, t);
     do {
         t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
     } while (t < tt);
     return false;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Warp-per-ray walk.  The candidate parameters of a ray form a FIXED lattice T_0 = t0,
+// T_{k+1} = T_k + clamp(T_k * dt_gamma, dt_min, dt_max): both branches of the reference loop advance t by exactly
+// that increment, occupancy only decides which lattice points are visited (an empty cell jumps to the first T_j >=
+// its exit parameter).  So 32 lanes evaluate 32 consecutive lattice points (each lane re-doing the serial additions
+// from the window base, which keeps every T bit-identical), classify their cells in parallel, turn "where do I go
+// next" into a pointer per lane and resolve the visited chain with 5 rounds of pointer doubling.
+// Returns the number of emitted samples (<= limit); WRITE stores them at rows [0, n) of the given pointers.
+// -------------------------------------------------------------------------------------------------
+template <bool WRITE>
+NGP_DEVINL uint32_t walk_ray_warp(const MarchParams& p, const Ray& r, float t0, float far, uint32_t limit, int lane,
+                                  float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    float Tb = t0;               // lattice value of lane 0 of the current window
+    float pending = -FLT_MAX;    // the next visited point is the first with T >= pending
+    float last_t = t0;           // t after the previously emitted sample (raymarching.cu:425,462)
+    uint32_t emitted = 0;
+    while (Tb < far && emitted < limit) {
+        // lane i: i serial increments from the window base
+        float T = Tb;
+#pragma unroll 1
+        for (int j = 0; j < 31; ++j) {
+            const float Tn = T + clampf(T * p.dt_gamma, p.dt_min, p.dt_max);
+            if (j < lane) T = Tn;
+        }
+        const float T_next = T + clampf(T * p.dt_gamma, p.dt_min, p.dt_max);  // == T of lane+1
+        const bool in_range = T < far;
+        const unsigned valid = __ballot_sync(FULL, in_range);
+        const unsigned start_mask = __ballot_sync(FULL, T >= pending);
+        if (start_mask == 0u) {       // the pending cell exit lies beyond this window
+            if (valid != FULL) break;
+            Tb = __shfl_sync(FULL, T_next, 31);
+            continue;
+        }
+        Cell c;
+        c.occ = false; c.x = c.y = c.z = c.dt = 0.f;
+        float tt = 0.f;
+        if (in_range) {
+            c = classify(p, r, T);
+            if (!c.occ) tt = cell_exit(p, r, c, T);
+        }
+        // next pointer: lower_bound over the lanes above me of T >= tt (the do-while always advances once)
+        uint32_t lo = lane + 1, hi = 32;
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const uint32_t mid = (lo + hi) >> 1;
+            const float Tm = __shfl_sync(FULL, T, mid & 31);
+            if (lo < hi) {
+                if (Tm >= tt) hi = mid; else lo = mid + 1;
+            }
+        }
+        // (lo == hi now, except for the degenerate single-candidate case handled by the loop above)
+        uint32_t nxt = !in_range ? 32u : (c.occ ? (uint32_t)lane + 1u : lo);
+        // visited = everything reachable from the start lane (pointer doubling, 2^5 >= 32 hops)
+        unsigned vis = 1u << (__ffs(start_mask) - 1);
+        uint32_t hop = nxt;
+#pragma unroll
+        for (int it = 0; it < 5; ++it) {
+            const unsigned contrib = (((vis >> lane) & 1u) && hop < 32u) ? (1u << hop) : 0u;
+            vis |= __reduce_or_sync(FULL, contrib);
+            const uint32_t h2 = __shfl_sync(FULL, hop, hop & 31);
+            hop = hop < 32u ? h2 : 32u;
+        }
+        vis &= valid;
+        unsigned emit_mask = vis & __ballot_sync(FULL, c.occ);
+        const uint32_t room = limit - emitted;
+        if ((uint32_t)__popc(emit_mask) > room) {   // keep the first `room` samples only (max_steps cap)
+            const uint32_t last = __fns(emit_mask, 0, (int)room);
+            emit_mask &= (last >= 31u) ? FULL : ((2u << last) - 1u);
+        }
+        if (WRITE) {
+            const unsigned below = emit_mask & lt_mask;
+            const int prev = below ? (31 - __clz(below)) : 0;
+            const float prev_after = __shfl_sync(FULL, T_next, prev);
+            if ((emit_mask >> lane) & 1u) {
+                const size_t row = emitted + __popc(below);
+                xyzs[row * 3 + 0] = c.x; xyzs[row * 3 + 1] = c.y; xyzs[row * 3 + 2] = c.z;
+                if (dirs) { dirs[row * 3 + 0] = r.dx; dirs[row * 3 + 1] = r.dy; dirs[row * 3 + 2] = r.dz; }
+                deltas[row * 2 + 0] = c.dt;
+                deltas[row * 2 + 1] = T_next - (below ? prev_after : last_t);  // t - last_t (:461)
+            }
+        }
+        if (emit_mask) {
+            last_t = __shfl_sync(FULL, T_next, 31 - __clz(emit_mask));
+            emitted += __popc(emit_mask);
+        }
+        if (valid != FULL || vis == 0u) break;   // the lattice passed `far` inside this window
+        // carry: the last visited lane points past the window; if it was empty its exit parameter is pending
+        const int last_vis = 31 - __clz(vis);
+        const float tt_last = __shfl_sync(FULL, tt, last_vis);
+        const bool occ_last = (__ballot_sync(FULL, c.occ) >> last_vis) & 1u;
+        pending = occ_last ? -FLT_MAX : tt_last;
+        Tb = __shfl_sync(FULL, T_next, 31);
+    }
+    return emitted;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -223,6 +338,43 @@ __global__ void __launch_bounds__(128) march_count_kernel(const float* __restric
         if (probe(p, r, t, x, y, z, dt)) { ++steps; t += dt; }
     }
     counts[n] = (int)steps;
+}
+
+// warp-per-ray variants of the count / write passes (see walk_ray_warp)
+__global__ void __launch_bounds__(128) march_count_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                               const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                               uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                                               const float* __restrict__ nears, const float* __restrict__ fars,
+                                                               const float* __restrict__ noises, int* __restrict__ counts) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, n);
+    const float t0 = perturbed_start(p, nears[n], noises[n]);
+    const uint32_t steps = walk_ray_warp<false>(p, r, t0, fars[n], max_steps, lane, nullptr, nullptr, nullptr);
+    if (lane == 0) counts[n] = (int)steps;
+}
+
+__global__ void __launch_bounds__(128) march_write_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                               const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                               uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                                               const float* __restrict__ nears, const float* __restrict__ fars,
+                                                               const float* __restrict__ noises, const int* __restrict__ counts,
+                                                               const int* __restrict__ rays, float* __restrict__ xyzs,
+                                                               float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t num_steps = (uint32_t)counts[n];
+    if (num_steps == 0) return;
+    const uint32_t offset = (uint32_t)rays[(size_t)n * 3 + 1];
+    if (offset + num_steps > M) return;  // raymarching.cu:416
+    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, n);
+    const float t0 = perturbed_start(p, nears[n], noises[n]);
+    walk_ray_warp<true>(p, r, t0, fars[n], num_steps, lane, xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr,
+                        deltas + (size_t)offset * 2);
 }
 
 // Single-CTA exclusive scan of the per-ray counts, in ray order.  Writes the (id, offset, count)
@@ -614,6 +766,11 @@ extern "C" int ngp_packbits(const float* grid, uint32_t N, float density_thresh,
     return launch_status();
 }
 
+extern "C" int ngp_march_set_option(int option, int value) {
+    if (option == 0) { march::g_thread_per_ray = (value != 0); return NGP_OK; }
+    return NGP_ERR_BAD_ARG;
+}
+
 extern "C" uint64_t ngp_march_rays_train_workspace(uint32_t N) { return (uint64_t)N * sizeof(int) + 16; }
 
 extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
@@ -628,11 +785,20 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
     if (N == 0) return NGP_OK;
     cudaStream_t st = as_stream(stream);
     int* counts = static_cast<int*>(workspace);
-    march::march_count_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
-                                                            fars, noises, counts);
-    march::march_scan_kernel<<<1, 1024, 0, st>>>(counts, N, rays, counter);
-    march::march_write_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
-                                                            fars, noises, counts, rays, xyzs, dirs, deltas);
+    if (march::g_thread_per_ray) {
+        march::march_count_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
+                                                                fars, noises, counts);
+        march::march_scan_kernel<<<1, 1024, 0, st>>>(counts, N, rays, counter);
+        march::march_write_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
+                                                                nears, fars, noises, counts, rays, xyzs, dirs, deltas);
+    } else {
+        const int blocks = cdiv((uint64_t)N * 32, 128);
+        march::march_count_warp_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
+                                                               fars, noises, counts);
+        march::march_scan_kernel<<<1, 1024, 0, st>>>(counts, N, rays, counter);
+        march::march_write_warp_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
+                                                               fars, noises, counts, rays, xyzs, dirs, deltas);
+    }
     return launch_status();
 }
 

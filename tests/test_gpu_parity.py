@@ -536,3 +536,26 @@ def test_grid_backward_warp_aggregated_on_ray_ordered_samples():
     truth = O.grid_encode_backward(g, x01[:n], offs, offs[-1], 2, np.float32(S), 16, gridtype=0, scale_override=dev_sc)
     ge, _ = my_grid_backward(T(g), T(x01[:n]), T(offs), int(offs[-1]), 2, np.float32(S), 16, 0)
     assert util.rel_l2(N_(ge), truth) < 1e-6
+
+
+@pytest.mark.parametrize("case", MARCH_CASES)
+def test_march_thread_per_ray_variant_is_bit_identical(case):
+    """The C ABI keeps the reference's one-thread-per-ray decomposition behind an option; both must agree bit for bit
+    with the oracle (the default tests above exercise the warp-per-ray walk)."""
+    c = cabi()
+    rays_o, rays_d, bits, nears, fars, noises = _march_setup(case, seed=6)
+    ox, od, ol, orays, ocounter = O.march_rays_train(rays_o, rays_d, case["bound"], bits, case["cascade"], 128, nears, fars,
+                                                     noises, case["dt_gamma"], case["max_steps"])
+    total = int(ocounter[0])
+    outs = []
+    for opt in (1, 0):
+        c.load().ngp_march_set_option(0, opt)
+        try:
+            outs.append(_my_march(case, rays_o, rays_d, bits, nears, fars, noises))
+        finally:
+            c.load().ngp_march_set_option(0, 0)
+    for xyzs, dirs, deltas, rays, counter in outs:
+        assert np.array_equal(N_(rays), orays) and np.array_equal(N_(counter), ocounter)
+        assert np.array_equal(N_(xyzs[:total]), ox[:total]) and np.array_equal(N_(deltas[:total]), ol[:total])
+        assert np.array_equal(N_(dirs[:total]), od[:total])
+        assert not xyzs[total:].any()
