@@ -100,15 +100,15 @@ int ngp_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
  * nondeterministic atomic slot allocation (raymarching.cu:405-406) rows are emitted in ray order:
  * rays[n] describes ray n and offsets are an exclusive prefix sum - one of the orders the
  * reference itself can produce.  A ray whose offset+count > M is recorded in `rays` but writes no
- * samples (raymarching.cu:416).  workspace: device scratch of >= ngp_march_rays_train_workspace(N)
- * bytes. */
+ * samples (raymarching.cu:416).  workspace: device scratch of >=
+ * ngp_march_rays_train_workspace(N, max_steps) bytes (per-ray counts + one max_steps-row slab per ray). */
 int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                          const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
                          int* rays, int* counter, const float* noises, void* workspace,
                          uint64_t workspace_bytes, void* stream);
 /* (dirs may be NULL: the albedo-shaded training path never reads the per-sample directions.) */
-uint64_t ngp_march_rays_train_workspace(uint32_t N);
+uint64_t ngp_march_rays_train_workspace(uint32_t N, uint32_t max_steps);
 /* option 0: value != 0 selects the one-thread-per-ray kernels (the reference's decomposition) instead of the
  * default warp-per-ray walk; results are bit-identical. */
 int ngp_march_set_option(int option, int value);

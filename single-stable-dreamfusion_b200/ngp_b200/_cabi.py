@@ -32,7 +32,7 @@ SIGNATURES = {
     "ngp_packbits": (_i32, [_vp, _u32, _f32, _vp, _vp]),
     "ngp_march_rays_train": (_i32, [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
     "ngp_march_set_option": (_i32, [_i32, _i32]),
-    "ngp_march_rays_train_workspace": (_u64, [_u32]),
+    "ngp_march_rays_train_workspace": (_u64, [_u32, _u32]),
     "ngp_composite_rays_train_forward": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
     "ngp_composite_rays_train_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp]),
     "ngp_march_rays": (_i32, [_u32, _u32, _vp, _vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

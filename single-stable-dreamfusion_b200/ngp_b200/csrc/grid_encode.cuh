@@ -70,6 +70,12 @@ NGP_DEVINL uint32_t lattice_row(uint32_t gridtype, bool align_corners, uint32_t 
         }
     }
     if (gridtype == NGP_GRID_HASH && stride > hashmap_size) index = spatial_hash<D>(p);
+    // `index % hashmap_size` (gridencoder.cu:71) without the ~25-instruction runtime modulo where it is a no-op
+    // or a mask; all three branches are uniform per level.
+    // dense level: every coordinate is <= resolution, so index < (resolution+1)^D = stride <= size
+    // (not with align_corners, where the +1 corner of x = 1 reaches `resolution` itself)
+    if (open && !align_corners && stride <= hashmap_size) return index;
+    if ((hashmap_size & (hashmap_size - 1)) == 0) return index & (hashmap_size - 1);
     return index % hashmap_size;
 }
 

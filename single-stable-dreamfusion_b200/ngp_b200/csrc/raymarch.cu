@@ -155,14 +155,39 @@ NGP_DEVINL uint32_t walk_ray_warp(const MarchParams& p, const Ray& r, float t0, 
     float last_t = t0;           // t after the previously emitted sample (raymarching.cu:425,462)
     uint32_t emitted = 0;
     while (Tb < far && emitted < limit) {
-        // lane i: i serial increments from the window base
-        float T = Tb;
-#pragma unroll 1
-        for (int j = 0; j < 31; ++j) {
-            const float Tn = T + clampf(T * p.dt_gamma, p.dt_min, p.dt_max);
-            if (j < lane) T = Tn;
+        // lane i holds lattice point i of the window: T = Tb advanced i times
+        float T, T_next;
+        bool closed_form = false;
+        if (p.dt_gamma == 0.f) {
+            // Constant step dtc.  Inside one binade [2^e, 2^(e+1)) every float is a multiple of u = 2^(e-23), so the
+            // rounded sum fl(T + dtc) equals T + m*u with m = rn(dtc / u) for EVERY T of the binade (no tie) - the
+            // serial additions collapse to integer arithmetic on the bit pattern.  Ties and binade crossings (a
+            // handful of windows per ray) fall back to the serial loop below.
+            const float dtc = clampf(0.f, p.dt_min, p.dt_max);
+            const int tb = __float_as_int(Tb);
+            const int e = ((tb >> 23) & 0xff) - 127;
+            if (tb > 0 && e > -100 && e < 100) {
+                const float rr = scalbnf(dtc, 23 - e);              // dtc / u, exact
+                const float fl = floorf(rr);
+                if (rr < 4194304.f && (rr - fl) != 0.5f) {
+                    const int m = __float2int_rn(rr);
+                    if ((tb & 0x7fffff) + 32 * m <= 0x7fffff) {     // all 33 values stay inside the binade
+                        T = __int_as_float(tb + lane * m);
+                        T_next = __int_as_float(tb + (lane + 1) * m);
+                        closed_form = true;
+                    }
+                }
+            }
         }
-        const float T_next = T + clampf(T * p.dt_gamma, p.dt_min, p.dt_max);  // == T of lane+1
+        if (!closed_form) {
+            T = Tb;
+#pragma unroll 1
+            for (int j = 0; j < 31; ++j) {
+                const float Tn = T + clampf(T * p.dt_gamma, p.dt_min, p.dt_max);
+                if (j < lane) T = Tn;
+            }
+            T_next = T + clampf(T * p.dt_gamma, p.dt_min, p.dt_max);  // == T of lane+1
+        }
         const bool in_range = T < far;
         const unsigned valid = __ballot_sync(FULL, in_range);
         const unsigned start_mask = __ballot_sync(FULL, T >= pending);
@@ -375,6 +400,47 @@ __global__ void __launch_bounds__(128) march_write_warp_kernel(const float* __re
     const float t0 = perturbed_start(p, nears[n], noises[n]);
     walk_ray_warp<true>(p, r, t0, fars[n], num_steps, lane, xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr,
                         deltas + (size_t)offset * 2);
+}
+
+// Single-pass variant: walk every ray ONCE, writing its samples into a private slab of max_steps rows, then (after
+// the scan has assigned the final offsets) copy the slabs to their packed positions.
+__global__ void __launch_bounds__(128) march_slab_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                         const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                         uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                                         const float* __restrict__ nears, const float* __restrict__ fars,
+                                                         const float* __restrict__ noises, int* __restrict__ counts,
+                                                         float* __restrict__ slab_xyz, float* __restrict__ slab_delta) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    const Ray r = load_ray(rays_o, rays_d, n);
+    const float t0 = perturbed_start(p, nears[n], noises[n]);
+    const uint32_t steps = walk_ray_warp<true>(p, r, t0, fars[n], max_steps, lane, slab_xyz + (size_t)n * max_steps * 3, nullptr,
+                                               slab_delta + (size_t)n * max_steps * 2);
+    if (lane == 0) counts[n] = (int)steps;
+}
+
+__global__ void __launch_bounds__(256) march_compact_kernel(const float* __restrict__ rays_d, const int* __restrict__ rays,
+                                                            const float* __restrict__ slab_xyz, const float* __restrict__ slab_delta,
+                                                            uint32_t max_steps, uint32_t N, uint32_t M, float* __restrict__ xyzs,
+                                                            float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)rays[(size_t)n * 3 + 1], count = (uint32_t)rays[(size_t)n * 3 + 2];
+    if (count == 0 || offset + count > M) return;  // raymarching.cu:415-416
+    const float* sx = slab_xyz + (size_t)n * max_steps * 3;
+    const float* sd = slab_delta + (size_t)n * max_steps * 2;
+    float* ox = xyzs + (size_t)offset * 3;
+    float* od = deltas + (size_t)offset * 2;
+    for (uint32_t i = lane; i < count * 3; i += 32) ox[i] = sx[i];
+    for (uint32_t i = lane; i < count * 2; i += 32) od[i] = sd[i];
+    if (dirs) {
+        const float d0 = rays_d[n * 3], d1 = rays_d[n * 3 + 1], d2 = rays_d[n * 3 + 2];
+        float* pd = dirs + (size_t)offset * 3;
+        for (uint32_t i = lane; i < count * 3; i += 32) { const uint32_t a = i % 3; pd[i] = a == 0 ? d0 : (a == 1 ? d1 : d2); }
+    }
 }
 
 // Single-CTA exclusive scan of the per-ray counts, in ray order.  Writes the (id, offset, count)
@@ -771,7 +837,10 @@ extern "C" int ngp_march_set_option(int option, int value) {
     return NGP_ERR_BAD_ARG;
 }
 
-extern "C" uint64_t ngp_march_rays_train_workspace(uint32_t N) { return (uint64_t)N * sizeof(int) + 16; }
+extern "C" uint64_t ngp_march_rays_train_workspace(uint32_t N, uint32_t max_steps) {
+    // per-ray counts + (warp-per-ray walk) a private slab of max_steps rows (xyz 12 B + deltas 8 B) per ray
+    return (((uint64_t)N * sizeof(int) + 255) / 256) * 256 + (uint64_t)N * max_steps * 20 + 256;
+}
 
 extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                                     float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
@@ -781,7 +850,7 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
     if (!rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !deltas || !rays || !counter || !noises)
         return NGP_ERR_BAD_ARG;
     if (C == 0 || H == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
-    if (!workspace || workspace_bytes < ngp_march_rays_train_workspace(N)) return NGP_ERR_WORKSPACE;
+    if (!workspace || workspace_bytes < ngp_march_rays_train_workspace(N, max_steps)) return NGP_ERR_WORKSPACE;
     if (N == 0) return NGP_OK;
     cudaStream_t st = as_stream(stream);
     int* counts = static_cast<int*>(workspace);
@@ -792,12 +861,15 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
         march::march_write_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M,
                                                                 nears, fars, noises, counts, rays, xyzs, dirs, deltas);
     } else {
+        // warp per ray, single walk into per-ray slabs (scratch after the counts), scan, packed copy
+        float* slab_xyz = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + (((size_t)N * sizeof(int) + 255) / 256) * 256);
+        float* slab_delta = slab_xyz + (size_t)N * max_steps * 3;
         const int blocks = cdiv((uint64_t)N * 32, 128);
-        march::march_count_warp_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
-                                                               fars, noises, counts);
+        march::march_slab_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                                         noises, counts, slab_xyz, slab_delta);
         march::march_scan_kernel<<<1, 1024, 0, st>>>(counts, N, rays, counter);
-        march::march_write_warp_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears,
-                                                               fars, noises, counts, rays, xyzs, dirs, deltas);
+        march::march_compact_kernel<<<cdiv((uint64_t)N * 32, 256), 256, 0, st>>>(rays_d, rays, slab_xyz, slab_delta, max_steps, N, M,
+                                                                                 xyzs, dirs, deltas);
     }
     return launch_status();
 }

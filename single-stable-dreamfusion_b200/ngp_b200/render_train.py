@@ -32,7 +32,7 @@ class TrainWorkspace:
         self.d_sigma, self.d_rgb, self.d_enc = e(cap), e(cap, 3), e(cap, 32, dtype=f16)
         self.rays = torch.empty(n_rays, 3, device=device, dtype=torch.int32)
         lib = _cabi.load()
-        self.march_ws = torch.empty(int(lib.ngp_march_rays_train_workspace(n_rays)), device=device, dtype=torch.uint8)
+        self.march_ws = torch.empty(int(lib.ngp_march_rays_train_workspace(n_rays, int(max_steps))), device=device, dtype=torch.uint8)
         self.counter = torch.zeros(2, device=device, dtype=torch.int32)
 
     @property

@@ -158,7 +158,7 @@ class _march_rays_train(Function):
             noises = torch.zeros(N, dtype=rays_o.dtype, device=device)
 
         lib = _cabi.load()
-        ws = _workspace(lib.ngp_march_rays_train_workspace(N), device)
+        ws = _workspace(lib.ngp_march_rays_train_workspace(N, int(max_steps)), device)
         _cabi.call("ngp_march_rays_train", device, _cabi.ptr(rays_o), _cabi.ptr(rays_d), _cabi.ptr(density_bitfield),
                    float(bound), float(dt_gamma), int(max_steps), N, int(C), int(H), M, _cabi.ptr(nears), _cabi.ptr(fars),
                    _cabi.ptr(xyzs), _cabi.ptr(dirs), _cabi.ptr(deltas), _cabi.ptr(rays), _cabi.ptr(step_counter),

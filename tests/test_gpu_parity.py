@@ -158,6 +158,16 @@ def test_grid_other_dims_and_channels_vs_oracle():
             out, _ = my_grid_forward(T(x), T(emb), T(offs), np.float32(S), 16, gridtype)
             want, _ = O.grid_encode_forward(x, emb, offs, np.float32(S), 16, gridtype=gridtype, scale_override=dev_sc)
             assert np.array_equal(N_(out), want), (D, C, dtype, gridtype)
+            if D == 3 and C in (2, 4):
+                # align_corners (grid.py:91): the +1 corner of x = 1 lands on `resolution` and must wrap like the reference
+                xa = x.copy(); xa[:5] = 1.0; xa[5:9] = 0.0
+                offs_a, S_a = util.make_offsets(num_levels=6, desired_resolution=96, log2_hashmap_size=12, input_dim=D,
+                                                align_corners=True)
+                emb_a = rng.uniform(-1, 1, (offs_a[-1], C)).astype(dtype)
+                out_a, _ = my_grid_forward(T(xa), T(emb_a), T(offs_a), np.float32(S_a), 16, gridtype, align=True)
+                want_a, _ = O.grid_encode_forward(xa, emb_a, offs_a, np.float32(S_a), 16, gridtype=gridtype, align_corners=True,
+                                                  scale_override=dev_sc)
+                assert np.array_equal(N_(out_a), want_a), ("align_corners", D, C, dtype, gridtype)
             g = rng.standard_normal((3000, 6 * C)).astype(dtype)
             ge, _ = my_grid_backward(T(g), T(x), T(offs), int(offs[-1]), C, np.float32(S), 16, gridtype)
             truth = O.grid_encode_backward(g, x, offs, offs[-1], C, np.float32(S), 16, gridtype=gridtype,
@@ -274,7 +284,7 @@ def _my_march(case, rays_o, rays_d, bits, nears, fars, noises, M=None):
     xyzs = torch.zeros(M, 3, device=DEV); dirs = torch.zeros(M, 3, device=DEV); deltas = torch.zeros(M, 2, device=DEV)
     rays = torch.empty(N, 3, dtype=torch.int32, device=DEV)
     counter = torch.zeros(2, dtype=torch.int32, device=DEV)
-    ws = torch.empty(int(lib.ngp_march_rays_train_workspace(N)), dtype=torch.uint8, device=DEV)
+    ws = torch.empty(int(lib.ngp_march_rays_train_workspace(N, int(case["max_steps"]))), dtype=torch.uint8, device=DEV)
     # keep every input tensor alive in a local: c.ptr() only returns an integer address
     ro, rd, bf, ne, fa, nz = T(rays_o), T(rays_d), T(bits), T(nears), T(fars), T(noises)
     c.call("ngp_march_rays_train", xyzs.device, c.ptr(ro), c.ptr(rd), c.ptr(bf), float(case["bound"]),
