@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=3)
     ap.add_argument("--lr", type=float, default=1e-5)
     ap.add_argument("--no-graph", action="store_true", help="run the train step eagerly instead of as one CUDA graph")
+    ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
     return ap.parse_args()
 
@@ -226,8 +227,14 @@ def run_b200_arm(args):
 
     sample_acc = step_fn.samples
 
-    def run_steps(n, e2e, start_index):
+    step_events = []
+
+    def run_steps(n, e2e, start_index, record=False):
         for s in range(n):
+            if record:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                step_events.append(ev)
             i = start_index + s
             if e2e:
                 ro, rd, G = (t.to(device, non_blocking=True) for t in host_batch(i))
@@ -251,10 +258,11 @@ def run_b200_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    run_steps(args.steps, False, 1000)
+    run_steps(args.steps, False, 1000, record=True)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    per_step = sorted(a.elapsed_time(b) for a, b in zip(step_events, step_events[1:] + [e1]))
     launches = _cabi.LAUNCHES - launches0
     n_updates = step_fn.n_updates - updates0
     samples = int(sample_acc.item())
@@ -270,6 +278,17 @@ def run_b200_arm(args):
     ms_e2e = f0.elapsed_time(f1)
     samples_e2e = int(sample_acc.item())
     clk = clocks.stop() if rank == 0 else None
+
+    if args.kernel_table and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        step_fn.global_step = 1
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
+            run_steps(5, False, 2500)
+            torch.cuda.synchronize()
+        with open(args.kernel_table, "w") as f:
+            f.write("# torch.profiler (CUPTI) kernel times over 5 steps of the graphed train step; divide by 5 for per step\n")
+            f.write(prof_t.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
 
     # ---- per-kernel durations for the roofline: a few EAGER steps with CUDA events around our entry points ----
     # (events cannot be recorded inside a graph replay; same kernels, same data shapes, same stream)
@@ -351,7 +370,8 @@ def run_b200_arm(args):
                             "synthetic SDS grad + entropy backward, grad all-reduce, Adam + GradScaler, occupancy "
                             "update every 16 steps" % (args.views, world),
                 "views_per_step": args.views, "rays_per_step": args.views * H * W,
-                "samples_per_step": samples / args.steps, "cuda_graph": not args.no_graph, "lr": args.lr, "timing": "inputs (3.5 MB/step) and the 7 MB table are "
+                "samples_per_step": samples / args.steps, "cuda_graph": not args.no_graph, "lr": args.lr,
+                "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]}, "timing": "inputs (3.5 MB/step) and the 7 MB table are "
                 "smaller than L2 by nature of the workload; each step runs on a different view batch (64-batch pool), "
                 "the 134+ MB/step of sample buffers exceed L2",
             },
