@@ -206,6 +206,51 @@ int ngp_grid_scatter_samples(const void* d_enc, const float* xyzs, float bound, 
                              int align_corners, float* grad_table, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * The steps either side of the render inside one train step.  The reference runs these as
+ * chains of eager PyTorch kernels; each entry point below is one launch.
+ * ------------------------------------------------------------------------------------------ */
+#define NGP_ADAM_MAX_SEGMENTS 8
+
+/* GradScaler's inf/nan check (torch.amp.GradScaler.unscale_, called from nerf/utils.py:709 scaler.step):
+ * sets *found_inf = 1.0f (device f32, never cleared here) if any of grads f32[n] is not finite.  grads 16-byte aligned. */
+int ngp_check_finite(const float* grads, uint64_t n, float* found_inf, void* stream);
+
+/* scaler.step(optimizer) + scaler.update() for Adam over ONE flat parameter buffer (main.py:128 Adam betas
+ * (0.9,0.99) eps 1e-15; network_grid.py:170-181 lr groups; main.py:131 LambdaLR 0.1^(iter/iters);
+ * nerf/utils.py:709-710).  All pointers are device pointers except seg_end / seg_lr (HOST arrays of n_segments
+ * entries: exclusive end index of each learning-rate group in the flat buffer, and its base lr).
+ *   state f32[5]: [0] loss scale, [1] growth tracker, [2] optimizer steps taken, [3] found_inf (from
+ *   ngp_check_finite), [4] skipped steps.  If state[3] != 0 the parameters are left untouched and the scale is
+ *   multiplied by backoff_factor; otherwise grads are divided by state[0] * grad_div, Adam is applied with
+ *   lr * exp(lr_decay_ln * min(steps, lr_decay_steps)), and the scale grows by growth_factor every
+ *   growth_interval clean steps.  half_shadow (optional f16[n]) receives the fp16 cast of the new parameters (what
+ *   autocast re-derives every forward, gridencoder/grid.py:38-39); zero_grads != 0 zero-fills grads on the way out
+ *   (optimizer.zero_grad, nerf/utils.py:700).  blocks_done: zero-initialised device u32 scratch (left zero). */
+int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow, uint64_t n,
+                  uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1, float beta2, float eps,
+                  float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor, float backoff_factor,
+                  uint32_t growth_interval, int zero_grads, float* state, uint32_t* blocks_done, void* stream);
+
+/* End of run_cuda (nerf/renderer.py:535-557): image_out = image + (1 - weights_sum) * bg, depth_out =
+ * clamp(depth - nears, 0) / (fars - nears) (NaN where the ray misses the box, as the reference), mask = nears < fars.
+ * bg is f32[N,3] (bg_per_ray != 0) or one f32[3] colour.  depth_out / mask may be NULL. */
+int ngp_blend_background_forward(const float* image, const float* weights_sum, const float* depth, const float* bg,
+                                 int bg_per_ray, const float* nears, const float* fars, uint32_t N, float* image_out,
+                                 float* depth_out, uint8_t* mask, void* stream);
+/* Its backward: grad_weights_sum[n] = -sum_c grad_image[n,c] * bg[n,c]; grad_bg = (1 - weights_sum) * grad_image
+ * (only when bg_per_ray; may be NULL).  The gradient wrt `image` is grad_image itself. */
+int ngp_blend_background_backward(const float* grad_image, const float* weights_sum, const float* bg, int bg_per_ray,
+                                  uint32_t N, float* grad_weights_sum, float* grad_bg, void* stream);
+
+/* Opacity-entropy regulariser of train_step (nerf/utils.py:389-394): *loss = lambda * mean(-a log2 a - (1-a) log2(1-a)),
+ * a = clamp(weights_sum, 1e-5, 1 - 1e-5).  Deterministic single-block reduction. */
+int ngp_entropy_loss_forward(const float* weights_sum, uint32_t N, float lambda, float* loss, void* stream);
+/* grad_weights_sum[n] (= or +=, per `accumulate`) (*grad_loss) * d loss / d weights_sum[n]; grad_loss is a DEVICE
+ * scalar (the GradScaler's scale when the loss is scaled). */
+int ngp_entropy_loss_backward(const float* weights_sum, uint32_t N, float lambda, const float* grad_loss,
+                              float* grad_weights_sum, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Roofline micro-benchmarks (measurement support; SURVEY 8d asks for a measured L2 peak)
  * ------------------------------------------------------------------------------------------ */
 /* Random 4-byte gathers: each of n_threads threads performs `iters` x 8 independent loads from

@@ -6,6 +6,8 @@ and back-propagates into the embedding table, the three Linear weights and biase
 as fp32 holding the fp16-rounded sigmoid (the reference hands a half tensor to compositing, which
 immediately widens it: raymarching.py:240).
 """
+import weakref
+
 import numpy as np
 import torch
 from torch.autograd import Function
@@ -22,9 +24,26 @@ def invalidate_half_cache():
     _cache_epoch[0] += 1
 
 
+_shadows = {}  # id(param) -> (weakref to param, fp16 shadow tensor, [param._version the shadow matches])
+
+
+def register_half_shadow(param, shadow):
+    """Declare `shadow` (fp16, same shape) as the maintained fp16 copy of `param`: the fused optimizer kernel rewrites
+    it together with the parameter (optim.py), so no per-forward cast is needed.  In-place edits made through torch
+    (load_state_dict, init code) bump param._version and trigger one refresh."""
+    _shadows[id(param)] = (weakref.ref(param), shadow, [param._version])
+
+
 def cached_half(t):
     """fp16 copy of a parameter, refreshed only when the parameter changes (autocast re-casts per forward)."""
     key = id(t)
+    s = _shadows.get(key)
+    if s is not None and s[0]() is t:
+        if t._version != s[2][0]:
+            with torch.no_grad():
+                s[1].copy_(t)
+            s[2][0] = t._version
+        return s[1]
     ver = (t.data_ptr(), t._version, tuple(t.shape), _cache_epoch[0])
     hit = _half_cache.get(key)
     # while a CUDA graph is being captured the cast must become part of the graph (replays do not bump _version)

@@ -1,0 +1,133 @@
+"""Adam + GradScaler over ONE flat parameter buffer, one launch per step (csrc/train_step.cu).
+
+The reference's optimisation step is ``scaler.step(optimizer); scaler.update()`` on ``torch.optim.Adam(
+model.get_params(lr), betas=(0.9, 0.99), eps=1e-15)`` with a ``LambdaLR(0.1 ** min(iter / iters, 1))`` schedule
+(main.py:128-131, nerf/utils.py:708-713) - per parameter tensor an unscale kernel, an inf check, the Adam update and,
+on the next forward, a fresh fp32 -> fp16 cast of the table (gridencoder/grid.py:38-39).  Here the parameters, their
+gradients, both Adam moments and an fp16 shadow copy live in five flat buffers with the same layout:
+
+    ngp_check_finite(grads)            -> state[found_inf]
+    ngp_adam_step(params, grads, ...)  -> unscale, Adam, LambdaLR, GradScaler.update, fp16 shadow, zero the grads
+
+``param.data`` / ``param.grad`` become views into the flat buffers, so autograd accumulates straight into the bucket
+that the data-parallel all-reduce sends (parallel.py) and ``state_dict()`` keeps the reference's names and shapes.
+All state (loss scale, growth tracker, step count) stays on the device: the step is CUDA-graph capturable.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _cabi, field
+
+_ALIGN = 8  # elements: every tensor starts 16-byte aligned in the fp16 shadow (32 bytes in fp32)
+
+
+class FusedAdamScaler:
+    def __init__(self, param_groups, betas=(0.9, 0.99), eps=1e-15, init_scale=65536.0, growth_factor=2.0,
+                 backoff_factor=0.5, growth_interval=2000, lr_decay=None, grad_div=1.0):
+        """param_groups: [{'params': iterable, 'lr': float}, ...] as NeRFNetwork.get_params returns.
+        lr_decay: None or (factor, iters) for lr * factor ** min(step / iters, 1)."""
+        groups = []
+        for g in param_groups:
+            ps = [p for p in g["params"] if p.requires_grad]
+            if ps:
+                groups.append((ps, float(g["lr"])))
+        if not groups or len(groups) > 8:
+            raise RuntimeError("1..8 non-empty parameter groups expected")
+        self.params = [p for ps, _ in groups for p in ps]
+        device = self.params[0].device
+        _cabi.require_cuda(*self.params)
+        self.device = device
+        # layout: groups back to back, each tensor aligned
+        self.offsets, seg_end, off = [], [], 0
+        for ps, _ in groups:
+            for p in ps:
+                if p.dtype != torch.float32:
+                    raise RuntimeError("fp32 master parameters expected")
+                self.offsets.append(off)
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            seg_end.append(off)
+        self.numel = off
+        self.seg_end = (ctypes.c_uint64 * len(groups))(*seg_end)
+        self.base_lrs = [lr for _, lr in groups]
+        self.seg_lr = (ctypes.c_float * len(groups))(*self.base_lrs)
+        self.n_seg = len(groups)
+        f = lambda dt=torch.float32: torch.zeros(off, device=device, dtype=dt)  # noqa: E731
+        self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq = f(), f(), f(), f()
+        self.flat_half = f(torch.half)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.flat_params[o:o + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+        self.attach_grads()
+        self.flat_half.copy_(self.flat_params)
+        for p, o in zip(self.params, self.offsets):
+            field.register_half_shadow(p, self.flat_half[o:o + p.numel()].view_as(p))
+        self.betas, self.eps = betas, eps
+        self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
+        self.grad_div = float(grad_div)
+        self.set_lr_decay(lr_decay)
+        # [scale, growth tracker, steps, found_inf, skipped]
+        self.state = torch.tensor([init_scale, 0.0, 0.0, 0.0, 0.0], device=device, dtype=torch.float32)
+        self._blocks_done = torch.zeros(1, device=device, dtype=torch.int32)
+
+    # -- layout helpers ------------------------------------------------------------------------------------------
+    def attach_grads(self):
+        """(Re-)point every .grad at its slice of the flat gradient buffer."""
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat_grads[o:].data_ptr():
+                p.grad = self.flat_grads[o:o + p.numel()].view_as(p)
+
+    def set_lr(self, lrs):
+        self.base_lrs = [float(x) for x in lrs]
+        self.seg_lr = (ctypes.c_float * self.n_seg)(*self.base_lrs)
+
+    def set_lr_decay(self, lr_decay):
+        if lr_decay is None:
+            self.lr_decay_ln, self.lr_decay_steps = 0.0, 0.0
+        else:
+            factor, iters = lr_decay
+            self.lr_decay_ln, self.lr_decay_steps = math.log(factor) / float(iters), float(iters)
+
+    # -- GradScaler surface ----------------------------------------------------------------------------------------
+    @property
+    def scale_tensor(self):
+        return self.state[0]
+
+    def scale(self, loss):
+        return loss * self.state[0]
+
+    def get_scale(self):
+        return float(self.state[0].item())
+
+    @property
+    def steps_taken(self):
+        return int(self.state[2].item())
+
+    def zero_grad(self):
+        self.flat_grads.zero_()
+
+    def step(self, zero_grads=True):
+        """scaler.step(optimizer) + scaler.update() (+ optimizer.zero_grad()): two launches, no host sync."""
+        dev = self.device
+        _cabi.call("ngp_check_finite", dev, _cabi.ptr(self.flat_grads), self.numel, self.state[3:].data_ptr())
+        _cabi.call("ngp_adam_step", dev, _cabi.ptr(self.flat_params), _cabi.ptr(self.flat_grads), _cabi.ptr(self.exp_avg),
+                   _cabi.ptr(self.exp_avg_sq), _cabi.ptr(self.flat_half), self.numel, self.n_seg, self.seg_end, self.seg_lr,
+                   float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,
+                   self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
+                   int(bool(zero_grads)), _cabi.ptr(self.state), _cabi.ptr(self._blocks_done))
+
+    # -- checkpointing (nerf/utils.py:847-968 saves optimizer / scaler state next to the model) ----------------------
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "state": self.state.clone(),
+                "base_lrs": list(self.base_lrs), "offsets": list(self.offsets), "numel": self.numel}
+
+    def load_state_dict(self, sd):
+        if sd["numel"] != self.numel or list(sd["offsets"]) != list(self.offsets):
+            raise RuntimeError("optimizer state does not match this parameter layout")
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.state.copy_(sd["state"])
+        self.set_lr(sd["base_lrs"])

@@ -203,13 +203,14 @@ class NeRFRenderer(nn.Module):
         elif bg_color is None:
             bg_color = 1
 
-        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        # blend + depth normalisation + hit mask (renderer.py:541-551) in one launch; depth is NaN for rays that miss
+        # the box (0/0), as in the reference
+        from .step_ops import blend_background
+        image, depth, mask = blend_background(image.float(), weights_sum, depth, bg_color, nears, fars)
         image = image.view(*prefix, 3)
-
-        depth = torch.clamp(depth - nears, min=0) / (fars - nears)  # NaN for rays that miss the box, as the reference
         depth = depth.view(*prefix)
         weights_sum = weights_sum.reshape(*prefix)
-        mask = (nears < fars).reshape(*prefix)
+        mask = mask.reshape(*prefix)
 
         results['image'] = image
         results['depth'] = depth

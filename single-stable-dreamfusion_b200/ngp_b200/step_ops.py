@@ -1,0 +1,87 @@
+"""One-launch versions of the small ops either side of the render (csrc/train_step.cu), as autograd Functions.
+
+``blend_background`` is the tail of ``run_cuda`` (nerf/renderer.py:535-557: background blend, depth normalisation,
+hit mask); ``entropy_loss`` is the opacity regulariser of ``Trainer.train_step`` (nerf/utils.py:389-394).  The
+reference evaluates each as a chain of ~10 eager elementwise kernels forward and as many backward; at sub-millisecond
+step times those launches are a visible share of the step, so each direction is a single kernel here.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _cabi
+
+
+class _BlendBackground(Function):
+    @staticmethod
+    def forward(ctx, image, weights_sum, depth, bg, nears, fars):
+        dev = image.device
+        N = image.shape[0]
+        per_ray = bg.dim() == 2
+        image_out = torch.empty_like(image)
+        depth_out = torch.empty_like(depth)
+        mask = torch.empty(N, device=dev, dtype=torch.bool)
+        _cabi.call("ngp_blend_background_forward", dev, _cabi.ptr(image), _cabi.ptr(weights_sum), _cabi.ptr(depth),
+                   _cabi.ptr(bg), int(per_ray), _cabi.ptr(nears), _cabi.ptr(fars), N, _cabi.ptr(image_out),
+                   _cabi.ptr(depth_out), _cabi.ptr(mask))
+        ctx.save_for_backward(weights_sum, bg)
+        ctx.per_ray = per_ray
+        # composite_rays_train does not propagate grad_depth (raymarching.py:275), so depth carries no gradient
+        ctx.mark_non_differentiable(depth_out, mask)
+        return image_out, depth_out, mask
+
+    @staticmethod
+    def backward(ctx, g_image, _g_depth, _g_mask):
+        weights_sum, bg = ctx.saved_tensors
+        dev = weights_sum.device
+        N = weights_sum.shape[0]
+        g_image = g_image.contiguous().float()
+        d_ws = torch.empty_like(weights_sum)
+        d_bg = torch.empty(N, 3, device=dev, dtype=torch.float32) if (ctx.per_ray and ctx.needs_input_grad[3]) else None
+        _cabi.call("ngp_blend_background_backward", dev, _cabi.ptr(g_image), _cabi.ptr(weights_sum), _cabi.ptr(bg),
+                   int(ctx.per_ray), N, _cabi.ptr(d_ws), _cabi.ptr(d_bg))
+        return g_image, d_ws, None, d_bg, None, None
+
+
+def blend_background(image, weights_sum, depth, bg_color, nears, fars):
+    """image [N,3], weights_sum [N], depth [N] (fp32, CUDA); bg_color: [N,3] tensor, [3] tensor or python scalar.
+    Returns (image + (1 - weights_sum) * bg, clamp(depth - nears, 0) / (fars - nears), nears < fars)."""
+    dev = image.device
+    if not torch.is_tensor(bg_color):
+        bg = torch.full((3,), float(bg_color), device=dev, dtype=torch.float32)
+    else:
+        bg = bg_color.to(device=dev, dtype=torch.float32)
+        if bg.dim() == 0:
+            bg = bg.expand(3)
+        elif bg.dim() >= 2:
+            bg = bg.reshape(-1, 3)
+            if bg.shape[0] == 1:
+                bg = bg[0]
+            elif bg.shape[0] != image.shape[0]:
+                raise RuntimeError("bg_color must be a colour or one colour per ray")
+        bg = bg.contiguous()
+    return _BlendBackground.apply(image.contiguous(), weights_sum.contiguous(), depth.contiguous(), bg, nears, fars)
+
+
+class _EntropyLoss(Function):
+    @staticmethod
+    def forward(ctx, weights_sum, lam):
+        ws = weights_sum.contiguous().view(-1)
+        loss = torch.empty((), device=ws.device, dtype=torch.float32)
+        _cabi.call("ngp_entropy_loss_forward", ws.device, _cabi.ptr(ws), ws.numel(), float(lam), _cabi.ptr(loss))
+        ctx.save_for_backward(ws)
+        ctx.lam, ctx.shape = float(lam), weights_sum.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (ws,) = ctx.saved_tensors
+        d_ws = torch.empty_like(ws)
+        g = g.contiguous().float()
+        _cabi.call("ngp_entropy_loss_backward", ws.device, _cabi.ptr(ws), ws.numel(), ctx.lam, _cabi.ptr(g), _cabi.ptr(d_ws), 0)
+        return d_ws.view(ctx.shape), None
+
+
+def entropy_loss(weights_sum, lam=1e-4):
+    """lam * mean binary entropy (base 2) of clamp(weights_sum, 1e-5, 1 - 1e-5)."""
+    _cabi.require_cuda(weights_sum)
+    return _EntropyLoss.apply(weights_sum.float(), lam)

@@ -16,27 +16,42 @@ import torch
 import torch.distributed as dist
 
 from . import _cabi
+from .optim import FusedAdamScaler
 from .parallel import FlatGradBucket
+from .step_ops import entropy_loss as fused_entropy_loss
 
 
 def entropy_loss(weights_sum, lam=1e-4):
-    """lambda_entropy * binary entropy of the per-ray opacity (nerf/utils.py:389-394)."""
+    """lambda_entropy * binary entropy of the per-ray opacity (nerf/utils.py:389-394), as the reference's chain of
+    torch ops (the one-launch version is step_ops.entropy_loss)."""
     alphas = weights_sum.clamp(1e-5, 1 - 1e-5)
     return lam * (-alphas * torch.log2(alphas) - (1 - alphas) * torch.log2(1 - alphas)).mean()
 
 
 class TrainStep:
     def __init__(self, model, H, W, lr=1e-3, max_steps=1024, lambda_entropy=1e-4, update_interval=16, graph=False,
-                 world_size=1):
+                 world_size=1, fused_optimizer=True, lr_decay=None):
         self.model, self.H, self.W = model, H, W
         self.max_steps, self.lam, self.update_interval = max_steps, lambda_entropy, update_interval
         self.world = world_size
         self.use_graph = graph
+        self.single_backward = True  # one engine pass for both roots (see _body); False = the reference's two passes
         device = next(model.parameters()).device
         self.device = device
-        self.opt = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=graph)
-        self.scaler = torch.amp.GradScaler("cuda")
-        self.bucket = FlatGradBucket(list(model.parameters()), device)
+        self.fused_optimizer = fused_optimizer
+        if fused_optimizer:
+            # one flat buffer each for params / grads / moments / fp16 shadow; unscale + Adam + scaler.update + shadow
+            # refresh + zero_grad in two launches (optim.py); the all-reduce mean is folded into the unscale
+            self.opt = FusedAdamScaler(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, grad_div=float(world_size),
+                                       lr_decay=lr_decay)
+            self.scaler = self.opt
+            self.bucket = None
+            self.flat_grads = self.opt.flat_grads
+        else:
+            self.opt = torch.optim.Adam(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, fused=True, capturable=graph)
+            self.scaler = torch.amp.GradScaler("cuda")
+            self.bucket = FlatGradBucket(list(model.parameters()), device)
+            self.flat_grads = self.bucket.flat
         self.global_step = 0
         self.n_updates = 0
         self.samples = torch.zeros(1, dtype=torch.int64, device=device)  # running count of marched samples
@@ -49,19 +64,33 @@ class TrainStep:
     def _body(self, rays_o, rays_d, G):
         model = self.model
         B = rays_o.shape[0]
-        self.bucket.zero()
+        if not self.fused_optimizer:
+            self.bucket.zero()  # (the fused optimizer kernel leaves the gradient buffer zeroed)
         with torch.autocast("cuda", torch.float16):
             out = model.render(rays_o, rays_d, staged=False, perturb=True, bg_color=None, ambient_ratio=1.0,
                                shading="albedo", force_all_rays=True, max_steps=self.max_steps, dt_gamma=0)
             pred_rgb = out["image"].reshape(B, self.H, self.W, 3).permute(0, 3, 1, 2).contiguous()
-            pred_rgb.backward(gradient=G, retain_graph=True)  # the (synthetic) guidance gradient
-            loss = entropy_loss(out["weights_sum"].reshape(B, 1, self.H, self.W), self.lam)
-        self.scaler.scale(loss).backward()
+            ws = out["weights_sum"].reshape(B, 1, self.H, self.W)
+            loss = fused_entropy_loss(ws, self.lam) if self.fused_optimizer else entropy_loss(ws, self.lam)
+        # The reference runs TWO backward passes over the render graph per step: the guidance's manual
+        # `pred_rgb.backward(gradient=G, retain_graph=True)` (nerf/sd.py:115) and `scaler.scale(loss).backward()`
+        # (nerf/utils.py:708).  Back-propagation is linear in the upstream gradient, so both roots are handed to the
+        # engine at once: it sums d(image), d(weights_sum) at the render node and walks the heavy part (composite,
+        # MLP, grid scatter) once.  Same accumulated .grad up to fp32 summation order (tests/test_gpu_pipeline.py).
+        if self.single_backward:
+            torch.autograd.backward([pred_rgb, self.scaler.scale(loss)], [G, None])
+        else:
+            pred_rgb.backward(gradient=G, retain_graph=True)
+            self.scaler.scale(loss).backward()
         if self.world > 1:
-            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM)
-            self.bucket.flat.div_(self.world)
-        self.scaler.step(self.opt)
-        self.scaler.update()
+            dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM)
+        if self.fused_optimizer:
+            self.opt.step(zero_grads=True)
+        else:
+            if self.world > 1:
+                self.bucket.flat.div_(self.world)
+            self.scaler.step(self.opt)
+            self.scaler.update()
         return loss
 
     def _bookkeeping_after(self, local_step_before):
@@ -76,14 +105,14 @@ class TrainStep:
     def __call__(self, rays_o, rays_d, G):
         model = self.model
         if self.global_step % self.update_interval == 0:
-            if self.use_graph:
+            if self.use_graph and not self.fused_optimizer:
                 from . import field
                 field.invalidate_half_cache()  # graph replays update the parameters without bumping ._version
             with torch.autocast("cuda", torch.float16):
                 model.update_extra_state()
             self.n_updates += 1
         self.global_step += 1
-        self.bucket.attach()
+        (self.opt.attach_grads if self.fused_optimizer else self.bucket.attach)()
 
         if not self.use_graph:
             loss = self._body(rays_o, rays_d, G)

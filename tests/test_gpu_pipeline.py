@@ -214,3 +214,29 @@ def test_lambertian_shading_path_runs():
     assert "loss_orient" in out and "loss_smooth" in out and torch.isfinite(out["image"]).all()
     (out["image"].sum() + out["loss_orient"]).backward()
     assert torch.isfinite(m.encoder.embeddings.grad).all()
+
+
+@pytest.mark.parametrize("g_scale,tol", [(1e-2, 2e-2), (30.0, 3e-3)])
+def test_single_backward_pass_equals_the_two_reference_passes(ref_ext, g_scale, tol):
+    """TrainStep hands both roots (guidance gradient on pred_rgb, scaled entropy loss) to autograd at once; the
+    accumulated gradient bucket must equal what the reference's two backward() calls accumulate.  The backward chain
+    carries fp16 activations-gradients (as the reference's autocast backward does); with the reference's UNSCALED
+    guidance gradient (~1e-2, nerf/sd.py:115) those sit in fp16's subnormal range, so each variant is ~1e-2 from the
+    exact sum - a guidance gradient of O(10) moves them out of it and the two variants agree to fp16 rounding."""
+    from ngp_b200.trainer import TrainStep
+    from ngp_b200 import provider
+    ro, rd = provider.make_training_views(2, 64, 64, seed=4, pin=False)
+    ro = ro.view(1, 2, 4096, 3).to(DEV); rd = rd.view(1, 2, 4096, 3).to(DEV)
+    G = torch.randn(1, 2, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * g_scale
+    grads = []
+    for single in (True, False):
+        m, _ = _models(ref_ext)
+        step = TrainStep(m, 64, 64, graph=False, lr=0.0, fused_optimizer=False)   # torch path keeps the grads around
+        step.single_backward = single
+        torch.manual_seed(5)
+        step(ro[0], rd[0], G[0])
+        grads.append(step.flat_grads.clone())
+    a, b = grads
+    assert torch.isfinite(a).all() and b.abs().sum() > 0
+    rel = ((a - b).norm() / b.norm()).item()
+    assert rel < tol, rel

@@ -1,0 +1,139 @@
+"""GPU tests of the one-launch train-step pieces (csrc/train_step.cu) against the torch ops the reference uses:
+Adam + GradScaler (main.py:128-131, nerf/utils.py:708-713), the run_cuda tail (nerf/renderer.py:535-557) and the
+entropy regulariser (nerf/utils.py:389-394)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _two_models():
+    torch.manual_seed(3)
+    shapes = [(1001, 2), (64, 32), (64,), (4, 64), (3,)]
+    a = [torch.nn.Parameter(torch.randn(s, device=DEV) * 0.1) for s in shapes]
+    b = [torch.nn.Parameter(p.detach().clone()) for p in a]
+    return a, b
+
+
+def test_fused_adam_scaler_matches_torch_adam_and_gradscaler():
+    from ngp_b200.optim import FusedAdamScaler
+    from ngp_b200 import field
+    a, b = _two_models()
+    lr = 1e-3
+    groups = lambda ps: [{"params": ps[:1], "lr": lr * 10}, {"params": ps[1:], "lr": lr}]  # noqa: E731
+    mine = FusedAdamScaler(groups(a), betas=(0.9, 0.99), eps=1e-15, growth_interval=3, lr_decay=(0.1, 10), grad_div=2.0)
+    opt = torch.optim.Adam(groups(b), betas=(0.9, 0.99), eps=1e-15)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda it: 0.1 ** min(it / 10, 1))
+    scaler = torch.amp.GradScaler("cuda", growth_interval=3)
+    g = torch.Generator(device=DEV).manual_seed(0)
+    for it in range(12):
+        raw = [torch.randn(p.shape, device=DEV, generator=g) * (10.0 ** (it % 5 - 3)) for p in a]
+        if it == 5:
+            raw[2][7] = float("inf")            # one overflow step: skipped, scale backs off
+        if it == 8:
+            raw[0][3, 1] = float("nan")
+        s_mine, s_ref = mine.get_scale(), scaler.get_scale()
+        assert s_mine == s_ref, (it, s_mine, s_ref)
+        for p, q, r in zip(a, b, raw):
+            p.grad.copy_(r * s_mine * 2.0)      # "all-reduced sum over 2 ranks" of scaled grads
+            q.grad = r * s_ref
+        mine.step(zero_grads=True)
+        scaler.step(opt)
+        scaler.update()
+        if it not in (5, 8):
+            sched.step()                        # the Trainer steps the scheduler once per (successful) iteration
+        for p, q in zip(a, b):
+            assert torch.isfinite(p).all()
+            np.testing.assert_allclose(p.detach().cpu().numpy(), q.detach().cpu().numpy(), rtol=2e-5, atol=1e-7)
+            assert torch.equal(field.cached_half(p), p.detach().half())      # fp16 shadow follows the parameter
+            assert p.grad.abs().sum().item() == 0                           # zero_grad folded in
+    assert mine.steps_taken == 10 and mine.state[4].item() == 2
+
+
+def test_fused_adam_params_are_views_and_state_dict_keeps_names():
+    import argparse
+    from ngp_b200.network_grid import NeRFNetwork
+    from ngp_b200.optim import FusedAdamScaler
+    opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)
+    m = NeRFNetwork(opt).to(DEV)
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    o = FusedAdamScaler(m.get_params(1e-3))
+    after = m.state_dict()
+    assert list(before) == list(after)
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+    assert o.numel >= sum(p.numel() for p in m.parameters())
+    assert m.encoder.embeddings.data_ptr() == o.flat_params.data_ptr()
+    m.load_state_dict(before)                   # in-place copies land in the flat buffer
+    assert torch.equal(o.flat_params[:10], m.encoder.embeddings.detach().view(-1)[:10])
+
+
+def test_blend_background_matches_torch_ops():
+    from ngp_b200.step_ops import blend_background
+    g = torch.Generator(device=DEV).manual_seed(1)
+    N = 5000
+    image = torch.rand(N, 3, device=DEV, generator=g).requires_grad_()
+    ws = torch.rand(N, device=DEV, generator=g).requires_grad_()
+    depth = torch.rand(N, device=DEV, generator=g) * 3
+    nears = torch.rand(N, device=DEV, generator=g) + 0.2
+    fars = nears + torch.rand(N, device=DEV, generator=g)
+    fars[::17] = nears[::17] = 3.4028234663852886e38        # box misses
+    up = torch.randn(N, 3, device=DEV, generator=g)
+    for bg in (torch.rand(N, 3, device=DEV, generator=g).half().requires_grad_(), torch.ones(3, device=DEV), 1):
+        img, dep, mask = blend_background(image, ws, depth, bg, nears, fars)
+        want = image + (1 - ws).unsqueeze(-1) * bg
+        want_d = torch.clamp(depth - nears, min=0) / (fars - nears)
+        assert torch.allclose(img, want.float(), rtol=1e-6, atol=1e-6)
+        assert torch.equal(torch.isnan(dep), torch.isnan(want_d)) and torch.allclose(dep[mask], want_d[mask], rtol=1e-6)
+        assert torch.equal(mask, nears < fars)
+        leaves = [image, ws] + ([bg] if torch.is_tensor(bg) and bg.requires_grad else [])
+        got = torch.autograd.grad(img, leaves, up)
+        ref = torch.autograd.grad(want, leaves, up)
+        for x, y in zip(got, ref):
+            assert torch.allclose(x.float(), y.float(), rtol=1e-3 if y.dtype == torch.half else 1e-5, atol=1e-5)
+
+
+def test_entropy_loss_matches_torch_ops():
+    from ngp_b200.step_ops import entropy_loss
+    from ngp_b200.trainer import entropy_loss as torch_entropy
+    g = torch.Generator(device=DEV).manual_seed(2)
+    ws = torch.rand(2, 1, 64, 64, device=DEV, generator=g)
+    ws.view(-1)[:100] = 0.0
+    ws.view(-1)[100:200] = 1.0
+    ws.view(-1)[200:300] = 1e-7
+    ws.requires_grad_()
+    scale = torch.tensor(65536.0, device=DEV)
+    a = entropy_loss(ws, 1e-4)
+    b = torch_entropy(ws, 1e-4)
+    assert abs(a.item() - b.item()) < 1e-6 * abs(b.item()) + 1e-12
+    ga, = torch.autograd.grad(a * scale, ws)
+    gb, = torch.autograd.grad(b * scale, ws)
+    assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-7)
+
+
+def test_train_step_fused_optimizer_tracks_torch_optimizer(ref_ext):
+    """Whole TrainStep: fused Adam/scaler/blend/entropy path vs the torch.optim path, same seeds, a few steps."""
+    import argparse
+    from ngp_b200 import provider
+    from ngp_b200.network_grid import NeRFNetwork
+    from ngp_b200.trainer import TrainStep
+    ro, rd = provider.make_training_views(4, 64, 64, seed=3, pin=False)
+    ro = ro.view(4, 1, 4096, 3).to(DEV); rd = rd.view(4, 1, 4096, 3).to(DEV)
+    G = torch.randn(4, 1, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 1e-2
+    finals = []
+    for fused in (True, False):
+        opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)
+        torch.manual_seed(0)
+        m = NeRFNetwork(opt).to(DEV).train()
+        step = TrainStep(m, 64, 64, lr=1e-3, graph=False, fused_optimizer=fused)
+        torch.manual_seed(5)
+        losses = [step(ro[i], rd[i], G[i]).item() for i in range(4)]
+        finals.append((losses, {n: p.detach().clone() for n, p in m.named_parameters()}))
+    np.testing.assert_allclose(finals[0][0], finals[1][0], rtol=2e-3)
+    for n in finals[0][1]:
+        a, b = finals[0][1][n], finals[1][1][n]
+        # Adam's first steps move every touched weight by ~lr regardless of gradient size: compare on that scale
+        assert (a - b).abs().max().item() < 2.5e-3 * (10 if "embeddings" in n else 1), n
+        assert ((a - b).norm() / (b.norm() + 1e-12)).item() < 0.2, n
