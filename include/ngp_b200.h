@@ -181,8 +181,10 @@ int ngp_update_density_grid(float* grid, const float* tmp_grid, uint32_t n_cells
 
 /* xyzs f32[M,3] in [-bound,bound]; table f16[rows,2]; w1..w3 and b1..b3 are the fp16 casts of the nn.Linear weights
  * ([out,in] row-major) and biases; count_ptr (optional, device i32) limits the rows actually processed.
- * Outputs: sigma f32[M]; rgb f32[M,3] (the fp16-rounded sigmoid, widened).  enc_save f16[M,32], h1_save /
- * h2_save f16[M,64] are optional (NULL for inference) and feed ngp_field_backward. */
+ * Outputs: sigma f32[M]; rgb f32[M,3] (the fp16-rounded sigmoid, widened).  enc_save / h1_save / h2_save are optional
+ * (NULL for inference) and feed ngp_field_backward: OPAQUE buffers of ceil(M/128)*128 rows x 32 / 64 / 64 fp16
+ * (16-byte aligned), written one whole 128-sample tile at a time in the kernels' shared-memory tile layout (one
+ * bulk copy per tile) - not row-major. */
 int ngp_field_forward(const float* xyzs, uint32_t M, const int* count_ptr, const void* table, const int* offsets,
                       uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, int align_corners, float bound,
                       const void* w1, const void* b1, const void* w2, const void* b2, const void* w3, const void* b3,
@@ -196,6 +198,10 @@ int ngp_field_backward(uint32_t M, const int* count_ptr, const void* w1, const v
                        uint32_t hidden, uint32_t out_dim, const float* d_sigma, const float* d_rgb, const float* sigma,
                        const float* rgb, const void* enc_save, const void* h1_save, const void* h2_save, void* d_enc,
                        float* gw1, float* gb1, float* gw2, float* gb2, float* gw3, float* gb3, void* stream);
+
+/* Tuning switch for the fused field kernels (profiling support): option 0 = forward CTAs per SM (1..7),
+ * option 1 = forward shared-memory carveout percent (-1: driver default). */
+int ngp_field_set_option(int option, int value);
 
 /* Table-gradient scatter for the sync-free training path: like ngp_grid_encode_backward for D=3, C=2, fp16
  * [M, L*C] gradients and an fp32 table, but (a) only the first *count_ptr rows (device i32, may be NULL) of the
@@ -260,6 +266,11 @@ int ngp_bench_gather4(const uint32_t* table, uint32_t table_words, uint32_t* sin
 /* Random 8-byte red.global.add.v2.f32 into table f32[table_words]. */
 int ngp_bench_red8(float* table, uint32_t table_words, uint32_t n_threads, uint32_t iters, uint32_t seed,
                    void* stream);
+
+/* Random red.global.add of `width` (1, 2 or 4) consecutive floats per op; only every lane_stride-th lane of a warp
+ * issues (1 = all 32 lanes).  Separates the per-lane issue cost from the L2 cost of the scatter. */
+int ngp_bench_red_width(float* table, uint32_t table_words, uint32_t n_threads, uint32_t iters, uint32_t seed,
+                        uint32_t width, uint32_t lane_stride, void* stream);
 
 /* Hardware self-test of the hand-written tcgen05 path (one CTA, one small fp16 GEMM with fp32 accumulate):
  * mode 0: D[128,N] = A[128,K] B[N,K]^T ; mode 1: D[M,N] = A[128,M]^T B[128,N] (M in {64,128}) ;

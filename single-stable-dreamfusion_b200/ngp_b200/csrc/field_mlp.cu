@@ -18,12 +18,18 @@
 namespace ngp {
 namespace field {
 
+int g_fwd_ctas_per_sm = 4;   // ngp_field_set_option(0, n): 46.5 KB of shared memory per CTA -> at most 4 resident
+int g_fwd_carveout = -1;     // ngp_field_set_option(1, percent); -1 = driver default
+
 constexpr uint32_t kTile = 128;   // samples per CTA tile == threads per CTA == TMEM lanes
 constexpr uint32_t kLevels = 16;  // grid levels (x 2 features = 32 MLP inputs)
 constexpr uint32_t kIn = 32, kHid = 64, kOut = 4, kOutPad = 16;
-constexpr uint32_t kRg32 = (32 / 8) * 128;  // row-group stride of a 32-column tile  (512 B)
-constexpr uint32_t kRg64 = (64 / 8) * 128;  // 64-column tile (1024 B)
-constexpr uint32_t kRg16 = (16 / 8) * 128;  // 16-column tile (256 B)
+// chunk strides (bytes between consecutive 8-column chunks) of the core-matrix tiles, = rows * 16 (tcgen05.cuh)
+constexpr uint32_t kCs128 = kTile * 16;  // activation / gradient tiles: 128 samples
+constexpr uint32_t kCs64 = kHid * 16;    // W1 [64 x 32], W2 [64 x 64]
+constexpr uint32_t kCs16 = kOutPad * 16; // W3 padded to [16 x 64]
+constexpr uint32_t kEncTileBytes = kTile * kIn * 2;   // 8 KB: one saved tile of encodings
+constexpr uint32_t kHidTileBytes = kTile * kHid * 2;  // 16 KB: one saved tile of hidden activations
 
 struct Weights {
     const __half *w1, *b1, *w2, *b2, *w3, *b3;  // fp16 copies, row-major [out, in] as nn.Linear stores them
@@ -39,13 +45,13 @@ struct GridDesc {
 };
 
 // global row-major [R x C] fp16 weights -> core-matrix tile; rows >= R_valid are zero-filled
-NGP_DEVINL void load_weight_tile(const __half* g, uint32_t R_valid, uint32_t R, uint32_t C, uint8_t* smem, uint32_t rg) {
+NGP_DEVINL void load_weight_tile(const __half* g, uint32_t R_valid, uint32_t R, uint32_t C, uint8_t* smem) {
     const uint32_t chunks = C / 8;
     for (uint32_t i = threadIdx.x; i < R * chunks; i += blockDim.x) {
         const uint32_t r = i / chunks, cc = i % chunks;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (r < R_valid) v = *reinterpret_cast<const uint4*>(g + (size_t)r * C + cc * 8);
-        *reinterpret_cast<uint4*>(smem + tc::tile_chunk_off(r, cc, rg)) = v;
+        *reinterpret_cast<uint4*>(smem + tc::tile_chunk_off(r, cc, R * 16)) = v;
     }
 }
 
@@ -55,54 +61,43 @@ NGP_DEVINL uint32_t pack_half2(float a, float b) {
 }
 NGP_DEVINL float2 unpack_half2(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
 
-// One level of one sample's encoding as a packed half2 - the arithmetic of encode_forward_kernel<__half, 3, 2>.
-NGP_DEVINL uint32_t encode_level(const float (&x01)[3], bool oob, const GridDesc& gd, const grid::LevelParams& lp) {
-    float acc[2] = {0.f, 0.f};
-    if (!oob) {
-        const __half* tbl = gd.table + (size_t)lp.offset * 2;
-        float frac[3];
-        uint32_t base[3];
-        grid::locate<3>(x01, lp.scale, gd.align_corners != 0, frac, base);
-        float rows[8][2], wts[8];
-        // levels that ignore trailing axes (tiled, resolution >= 256: z) have only 4 distinct rows per cell
-        const uint32_t axes_used = grid::level_axes_used<3>(gd.gridtype, gd.align_corners != 0, lp.hashmap_size, lp.resolution);
-        const uint32_t distinct = 1u << axes_used;
+// One level of one sample's encoding as a packed half2 - the arithmetic of encode_forward_kernel<__half, 3, 2>
+// (bit-equal to the reference's half kernel): rows resolved by FastLevel, one 4-byte gather per distinct corner,
+// packed-half accumulate in the reference's corner order.
+NGP_DEVINL uint32_t encode_level(const float (&x01)[3], const uint32_t* __restrict__ table_u32, bool align_corners,
+                                 const grid::FastLevel<3>& lp) {
+    float frac[3];
+    uint32_t base[3];
+    grid::locate<3>(x01, lp.scale, align_corners, frac, base);
+    uint32_t ridx[8];
+    grid::corner_rows<3>(lp, base, ridx);
+    const uint32_t* __restrict__ tbl = table_u32 + lp.offset;
+    uint32_t raw[8];
+    // levels that ignore trailing axes (tiled, resolution >= 256: z) have only 4 distinct rows per cell
+    if (lp.used == 2) {
 #pragma unroll
-        for (uint32_t corner = 0; corner < 8; ++corner) {
-            float w = 1;
-            uint32_t p[3];
+        for (uint32_t c = 0; c < 4; ++c) { raw[c] = __ldg(tbl + ridx[c]); raw[c + 4] = raw[c]; }
+    } else {
 #pragma unroll
-            for (uint32_t d = 0; d < 3; ++d) {
-                if ((corner & (1u << d)) == 0) { w *= 1 - frac[d]; p[d] = base[d]; }
-                else                           { w *= frac[d];     p[d] = base[d] + 1; }
-            }
-            wts[corner] = w;
-            if (corner < distinct) {
-                const uint32_t row = grid::lattice_row<3>(gd.gridtype, gd.align_corners != 0, lp.hashmap_size, lp.resolution, p);
-                grid::load_row<__half, 2>(tbl + (size_t)row * 2, rows[corner]);
-            }
-        }
-        grid::replicate_rows<3, 2>(rows, axes_used);
-#pragma unroll
-        for (uint32_t corner = 0; corner < 8; ++corner) {
-#pragma unroll
-            for (uint32_t c = 0; c < 2; ++c) {
-                const float prod = grid::ElemOps<__half>::round(wts[corner] * rows[corner][c]);
-                acc[c] = grid::ElemOps<__half>::round(acc[c] + prod);
-            }
-        }
+        for (uint32_t c = 0; c < 8; ++c) raw[c] = __ldg(tbl + ridx[c]);  // (used == 1 reloads equal rows: same values)
     }
-    return pack_half2(acc[0], acc[1]);
+    float wts[8];
+    grid::corner_weights<3>(frac, wts);
+    __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (uint32_t c = 0; c < 8; ++c) acc = grid::half2_axpy(acc, wts[c], raw[c]);
+    return *reinterpret_cast<uint32_t*>(&acc);
 }
 
-// shared-memory carve-up of the forward kernel
+// shared-memory carve-up of the forward kernel.  Two activation buffers used alternately: phase k of a tile writes
+// one while the bulk store + MMAs of phase k-1 may still be reading the other (see the hazard notes in the kernel).
 struct FwdSmem {
-    static constexpr uint32_t a0 = 0;                       // [128 x 32] encodings
-    static constexpr uint32_t a1 = a0 + 16 * kRg32;         // [128 x 64] hidden activations
-    static constexpr uint32_t w1 = a1 + 16 * kRg64;         // [64 x 32]
-    static constexpr uint32_t w2 = w1 + 8 * kRg32;          // [64 x 64]
-    static constexpr uint32_t w3 = w2 + 8 * kRg64;          // [16 x 64] (rows 4.. zero)
-    static constexpr uint32_t bias = w3 + 2 * kRg64;        // b1[64] b2[64] b3[4] as float
+    static constexpr uint32_t buf0 = 0;                     // [128 x 64] (or the [128 x 32] encodings in its first 8 KB)
+    static constexpr uint32_t buf1 = buf0 + kHidTileBytes;
+    static constexpr uint32_t w1 = buf1 + kHidTileBytes;    // [64 x 32]
+    static constexpr uint32_t w2 = w1 + 4 * kCs64;          // [64 x 64]
+    static constexpr uint32_t w3 = w2 + 8 * kCs64;          // [16 x 64] (rows 4.. zero)
+    static constexpr uint32_t bias = w3 + 8 * kCs16;        // b1[64] b2[64] b3[4] as float
     static constexpr uint32_t total = bias + (64 + 64 + 4) * 4;
 };
 
@@ -114,15 +109,14 @@ struct FwdArgs {
     Weights w;
     float* sigma;   // [M] fp32
     float* rgb;     // [M, 3] fp32 holding the fp16-rounded sigmoid
-    __half* enc;    // optional saves for the backward
+    __half* enc;    // optional saves for the backward, TILE-MAJOR: tile t = the smem image of its 128 rows
     __half* h1;
     __half* h2;
 };
 
 // bias + fp16 rounding + ReLU of one accumulator row segment, written as 16-byte chunks of the next operand tile
 template <uint32_t NCOLS>
-NGP_DEVINL void hidden_epilogue(const uint32_t (&acc)[NCOLS], const float* bias, uint32_t col0, uint32_t r, uint8_t* tile,
-                                __half* save_row) {
+NGP_DEVINL void hidden_epilogue(const uint32_t (&acc)[NCOLS], const float* bias, uint32_t col0, uint32_t r, uint8_t* tile) {
 #pragma unroll
     for (uint32_t q = 0; q < NCOLS / 8; ++q) {
         uint32_t w[4];
@@ -134,25 +128,30 @@ NGP_DEVINL void hidden_epilogue(const uint32_t (&acc)[NCOLS], const float* bias,
             const float v1 = fmaxf(__half2float(__float2half_rn(__uint_as_float(acc[c + 1]) + bias[col0 + c + 1])), 0.f);
             w[j] = pack_half2(v0, v1);
         }
-        const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(tile + tc::tile_chunk_off(r, col0 / 8 + q, kRg64)) = v;
-        if (save_row) *reinterpret_cast<uint4*>(save_row + col0 + q * 8) = v;
+        *reinterpret_cast<uint4*>(tile + tc::tile_chunk_off(r, col0 / 8 + q, kCs128)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
+// Forward.  Per tile three phases, each: all threads write one operand tile -> fence + barrier -> thread 0 issues the
+// bulk (TMA) store of that tile to the save buffer and the layer's MMAs -> everyone waits for the MMAs on an mbarrier
+// and reads its accumulator row from TMEM.  Shared-memory hazards:
+//   * a tile buffer is rewritten two phases after it was last read (buffers alternate), and thread 0 waits for the
+//     READ side of its outstanding bulk stores right before every barrier - so the barrier that precedes a write to
+//     buffer X also publishes "the store that read X has finished reading";
+//   * MMAs that read a buffer were awaited by every thread (mbarrier) before the phase that wrote the other buffer.
 __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ grid::LevelParams s_levels[kLevels];
+    __shared__ grid::FastLevel<3> s_levels[kLevels];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const uint32_t r = threadIdx.x, warp = r >> 5;
 
-    if (r < kLevels) s_levels[r] = grid::make_level(a.gd.offsets, r, a.gd.S, a.gd.H);
+    if (r < kLevels) s_levels[r] = grid::make_fast_level<3>(a.gd.offsets, r, a.gd.S, a.gd.H, a.gd.gridtype, a.gd.align_corners != 0);
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
     if (r == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-    load_weight_tile(a.w.w1, kHid, kHid, kIn, smem + FwdSmem::w1, kRg32);
-    load_weight_tile(a.w.w2, kHid, kHid, kHid, smem + FwdSmem::w2, kRg64);
-    load_weight_tile(a.w.w3, kOut, kOutPad, kHid, smem + FwdSmem::w3, kRg64);
+    load_weight_tile(a.w.w1, kHid, kHid, kIn, smem + FwdSmem::w1);
+    load_weight_tile(a.w.w2, kHid, kHid, kHid, smem + FwdSmem::w2);
+    load_weight_tile(a.w.w3, kOut, kOutPad, kHid, smem + FwdSmem::w3);
     float* s_bias = reinterpret_cast<float*>(smem + FwdSmem::bias);
     if (r < 64) { s_bias[r] = __half2float(a.w.b1[r]); s_bias[64 + r] = __half2float(a.w.b2[r]); }
     if (r < 4) s_bias[128 + r] = __half2float(a.w.b3[r]);
@@ -163,7 +162,6 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
     const uint32_t tmem = tmem_base_s;
     const uint32_t tmem_row = tc::tmem_addr(tmem, warp * 32, 0);
 
-    const uint32_t sa0 = tc::smem_u32(smem + FwdSmem::a0), sa1 = tc::smem_u32(smem + FwdSmem::a1);
     const uint32_t sw1 = tc::smem_u32(smem + FwdSmem::w1), sw2 = tc::smem_u32(smem + FwdSmem::w2);
     const uint32_t sw3 = tc::smem_u32(smem + FwdSmem::w3);
     constexpr uint32_t idesc_h = tc::instr_desc(128, kHid, false, false);
@@ -172,9 +170,15 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
     const uint32_t M = a.count_ptr ? min((uint32_t)max(*a.count_ptr, 0), a.M) : a.M;
     const uint32_t n_tiles = (M + kTile - 1) / kTile;
     const float inv_2b = __fdiv_rn(1.0f, 2 * a.gd.bound);
-    uint32_t phase = 0;
+    const bool save = a.enc != nullptr;
+    const uint32_t* table_u32 = reinterpret_cast<const uint32_t*>(a.gd.table);
+    const bool align = a.gd.align_corners != 0;
+    uint32_t phase = 0, par = 0;
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
+        uint8_t* bufA = smem + (par ? FwdSmem::buf1 : FwdSmem::buf0);  // encodings, then h2
+        uint8_t* bufB = smem + (par ? FwdSmem::buf0 : FwdSmem::buf1);  // h1
+        const uint32_t sA = tc::smem_u32(bufA), sB = tc::smem_u32(bufB);
         const uint32_t m = tile * kTile + r;
         const bool active = m < M;
         float x[3] = {0.f, 0.f, 0.f};
@@ -184,13 +188,14 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
                               __fmul_rn(__fadd_rn(x[2], a.gd.bound), inv_2b)};
         const bool oob = grid::out_of_unit_cube<3>(x01);
         for (uint32_t cc = 0; cc < 4; ++cc) {  // 4 levels = one 16-byte chunk of the operand row
-            uint32_t e[4];
+            uint32_t e[4] = {0u, 0u, 0u, 0u};  // out-of-cube samples encode to zeros (gridencoder.cu:106-122)
+            if (!oob) {
 #pragma unroll
-            for (uint32_t j = 0; j < 4; ++j) e[j] = encode_level(x01, oob, a.gd, s_levels[cc * 4 + j]);
-            const uint4 v = make_uint4(e[0], e[1], e[2], e[3]);
-            *reinterpret_cast<uint4*>(smem + FwdSmem::a0 + tc::tile_chunk_off(r, cc, kRg32)) = v;
-            if (a.enc && active) *reinterpret_cast<uint4*>(a.enc + (size_t)m * kIn + cc * 8) = v;
+                for (uint32_t j = 0; j < 4; ++j) e[j] = encode_level(x01, table_u32, align, s_levels[cc * 4 + j]);
+            }
+            *reinterpret_cast<uint4*>(bufA + tc::tile_chunk_off(r, cc, kCs128)) = make_uint4(e[0], e[1], e[2], e[3]);
         }
+        if (save && r == 0) tc::bulk_store_wait_read();
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
@@ -198,9 +203,10 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
         // ---- layer 1: [128 x 32] x W1^T -> TMEM [128 x 64] ----
         if (r == 0) {
             tc::tc_fence_after_sync();
+            if (save) tc::bulk_store(a.enc + (size_t)tile * (kTile * kIn), bufA, kEncTileBytes);
 #pragma unroll
             for (uint32_t k = 0; k < kIn / 16; ++k)
-                tc::umma_f16(tmem, tc::smem_desc(sa0 + k * 256, 128, kRg32), tc::smem_desc(sw1 + k * 256, 128, kRg32), idesc_h, k > 0);
+                tc::umma_f16(tmem, tc::desc_k_major(sA, kCs128, k), tc::desc_k_major(sw1, kCs64, k), idesc_h, k > 0);
             tc::umma_commit(&bar);
         }
         tc::mbar_wait(&bar, phase); phase ^= 1;
@@ -210,8 +216,9 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
             uint32_t acc[32];
             tc::tmem_ld_x32(tmem_row + half * 32, acc);
             tc::tmem_ld_wait();
-            hidden_epilogue<32>(acc, s_bias, half * 32, r, smem + FwdSmem::a1, (a.h1 && active) ? a.h1 + (size_t)m * kHid : nullptr);
+            hidden_epilogue<32>(acc, s_bias, half * 32, r, bufB);
         }
+        if (save && r == 0) tc::bulk_store_wait_read();
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
@@ -219,9 +226,10 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
         // ---- layer 2: [128 x 64] x W2^T ----
         if (r == 0) {
             tc::tc_fence_after_sync();
+            if (save) tc::bulk_store(a.h1 + (size_t)tile * (kTile * kHid), bufB, kHidTileBytes);
 #pragma unroll
             for (uint32_t k = 0; k < kHid / 16; ++k)
-                tc::umma_f16(tmem, tc::smem_desc(sa1 + k * 256, 128, kRg64), tc::smem_desc(sw2 + k * 256, 128, kRg64), idesc_h, k > 0);
+                tc::umma_f16(tmem, tc::desc_k_major(sB, kCs128, k), tc::desc_k_major(sw2, kCs64, k), idesc_h, k > 0);
             tc::umma_commit(&bar);
         }
         tc::mbar_wait(&bar, phase); phase ^= 1;
@@ -231,8 +239,9 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
             uint32_t acc[32];
             tc::tmem_ld_x32(tmem_row + half * 32, acc);
             tc::tmem_ld_wait();
-            hidden_epilogue<32>(acc, s_bias + 64, half * 32, r, smem + FwdSmem::a1, (a.h2 && active) ? a.h2 + (size_t)m * kHid : nullptr);
+            hidden_epilogue<32>(acc, s_bias + 64, half * 32, r, bufA);
         }
+        if (save && r == 0) tc::bulk_store_wait_read();
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
@@ -240,9 +249,10 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
         // ---- layer 3: [128 x 64] x W3^T (4 outputs padded to 16) ----
         if (r == 0) {
             tc::tc_fence_after_sync();
+            if (save) tc::bulk_store(a.h2 + (size_t)tile * (kTile * kHid), bufA, kHidTileBytes);
 #pragma unroll
             for (uint32_t k = 0; k < kHid / 16; ++k)
-                tc::umma_f16(tmem, tc::smem_desc(sa1 + k * 256, 128, kRg64), tc::smem_desc(sw3 + k * 256, 128, kRg64), idesc_o, k > 0);
+                tc::umma_f16(tmem, tc::desc_k_major(sA, kCs128, k), tc::desc_k_major(sw3, kCs16, k), idesc_o, k > 0);
             tc::umma_commit(&bar);
         }
         tc::mbar_wait(&bar, phase); phase ^= 1;
@@ -266,6 +276,7 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
         }
         tc::tc_fence_before_sync();  // the next tile's first MMA overwrites these TMEM columns
     }
+    if (save && r == 0) tc::bulk_store_wait_all();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
@@ -273,17 +284,28 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
 // -------------------------------------------------------------------------------------------------------------
 // backward
 // -------------------------------------------------------------------------------------------------------------
+// Shared memory: the three saved activation tiles of the current sample tile arrive by bulk (TMA) loads, each into
+// its own buffer with its own mbarrier, and are re-armed for the NEXT tile as soon as their last reader is done, so
+// the loads of tile t+1 overlap the GEMMs of tile t.  The h1 and encoding tiles are followed by a constant chunk
+// whose first column is 1: read as a [128 x (C+8)] MN-major operand, column C makes the weight-gradient GEMM
+// deliver the bias gradient as well (sum over samples of dh x 1).
 struct BwdSmem {
-    static constexpr uint32_t x = 0;                     // [128 x 64] activations (h2, then h1, then the 32-wide encoding)
-    static constexpr uint32_t g = x + 16 * kRg64;        // [128 x 64] upstream grads of the current layer (dh2, then dh1)
-    static constexpr uint32_t g3 = g + 16 * kRg64;       // [128 x 16] dh_out (4 used)
-    static constexpr uint32_t w1 = g3 + 16 * kRg16;
-    static constexpr uint32_t w2 = w1 + 8 * kRg32;
-    static constexpr uint32_t w3 = w2 + 8 * kRg64;
-    static constexpr uint32_t total = w3 + 2 * kRg64;
+    static constexpr uint32_t xh2 = 0;                          // [128 x 64] h2
+    static constexpr uint32_t xh1 = xh2 + kHidTileBytes;        // [128 x 64] h1
+    static constexpr uint32_t one1 = xh1 + kHidTileBytes;       // [128 x 8] ones chunk (column 64 of the h1 operand)
+    static constexpr uint32_t xe = one1 + kCs128;               // [128 x 32] encodings
+    static constexpr uint32_t onee = xe + kEncTileBytes;        // [128 x 8] ones chunk (column 32 of the encoding operand)
+    static constexpr uint32_t g = onee + kCs128;                // [128 x 64] upstream grads of the current layer (dh2, then dh1)
+    static constexpr uint32_t g3 = g + kHidTileBytes;           // [128 x 16] dh_out (4 used)
+    static constexpr uint32_t w1 = g3 + 2 * kCs128;
+    static constexpr uint32_t w2 = w1 + 4 * kCs64;
+    static constexpr uint32_t w3 = w2 + 8 * kCs64;
+    static constexpr uint32_t total = w3 + 8 * kCs16;
 };
-// TMEM columns
-constexpr uint32_t kColD = 0, kColW3 = 64, kColW1 = 96, kColW2 = 128, kTmemColsBwd = 256;
+// TMEM columns: D = data gradients [128 lanes x 64]; W3 = [64(in) x 16(out)]; W1 = [64(out) x 32(in) + bias col];
+// W2 = [64(out) x 64(in) + bias col]
+constexpr uint32_t kColD = 0, kColW3 = 64, kColW1 = 80, kColW2 = 128, kTmemColsBwd = 256;
+constexpr uint32_t kNW1 = kIn + 8, kNW2 = kHid + 8;
 
 struct BwdArgs {
     uint32_t M;
@@ -293,21 +315,12 @@ struct BwdArgs {
     const float* d_rgb;     // [M, 3]
     const float* sigma;     // forward outputs
     const float* rgb;
-    const __half* enc;      // forward saves
+    const __half* enc;      // forward saves (tile-major)
     const __half* h1;
     const __half* h2;
-    __half* d_enc;          // [M, 32] out: gradient wrt the encoding (feeds the grid scatter)
+    __half* d_enc;          // [M, 32] row-major out: gradient wrt the encoding (feeds the grid scatter)
     float *gw1, *gb1, *gw2, *gb2, *gw3, *gb3;  // fp32 accumulators (+=, atomics)
 };
-
-NGP_DEVINL void load_row_to_tile(const __half* src_row, uint32_t ncols, uint32_t r, uint8_t* tile, uint32_t rg, bool active) {
-#pragma unroll 8
-    for (uint32_t cc = 0; cc < ncols / 8; ++cc) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (active) v = __ldg(reinterpret_cast<const uint4*>(src_row) + cc);
-        *reinterpret_cast<uint4*>(tile + tc::tile_chunk_off(r, cc, rg)) = v;
-    }
-}
 
 // dh = relu'(h) * half(acc): reads this thread's activation row from the X tile, writes its row of the G tile
 NGP_DEVINL void relu_backward_epilogue(uint32_t tmem_row, uint32_t r, const uint8_t* xtile, uint8_t* gtile) {
@@ -319,7 +332,7 @@ NGP_DEVINL void relu_backward_epilogue(uint32_t tmem_row, uint32_t r, const uint
 #pragma unroll
         for (uint32_t q = 0; q < 4; ++q) {
             const uint32_t cc = half * 4 + q;
-            const uint4 hv = *reinterpret_cast<const uint4*>(xtile + tc::tile_chunk_off(r, cc, kRg64));
+            const uint4 hv = *reinterpret_cast<const uint4*>(xtile + tc::tile_chunk_off(r, cc, kCs128));
             const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
             uint32_t w[4];
 #pragma unroll
@@ -329,32 +342,33 @@ NGP_DEVINL void relu_backward_epilogue(uint32_t tmem_row, uint32_t r, const uint
                 const float g1 = h.y > 0.f ? __uint_as_float(acc[q * 8 + 2 * j + 1]) : 0.f;
                 w[j] = pack_half2(g0, g1);
             }
-            *reinterpret_cast<uint4*>(gtile + tc::tile_chunk_off(r, cc, kRg64)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(gtile + tc::tile_chunk_off(r, cc, kCs128)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }
 
-// column sum over the 128 rows of a gradient tile (bias gradient); thread j owns column j
-NGP_DEVINL float tile_column_sum(const uint8_t* tile, uint32_t rg, uint32_t col) {
-    float s = 0.f;
-    const uint8_t* base = tile + (col >> 3) * 128u + (col & 7u) * 2u;
-#pragma unroll 8
-    for (uint32_t row = 0; row < kTile; ++row)
-        s += __half2float(*reinterpret_cast<const __half*>(base + (row >> 3) * rg + (row & 7u) * 16u));
-    return s;
-}
-
 __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const BwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar_mma, bar_h2, bar_h1, bar_e;
     __shared__ uint32_t tmem_base_s;
     const uint32_t r = threadIdx.x, warp = r >> 5, lane = r & 31;
 
+    const uint32_t M = a.count_ptr ? min((uint32_t)max(*a.count_ptr, 0), a.M) : a.M;
+    const uint32_t n_tiles = (M + kTile - 1) / kTile;
+
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, kTmemColsBwd);
-    if (r == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
-    load_weight_tile(a.w.w1, kHid, kHid, kIn, smem + BwdSmem::w1, kRg32);
-    load_weight_tile(a.w.w2, kHid, kHid, kHid, smem + BwdSmem::w2, kRg64);
-    load_weight_tile(a.w.w3, kOut, kOutPad, kHid, smem + BwdSmem::w3, kRg64);
+    if (r == 0) {
+        tc::mbar_init(&bar_mma, 1); tc::mbar_init(&bar_h2, 1); tc::mbar_init(&bar_h1, 1); tc::mbar_init(&bar_e, 1);
+        tc::fence_mbar_init();
+    }
+    load_weight_tile(a.w.w1, kHid, kHid, kIn, smem + BwdSmem::w1);
+    load_weight_tile(a.w.w2, kHid, kHid, kHid, smem + BwdSmem::w2);
+    load_weight_tile(a.w.w3, kOut, kOutPad, kHid, smem + BwdSmem::w3);
+    {   // the two constant chunks: row r = (1.0h, 0, 0, 0, 0, 0, 0, 0)
+        const uint4 one = make_uint4(0x00003C00u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(smem + BwdSmem::one1 + tc::tile_chunk_off(r, 0, kCs128)) = one;
+        *reinterpret_cast<uint4*>(smem + BwdSmem::onee + tc::tile_chunk_off(r, 0, kCs128)) = one;
+    }
     tc::fence_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -362,25 +376,31 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const BwdArgs 
     const uint32_t tmem = tmem_base_s;
     const uint32_t tmem_row = tc::tmem_addr(tmem, warp * 32, 0);
 
-    const uint32_t sx = tc::smem_u32(smem + BwdSmem::x), sg = tc::smem_u32(smem + BwdSmem::g), sg3 = tc::smem_u32(smem + BwdSmem::g3);
+    auto load_h2 = [&](uint32_t t) { tc::mbar_expect_tx(&bar_h2, kHidTileBytes); tc::bulk_load(smem + BwdSmem::xh2, a.h2 + (size_t)t * (kTile * kHid), kHidTileBytes, &bar_h2); };
+    auto load_h1 = [&](uint32_t t) { tc::mbar_expect_tx(&bar_h1, kHidTileBytes); tc::bulk_load(smem + BwdSmem::xh1, a.h1 + (size_t)t * (kTile * kHid), kHidTileBytes, &bar_h1); };
+    auto load_e = [&](uint32_t t) { tc::mbar_expect_tx(&bar_e, kEncTileBytes); tc::bulk_load(smem + BwdSmem::xe, a.enc + (size_t)t * (kTile * kIn), kEncTileBytes, &bar_e); };
+    if (r == 0 && blockIdx.x < n_tiles) { load_h2(blockIdx.x); load_h1(blockIdx.x); load_e(blockIdx.x); }
+
+    const uint32_t sx2 = tc::smem_u32(smem + BwdSmem::xh2), sx1 = tc::smem_u32(smem + BwdSmem::xh1), sxe = tc::smem_u32(smem + BwdSmem::xe);
+    const uint32_t sg = tc::smem_u32(smem + BwdSmem::g), sg3 = tc::smem_u32(smem + BwdSmem::g3);
     const uint32_t sw1 = tc::smem_u32(smem + BwdSmem::w1), sw2 = tc::smem_u32(smem + BwdSmem::w2), sw3 = tc::smem_u32(smem + BwdSmem::w3);
     // data gradients: A = upstream grads (K-major), B = weights [out, in] read MN-major (K = out)
     constexpr uint32_t id_dgrad64 = tc::instr_desc(128, 64, false, true);
     constexpr uint32_t id_dgrad32 = tc::instr_desc(128, 32, false, true);
     // weight gradients: both operands MN-major, K = samples
-    constexpr uint32_t id_w3 = tc::instr_desc(64, 16, true, true);   // D[i, o] = sum_m h2[m, i] dh3[m, o]
-    constexpr uint32_t id_w2 = tc::instr_desc(64, 64, true, true);   // D[i, o] = sum_m h1[m, i] dh2[m, o]
-    constexpr uint32_t id_w1 = tc::instr_desc(64, 32, true, true);   // D[o, i] = sum_m dh1[m, o] enc[m, i]
+    constexpr uint32_t id_w3 = tc::instr_desc(64, 16, true, true);     // D[i, o]  = sum_m h2[m, i] dh3[m, o]
+    constexpr uint32_t id_w2 = tc::instr_desc(64, kNW2, true, true);   // D[o, i'] = sum_m dh2[m, o] [h1 | 1][m, i']
+    constexpr uint32_t id_w1 = tc::instr_desc(64, kNW1, true, true);   // D[o, i'] = sum_m dh1[m, o] [enc | 1][m, i']
 
-    const uint32_t M = a.count_ptr ? min((uint32_t)max(*a.count_ptr, 0), a.M) : a.M;
-    const uint32_t n_tiles = (M + kTile - 1) / kTile;
-    uint32_t phase = 0;
-    float gb_acc2 = 0.f, gb_acc1 = 0.f, gb_acc3 = 0.f;  // thread j accumulates column j of the bias gradients
+    uint32_t ph_mma = 0, ph_ld = 0;
+    float gb3_acc[4] = {0.f, 0.f, 0.f, 0.f};  // this thread's share of the output-layer bias gradient
     bool first = true;
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ph_ld ^= 1) {
         const uint32_t m = tile * kTile + r;
         const bool active = m < M;
+        const uint32_t next = tile + gridDim.x;
+        const bool has_next = next < n_tiles;
 
         // ---- output layer: dh_out from (d_sigma, d_rgb) through trunc_exp / sigmoid -----------------------------
         float dh[4] = {0.f, 0.f, 0.f, 0.f};
@@ -395,29 +415,32 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const BwdArgs 
                 dh[j + 1] = __half2float(__float2half_rn(gh * (1.f - y) * y));
             }
         }
-        *reinterpret_cast<uint4*>(smem + BwdSmem::g3 + tc::tile_chunk_off(r, 0, kRg16)) =
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gb3_acc[j] += dh[j];
+        // (the previous tile's d_enc bulk store read the G tile, not G3; G3's last readers were awaited MMAs)
+        *reinterpret_cast<uint4*>(smem + BwdSmem::g3 + tc::tile_chunk_off(r, 0, kCs128)) =
             make_uint4(pack_half2(dh[0], dh[1]), pack_half2(dh[2], dh[3]), 0u, 0u);
-        *reinterpret_cast<uint4*>(smem + BwdSmem::g3 + tc::tile_chunk_off(r, 1, kRg16)) = make_uint4(0u, 0u, 0u, 0u);
-        load_row_to_tile(a.h2 + (size_t)m * kHid, kHid, r, smem + BwdSmem::x, kRg64, active);
+        *reinterpret_cast<uint4*>(smem + BwdSmem::g3 + tc::tile_chunk_off(r, 1, kCs128)) = make_uint4(0u, 0u, 0u, 0u);
+        tc::mbar_wait(&bar_h2, ph_ld);   // h2 tile has landed (async-proxy write, visible after the wait)
+        if (r == 0) tc::bulk_store_wait_read();   // the previous tile's d_enc store has finished reading G
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
         if (r == 0) {
             tc::tc_fence_after_sync();
             // dh2_pre[128 x 64] = dh3[128 x 16] x W3[16(out) x 64(in)]
-            tc::umma_f16(tmem + kColD, tc::smem_desc(sg3, 128, kRg16), tc::smem_desc(sw3, kRg64, 128), id_dgrad64, 0);
+            tc::umma_f16(tmem + kColD, tc::desc_k_major(sg3, kCs128, 0), tc::desc_mn_major(sw3, kCs16, 0), id_dgrad64, 0);
             // gW3^T[64(in) x 16(out)] += h2^T dh3
 #pragma unroll
             for (uint32_t k = 0; k < kTile / 16; ++k)
-                tc::umma_f16(tmem + kColW3, tc::smem_desc(sx + k * 2 * kRg64, kRg64, 128), tc::smem_desc(sg3 + k * 2 * kRg16, kRg16, 128),
-                             id_w3, (!first || k > 0) ? 1u : 0u);
-            tc::umma_commit(&bar);
+                tc::umma_f16(tmem + kColW3, tc::desc_mn_major(sx2, kCs128, k), tc::desc_mn_major(sg3, kCs128, k), id_w3,
+                             (!first || k > 0) ? 1u : 0u);
+            tc::umma_commit(&bar_mma);
         }
-        if (r < 4) gb_acc3 += tile_column_sum(smem + BwdSmem::g3, kRg16, r);
-        tc::mbar_wait(&bar, phase); phase ^= 1;
+        tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
         tc::tc_fence_after_sync();
-        relu_backward_epilogue(tmem_row, r, smem + BwdSmem::x, smem + BwdSmem::g);      // dh2 -> G
-        load_row_to_tile(a.h1 + (size_t)m * kHid, kHid, r, smem + BwdSmem::x, kRg64, active);  // X <- h1 (after reading h2 above)
+        relu_backward_epilogue(tmem_row, r, smem + BwdSmem::xh2, smem + BwdSmem::g);      // dh2 -> G
+        tc::mbar_wait(&bar_h1, ph_ld);
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
@@ -425,21 +448,20 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const BwdArgs 
         // ---- hidden layer 2 ------------------------------------------------------------------------------------
         if (r == 0) {
             tc::tc_fence_after_sync();
+            if (has_next) load_h2(next);   // h2's readers (the weight-gradient MMAs above, the epilogue) are done
 #pragma unroll
             for (uint32_t k = 0; k < kHid / 16; ++k)   // dh1_pre = dh2[128 x 64] x W2[64(out) x 64(in)]
-                tc::umma_f16(tmem + kColD, tc::smem_desc(sg + k * 256, 128, kRg64), tc::smem_desc(sw2 + k * 2 * kRg64, kRg64, 128), id_dgrad64, k > 0);
+                tc::umma_f16(tmem + kColD, tc::desc_k_major(sg, kCs128, k), tc::desc_mn_major(sw2, kCs64, k), id_dgrad64, k > 0);
 #pragma unroll
-            for (uint32_t k = 0; k < kTile / 16; ++k)  // gW2^T[64(in) x 64(out)] += h1^T dh2
-                tc::umma_f16(tmem + kColW2, tc::smem_desc(sx + k * 2 * kRg64, kRg64, 128), tc::smem_desc(sg + k * 2 * kRg64, kRg64, 128),
-                             id_w2, (!first || k > 0) ? 1u : 0u);
-            tc::umma_commit(&bar);
+            for (uint32_t k = 0; k < kTile / 16; ++k)  // [gW2 | gb2][64(out) x 72] += dh2^T [h1 | 1]
+                tc::umma_f16(tmem + kColW2, tc::desc_mn_major(sg, kCs128, k), tc::desc_mn_major(sx1, kCs128, k), id_w2,
+                             (!first || k > 0) ? 1u : 0u);
+            tc::umma_commit(&bar_mma);
         }
-        if (r < 64) gb_acc2 += tile_column_sum(smem + BwdSmem::g, kRg64, r);
-        tc::mbar_wait(&bar, phase); phase ^= 1;
-        __syncthreads();  // the column sums above read every row of G; the epilogue below rewrites it
+        tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
         tc::tc_fence_after_sync();
-        relu_backward_epilogue(tmem_row, r, smem + BwdSmem::x, smem + BwdSmem::g);      // dh1 -> G
-        load_row_to_tile(a.enc + (size_t)m * kIn, kIn, r, smem + BwdSmem::x, kRg32, active);   // X <- encoding (32 wide)
+        relu_backward_epilogue(tmem_row, r, smem + BwdSmem::xh1, smem + BwdSmem::g);      // dh1 -> G
+        tc::mbar_wait(&bar_e, ph_ld);
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
@@ -447,34 +469,44 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const BwdArgs 
         // ---- hidden layer 1 ------------------------------------------------------------------------------------
         if (r == 0) {
             tc::tc_fence_after_sync();
+            if (has_next) load_h1(next);
 #pragma unroll
             for (uint32_t k = 0; k < kHid / 16; ++k)   // d_enc[128 x 32] = dh1[128 x 64] x W1[64(out) x 32(in)]
-                tc::umma_f16(tmem + kColD, tc::smem_desc(sg + k * 256, 128, kRg64), tc::smem_desc(sw1 + k * 2 * kRg32, kRg32, 128), id_dgrad32, k > 0);
+                tc::umma_f16(tmem + kColD, tc::desc_k_major(sg, kCs128, k), tc::desc_mn_major(sw1, kCs64, k), id_dgrad32, k > 0);
 #pragma unroll
-            for (uint32_t k = 0; k < kTile / 16; ++k)  // gW1[64(out) x 32(in)] += dh1^T enc
-                tc::umma_f16(tmem + kColW1, tc::smem_desc(sg + k * 2 * kRg64, kRg64, 128), tc::smem_desc(sx + k * 2 * kRg32, kRg32, 128),
-                             id_w1, (!first || k > 0) ? 1u : 0u);
-            tc::umma_commit(&bar);
+            for (uint32_t k = 0; k < kTile / 16; ++k)  // [gW1 | gb1][64(out) x 40] += dh1^T [enc | 1]
+                tc::umma_f16(tmem + kColW1, tc::desc_mn_major(sg, kCs128, k), tc::desc_mn_major(sxe, kCs128, k), id_w1,
+                             (!first || k > 0) ? 1u : 0u);
+            tc::umma_commit(&bar_mma);
         }
-        if (r < 64) gb_acc1 += tile_column_sum(smem + BwdSmem::g, kRg64, r);
-        tc::mbar_wait(&bar, phase); phase ^= 1;
+        tc::mbar_wait(&bar_mma, ph_mma); ph_mma ^= 1;
         tc::tc_fence_after_sync();
         {
             uint32_t acc[32];
             tc::tmem_ld_x32(tmem_row + kColD, acc);
             tc::tmem_ld_wait();
-            if (active) {
+            uint32_t w[16];
 #pragma unroll
-                for (uint32_t cc = 0; cc < 4; ++cc) {
-                    uint32_t w[4];
+            for (uint32_t j = 0; j < 16; ++j) w[j] = pack_half2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+            const bool full_tile = (tile + 1) * kTile <= M;
+            if (full_tile) {
+                // stage the tile's [128 x 32] d_enc rows row-major in the (now idle) G tile: one 8 KB bulk store
+                uint4* dst = reinterpret_cast<uint4*>(smem + BwdSmem::g + r * (kIn * 2));
 #pragma unroll
-                    for (uint32_t j = 0; j < 4; ++j) w[j] = pack_half2(__uint_as_float(acc[cc * 8 + 2 * j]), __uint_as_float(acc[cc * 8 + 2 * j + 1]));
-                    *reinterpret_cast<uint4*>(a.d_enc + (size_t)m * kIn + cc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
+                for (uint32_t cc = 0; cc < 4; ++cc) dst[cc] = make_uint4(w[4 * cc], w[4 * cc + 1], w[4 * cc + 2], w[4 * cc + 3]);
+            } else if (active) {
+#pragma unroll
+                for (uint32_t cc = 0; cc < 4; ++cc)
+                    *reinterpret_cast<uint4*>(a.d_enc + (size_t)m * kIn + cc * 8) = make_uint4(w[4 * cc], w[4 * cc + 1], w[4 * cc + 2], w[4 * cc + 3]);
+            }
+            tc::fence_async_smem();
+            tc::tc_fence_before_sync();
+            __syncthreads();   // staged rows complete; every thread is done with TMEM D and (generic) reads of X tiles
+            if (r == 0) {
+                if (full_tile) tc::bulk_store(a.d_enc + (size_t)tile * (kTile * kIn), smem + BwdSmem::g, kEncTileBytes);
+                if (has_next) load_e(next);
             }
         }
-        tc::tc_fence_before_sync();
-        __syncthreads();  // X / G / G3 tiles are rewritten by the next tile
         first = false;
     }
 
@@ -489,12 +521,18 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const BwdArgs 
             if (lane < 16)
                 for (uint32_t o = 0; o < kOut; ++o) atomicAdd(a.gw3 + o * kHid + row, __uint_as_float(acc[o]));
         }
-        for (uint32_t c0 = 0; c0 < 64; c0 += 32) {  // gW2[o, i] = D[i, o]
+        for (uint32_t c0 = 0; c0 < kHid; c0 += 32) {  // gW2[o, i] = D[o, i]
             uint32_t acc[32];
             tc::tmem_ld_x32(tmem_row + kColW2 + c0, acc);
             tc::tmem_ld_wait();
             if (lane < 16)
-                for (uint32_t o = 0; o < 32; ++o) atomicAdd(a.gw2 + (c0 + o) * kHid + row, __uint_as_float(acc[o]));
+                for (uint32_t i = 0; i < 32; ++i) atomicAdd(a.gw2 + row * kHid + c0 + i, __uint_as_float(acc[i]));
+        }
+        {   // gb2[o] = D[o, 64]
+            uint32_t acc[8];
+            tc::tmem_ld_x8(tmem_row + kColW2 + kHid, acc);
+            tc::tmem_ld_wait();
+            if (lane < 16) atomicAdd(a.gb2 + row, __uint_as_float(acc[0]));
         }
         {   // gW1[o, i] = D[o, i]
             uint32_t acc[32];
@@ -503,9 +541,19 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const BwdArgs 
             if (lane < 16)
                 for (uint32_t i = 0; i < kIn; ++i) atomicAdd(a.gw1 + row * kIn + i, __uint_as_float(acc[i]));
         }
-        if (r < 64) { atomicAdd(a.gb2 + r, gb_acc2); atomicAdd(a.gb1 + r, gb_acc1); }
-        if (r < 4) atomicAdd(a.gb3 + r, gb_acc3);
+        {   // gb1[o] = D[o, 32]
+            uint32_t acc[8];
+            tc::tmem_ld_x8(tmem_row + kColW1 + kIn, acc);
+            tc::tmem_ld_wait();
+            if (lane < 16) atomicAdd(a.gb1 + row, __uint_as_float(acc[0]));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float s = warp_sum(gb3_acc[j]);
+            if (lane == 0) atomicAdd(a.gb3 + j, s);
+        }
     }
+    if (r == 0) tc::bulk_store_wait_all();
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, kTmemColsBwd);
@@ -537,15 +585,25 @@ extern "C" int ngp_field_forward(const float* xyzs, uint32_t M, const int* count
            static_cast<const __half*>(b2), static_cast<const __half*>(w3), static_cast<const __half*>(b3)};
     a.sigma = sigma; a.rgb = rgb;
     a.enc = static_cast<__half*>(enc_save); a.h1 = static_cast<__half*>(h1_save); a.h2 = static_cast<__half*>(h2_save);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int attr_set = -1;
+    if (attr_set != field::g_fwd_carveout) {
         cudaFuncSetAttribute(field::field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)field::FwdSmem::total);
-        attr_set = true;
+        if (field::g_fwd_carveout >= 0)
+            cudaFuncSetAttribute(field::field_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, field::g_fwd_carveout);
+        attr_set = field::g_fwd_carveout;
     }
     const int tiles = cdiv(M, field::kTile);
-    const int grid = min(tiles, num_sms() * 4);
+    const int grid = min(tiles, num_sms() * field::g_fwd_ctas_per_sm);
     field::field_forward_kernel<<<grid, field::kTile, field::FwdSmem::total, as_stream(stream)>>>(a);
     return launch_status();
+}
+
+// tuning switches (profiles/kbench.py): 0 = forward CTAs per SM (grid size), 1 = forward smem carveout percent
+// (-1 = driver default).  More resident CTAs mean more gathers in flight but a smaller L1 for the table.
+extern "C" int ngp_field_set_option(int option, int value) {
+    if (option == 0 && value >= 1 && value <= 4) { field::g_fwd_ctas_per_sm = value; return NGP_OK; }
+    if (option == 1 && value >= -1 && value <= 100) { field::g_fwd_carveout = value; return NGP_OK; }
+    return NGP_ERR_BAD_ARG;
 }
 
 extern "C" int ngp_field_backward(uint32_t M, const int* count_ptr, const void* w1, const void* w2, const void* w3,

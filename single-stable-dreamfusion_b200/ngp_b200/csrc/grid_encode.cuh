@@ -43,58 +43,106 @@ NGP_DEVINL LevelParams make_level(const int* __restrict__ offsets, uint32_t leve
     return p;
 }
 
-template <uint32_t D>
-NGP_DEVINL uint32_t spatial_hash(const uint32_t (&p)[D]) {
-    // gridencoder.cu:42 - the instant-ngp primes; 1 for the first axis keeps x-neighbours adjacent.
-    constexpr uint32_t primes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
-    uint32_t h = 0;
-#pragma unroll
-    for (uint32_t d = 0; d < D; ++d) h ^= p[d] * primes[d];
-    return h;
-}
+// ---- per-level addressing, resolved ONCE per level instead of once per corner ------------------------------------
+// lattice_row() re-derives, for every corner, which axes enter the index, whether the level is hashed and how the
+// index wraps.  All of that depends only on the level, so FastLevel holds the outcome: the linear stride of each
+// used axis (0 for dropped axes), hash-or-linear, and the wrap (none / AND mask / modulo).  corner_rows() then turns
+// a base lattice point into the 2^D row indices with a handful of adds (linear) or XORs (hash:
+// (p + 1) * prime == p * prime + prime in uint32).  Same uint32 arithmetic as gridencoder.cu:54-72, so same rows.
+constexpr uint32_t kWrapNone = 0, kWrapMask = 1, kWrapMod = 2;
 
-// Row index of a lattice point inside one level (gridencoder.cu:54-72, without the *C + ch).
-// Dense while the running stride fits the level's table; the stride loop stops at the first
-// axis whose stride exceeds the table (so a 'tiled' level silently drops the remaining axes).
 template <uint32_t D>
-NGP_DEVINL uint32_t lattice_row(uint32_t gridtype, bool align_corners, uint32_t hashmap_size, uint32_t resolution,
-                                const uint32_t (&p)[D]) {
-    uint32_t stride = 1, index = 0;
+struct FastLevel {
+    float scale;
+    uint32_t offset;     // first row of the level
+    uint32_t size;       // rows in the level
+    uint32_t mask;       // size - 1 when size is a power of two
+    uint32_t wrap;       // kWrapNone / kWrapMask / kWrapMod
+    uint32_t hashed;     // 1: spatial hash of all axes; 0: linear index over the leading `used` axes
+    uint32_t used;       // axes that enter the index (D when hashed)
+    uint32_t stride[D];  // linear stride per axis (0: axis ignored)
+};
+
+template <uint32_t D>
+NGP_DEVINL FastLevel<D> make_fast_level(const int* __restrict__ offsets, uint32_t level, float S, uint32_t H,
+                                        uint32_t gridtype, bool align_corners) {
+    const LevelParams lp = make_level(offsets, level, S, H);
+    FastLevel<D> f;
+    f.scale = lp.scale;
+    f.offset = lp.offset;
+    f.size = lp.hashmap_size;
+    f.mask = lp.hashmap_size - 1;
+    uint32_t stride = 1, used = 0;
     bool open = true;
 #pragma unroll
     for (uint32_t d = 0; d < D; ++d) {
-        open = open && (stride <= hashmap_size);
+        open = open && (stride <= lp.hashmap_size);
+        f.stride[d] = 0;
         if (open) {
-            index += p[d] * stride;
-            stride *= align_corners ? resolution : (resolution + 1);
+            f.stride[d] = stride;
+            stride *= align_corners ? lp.resolution : (lp.resolution + 1);
+            ++used;
         }
     }
-    if (gridtype == NGP_GRID_HASH && stride > hashmap_size) index = spatial_hash<D>(p);
-    // `index % hashmap_size` (gridencoder.cu:71) without the ~25-instruction runtime modulo where it is a no-op
-    // or a mask; all three branches are uniform per level.
-    // dense level: every coordinate is <= resolution, so index < (resolution+1)^D = stride <= size
-    // (not with align_corners, where the +1 corner of x = 1 reaches `resolution` itself)
-    if (open && !align_corners && stride <= hashmap_size) return index;
-    if ((hashmap_size & (hashmap_size - 1)) == 0) return index & (hashmap_size - 1);
-    return index % hashmap_size;
+    f.hashed = (gridtype == NGP_GRID_HASH && stride > lp.hashmap_size) ? 1u : 0u;
+    f.used = f.hashed ? D : used;
+    if (!f.hashed && open && !align_corners && stride <= lp.hashmap_size) f.wrap = kWrapNone;
+    else if ((lp.hashmap_size & (lp.hashmap_size - 1)) == 0) f.wrap = kWrapMask;
+    else f.wrap = kWrapMod;
+    return f;
 }
 
-// How many leading axes actually enter a level's row index.  The stride loop of lattice_row stops at the first axis
-// whose stride exceeds the table, so a 'tiled' level (or any level that is not hashed) can ignore trailing axes:
-// with 2^16 rows the reference's field drops z for every resolution >= 256 (gridencoder.cu:60-63).  Corners that
-// differ only in ignored axes address the SAME row - the kernels below fetch / update such rows once.
+// rows[corner] for all 2^D corners of the cell at `base` (bit d of corner = +1 along axis d).
 template <uint32_t D>
-NGP_DEVINL uint32_t level_axes_used(uint32_t gridtype, bool align_corners, uint32_t hashmap_size, uint32_t resolution) {
-    uint32_t stride = 1, used = 0;
+NGP_DEVINL void corner_rows(const FastLevel<D>& f, const uint32_t (&base)[D], uint32_t (&rows)[1u << D]) {
+    if (f.hashed) {
+        // gridencoder.cu:42 - the instant-ngp primes; 1 for the first axis keeps x-neighbours adjacent
+        constexpr uint32_t kPrimes[7] = {1u, 2654435761u, 805459861u, 3674653429u, 2097192037u, 1434869437u, 2165219737u};
+        rows[0] = 0;
 #pragma unroll
-    for (uint32_t d = 0; d < D; ++d) {
-        if (stride <= hashmap_size && used == d) {
-            ++used;
-            stride *= align_corners ? resolution : (resolution + 1);
+        for (uint32_t d = 0; d < D; ++d) {
+            const uint32_t h0 = base[d] * kPrimes[d], h1 = h0 + kPrimes[d];
+#pragma unroll
+            for (uint32_t c = 0; c < (1u << d); ++c) {
+                rows[c | (1u << d)] = rows[c] ^ h1;
+                rows[c] ^= h0;
+            }
+        }
+    } else {
+        uint32_t lin = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) lin += base[d] * f.stride[d];
+        rows[0] = lin;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) {
+#pragma unroll
+            for (uint32_t c = 0; c < (1u << d); ++c) rows[c | (1u << d)] = rows[c] + f.stride[d];
         }
     }
-    if (gridtype == NGP_GRID_HASH && stride > hashmap_size) return D;  // hashed: every axis is mixed in
-    return used;
+    if (f.wrap == kWrapMask) {
+#pragma unroll
+        for (uint32_t c = 0; c < (1u << D); ++c) rows[c] &= f.mask;
+    } else if (f.wrap == kWrapMod) {
+#pragma unroll
+        for (uint32_t c = 0; c < (1u << D); ++c) rows[c] %= f.size;
+    }
+}
+
+// Trilinear (2^D-linear) weights in the reference's multiplication order: w = ((1 * a0) * a1) * a2 ...
+template <uint32_t D>
+NGP_DEVINL void corner_weights(const float (&frac)[D], float (&wts)[1u << D]) {
+    wts[0] = 1.0f;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        const float lo = 1 - frac[d], hi = frac[d];
+        // process corners top-down so that wts[c] (prefix over axes < d) is still intact when read
+#pragma unroll
+        for (uint32_t c = 0; c < (1u << d); ++c) {
+            const float prefix = wts[c];
+            wts[c | (1u << d)] = prefix * hi;
+            wts[c] = prefix * lo;
+        }
+    }
 }
 
 // Static-index helpers for the above (dynamic indexing would push the per-corner arrays to local memory).
@@ -244,13 +292,22 @@ NGP_DEVINL bool out_of_unit_cube(const float (&x)[D]) {
 // -------------------------------------------------------------------------------------------------
 // Forward
 // -------------------------------------------------------------------------------------------------
+// Packed-half accumulation of one corner for the C = 2 half table: `acc += w * row` with c10::Half semantics
+// (gridencoder.cu:165: the float product is rounded to half, then the half + half sum is rounded again).  HADD2
+// rounds each lane's exact sum once, which equals rounding the fp32 sum of two halves (that fp32 sum is exact
+// whenever it could land on a half tie).
+NGP_DEVINL __half2 half2_axpy(__half2 acc, float w, uint32_t raw_row) {
+    const float2 r = __half22float2(*reinterpret_cast<const __half2*>(&raw_row));
+    return __hadd2(acc, __floats2half2_rn(w * r.x, w * r.y));
+}
+
 template <typename T, uint32_t D, uint32_t C, uint32_t LPT, bool OUT_BLC, bool WITH_DYDX>
 __global__ void __launch_bounds__(256) encode_forward_kernel(
     const float* __restrict__ inputs, const T* __restrict__ table, const int* __restrict__ offsets,
     T* __restrict__ outputs, T* __restrict__ dy_dx, uint32_t B, uint32_t L, float S, uint32_t H,
     uint32_t gridtype, bool align_corners) {
-    __shared__ LevelParams s_levels[kMaxLevels];
-    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_level(offsets, l, S, H);
+    __shared__ FastLevel<D> s_levels[kMaxLevels];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_fast_level<D>(offsets, l, S, H, gridtype, align_corners);
     __syncthreads();
 
     const uint32_t groups = (L + LPT - 1) / LPT;
@@ -283,85 +340,104 @@ __global__ void __launch_bounds__(256) encode_forward_kernel(
             continue;
         }
 
-        const LevelParams lp = s_levels[level];
+        const FastLevel<D>& lp = s_levels[level];
         const T* __restrict__ tbl = table + (size_t)lp.offset * C;
         float frac[D];
         uint32_t base[D];
         locate<D>(x, lp.scale, align_corners, frac, base);
-
-        // Issue all 2^D row gathers first (independent loads in flight), then blend.  Corners that differ only in an
-        // axis the level ignores share a row: it is fetched once and reused (same values, same arithmetic).
-        float rows[1u << D][C];
+        uint32_t ridx[1u << D];
+        corner_rows<D>(lp, base, ridx);
         float wts[1u << D];
-        const uint32_t axes_used = level_axes_used<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution);
-        const uint32_t distinct = 1u << axes_used;
+        corner_weights<D>(frac, wts);
+
+        // Issue all row gathers first (independent loads in flight), then blend.  Corners that differ only in an
+        // axis the level ignores share a row: it is fetched once and reused (same values, same arithmetic).
+        const uint32_t distinct = 1u << lp.used;
+        if constexpr (sizeof(T) == 2 && C == 2) {
+            uint32_t raw[1u << D];
 #pragma unroll
-        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-            float w = 1;
-            uint32_t p[D];
+            for (uint32_t corner = 0; corner < (1u << D); ++corner)
+                if (corner < distinct) raw[corner] = __ldg(reinterpret_cast<const uint32_t*>(tbl) + ridx[corner]);
 #pragma unroll
-            for (uint32_t d = 0; d < D; ++d) {
-                if ((corner & (1u << d)) == 0) { w *= 1 - frac[d]; p[d] = base[d]; }
-                else                           { w *= frac[d];     p[d] = base[d] + 1; }
-            }
-            wts[corner] = w;
-            if (corner < distinct) {
-                const uint32_t row = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
-                load_row<T, C>(tbl + (size_t)row * C, rows[corner]);
-            }
-        }
-        replicate_rows<D, C>(rows, axes_used);
+            for (uint32_t corner = 0; corner < (1u << D); ++corner)
+                if (corner >= distinct) raw[corner] = raw[corner & (distinct - 1)];
+            __half2 acc2 = __floats2half2_rn(0.f, 0.f);
 #pragma unroll
-        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+            for (uint32_t corner = 0; corner < (1u << D); ++corner) acc2 = half2_axpy(acc2, wts[corner], raw[corner]);
+            *reinterpret_cast<__half2*>(out) = acc2;
+            if (WITH_DYDX) {
 #pragma unroll
-            for (uint32_t c = 0; c < C; ++c) {
-                if constexpr (sizeof(T) == 4) {
-                    acc[c] += wts[corner] * rows[corner][c];  // contracts to one FFMA, as in the reference
-                } else {
-                    // c10::Half semantics of `results[ch] += w * grid[..]` (gridencoder.cu:165): the float
-                    // product is rounded to half, then the half+half sum is rounded again.
-                    const float prod = ElemOps<T>::round(wts[corner] * rows[corner][c]);
-                    acc[c] = ElemOps<T>::round(acc[c] + prod);
+                for (uint32_t gd = 0; gd < D; ++gd) {
+                    __half2 g2 = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+                    for (uint32_t corner = 0; corner < (1u << (D - 1)); ++corner) {
+                        // spread the D-1 bits of `corner` around axis gd; weight in the reference's order (:186-196)
+                        float w = lp.scale;
+                        uint32_t left = 0;
+#pragma unroll
+                        for (uint32_t nd = 0; nd < D - 1; ++nd) {
+                            const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
+                            if ((corner & (1u << nd)) == 0) w *= 1 - frac[d];
+                            else { w *= frac[d]; left |= 1u << d; }
+                        }
+                        const __half2 lo = *reinterpret_cast<const __half2*>(&raw[left]);
+                        const __half2 hi = *reinterpret_cast<const __half2*>(&raw[left | (1u << gd)]);
+                        const float2 diff = __half22float2(__hsub2(hi, lo));
+                        g2 = __hadd2(g2, __floats2half2_rn(w * diff.x, w * diff.y));
+                    }
+                    *reinterpret_cast<__half2*>(dout + gd * C) = g2;
                 }
             }
-        }
-        store_row<T, C>(out, acc);
-
-        if (WITH_DYDX) {  // gridencoder.cu:179-222
+        } else {
+            float rows[1u << D][C];
 #pragma unroll
-            for (uint32_t gd = 0; gd < D; ++gd) {
-                float gacc[C];
+            for (uint32_t corner = 0; corner < (1u << D); ++corner)
+                if (corner < distinct) load_row<T, C>(tbl + (size_t)ridx[corner] * C, rows[corner]);
+            replicate_rows<D, C>(rows, lp.used);
 #pragma unroll
-                for (uint32_t c = 0; c < C; ++c) gacc[c] = 0.f;
+            for (uint32_t corner = 0; corner < (1u << D); ++corner) {
 #pragma unroll
-                for (uint32_t corner = 0; corner < (1u << (D - 1)); ++corner) {
-                    float w = lp.scale;
-                    uint32_t p[D];
-#pragma unroll
-                    for (uint32_t nd = 0; nd < D - 1; ++nd) {
-                        const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
-                        if ((corner & (1u << nd)) == 0) { w *= 1 - frac[d]; p[d] = base[d]; }
-                        else                            { w *= frac[d];     p[d] = base[d] + 1; }
+                for (uint32_t c = 0; c < C; ++c) {
+                    if constexpr (sizeof(T) == 4) {
+                        acc[c] += wts[corner] * rows[corner][c];  // contracts to one FFMA, as in the reference
+                    } else {
+                        const float prod = ElemOps<T>::round(wts[corner] * rows[corner][c]);
+                        acc[c] = ElemOps<T>::round(acc[c] + prod);
                     }
-                    p[gd] = base[gd];
-                    const uint32_t left = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
-                    p[gd] = base[gd] + 1;
-                    const uint32_t right = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
-                    float lo[C], hi[C];
-                    load_row<T, C>(tbl + (size_t)left * C, lo);
-                    load_row<T, C>(tbl + (size_t)right * C, hi);
+                }
+            }
+            store_row<T, C>(out, acc);
+
+            if (WITH_DYDX) {  // gridencoder.cu:179-222
 #pragma unroll
-                    for (uint32_t c = 0; c < C; ++c) {
-                        if constexpr (sizeof(T) == 4) {
-                            gacc[c] += w * (hi[c] - lo[c]);
-                        } else {
-                            const float diff = ElemOps<T>::round(hi[c] - lo[c]);
-                            const float prod = ElemOps<T>::round(w * diff);
-                            gacc[c] = ElemOps<T>::round(gacc[c] + prod);
+                for (uint32_t gd = 0; gd < D; ++gd) {
+                    float gacc[C];
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c) gacc[c] = 0.f;
+#pragma unroll
+                    for (uint32_t corner = 0; corner < (1u << (D - 1)); ++corner) {
+                        float w = lp.scale;
+                        uint32_t left = 0;
+#pragma unroll
+                        for (uint32_t nd = 0; nd < D - 1; ++nd) {
+                            const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
+                            if ((corner & (1u << nd)) == 0) w *= 1 - frac[d];
+                            else { w *= frac[d]; left |= 1u << d; }
+                        }
+                        const uint32_t right = left | (1u << gd);
+#pragma unroll
+                        for (uint32_t c = 0; c < C; ++c) {
+                            if constexpr (sizeof(T) == 4) {
+                                gacc[c] += w * (rows[right][c] - rows[left][c]);
+                            } else {
+                                const float diff = ElemOps<T>::round(rows[right][c] - rows[left][c]);
+                                const float prod = ElemOps<T>::round(w * diff);
+                                gacc[c] = ElemOps<T>::round(gacc[c] + prod);
+                            }
                         }
                     }
+                    store_row<T, C>(dout + gd * C, gacc);
                 }
-                store_row<T, C>(dout + gd * C, gacc);
             }
         }
     }
@@ -398,8 +474,8 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
     const T* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
     GT* __restrict__ grad_table, uint32_t B, uint32_t L, float S, uint32_t H, uint32_t gridtype,
     bool align_corners) {
-    __shared__ LevelParams s_levels[kMaxLevels];
-    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_level(offsets, l, S, H);
+    __shared__ FastLevel<D> s_levels[kMaxLevels];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_fast_level<D>(offsets, l, S, H, gridtype, align_corners);
     __syncthreads();
 
     const uint32_t groups = (L + LPT - 1) / LPT;
@@ -417,7 +493,7 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
     for (uint32_t li = 0; li < LPT; ++li) {
         const uint32_t level = g * LPT + li;
         if (level >= L) break;
-        const LevelParams lp = s_levels[level];
+        const FastLevel<D>& lp = s_levels[level];
         const T* gsrc = GRAD_BLC ? grad + ((size_t)b * L + level) * C : grad + ((size_t)level * B + b) * C;
         float gr[C];
         load_row<T, C>(gsrc, gr);
@@ -425,19 +501,13 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
         float frac[D];
         uint32_t base[D];
         locate<D>(x, lp.scale, align_corners, frac, base);
+        uint32_t ridx[1u << D];
+        corner_rows<D>(lp, base, ridx);
+        float wts[1u << D];
+        corner_weights<D>(frac, wts);
         GT* tbl = grad_table + (size_t)lp.offset * C;
 #pragma unroll
-        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-            float w = 1;
-            uint32_t p[D];
-#pragma unroll
-            for (uint32_t d = 0; d < D; ++d) {
-                if ((corner & (1u << d)) == 0) { w *= 1 - frac[d]; p[d] = base[d]; }
-                else                           { w *= frac[d];     p[d] = base[d] + 1; }
-            }
-            const uint32_t row = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
-            scatter_row<GT, C>(tbl + (size_t)row * C, w, gr);
-        }
+        for (uint32_t corner = 0; corner < (1u << D); ++corner) scatter_row<GT, C>(tbl + (size_t)ridx[corner] * C, wts[corner], gr);
     }
 }
 
@@ -457,8 +527,8 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
     float* __restrict__ grad_table, uint32_t B_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype,
     bool align_corners, const int* __restrict__ count_ptr, float bound) {
     constexpr uint32_t D = 3;
-    __shared__ LevelParams s_levels[kMaxLevels];
-    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_level(offsets, l, S, H);
+    __shared__ FastLevel<D> s_levels[kMaxLevels];
+    for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_fast_level<D>(offsets, l, S, H, gridtype, align_corners);
     __syncthreads();
 
     // optional device-side row count (sync-free training path) and optional [-bound, bound] -> [0, 1] mapping
@@ -479,8 +549,27 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
         valid = !out_of_unit_cube<D>(x);  // gridencoder.cu:253-258
     }
 
-    for (uint32_t level = 0; level < L; ++level) {
-        const LevelParams lp = s_levels[level];
+    // half2 gradient rows are fetched four levels (one 16-byte load) at a time: a sample's [L*C] row is 2 sectors, and
+    // 16 separate 4-byte loads spread over the whole level loop kept missing L1
+    constexpr bool kPacked = (sizeof(T) == 2 && C == 2);
+    uint32_t graw[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t level0 = 0; level0 < L; level0 += 4) {
+      if constexpr (kPacked) {
+        if (level0 + 4 <= L && (L % 4) == 0) {
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) q = __ldg(reinterpret_cast<const uint4*>(grad + ((size_t)b * L + level0) * C));
+            graw[0] = q.x; graw[1] = q.y; graw[2] = q.z; graw[3] = q.w;
+        } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j)
+                graw[j] = (valid && level0 + j < L) ? __ldg(reinterpret_cast<const uint32_t*>(grad + ((size_t)b * L + level0 + j) * C)) : 0u;
+        }
+      }
+#pragma unroll
+      for (uint32_t lj = 0; lj < 4; ++lj) {
+        const uint32_t level = level0 + lj;
+        if (level >= L) break;
+        const FastLevel<D>& lp = s_levels[level];
         float frac[D];
         uint32_t base[D];
         locate<D>(x, lp.scale, align_corners, frac, base);
@@ -488,11 +577,19 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
         float g[C];
 #pragma unroll
         for (uint32_t c = 0; c < C; ++c) g[c] = 0.f;
-        if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
+        if constexpr (kPacked) {
+            const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&graw[lj]));
+            g[0] = gf.x; g[1] = gf.y;
+        } else {
+            if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
+        }
 
-        // run detection: same cell as the previous lane (both valid)
-        const uint32_t kxy = valid ? (base[0] | (base[1] << 16)) : 0xffffffffu;
-        const uint32_t kz = valid ? base[2] : (0x80000000u | lane);
+        // run detection: same cell as the previous lane (both valid).  Axes the level ignores do not enter the key:
+        // a 'tiled' level that drops z addresses the same 4 rows for every sample of a ray segment that stays in one
+        // (x, y) column, however many z cells it crosses.
+        const uint32_t ky = lp.used >= 2 ? base[1] : 0u, kzz = lp.used >= 3 ? base[2] : 0u;
+        const uint32_t kxy = valid ? (base[0] | (ky << 16)) : 0xffffffffu;
+        const uint32_t kz = valid ? kzz : (0x80000000u | lane);
         const uint32_t pxy = __shfl_up_sync(0xffffffffu, kxy, 1);
         const uint32_t pz = __shfl_up_sync(0xffffffffu, kz, 1);
         const bool head = (lane == 0) || !valid || (pxy != kxy) || (pz != kz);
@@ -505,16 +602,15 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
         const uint32_t max_len = __reduce_max_sync(0xffffffffu, my_len);
 
         float v[1u << D][C];
+        float wts[1u << D];
+        corner_weights<D>(frac, wts);
 #pragma unroll
         for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-            float w = 1;
 #pragma unroll
-            for (uint32_t d = 0; d < D; ++d) w *= (corner & (1u << d)) ? frac[d] : 1 - frac[d];
-#pragma unroll
-            for (uint32_t c = 0; c < C; ++c) v[corner][c] = w * g[c];
+            for (uint32_t c = 0; c < C; ++c) v[corner][c] = wts[corner] * g[c];
         }
         // corners that differ only in an axis this level ignores hit the same row: fold them first (warp-uniform)
-        const uint32_t axes_used = level_axes_used<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution);
+        const uint32_t axes_used = lp.used;
         const uint32_t distinct = 1u << axes_used;
         fold_rows<D, C>(v, axes_used);
         for (uint32_t off = 1; off < max_len; off <<= 1) {
@@ -532,14 +628,32 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
         }
         if (head && valid) {
             float* tbl = grad_table + (size_t)lp.offset * C;
+            uint32_t ridx[1u << D];
+            corner_rows<D>(lp, base, ridx);
+            if constexpr (C == 2) {
+                // The SM issues reds at a fixed rate per LANE-op whatever their width (profiles/: 217 G ops/s for 4,
+                // 8 and 16-byte reds alike), so the two x-neighbours of a corner pair - adjacent rows of a linear
+                // level - go out as ONE 16-byte red whenever the pair is 16-byte aligned.
+                if (!lp.hashed) {
+#pragma unroll
+                    for (uint32_t corner = 0; corner < (1u << D); corner += 2) {
+                        if (corner >= distinct) continue;
+                        const uint32_t lo = ridx[corner], hi = ridx[corner + 1];
+                        float* dst = tbl + (size_t)lo * 2;
+                        if (distinct > 1 && hi == lo + 1 && (((lp.offset + lo) & 1u) == 0)) {
+                            red_add_f32x4(dst, v[corner][0], v[corner][1], v[corner + 1][0], v[corner + 1][1]);
+                        } else {
+                            red_add_f32x2(dst, v[corner][0], v[corner][1]);
+                            if (distinct > 1) red_add_f32x2(tbl + (size_t)hi * 2, v[corner + 1][0], v[corner + 1][1]);
+                        }
+                    }
+                    continue;
+                }
+            }
 #pragma unroll
             for (uint32_t corner = 0; corner < (1u << D); ++corner) {
                 if (corner >= distinct) continue;
-                uint32_t p[D];
-#pragma unroll
-                for (uint32_t d = 0; d < D; ++d) p[d] = base[d] + ((corner >> d) & 1u);
-                const uint32_t row = lattice_row<D>(gridtype, align_corners, lp.hashmap_size, lp.resolution, p);
-                float* dst = tbl + (size_t)row * C;
+                float* dst = tbl + (size_t)ridx[corner] * C;
                 if constexpr (C == 1) red_add_f32(dst, v[corner][0]);
                 else if constexpr (C == 2) red_add_f32x2(dst, v[corner][0], v[corner][1]);
                 else {
@@ -548,6 +662,7 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
                 }
             }
         }
+      }
     }
   }
 }

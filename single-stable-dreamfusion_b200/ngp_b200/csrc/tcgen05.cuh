@@ -50,14 +50,18 @@ NGP_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 
 // ---- descriptors ------------------------------------------------------------------------------------
 // Operand tiles use ONE physical layout everywhere ("core-matrix tile"): element (r, c) of a [R x C] fp16 tile
-// lives at byte  (r/8)*row_group + (c/8)*128 + (r%8)*16 + (c%8)*2 ,  i.e. 8x8 core matrices of 128 contiguous
-// bytes, the C/8 core matrices of one 8-row group contiguous, row groups `row_group` bytes apart.
-//   * read as a K-major operand  (MN index = r, K index = c):  LBO = 128 (next core matrix along K),
-//                                                               SBO = row_group (next 8 rows);
-//   * read as an MN-major operand (K index = r, MN index = c):  LBO = row_group (next 8 K-rows),
-//                                                               SBO = 128 (next 8 MN-elements).
+// lives at byte  (c/8)*chunk_stride + (r/8)*128 + (r%8)*16 + (c%8)*2  with chunk_stride = R*16, i.e. 8x8 core
+// matrices of 128 contiguous bytes; the R/8 core matrices of one 8-column chunk are contiguous (one chunk = the
+// 16-byte slices of all R rows = R*16 bytes), chunks follow each other.
+//   * read as a K-major operand  (MN index = r, K index = c):  LBO = chunk_stride (next core matrix along K),
+//                                                               SBO = 128 (next 8 rows);
+//   * read as an MN-major operand (K index = r, MN index = c):  LBO = 128 (next 8 K-rows),
+//                                                               SBO = chunk_stride (next 8 MN-elements).
 // The second reading is what lets the SAME tile feed the forward / dgrad GEMM (K = features) and the
-// weight-gradient GEMM (K = samples) without a transposed copy.
+// weight-gradient GEMM (K = samples) without a transposed copy.  Chunk-major order also means a tile can grow by
+// whole column chunks (the constant "ones" chunk that turns a weight-gradient GEMM into weight + bias gradient),
+// that a thread-per-row write of one chunk is 512 contiguous bytes per warp (conflict-free), and that a whole tile
+// is ONE contiguous block - saved to / restored from global memory with a single bulk (TMA) copy.
 // Field layout (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
 // base_offset [49,52), lbo_mode [52], layout_type [61,64) (0 = no swizzle).
 NGP_DEVINL uint64_t smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -125,10 +129,38 @@ NGP_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" :
 NGP_DEVINL uint32_t tmem_addr(uint32_t base, uint32_t lane, uint32_t col) { return base + (lane << 16) + col; }
 
 // ---- the core-matrix tile ------------------------------------------------------------------------------
-// byte offset of the 16-byte chunk holding columns [8*cc, 8*cc+8) of row r
-NGP_DEVINL uint32_t tile_chunk_off(uint32_t r, uint32_t cc, uint32_t row_group_bytes) {
-    return (r >> 3) * row_group_bytes + cc * 128u + (r & 7u) * 16u;
+// byte offset of the 16-byte chunk holding columns [8*cc, 8*cc+8) of row r; chunk_stride = rows of the tile * 16
+NGP_DEVINL uint32_t tile_chunk_off(uint32_t r, uint32_t cc, uint32_t chunk_stride) {
+    return cc * chunk_stride + (r >> 3) * 128u + (r & 7u) * 16u;
 }
+// descriptors of the tile at `addr` for the k-th K=16 step of an MMA
+NGP_DEVINL uint64_t desc_k_major(uint32_t addr, uint32_t chunk_stride, uint32_t k) {   // K = columns: 2 chunks per step
+    return smem_desc(addr + k * 2u * chunk_stride, chunk_stride, 128u);
+}
+NGP_DEVINL uint64_t desc_mn_major(uint32_t addr, uint32_t chunk_stride, uint32_t k) {  // K = rows: 2 row groups per step
+    return smem_desc(addr + k * 256u, 128u, chunk_stride);
+}
+
+// ---- bulk (TMA, non-tensor) copies of whole tiles ----------------------------------------------------------
+// global -> shared, completion counted in bytes on an mbarrier (the caller arms it with mbar_expect_tx first)
+NGP_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+NGP_DEVINL void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group
+NGP_DEVINL void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// wait until the bulk stores of this thread have finished READING shared memory (the source may be rewritten)
+NGP_DEVINL void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// wait until they are complete (writes performed)
+NGP_DEVINL void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 }  // namespace tc
 }  // namespace ngp

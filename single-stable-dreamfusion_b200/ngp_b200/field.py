@@ -46,13 +46,14 @@ def cached_half(t):
         return s[1]
     ver = (t.data_ptr(), t._version, tuple(t.shape), _cache_epoch[0])
     hit = _half_cache.get(key)
+    # the entry must belong to THIS tensor object (ids and device addresses are recycled once a model is freed), and
     # while a CUDA graph is being captured the cast must become part of the graph (replays do not bump _version)
-    if hit is not None and hit[0] == ver and not torch.cuda.is_current_stream_capturing():
+    if hit is not None and hit[2]() is t and hit[0] == ver and not torch.cuda.is_current_stream_capturing():
         return hit[1]
     h = t.detach().to(torch.half).contiguous()
     if len(_half_cache) > 256:
         _half_cache.clear()
-    _half_cache[key] = (ver, h)
+    _half_cache[key] = (ver, h, weakref.ref(t))
     return h
 
 
@@ -70,9 +71,11 @@ class _FusedField(Function):
         need_grad = any(ctx.needs_input_grad[1:8])
         sigma = torch.empty(M, device=dev, dtype=torch.float32)
         rgb = torch.empty(M, 3, device=dev, dtype=torch.float32)
-        enc = torch.empty(M, 32, device=dev, dtype=torch.half) if need_grad else None
-        h1 = torch.empty(M, 64, device=dev, dtype=torch.half) if need_grad else None
-        h2 = torch.empty(M, 64, device=dev, dtype=torch.half) if need_grad else None
+        # saves for the backward: whole 128-sample tiles in the kernels' own (tile-major) layout - opaque to the host
+        Mp = (M + 127) // 128 * 128
+        enc = torch.empty(Mp, 32, device=dev, dtype=torch.half) if need_grad else None
+        h1 = torch.empty(Mp, 64, device=dev, dtype=torch.half) if need_grad else None
+        h2 = torch.empty(Mp, 64, device=dev, dtype=torch.half) if need_grad else None
         L = offsets.shape[0] - 1
         _cabi.call("ngp_field_forward", dev, _cabi.ptr(xyzs), M, _cabi.ptr(count), _cabi.ptr(table), _cabi.ptr(offsets), L,
                    embeddings.shape[1], float(S), int(H), int(gridtype), int(bool(align_corners)), float(bound),

@@ -23,6 +23,7 @@ class TrainWorkspace:
 
     def __init__(self, n_rays, max_steps, device, cap_rows=None):
         cap = n_rays * max_steps if cap_rows is None else min(int(cap_rows), n_rays * max_steps)
+        cap = (cap + 127) // 128 * 128  # the field kernels save / restore whole 128-sample tiles
         self.n_rays, self.max_steps, self.cap = n_rays, max_steps, cap
         f32, f16 = torch.float32, torch.half
         e = lambda *shape, dtype=f32: torch.empty(*shape, device=device, dtype=dtype)  # noqa: E731

@@ -25,7 +25,7 @@ def test_umma_k_major(N, K):
     assert torch.allclose(D, want, rtol=1e-3, atol=1e-3), (D - want).abs().max().item()
 
 
-@pytest.mark.parametrize("M,N", [(64, 16), (64, 64), (64, 32), (128, 64)])
+@pytest.mark.parametrize("M,N", [(64, 16), (64, 64), (64, 32), (128, 64), (64, 40), (64, 72)])
 def test_umma_mn_major_weight_gradient_shape(M, N):
     g = torch.Generator().manual_seed(M * 1000 + N)
     A = torch.randn(128, M, generator=g).half().to(DEV)    # [samples, M]
