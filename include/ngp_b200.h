@@ -237,6 +237,17 @@ int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq
                   float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor, float backoff_factor,
                   uint32_t growth_interval, int zero_grads, float* state, uint32_t* blocks_done, void* stream);
 
+/* Background colour network (nerf/network_grid.py:54-62,158-167 under fp16 autocast): FreqEncoder(degree 6) ->
+ * Linear(39,64)+ReLU -> Linear(64,3) -> sigmoid, one launch.  dirs f32[N,3]; w1 f16[64,39], b1 f16[64], w2 f16[3,64],
+ * b2 f16[3] (the fp16 casts of bg_net.net.{0,1}); out_rgb f16[N,3].  Only degree 6 / hidden 64 is built. */
+int ngp_bg_forward(const float* dirs, uint32_t N, const void* w1, const void* b1, const void* w2, const void* b2,
+                   uint32_t degree, uint32_t hidden, void* out_rgb, void* stream);
+/* Its backward wrt the parameters (the forward is recomputed per ray): grad_rgb f32[N,3]; gw1 f32[64,39], gb1 f32[64],
+ * gw2 f32[3,64], gb2 f32[3] are ACCUMULATED (+=). */
+int ngp_bg_backward(const float* dirs, const float* grad_rgb, uint32_t N, const void* w1, const void* b1, const void* w2,
+                    const void* b2, uint32_t degree, uint32_t hidden, float* gw1, float* gb1, float* gw2, float* gb2,
+                    void* stream);
+
 /* End of run_cuda (nerf/renderer.py:535-557): image_out = image + (1 - weights_sum) * bg, depth_out =
  * clamp(depth - nears, 0) / (fars - nears) (NaN where the ray misses the box, as the reference), mask = nears < fars.
  * bg is f32[N,3] (bg_per_ray != 0) or one f32[3] colour.  depth_out / mask may be NULL. */

@@ -1,0 +1,259 @@
+// Background colour network of network_grid.NeRFNetwork as ONE kernel per direction:
+//   FreqEncoder(degree 6) -> Linear(39, 64) + ReLU -> Linear(64, 3) -> sigmoid      (per ray, not per sample)
+// Behavioural contract: nerf/network_grid.py:54-62,158-167 under fp16 autocast (freqencoder.cu:30-58 for the
+// encoding; every Linear = half inputs x half weights, fp32 accumulate, half output).  The reference spends ~25 eager
+// launches on this per step (encode, 3 casts, 2 GEMMs with K = 39 unaligned, bias/ReLU/sigmoid and their backward);
+// the work itself is ~5 kFLOP per ray, so it is plain SIMT here: no tensor cores, weights broadcast from shared
+// memory, and in the backward a register-blocked [64 x 40] += gz1^T [enc | 1] product over each 128-ray tile whose
+// accumulators stay in registers across all tiles of the CTA (one flush of atomics per CTA).
+#include "common.cuh"
+
+namespace ngp {
+namespace bg {
+
+constexpr uint32_t kDeg = 6, kEnc = 3 + 3 * 2 * kDeg;  // 39
+constexpr uint32_t kEncPad = 48;                      // encoding columns in shared memory: 39 features, a 1, zeros
+constexpr uint32_t kHid = 64, kOut = 3, kRays = 128;
+
+NGP_DEVINL float round_h(float v) { return __half2float(__float2half_rn(v)); }
+
+// feature c of the frequency encoding of direction d (same expression as freq_forward_kernel)
+NGP_DEVINL float freq_feature(const float (&d)[3], uint32_t c) {
+    if (c < 3) return d[c];
+    const uint32_t col = c / 3 - 1, ax = c % 3;
+    return __sinf(scalbnf(d[ax], (int)(col / 2)) + (col % 2) * (3.141592653589793f / 2));
+}
+
+struct Weights {
+    const __half *w1, *b1, *w2, *b2;  // fp16 casts of bg_net.net.{0,1}.{weight,bias}: [64,39] [64] [3,64] [3]
+};
+
+// shared-memory weights as floats: W1 rows padded to 40, then b1, W2 [3][64], b2
+struct SmemW {
+    static constexpr uint32_t w1 = 0, b1 = w1 + kHid * 40, w2 = b1 + kHid, b2 = w2 + kOut * kHid, total = b2 + 4;
+};
+
+NGP_DEVINL void load_weights(const Weights& w, float* s) {
+    for (uint32_t i = threadIdx.x; i < kHid * 40; i += blockDim.x) {
+        const uint32_t j = i / 40, k = i % 40;
+        s[SmemW::w1 + i] = k < kEnc ? __half2float(w.w1[j * kEnc + k]) : 0.f;
+    }
+    for (uint32_t i = threadIdx.x; i < kHid; i += blockDim.x) s[SmemW::b1 + i] = __half2float(w.b1[i]);
+    for (uint32_t i = threadIdx.x; i < kOut * kHid; i += blockDim.x) s[SmemW::w2 + i] = __half2float(w.w2[i]);
+    if (threadIdx.x < kOut) s[SmemW::b2 + threadIdx.x] = __half2float(w.b2[threadIdx.x]);
+}
+
+// hidden pre-activation j of one ray: half(enc_h . W1[j] + b1[j])
+NGP_DEVINL float hidden_pre(const float (&enc)[40], const float* sw, uint32_t j) {
+    const float4* row = reinterpret_cast<const float4*>(sw + SmemW::w1 + j * 40);
+    float acc = 0.f;
+#pragma unroll
+    for (uint32_t q = 0; q < 10; ++q) {
+        const float4 w = row[q];
+        acc = fmaf(enc[4 * q], w.x, acc); acc = fmaf(enc[4 * q + 1], w.y, acc);
+        acc = fmaf(enc[4 * q + 2], w.z, acc); acc = fmaf(enc[4 * q + 3], w.w, acc);
+    }
+    return round_h(acc + sw[SmemW::b1 + j]);
+}
+
+__global__ void __launch_bounds__(kRays) bg_forward_kernel(const float* __restrict__ dirs, uint32_t N, const Weights w,
+                                                           __half* __restrict__ out) {
+    extern __shared__ __align__(16) float sw[];
+    load_weights(w, sw);
+    __syncthreads();
+    for (uint32_t n = blockIdx.x * kRays + threadIdx.x; n < N; n += gridDim.x * kRays) {
+        const float d[3] = {dirs[(size_t)n * 3], dirs[(size_t)n * 3 + 1], dirs[(size_t)n * 3 + 2]};
+        float enc[40];
+#pragma unroll
+        for (uint32_t c = 0; c < 40; ++c) enc[c] = c < kEnc ? round_h(freq_feature(d, c)) : 0.f;
+        float z2[3] = {0.f, 0.f, 0.f};
+        for (uint32_t j = 0; j < kHid; ++j) {
+            const float a = fmaxf(hidden_pre(enc, sw, j), 0.f);
+#pragma unroll
+            for (uint32_t c = 0; c < 3; ++c) z2[c] = fmaf(a, sw[SmemW::w2 + c * kHid + j], z2[c]);
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < 3; ++c) {
+            const float z = round_h(z2[c] + sw[SmemW::b2 + c]);
+            out[(size_t)n * 3 + c] = __float2half_rn(1.0f / (1.0f + expf(-z)));
+        }
+    }
+}
+
+// Backward: recomputes the forward per ray (cheaper than saving [N,64] activations), then
+//   gz2 = half(half(g) * y (1 - y)),  ga1 = half(gz2 . W2),  gz1 = ga1 * (z1 > 0)
+//   [gW1 | gb1] += gz1^T [enc | 1],   [gW2 ; gb2] += gz2^T [a1 | 1]
+// Shared-memory tiles per 128 rays: gz1 half [128][64], a1 half [128][64], enc half [128][48], gz2 float [128][4].
+struct SmemB {
+    static constexpr uint32_t gz1 = SmemW::total * 4;                  // bytes
+    static constexpr uint32_t a1 = gz1 + kRays * kHid * 2;
+    static constexpr uint32_t enc = a1 + kRays * kHid * 2;
+    static constexpr uint32_t gz2 = enc + kRays * kEncPad * 2;
+    static constexpr uint32_t total = gz2 + kRays * 4 * 4;
+};
+
+__global__ void __launch_bounds__(kRays) bg_backward_kernel(const float* __restrict__ dirs, const float* __restrict__ grad_out,
+                                                            uint32_t N, const Weights w, float* __restrict__ gw1,
+                                                            float* __restrict__ gb1, float* __restrict__ gw2,
+                                                            float* __restrict__ gb2) {
+    extern __shared__ __align__(16) float sw[];
+    uint8_t* sbytes = reinterpret_cast<uint8_t*>(sw);
+    __half* s_gz1 = reinterpret_cast<__half*>(sbytes + SmemB::gz1);
+    __half* s_a1 = reinterpret_cast<__half*>(sbytes + SmemB::a1);
+    __half* s_enc = reinterpret_cast<__half*>(sbytes + SmemB::enc);
+    float* s_gz2 = reinterpret_cast<float*>(sbytes + SmemB::gz2);
+    load_weights(w, sw);
+    __syncthreads();
+
+    const uint32_t t = threadIdx.x;
+    // phase-2 ownership: threads 0..95 own a [4 j] x [8 k] block of [gW1 | gb1 | 0]; threads 96..111 own [4 j] x
+    // [gz2 c = 0..2] of gW2^T; thread 112 owns gb2
+    const uint32_t jb = t < 96 ? t / 6 : (t - 96), kb = t % 6;
+    float acc[32];
+#pragma unroll
+    for (uint32_t i = 0; i < 32; ++i) acc[i] = 0.f;
+
+    const uint32_t n_tiles = (N + kRays - 1) / kRays;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t n = tile * kRays + t;
+        const bool active = n < N;
+        {   // ---- phase 1: one ray per thread -------------------------------------------------------------------
+            float d[3] = {0.f, 0.f, 0.f}, g[3] = {0.f, 0.f, 0.f};
+            if (active) {
+#pragma unroll
+                for (uint32_t c = 0; c < 3; ++c) { d[c] = dirs[(size_t)n * 3 + c]; g[c] = round_h(grad_out[(size_t)n * 3 + c]); }
+            }
+            float enc[40];
+#pragma unroll
+            for (uint32_t c = 0; c < 40; ++c) enc[c] = c < kEnc ? round_h(freq_feature(d, c)) : 0.f;
+            // [enc | 1 | 0...] row of the tile (inactive rays contribute nothing: their gz are zero)
+#pragma unroll
+            for (uint32_t c = 0; c < kEncPad; c += 2) {
+                const float e0 = c < kEnc ? enc[c < 40 ? c : 0] : (c == kEnc ? 1.f : 0.f);
+                const float e1 = (c + 1) < kEnc ? enc[(c + 1) < 40 ? (c + 1) : 0] : ((c + 1) == kEnc ? 1.f : 0.f);
+                *reinterpret_cast<__half2*>(s_enc + t * kEncPad + c) = __floats2half2_rn(e0, e1);
+            }
+            // forward recompute: z1 sign + a1 into the tile, z2
+            float z2[3] = {0.f, 0.f, 0.f};
+            for (uint32_t j = 0; j < kHid; ++j) {
+                const float a = fmaxf(hidden_pre(enc, sw, j), 0.f);
+                s_a1[t * kHid + j] = __float2half_rn(a);
+#pragma unroll
+                for (uint32_t c = 0; c < 3; ++c) z2[c] = fmaf(a, sw[SmemW::w2 + c * kHid + j], z2[c]);
+            }
+            float gz2[3];
+#pragma unroll
+            for (uint32_t c = 0; c < 3; ++c) {
+                const float z = round_h(z2[c] + sw[SmemW::b2 + c]);
+                const float y = round_h(1.0f / (1.0f + expf(-z)));
+                gz2[c] = active ? round_h(g[c] * (1.f - y) * y) : 0.f;
+                s_gz2[t * 4 + c] = gz2[c];
+            }
+            s_gz2[t * 4 + 3] = 0.f;
+            for (uint32_t j = 0; j < kHid; ++j) {
+                float ga = 0.f;
+#pragma unroll
+                for (uint32_t c = 0; c < 3; ++c) ga = fmaf(gz2[c], sw[SmemW::w2 + c * kHid + j], ga);
+                const float a = __half2float(s_a1[t * kHid + j]);
+                s_gz1[t * kHid + j] = __float2half_rn(a > 0.f ? round_h(ga) : 0.f);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: block-wide products over the tile's 128 rays, accumulators in registers --------------------
+        if (t < 96) {
+            for (uint32_t ray = 0; ray < kRays; ++ray) {
+                const uint2 gq = *reinterpret_cast<const uint2*>(s_gz1 + ray * kHid + jb * 4);
+                const uint4 eq = *reinterpret_cast<const uint4*>(s_enc + ray * kEncPad + kb * 8);
+                const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&gq.x));
+                const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&gq.y));
+                const float gj[4] = {g01.x, g01.y, g23.x, g23.y};
+                const uint32_t ew[4] = {eq.x, eq.y, eq.z, eq.w};
+                float ek[8];
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) {
+                    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&ew[q]));
+                    ek[2 * q] = e.x; ek[2 * q + 1] = e.y;
+                }
+#pragma unroll
+                for (uint32_t a = 0; a < 4; ++a)
+#pragma unroll
+                    for (uint32_t b = 0; b < 8; ++b) acc[a * 8 + b] = fmaf(gj[a], ek[b], acc[a * 8 + b]);
+            }
+        } else if (t < 112) {
+            for (uint32_t ray = 0; ray < kRays; ++ray) {
+                const float4 gz = *reinterpret_cast<const float4*>(s_gz2 + ray * 4);
+                const uint2 aq = *reinterpret_cast<const uint2*>(s_a1 + ray * kHid + jb * 4);
+                const float2 a01 = __half22float2(*reinterpret_cast<const __half2*>(&aq.x));
+                const float2 a23 = __half22float2(*reinterpret_cast<const __half2*>(&aq.y));
+                const float aj[4] = {a01.x, a01.y, a23.x, a23.y};
+                const float gc[3] = {gz.x, gz.y, gz.z};
+#pragma unroll
+                for (uint32_t a = 0; a < 4; ++a)
+#pragma unroll
+                    for (uint32_t c = 0; c < 3; ++c) acc[a * 3 + c] = fmaf(aj[a], gc[c], acc[a * 3 + c]);
+            }
+        } else if (t == 112) {
+            for (uint32_t ray = 0; ray < kRays; ++ray) {
+                const float4 gz = *reinterpret_cast<const float4*>(s_gz2 + ray * 4);
+                acc[0] += gz.x; acc[1] += gz.y; acc[2] += gz.z;
+            }
+        }
+        __syncthreads();  // tiles are rewritten by the next iteration
+    }
+
+    // ---- flush ------------------------------------------------------------------------------------------------
+    if (t < 96) {
+#pragma unroll
+        for (uint32_t a = 0; a < 4; ++a) {
+            const uint32_t j = jb * 4 + a;
+#pragma unroll
+            for (uint32_t b = 0; b < 8; ++b) {
+                const uint32_t k = kb * 8 + b;
+                if (k < kEnc) atomicAdd(gw1 + j * kEnc + k, acc[a * 8 + b]);
+                else if (k == kEnc) atomicAdd(gb1 + j, acc[a * 8 + b]);
+            }
+        }
+    } else if (t < 112) {
+#pragma unroll
+        for (uint32_t a = 0; a < 4; ++a)
+#pragma unroll
+            for (uint32_t c = 0; c < 3; ++c) atomicAdd(gw2 + c * kHid + jb * 4 + a, acc[a * 3 + c]);
+    } else if (t == 112) {
+        atomicAdd(gb2 + 0, acc[0]); atomicAdd(gb2 + 1, acc[1]); atomicAdd(gb2 + 2, acc[2]);
+    }
+}
+
+}  // namespace bg
+}  // namespace ngp
+
+using namespace ngp;
+
+extern "C" int ngp_bg_forward(const float* dirs, uint32_t N, const void* w1, const void* b1, const void* w2, const void* b2,
+                              uint32_t degree, uint32_t hidden, void* out_rgb, void* stream) {
+    if (!dirs || !w1 || !b1 || !w2 || !b2 || !out_rgb) return NGP_ERR_BAD_ARG;
+    if (degree != bg::kDeg || hidden != bg::kHid) return NGP_ERR_UNSUPPORTED;
+    if (N == 0) return NGP_OK;
+    const bg::Weights w = {static_cast<const __half*>(w1), static_cast<const __half*>(b1), static_cast<const __half*>(w2),
+                           static_cast<const __half*>(b2)};
+    const int blocks = min(cdiv(N, bg::kRays), num_sms() * 4);
+    bg::bg_forward_kernel<<<blocks, bg::kRays, bg::SmemW::total * 4, as_stream(stream)>>>(dirs, N, w, static_cast<__half*>(out_rgb));
+    return launch_status();
+}
+
+extern "C" int ngp_bg_backward(const float* dirs, const float* grad_rgb, uint32_t N, const void* w1, const void* b1,
+                               const void* w2, const void* b2, uint32_t degree, uint32_t hidden, float* gw1, float* gb1,
+                               float* gw2, float* gb2, void* stream) {
+    if (!dirs || !grad_rgb || !w1 || !b1 || !w2 || !b2 || !gw1 || !gb1 || !gw2 || !gb2) return NGP_ERR_BAD_ARG;
+    if (degree != bg::kDeg || hidden != bg::kHid) return NGP_ERR_UNSUPPORTED;
+    if (N == 0) return NGP_OK;
+    const bg::Weights w = {static_cast<const __half*>(w1), static_cast<const __half*>(b1), static_cast<const __half*>(w2),
+                           static_cast<const __half*>(b2)};
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(bg::bg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg::SmemB::total);
+        attr_set = true;
+    }
+    const int blocks = min(cdiv(N, bg::kRays), num_sms());
+    bg::bg_backward_kernel<<<blocks, bg::kRays, bg::SmemB::total, as_stream(stream)>>>(dirs, grad_rgb, N, w, gw1, gb1, gw2, gb2);
+    return launch_status();
+}

@@ -161,22 +161,6 @@ NGP_DEVINL void replicate_rows(float (&rows)[1u << D][C], uint32_t axes_used) {
     if constexpr (D >= 4) { if (axes_used == 3) { replicate_rows_static<D, C, 3>(rows); return; } }
     if constexpr (D >= 5) { if (axes_used == 4) { replicate_rows_static<D, C, 4>(rows); return; } }
 }
-template <uint32_t D, uint32_t C, uint32_t U>
-NGP_DEVINL void fold_rows_static(float (&v)[1u << D][C]) {
-#pragma unroll
-    for (uint32_t corner = (1u << U); corner < (1u << D); ++corner) {
-#pragma unroll
-        for (uint32_t c = 0; c < C; ++c) v[corner & ((1u << U) - 1)][c] += v[corner][c];
-    }
-}
-template <uint32_t D, uint32_t C>
-NGP_DEVINL void fold_rows(float (&v)[1u << D][C], uint32_t axes_used) {
-    if constexpr (D >= 2) { if (axes_used == 1) { fold_rows_static<D, C, 1>(v); return; } }
-    if constexpr (D >= 3) { if (axes_used == 2) { fold_rows_static<D, C, 2>(v); return; } }
-    if constexpr (D >= 4) { if (axes_used == 3) { fold_rows_static<D, C, 3>(v); return; } }
-    if constexpr (D >= 5) { if (axes_used == 4) { fold_rows_static<D, C, 4>(v); return; } }
-}
-
 // ---- element-type plumbing ----------------------------------------------------------------------
 template <typename T> struct ElemOps;
 template <> struct ElemOps<float> {
@@ -521,6 +505,118 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
 // active LANE, so fewer active lanes is a direct speed-up; levels whose cells are finer than the sample
 // spacing have runs of length 1 and pay only two shuffles and a ballot.
 // -------------------------------------------------------------------------------------------------
+// One level of the warp-aggregated scatter, specialised at compile time on how the level addresses its rows:
+// USED = axes that enter the row index (a 'tiled' level whose table is smaller than (res+1)^2 drops z: 4 distinct
+// rows per cell, and since the weights of the two z corners sum to 1 only the (x, y) bilinear weights are needed),
+// HASHED = spatial hash of all three axes.
+template <uint32_t USED, bool HASHED, uint32_t C>
+NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool align_corners, bool valid, const float (&g)[C],
+                              uint32_t lane, float* __restrict__ grad_table) {
+    constexpr uint32_t NC = 1u << USED;  // distinct rows per cell
+    float frac[USED];
+    uint32_t base[USED];
+    {
+        float xs[USED];
+#pragma unroll
+        for (uint32_t d = 0; d < USED; ++d) xs[d] = x[d];
+        locate<USED>(xs, lp.scale, align_corners, frac, base);
+    }
+    // run detection: same cell (over the axes the level uses) as the previous lane, both valid
+    uint32_t kxy = base[0], kz = 0u;
+    if constexpr (USED >= 2) kxy |= base[1] << 16;
+    if constexpr (USED >= 3) kz = base[2];
+    if (!valid) { kxy = 0xffffffffu; kz = 0x80000000u | lane; }
+    const uint32_t pxy = __shfl_up_sync(0xffffffffu, kxy, 1);
+    uint32_t pz = kz;
+    if constexpr (USED >= 3) pz = __shfl_up_sync(0xffffffffu, kz, 1);  // every lane shuffles (no short-circuit around it)
+    const bool head = (lane == 0) || !valid || (pxy != kxy) || (pz != kz);
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    // last lane of my run = (next head above me) - 1
+    const uint32_t above = (lane == 31) ? 0u : (heads >> (lane + 1));
+    const uint32_t run_end = above ? (lane + (uint32_t)__ffs(above) - 1u) : 31u;
+    // longest run in the warp bounds the number of reduction steps (warp-uniform)
+    const uint32_t my_len = head ? (run_end - lane + 1u) : 0u;
+    const uint32_t max_len = __reduce_max_sync(0xffffffffu, my_len);
+
+    float wts[NC];
+    corner_weights<USED>(frac, wts);
+    float v[NC][C];
+#pragma unroll
+    for (uint32_t corner = 0; corner < NC; ++corner) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) v[corner][c] = wts[corner] * g[c];
+    }
+    for (uint32_t off = 1; off < max_len; off <<= 1) {
+        const bool take = (lane + off) <= run_end;
+#pragma unroll
+        for (uint32_t corner = 0; corner < NC; ++corner) {
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) {
+                const float o = __shfl_down_sync(0xffffffffu, v[corner][c], off);
+                if (take) v[corner][c] += o;
+            }
+        }
+    }
+    if (head && valid) {
+    uint32_t rows[NC];
+    if constexpr (HASHED) {
+        constexpr uint32_t kPrimes[3] = {1u, 2654435761u, 805459861u};
+        rows[0] = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < USED; ++d) {
+            const uint32_t h0 = base[d] * kPrimes[d], h1 = h0 + kPrimes[d];
+#pragma unroll
+            for (uint32_t c = 0; c < (1u << d); ++c) { rows[c | (1u << d)] = rows[c] ^ h1; rows[c] ^= h0; }
+        }
+    } else {
+        uint32_t lin = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < USED; ++d) lin += base[d] * lp.stride[d];
+        rows[0] = lin;
+#pragma unroll
+        for (uint32_t d = 0; d < USED; ++d) {
+#pragma unroll
+            for (uint32_t c = 0; c < (1u << d); ++c) rows[c | (1u << d)] = rows[c] + lp.stride[d];
+        }
+    }
+    if (lp.wrap == kWrapMask) {
+#pragma unroll
+        for (uint32_t c = 0; c < NC; ++c) rows[c] &= lp.mask;
+    } else if (lp.wrap == kWrapMod) {
+#pragma unroll
+        for (uint32_t c = 0; c < NC; ++c) rows[c] %= lp.size;
+    }
+    float* tbl = grad_table + (size_t)lp.offset * C;
+    if constexpr (C == 2 && !HASHED && USED >= 1) {
+        // The SM issues reds at a fixed rate per LANE-op whatever their width (profiles/: ~217 G ops/s for 4-, 8- and
+        // 16-byte reds alike), so the two x-neighbours of a corner pair - adjacent rows of a linear level - go out
+        // as ONE 16-byte red whenever the pair is 16-byte aligned.
+#pragma unroll
+        for (uint32_t corner = 0; corner < NC; corner += 2) {
+            const uint32_t lo = rows[corner], hi = rows[corner + 1];
+            float* dst = tbl + (size_t)lo * 2;
+            if (hi == lo + 1 && (((lp.offset + lo) & 1u) == 0)) {
+                red_add_f32x4(dst, v[corner][0], v[corner][1], v[corner + 1][0], v[corner + 1][1]);
+            } else {
+                red_add_f32x2(dst, v[corner][0], v[corner][1]);
+                red_add_f32x2(tbl + (size_t)hi * 2, v[corner + 1][0], v[corner + 1][1]);
+            }
+        }
+    } else {
+#pragma unroll
+        for (uint32_t corner = 0; corner < NC; ++corner) {
+            float* dst = tbl + (size_t)rows[corner] * C;
+            if constexpr (C == 1) red_add_f32(dst, v[corner][0]);
+            else if constexpr (C == 2) red_add_f32x2(dst, v[corner][0], v[corner][1]);
+            else {
+#pragma unroll
+                for (uint32_t c = 0; c < C; c += 4) red_add_f32x4(dst + c, v[corner][c], v[corner][c + 1], v[corner][c + 2], v[corner][c + 3]);
+            }
+        }
+    }
+    }  // head && valid
+}
+
 template <typename T, uint32_t C>
 __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
     const T* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
@@ -535,136 +631,57 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
     const uint32_t B = count_ptr ? min((uint32_t)max(*count_ptr, 0), B_cap) : B_cap;
     const float inv_2b = bound > 0.f ? __fdiv_rn(1.0f, 2 * bound) : 1.0f;
     const uint32_t lane = threadIdx.x & 31;
-
-  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; (b & ~31u) < B; b += gridDim.x * blockDim.x) {
-    // whole warps stay alive (shuffles below); out-of-range / out-of-cube samples just contribute nothing
-    bool valid = b < B;
-    float x[D] = {0.f, 0.f, 0.f};
-    if (valid) {
-#pragma unroll
-        for (uint32_t d = 0; d < D; ++d) {
-            x[d] = __ldg(inputs + (size_t)b * D + d);
-            if (bound > 0.f) x[d] = __fmul_rn(__fadd_rn(x[d], bound), inv_2b);  // GridEncoder.forward's mapping (grid.py:142)
-        }
-        valid = !out_of_unit_cube<D>(x);  // gridencoder.cu:253-258
-    }
-
-    // half2 gradient rows are fetched four levels (one 16-byte load) at a time: a sample's [L*C] row is 2 sectors, and
-    // 16 separate 4-byte loads spread over the whole level loop kept missing L1
     constexpr bool kPacked = (sizeof(T) == 2 && C == 2);
-    uint32_t graw[4] = {0u, 0u, 0u, 0u};
-    for (uint32_t level0 = 0; level0 < L; level0 += 4) {
-      if constexpr (kPacked) {
-        if (level0 + 4 <= L && (L % 4) == 0) {
-            uint4 q = make_uint4(0u, 0u, 0u, 0u);
-            if (valid) q = __ldg(reinterpret_cast<const uint4*>(grad + ((size_t)b * L + level0) * C));
-            graw[0] = q.x; graw[1] = q.y; graw[2] = q.z; graw[3] = q.w;
-        } else {
-#pragma unroll
-            for (uint32_t j = 0; j < 4; ++j)
-                graw[j] = (valid && level0 + j < L) ? __ldg(reinterpret_cast<const uint32_t*>(grad + ((size_t)b * L + level0 + j) * C)) : 0u;
-        }
-      }
-#pragma unroll
-      for (uint32_t lj = 0; lj < 4; ++lj) {
-        const uint32_t level = level0 + lj;
-        if (level >= L) break;
-        const FastLevel<D>& lp = s_levels[level];
-        float frac[D];
-        uint32_t base[D];
-        locate<D>(x, lp.scale, align_corners, frac, base);
 
-        float g[C];
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; (b & ~31u) < B; b += gridDim.x * blockDim.x) {
+        // whole warps stay alive (shuffles below); out-of-range / out-of-cube samples just contribute nothing
+        bool valid = b < B;
+        float x[D] = {0.f, 0.f, 0.f};
+        if (valid) {
 #pragma unroll
-        for (uint32_t c = 0; c < C; ++c) g[c] = 0.f;
-        if constexpr (kPacked) {
-            const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&graw[lj]));
-            g[0] = gf.x; g[1] = gf.y;
-        } else {
-            if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
-        }
-
-        // run detection: same cell as the previous lane (both valid).  Axes the level ignores do not enter the key:
-        // a 'tiled' level that drops z addresses the same 4 rows for every sample of a ray segment that stays in one
-        // (x, y) column, however many z cells it crosses.
-        const uint32_t ky = lp.used >= 2 ? base[1] : 0u, kzz = lp.used >= 3 ? base[2] : 0u;
-        const uint32_t kxy = valid ? (base[0] | (ky << 16)) : 0xffffffffu;
-        const uint32_t kz = valid ? kzz : (0x80000000u | lane);
-        const uint32_t pxy = __shfl_up_sync(0xffffffffu, kxy, 1);
-        const uint32_t pz = __shfl_up_sync(0xffffffffu, kz, 1);
-        const bool head = (lane == 0) || !valid || (pxy != kxy) || (pz != kz);
-        const uint32_t heads = __ballot_sync(0xffffffffu, head);
-        // last lane of my run = (next head above me) - 1
-        const uint32_t above = (lane == 31) ? 0u : (heads >> (lane + 1));
-        const uint32_t run_end = above ? (lane + (uint32_t)__ffs(above) - 1u) : 31u;
-        // longest run in the warp bounds the number of reduction steps (warp-uniform)
-        const uint32_t my_len = head ? (run_end - lane + 1u) : 0u;
-        const uint32_t max_len = __reduce_max_sync(0xffffffffu, my_len);
-
-        float v[1u << D][C];
-        float wts[1u << D];
-        corner_weights<D>(frac, wts);
-#pragma unroll
-        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-#pragma unroll
-            for (uint32_t c = 0; c < C; ++c) v[corner][c] = wts[corner] * g[c];
-        }
-        // corners that differ only in an axis this level ignores hit the same row: fold them first (warp-uniform)
-        const uint32_t axes_used = lp.used;
-        const uint32_t distinct = 1u << axes_used;
-        fold_rows<D, C>(v, axes_used);
-        for (uint32_t off = 1; off < max_len; off <<= 1) {
-            const bool take = (lane + off) <= run_end;
-#pragma unroll
-            for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-                if (corner < distinct) {
-#pragma unroll
-                    for (uint32_t c = 0; c < C; ++c) {
-                        const float o = __shfl_down_sync(0xffffffffu, v[corner][c], off);
-                        if (take) v[corner][c] += o;
-                    }
-                }
+            for (uint32_t d = 0; d < D; ++d) {
+                x[d] = __ldg(inputs + (size_t)b * D + d);
+                if (bound > 0.f) x[d] = __fmul_rn(__fadd_rn(x[d], bound), inv_2b);  // GridEncoder.forward's mapping (grid.py:142)
             }
+            valid = !out_of_unit_cube<D>(x);  // gridencoder.cu:253-258
         }
-        if (head && valid) {
-            float* tbl = grad_table + (size_t)lp.offset * C;
-            uint32_t ridx[1u << D];
-            corner_rows<D>(lp, base, ridx);
-            if constexpr (C == 2) {
-                // The SM issues reds at a fixed rate per LANE-op whatever their width (profiles/: 217 G ops/s for 4,
-                // 8 and 16-byte reds alike), so the two x-neighbours of a corner pair - adjacent rows of a linear
-                // level - go out as ONE 16-byte red whenever the pair is 16-byte aligned.
-                if (!lp.hashed) {
+        // half2 gradient rows are fetched four levels (one 16-byte load) at a time: a sample's [L*C] row is 2 sectors,
+        // and 16 separate 4-byte loads spread over the whole level loop kept missing L1
+        uint32_t graw[4] = {0u, 0u, 0u, 0u};
+        for (uint32_t level0 = 0; level0 < L; level0 += 4) {
+            if constexpr (kPacked) {
+                if ((L % 4) == 0) {
+                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid) q = __ldg(reinterpret_cast<const uint4*>(grad + ((size_t)b * L + level0) * C));
+                    graw[0] = q.x; graw[1] = q.y; graw[2] = q.z; graw[3] = q.w;
+                } else {
 #pragma unroll
-                    for (uint32_t corner = 0; corner < (1u << D); corner += 2) {
-                        if (corner >= distinct) continue;
-                        const uint32_t lo = ridx[corner], hi = ridx[corner + 1];
-                        float* dst = tbl + (size_t)lo * 2;
-                        if (distinct > 1 && hi == lo + 1 && (((lp.offset + lo) & 1u) == 0)) {
-                            red_add_f32x4(dst, v[corner][0], v[corner][1], v[corner + 1][0], v[corner + 1][1]);
-                        } else {
-                            red_add_f32x2(dst, v[corner][0], v[corner][1]);
-                            if (distinct > 1) red_add_f32x2(tbl + (size_t)hi * 2, v[corner + 1][0], v[corner + 1][1]);
-                        }
-                    }
-                    continue;
+                    for (uint32_t j = 0; j < 4; ++j)
+                        graw[j] = (valid && level0 + j < L) ? __ldg(reinterpret_cast<const uint32_t*>(grad + ((size_t)b * L + level0 + j) * C)) : 0u;
                 }
             }
 #pragma unroll
-            for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-                if (corner >= distinct) continue;
-                float* dst = tbl + (size_t)ridx[corner] * C;
-                if constexpr (C == 1) red_add_f32(dst, v[corner][0]);
-                else if constexpr (C == 2) red_add_f32x2(dst, v[corner][0], v[corner][1]);
-                else {
+            for (uint32_t lj = 0; lj < 4; ++lj) {
+                const uint32_t level = level0 + lj;
+                if (level >= L) break;
+                const FastLevel<D>& lp = s_levels[level];
+                float g[C];
 #pragma unroll
-                    for (uint32_t c = 0; c < C; c += 4) red_add_f32x4(dst + c, v[corner][c], v[corner][c + 1], v[corner][c + 2], v[corner][c + 3]);
+                for (uint32_t c = 0; c < C; ++c) g[c] = 0.f;
+                if constexpr (kPacked) {
+                    const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&graw[lj]));
+                    g[0] = gf.x; g[1] = gf.y;
+                } else {
+                    if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
                 }
+                // warp-uniform dispatch on the level's addressing class
+                if (lp.hashed)          warpagg_level<3, true, C>(lp, x, align_corners, valid, g, lane, grad_table);
+                else if (lp.used == 3)  warpagg_level<3, false, C>(lp, x, align_corners, valid, g, lane, grad_table);
+                else if (lp.used == 2)  warpagg_level<2, false, C>(lp, x, align_corners, valid, g, lane, grad_table);
+                else                    warpagg_level<1, false, C>(lp, x, align_corners, valid, g, lane, grad_table);
             }
         }
-      }
     }
-  }
 }
 
 // grad_inputs[b,d] = sum_{l,c} grad[l,b,c] * dy_dx[b,l,d,c]   (gridencoder.cu:317-342).  In half mode the

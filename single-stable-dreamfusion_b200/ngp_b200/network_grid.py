@@ -105,6 +105,10 @@ class NeRFNetwork(NeRFRenderer):
         return {'sigma': sigma, 'albedo': albedo}
 
     def background(self, d):
+        if self.fused:
+            from . import step_ops
+            if step_ops.can_fuse_background(d, self.encoder_bg, self.bg_net):
+                return step_ops.background_net(d, self.bg_net)
         h = self.encoder_bg(d)  # [N, C]
         h = self.bg_net(h)
         return torch.sigmoid(h)

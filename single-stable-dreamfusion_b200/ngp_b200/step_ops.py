@@ -9,6 +9,7 @@ import torch
 from torch.autograd import Function
 
 from . import _cabi
+from .field import cached_half
 
 
 class _BlendBackground(Function):
@@ -85,3 +86,46 @@ def entropy_loss(weights_sum, lam=1e-4):
     """lam * mean binary entropy (base 2) of clamp(weights_sum, 1e-5, 1 - 1e-5)."""
     _cabi.require_cuda(weights_sum)
     return _EntropyLoss.apply(weights_sum.float(), lam)
+
+
+class _BackgroundNet(Function):
+    """FreqEncoder(6) -> Linear(39,64)+ReLU -> Linear(64,3) -> sigmoid under fp16 autocast, one launch each way."""
+
+    @staticmethod
+    def forward(ctx, dirs, w1, b1, w2, b2):
+        dev = dirs.device
+        N = dirs.shape[0]
+        hw = [cached_half(t) for t in (w1, b1, w2, b2)]
+        out = torch.empty(N, 3, device=dev, dtype=torch.half)
+        _cabi.call("ngp_bg_forward", dev, _cabi.ptr(dirs), N, *[_cabi.ptr(t) for t in hw], 6, 64, _cabi.ptr(out))
+        ctx.save_for_backward(dirs, *hw)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        dirs, w1h, b1h, w2h, b2h = ctx.saved_tensors
+        dev = dirs.device
+        g = g.contiguous().float()
+        sizes = [64 * 39, 64, 3 * 64, 3]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        gw1, gb1, gw2, gb2 = torch.split(flat, sizes)
+        _cabi.call("ngp_bg_backward", dev, _cabi.ptr(dirs), _cabi.ptr(g), dirs.shape[0], _cabi.ptr(w1h), _cabi.ptr(b1h),
+                   _cabi.ptr(w2h), _cabi.ptr(b2h), 6, 64, _cabi.ptr(gw1), _cabi.ptr(gb1), _cabi.ptr(gw2), _cabi.ptr(gb2))
+        return None, gw1.view(64, 39), gb1, gw2.view(3, 64), gb2
+
+
+def can_fuse_background(d, encoder_bg, bg_net):
+    try:
+        return (d.is_cuda and d.dim() == 2 and d.shape[-1] == 3 and not d.requires_grad
+                and torch.is_autocast_enabled('cuda') and torch.get_autocast_dtype('cuda') == torch.float16
+                and encoder_bg.input_dim == 3 and encoder_bg.degree == 6 and bg_net.num_layers == 2
+                and bg_net.dim_hidden == 64 and bg_net.dim_out == 3 and bg_net.net[0].bias is not None
+                and bg_net.net[0].weight.dtype == torch.float32)
+    except AttributeError:
+        return False
+
+
+def background_net(d, bg_net):
+    """sigmoid(bg_net(freq_encode(d))) as a half tensor [N,3] (what NeRFNetwork.background returns under autocast)."""
+    l0, l1 = bg_net.net
+    return _BackgroundNet.apply(d.contiguous().float(), l0.weight, l0.bias, l1.weight, l1.bias)

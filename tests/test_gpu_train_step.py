@@ -141,3 +141,30 @@ def test_train_step_fused_optimizer_tracks_torch_optimizer(ref_ext):
         a, b = finals[0][1][n], finals[1][1][n]
         assert torch.isfinite(a).all()
         assert ((a - b).norm() / (b.norm() + 1e-12)).item() < 0.5, n
+
+
+def test_fused_background_net_matches_torch_modules():
+    """FreqEncoder + bg_net + sigmoid as one kernel each way vs the module chain under autocast (cuBLAS half GEMMs)."""
+    import argparse
+    from ngp_b200.network_grid import NeRFNetwork
+    opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)
+    torch.manual_seed(0)
+    m = NeRFNetwork(opt).to(DEV).train()
+    g = torch.Generator(device=DEV).manual_seed(4)
+    for N in (1, 100, 4096 + 37):
+        d = torch.nn.functional.normalize(torch.randn(N, 3, device=DEV, generator=g), dim=-1)
+        up = torch.randn(N, 3, device=DEV, generator=g) * 1e-2
+        res = []
+        for fused in (True, False):
+            m.fused = fused
+            m.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", torch.float16):
+                y = m.background(d)
+            assert y.dtype == torch.half and y.shape == (N, 3)
+            y.float().backward(up)
+            res.append((y.detach().float(), {n: p.grad.clone() for n, p in m.bg_net.named_parameters()}))
+        assert torch.allclose(res[0][0], res[1][0], atol=2e-3), (res[0][0] - res[1][0]).abs().max().item()
+        for n in res[0][1]:
+            a, b = res[0][1][n].float(), res[1][1][n].float()
+            rel = ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+            assert rel < 2e-2, (N, n, rel)       # the torch path rounds weight gradients (and their split-K partials) to fp16
