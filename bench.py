@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--cpu-sample-steps", type=int, default=3)
     ap.add_argument("--lr", type=float, default=1e-5)
     ap.add_argument("--no-graph", action="store_true", help="run the train step eagerly instead of as one CUDA graph")
+    ap.add_argument("--autograd", action="store_true", help="autograd version of the step instead of the hand-scheduled kernels")
+    ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce instead of the fused peer-memory all-reduce + Adam")
     ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
     return ap.parse_args()
@@ -187,7 +189,7 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     from ngp_b200 import _cabi, provider
-    from ngp_b200.parallel import shard_views
+    from ngp_b200.parallel import shard_rows
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,25 +201,32 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=device)
     _cabi.load()
 
-    first, n_local = shard_views(args.views, rank, world)
+    # Data-parallel sharding: every rank renders image rows rank, rank + world, ... of ALL views of the step (an even
+    # split of the step's 8 x 4096 rays whose per-rank sample counts stay balanced; whole views differ 4x in samples)
+    if H % world != 0:
+        raise SystemExit("--gpus must divide the image height %d" % H)
+    rows = shard_rows(H, rank, world)
+    Hl = len(rows)
     n_pool = 64
-    ro_all, rd_all = provider.make_training_views(n_pool * args.views, H, W, seed=0)
-    ro_all = ro_all.view(n_pool, args.views, H * W, 3)
-    rd_all = rd_all.view(n_pool, args.views, H * W, 3)
-    g_host = (torch.randn(n_pool, args.views, 3, H, W, generator=torch.Generator().manual_seed(2)) * 1e-2).pin_memory()
+    ro_all, rd_all = provider.make_training_views(n_pool * args.views, H, W, seed=0, pin=False)
+    ro_all = ro_all.view(n_pool, args.views, H, W, 3)[:, :, rows].reshape(n_pool, args.views, Hl * W, 3)
+    rd_all = rd_all.view(n_pool, args.views, H, W, 3)[:, :, rows].reshape(n_pool, args.views, Hl * W, 3)
+    g_all = (torch.randn(n_pool, args.views, 3, H, W, generator=torch.Generator().manual_seed(2)) * 1e-2)[:, :, :, rows]
 
     from ngp_b200.trainer import TrainStep
     model = build_model(device)
     # lr: the optimizer step runs in full, but a small step keeps the synthetic (random-gradient) scene at its
     # random-init occupancy so that every timed pass sees the same ~3.4 M samples per step
-    step_fn = TrainStep(model, H, W, lr=args.lr, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world)
+    step_fn = TrainStep(model, Hl, W, lr=args.lr, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world,
+                        manual=False if args.autograd else None, peer_allreduce=False if args.nccl else None)
+    # one packed, pinned host buffer per batch [rays_o | rays_d | G]: a step's inputs are ONE copy
+    host_pool = torch.stack([step_fn.pack_inputs(ro_all[k], rd_all[k], g_all[k].contiguous()) for k in range(n_pool)]).pin_memory()
 
     def host_batch(i):
-        k = i % n_pool
-        return (ro_all[k, first:first + n_local], rd_all[k, first:first + n_local], g_host[k, first:first + n_local])
+        return host_pool[i % n_pool]
 
     # inputs resident in HBM for the `value` measurement
-    dev_pool = [tuple(t.to(device, non_blocking=True) for t in host_batch(i)) for i in range(n_pool)]
+    dev_pool = host_pool.to(device)
     torch.cuda.synchronize()
 
     def barrier():
@@ -236,22 +245,22 @@ def run_b200_arm(args):
                 ev.record()
                 step_events.append(ev)
             i = start_index + s
-            if e2e:
-                ro, rd, G = (t.to(device, non_blocking=True) for t in host_batch(i))
-            else:
-                ro, rd, G = dev_pool[i % n_pool]
-            loss = step_fn(ro, rd, G)
+            # graph mode copies the packed batch straight into the step's static input buffer (H2D when it is a host batch)
+            loss = step_fn(host_batch(i) if e2e else dev_pool[i % n_pool])
             if e2e:
                 loss.item()  # device -> host read of the step's result
 
     # ---- warm-up ------------------------------------------------------------------------------------
+    # the clock sampler (an nvidia-smi child process) is started BEFORE the warm-up: its start-up takes driver locks that
+    # stall kernel launches for 10-25 ms, which must not land inside the timed region; its samples span both timed regions
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(1.0)
     run_steps(max(args.warmup, 3), False, 0)
     barrier()
 
     # ---- timed: inputs resident ----------------------------------------------------------------------
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     sample_acc.zero_()
     updates0 = step_fn.n_updates
     launches0 = _cabi.LAUNCHES
@@ -262,7 +271,8 @@ def run_b200_arm(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    per_step = sorted(a.elapsed_time(b) for a, b in zip(step_events, step_events[1:] + [e1]))
+    per_step_raw = [a.elapsed_time(b) for a, b in zip(step_events, step_events[1:] + [e1])]
+    per_step = sorted(per_step_raw)
     launches = _cabi.LAUNCHES - launches0
     n_updates = step_fn.n_updates - updates0
     samples = int(sample_acc.item())
@@ -299,7 +309,8 @@ def run_b200_arm(args):
         step_fn.use_graph = False
         names = ["ngp_grid_scatter_samples", "ngp_grid_encode_backward", "ngp_field_forward", "ngp_field_backward",
                  "ngp_march_rays_train", "ngp_composite_rays_train_forward", "ngp_composite_rays_train_backward",
-                 "ngp_grid_encode_forward"]
+                 "ngp_grid_encode_forward", "ngp_train_prologue", "ngp_train_ray_loss", "ngp_bg_forward", "ngp_bg_backward",
+                 "ngp_adam_step_fused"]
         step_fn.global_step = 1  # keep the occupancy refresh out of the profiled steps
         run_steps(2, False, 3000)
         torch.cuda.synchronize()
@@ -329,7 +340,7 @@ def run_b200_arm(args):
     if rank == 0:
         value = samples / (ms * 1e-3)
         e2e_value = samples_e2e / (ms_e2e * 1e-3)
-        h2d = sum(t.numel() * t.element_size() for t in host_batch(0)) * world
+        h2d = host_batch(0).numel() * host_batch(0).element_size() * world
         # roofline of the dominant kernel (the grid-encode scatter or gather), against the measured L2 ceilings
         gathers_s, reds_s = measure_l2_peaks(device)
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
@@ -371,7 +382,13 @@ def run_b200_arm(args):
                             "update every 16 steps" % (args.views, world),
                 "views_per_step": args.views, "rays_per_step": args.views * H * W,
                 "samples_per_step": samples / args.steps, "cuda_graph": not args.no_graph, "lr": args.lr,
-                "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]}, "timing": "inputs (3.5 MB/step) and the 7 MB table are "
+                "hand_scheduled_step": step_fn.manual, "comm_error": bool(step_fn.fused_optimizer and step_fn.opt.comm_error),
+                "sharding": "image rows interleaved over ranks (every rank renders rows r::N of all views)",
+                "grad_allreduce": ("none (1 GPU)" if world == 1 else
+                                   ("fused into the optimizer kernel over NVLink peer memory (%s)" % step_fn.peer.used
+                                    if step_fn.opt.peer_ptrs is not None else "NCCL all_reduce (%s)" % (step_fn.peer_error or "requested"))),
+                "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "p90": per_step[(len(per_step) * 9) // 10],
+                            "max": per_step[-1], "argmax": per_step_raw.index(per_step[-1])}, "timing": "inputs (3.5 MB/step) and the 7 MB table are "
                 "smaller than L2 by nature of the workload; each step runs on a different view batch (64-batch pool), "
                 "the 134+ MB/step of sample buffers exceed L2",
             },

@@ -248,6 +248,47 @@ int ngp_bg_backward(const float* dirs, const float* grad_rgb, uint32_t N, const 
                     const void* b2, uint32_t degree, uint32_t hidden, float* gw1, float* gb1, float* gw2, float* gb2,
                     void* stream);
 
+/* The optimisation step as ONE cooperative launch, with the data-parallel gradient all-reduce fused in over NVLink
+ * peer memory (csrc/dp_step.cu): replaces ngp_check_finite + ngp_adam_step (world == 1) and, for world > 1, the
+ * all_reduce DistributedDataParallel would issue for the reference's dormant wrap (nerf/utils.py:200-202) as well.
+ *   state f32[8]: as ngp_adam_step, plus [5] = 1 if a cross-GPU wait timed out.  sync u32[2], zero-initialised:
+ *   [0] block election, [1] barrier epoch.  n must be a multiple of 4.
+ *   world > 1: peer_* are HOST arrays of `world` device addresses (this rank's own buffers included, in rank order) of
+ *   every rank's gradient bucket, parameter buffer, fp16 shadow and flag pad (ngp_dp_flags_bytes() bytes, zeroed once),
+ *   all mapped into this process (symmetric memory / CUDA IPC).  Each rank reduces and updates slice `rank` and writes
+ *   the new parameters to every replica; exp_avg / exp_avg_sq are maintained for that slice only.  The gradient bucket
+ *   is zero-filled on the way out.  All ranks must launch the same sequence of calls. */
+#define NGP_DP_MAX_WORLD 8
+#define NGP_DP_MAX_BLOCKS 256
+int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow, uint64_t n,
+                        uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1, float beta2,
+                        float eps, float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor,
+                        float backoff_factor, uint32_t growth_interval, float* state, uint32_t* sync, uint32_t rank,
+                        uint32_t world, const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half,
+                        const uint64_t* peer_flags, void* stream);
+uint64_t ngp_dp_flags_bytes(void);
+/* cudaDeviceEnablePeerAccess(peer_device) from the current device (idempotent). */
+int ngp_enable_peer_access(int peer_device);
+
+/* First and middle kernels of the hand-scheduled train step (ngp_b200/trainer.py).
+ * ngp_train_prologue: near_far_from_aabb (raymarching.cu:92-156) for N rays + zero-fill of counter i32[2] and loss f32[1]
+ * (either may be NULL).
+ * ngp_train_ray_loss: per ray, in one launch: composite_rays_train forward (raymarching.cu:501-588), the background blend
+ * (nerf/renderer.py:541-545), the gradients of the two losses of Trainer.train_step at the ray - grad_pred (the guidance
+ * gradient wrt the blended image, [B,3,pixels_per_view] NCHW as nerf/sd.py:115 passes it, or [N,3] if pixels_per_view is
+ * 0) and lambda * mean opacity entropy times *scale (nerf/utils.py:389-394,708) - and composite_rays_train backward
+ * (raymarching.cu:602-693).  Outputs: weights_sum[N], depth[N], image[N,3] (before the blend), grad_bg[N,3] (optional),
+ * grad_sigmas[M], grad_rgbs[M,3]; *loss += the entropy loss.  bg_half: f16[N,3] or NULL (then the colour bg_const).
+ * Optional device-side bookkeeping when counter != NULL: *samples_total += counter[0];
+ * step_counter[*local_step % 16] = counter; ++*local_step (nerf/renderer.py:466-467). */
+int ngp_train_prologue(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near, float* nears,
+                       float* fars, int* counter, float* loss, void* stream);
+int ngp_train_ray_loss(const float* sigmas, const float* rgbs, const float* deltas, const int* rays, uint32_t M, uint32_t N,
+                       float T_thresh, const void* bg_half, float bg_const, const float* grad_pred, uint32_t pixels_per_view,
+                       float lambda_entropy, const float* scale, float* weights_sum, float* depth, float* image,
+                       float* grad_bg, float* grad_sigmas, float* grad_rgbs, float* loss, const int* counter,
+                       long long* samples_total, int* step_counter, int* local_step, void* stream);
+
 /* End of run_cuda (nerf/renderer.py:535-557): image_out = image + (1 - weights_sum) * bg, depth_out =
  * clamp(depth - nears, 0) / (fars - nears) (NaN where the ray misses the box, as the reference), mask = nears < fars.
  * bg is f32[N,3] (bg_per_ray != 0) or one f32[3] colour.  depth_out / mask may be NULL. */

@@ -253,6 +253,8 @@ extern "C" int ngp_bg_backward(const float* dirs, const float* grad_rgb, uint32_
         cudaFuncSetAttribute(bg::bg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg::SmemB::total);
         attr_set = true;
     }
+    // one CTA per SM at most: in the train step this kernel runs beside the (persistent, shared-memory hungry) field
+    // kernels on a side stream and should fill their gaps, not evict them
     const int blocks = min(cdiv(N, bg::kRays), num_sms());
     bg::bg_backward_kernel<<<blocks, bg::kRays, bg::SmemB::total, as_stream(stream)>>>(dirs, grad_rgb, N, w, gw1, gb1, gw2, gb2);
     return launch_status();

@@ -1,0 +1,308 @@
+// The optimisation step of the data-parallel `-O` train step as ONE cooperative kernel (ngp_adam_step_fused):
+//
+//   world == 1:  GradScaler inf/nan check -> grid barrier -> Adam + LambdaLR + GradScaler.update + fp16 shadow refresh
+//                + zero-fill of the gradient bucket                       (what ngp_check_finite + ngp_adam_step do in two)
+//   world  > 1:  the gradient all-reduce is fused in, over NVLink peer memory (no NCCL call on the step):
+//                  B0  cross-GPU barrier: every rank's backward has finished writing its gradient bucket
+//                  P1  reduce-scatter by P2P loads: rank r sums slice r of all `world` buckets (fixed rank order),
+//                      keeps the sum in its own bucket and checks it for inf/nan
+//                  B1  cross-GPU barrier that also ORs the found_inf flags, so every rank takes the same branch
+//                  P2  Adam on slice r only (the moments are sharded: rank r owns slice r of exp_avg / exp_avg_sq),
+//                      then the new fp32 parameters and their fp16 shadow are written to EVERY rank's replica by P2P
+//                      stores (the all-gather half of the all-reduce moves parameters instead of gradients, so the
+//                      optimizer arithmetic is done once per element, not `world` times); zero-fill of the local bucket
+//                  B2  cross-GPU barrier: all replicas are complete before anybody's next forward reads them
+//
+// Reference semantics: `scaler.step(optimizer); scaler.update()` on Adam(betas (0.9, 0.99), eps 1e-15) with per-group lr
+// and LambdaLR (main.py:128-131, network_grid.py:170-181, nerf/utils.py:708-713), gradients averaged over ranks as
+// DistributedDataParallel (the reference's dormant wrap, nerf/utils.py:200-202) would.
+//
+// Cross-GPU barriers are flag exchanges in peer memory (st.release.sys / ld.acquire.sys), one slot per (barrier, block,
+// source rank), carrying a monotonically increasing epoch kept on the device, so the kernel is CUDA-graph replayable.
+// Every spin is bounded by a wall-clock timeout (kSpinTimeoutNs): a lost peer raises the error flag instead of hanging
+// the GPU.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ngp {
+namespace dp {
+
+constexpr uint32_t kMaxWorld = NGP_DP_MAX_WORLD;
+constexpr uint32_t kMaxBlocks = NGP_DP_MAX_BLOCKS;
+constexpr uint64_t kSpinTimeoutNs = 20ull * 1000 * 1000 * 1000;  // 20 s
+
+struct Args {
+    float* p;          // parameters (flat fp32), this rank's replica
+    float* g;          // gradient bucket (flat fp32), scaled by state[0]
+    float* m;          // exp_avg      (only this rank's slice is maintained when world > 1)
+    float* v;          // exp_avg_sq
+    __half* h;         // optional fp16 shadow of p
+    uint64_t n;        // elements; a multiple of 4
+    uint32_t n_seg;
+    uint64_t seg_end[NGP_ADAM_MAX_SEGMENTS];
+    float seg_lr[NGP_ADAM_MAX_SEGMENTS];
+    float beta1, beta2, eps;
+    float grad_div;
+    float lr_decay_ln, lr_decay_steps;
+    float growth, backoff;
+    uint32_t growth_interval;
+    float* state;          // [0] scale [1] growth tracker [2] steps [3] found_inf [4] skipped [5] error flag
+    uint32_t* sync;        // [0] blocks_done [1] epoch
+    // data parallel
+    uint32_t rank, world;
+    float* peer_g[kMaxWorld];
+    float* peer_p[kMaxWorld];
+    __half* peer_h[kMaxWorld];
+    uint32_t* peer_flags[kMaxWorld];  // each: [3][kMaxBlocks][kMaxWorld] uint32, zero-initialised
+};
+
+NGP_DEVINL void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+NGP_DEVINL uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+NGP_DEVINL float4 ld_relaxed_sys_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+NGP_DEVINL uint64_t now_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+NGP_DEVINL uint32_t* flag_slot(uint32_t* pad, uint32_t barrier, uint32_t block, uint32_t src) {
+    return pad + ((size_t)barrier * kMaxBlocks + block) * kMaxWorld + src;
+}
+
+// Block-level barrier across ranks: block b of every rank meets block b of every other rank.  `payload` (0/1) is OR-ed
+// over the ranks and returned (to thread 0..world-1; callers combine with __syncthreads_or).
+NGP_DEVINL uint32_t xrank_barrier(const Args& a, uint32_t barrier, uint32_t block, uint32_t epoch, uint32_t payload) {
+    uint32_t got = 0;
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+        const uint32_t q = threadIdx.x;
+        __threadfence_system();
+        st_release_sys(flag_slot(a.peer_flags[q], barrier, block, a.rank), epoch * 2 + payload);
+        const uint32_t* mine = flag_slot(a.peer_flags[a.rank], barrier, block, q);
+        const uint64_t t0 = now_ns();
+        for (;;) {
+            const uint32_t f = ld_acquire_sys(mine);
+            if ((int32_t)((f >> 1) - epoch) >= 0) { got = f & 1u; break; }
+            if (now_ns() - t0 > kSpinTimeoutNs) { a.state[5] = 1.f; break; }
+        }
+    }
+    return __syncthreads_or((int)got) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(512) adam_step_fused_kernel(const Args a) {
+    cg::grid_group grid = cg::this_grid();
+    const float scale = a.state[0];
+    const float step0 = a.state[2];
+    const uint32_t epoch = a.sync[1] + 1;
+    const uint64_t n4 = a.n / 4;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (uint64_t)gridDim.x * blockDim.x;
+
+    // this rank's slice of the flat buffers, in float4 units
+    uint64_t lo = 0, hi = n4;
+    if (a.world > 1) {
+        const uint64_t per = (n4 + a.world - 1) / a.world;
+        lo = per * a.rank < n4 ? per * a.rank : n4;
+        hi = lo + per < n4 ? lo + per : n4;
+        xrank_barrier(a, 0, blockIdx.x, epoch, 0);   // B0
+    }
+
+    // ---- P1: (reduce the slice across ranks,) look for inf / nan -----------------------------------------------------
+    bool bad = false;
+    for (uint64_t i = lo + tid; i < hi; i += nthreads) {
+        float4 s;
+        if (a.world > 1) {
+            s = ld_relaxed_sys_f4(a.peer_g[0] + i * 4);
+            for (uint32_t q = 1; q < a.world; ++q) {
+                const float4 t = ld_relaxed_sys_f4(a.peer_g[q] + i * 4);
+                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+            }
+            *reinterpret_cast<float4*>(a.g + i * 4) = s;  // nobody else reads slice `rank` of this rank's bucket
+        } else {
+            s = *reinterpret_cast<const float4*>(a.g + i * 4);
+        }
+        // x - x is 0 for finite x and NaN for +-inf / NaN
+        bad = bad || (((s.x - s.x) + (s.y - s.y) + (s.z - s.z) + (s.w - s.w)) != 0.f);
+    }
+    if (__syncthreads_or((int)bad) && threadIdx.x == 0) a.state[3] = 1.0f;
+    __threadfence();
+    grid.sync();
+    if (a.world > 1) {   // B1: OR the flags of all ranks (block 0 talks to the peers, the grid barrier spreads the result)
+        if (blockIdx.x == 0) {
+            const uint32_t any = xrank_barrier(a, 1, 0, epoch, *(volatile float*)(a.state + 3) != 0.f ? 1u : 0u);
+            if (threadIdx.x == 0 && any) a.state[3] = 1.0f;
+            __threadfence();
+        }
+        grid.sync();
+    }
+    const bool skip = *(volatile float*)(a.state + 3) != 0.f;
+
+    // ---- P2: Adam on the slice; new parameters to every replica; zero the whole local bucket --------------------------
+    const float t = step0 + 1.f;
+    // same expressions as torch's fused Adam (bias corrections evaluated in double, then narrowed); once per block
+    __shared__ float s_coef[3];
+    if (threadIdx.x == 0) {
+        s_coef[0] = (float)(1.0 - pow((double)a.beta1, (double)t));
+        s_coef[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)t));
+        s_coef[2] = a.lr_decay_ln != 0.f ? expf(a.lr_decay_ln * fminf(step0, a.lr_decay_steps)) : 1.f;
+    }
+    __syncthreads();
+    const float bc1 = s_coef[0], bc2_sqrt = s_coef[1], lr_mult = s_coef[2];
+    const float inv = 1.0f / (scale * a.grad_div);
+    const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
+    if (!skip) {
+        for (uint64_t i = lo + tid; i < hi; i += nthreads) {
+            const uint64_t e0 = i * 4;
+            const float4 g4 = *reinterpret_cast<const float4*>(a.g + e0);
+            const float4 p4 = *reinterpret_cast<const float4*>(a.p + e0);
+            const float4 m4 = *reinterpret_cast<const float4*>(a.m + e0);
+            const float4 v4 = *reinterpret_cast<const float4*>(a.v + e0);
+            float g[4] = {g4.x, g4.y, g4.z, g4.w}, p[4] = {p4.x, p4.y, p4.z, p4.w};
+            float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) {
+                float lr = a.seg_lr[0];
+#pragma unroll
+                for (uint32_t s = 1; s < NGP_ADAM_MAX_SEGMENTS; ++s)
+                    if (s < a.n_seg && e0 + j >= a.seg_end[s - 1]) lr = a.seg_lr[s];
+                const float step_size = lr * lr_mult / bc1;
+                const float gr = g[j] * inv;
+                m[j] = fmaf(w1, gr - m[j], m[j]);                 // exp_avg.lerp_(grad, 1 - beta1)
+                v[j] = a.beta2 * v[j] + w2 * gr * gr;
+                const float denom = sqrtf(v[j]) / bc2_sqrt + a.eps;
+                p[j] -= step_size * m[j] / denom;
+            }
+            *reinterpret_cast<float4*>(a.m + e0) = make_float4(m[0], m[1], m[2], m[3]);
+            *reinterpret_cast<float4*>(a.v + e0) = make_float4(v[0], v[1], v[2], v[3]);
+            const float4 pn = make_float4(p[0], p[1], p[2], p[3]);
+            __half2 h0 = __floats2half2_rn(p[0], p[1]), h1 = __floats2half2_rn(p[2], p[3]);
+            uint2 raw;
+            raw.x = *reinterpret_cast<uint32_t*>(&h0); raw.y = *reinterpret_cast<uint32_t*>(&h1);
+            if (a.world > 1) {
+                for (uint32_t q = 0; q < a.world; ++q) {
+                    const uint32_t dst = (a.rank + q) % a.world;   // start with the own replica, spread the link load
+                    *reinterpret_cast<float4*>(a.peer_p[dst] + e0) = pn;
+                    if (a.h) *reinterpret_cast<uint2*>(a.peer_h[dst] + e0) = raw;
+                }
+            } else {
+                *reinterpret_cast<float4*>(a.p + e0) = pn;
+                if (a.h) *reinterpret_cast<uint2*>(a.h + e0) = raw;
+            }
+            *reinterpret_cast<float4*>(a.g + e0) = make_float4(0.f, 0.f, 0.f, 0.f);  // by the thread that consumed it
+        }
+    } else {
+        for (uint64_t i = lo + tid; i < hi; i += nthreads) *reinterpret_cast<float4*>(a.g + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // the rest of the bucket: every rank has finished reading it (B1 was a full barrier), clear it for the next backward.
+    // (The own slice was cleared above by the threads that read it - a different thread mapping here would race them.)
+    for (uint64_t i = tid; i < n4; i += nthreads)
+        if (i < lo || i >= hi) *reinterpret_cast<float4*>(a.g + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (a.world > 1) xrank_barrier(a, 2, blockIdx.x, epoch, 0);   // B2
+
+    // ---- last block: GradScaler.update() + step count + epoch ---------------------------------------------------------
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&a.sync[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        float tracker = a.state[1];
+        float new_scale = scale;
+        if (skip) {
+            new_scale = scale * a.backoff;
+            tracker = 0.f;
+            a.state[4] += 1.f;
+        } else {
+            a.state[2] = t;
+            tracker += 1.f;
+            if (tracker >= (float)a.growth_interval) {
+                const float grown = scale * a.growth;
+                if (isfinite(grown)) new_scale = grown;
+                tracker = 0.f;
+            }
+        }
+        a.state[0] = new_scale;
+        a.state[1] = tracker;
+        a.state[3] = 0.f;
+        a.sync[0] = 0u;
+        a.sync[1] = epoch;
+    }
+}
+
+}  // namespace dp
+}  // namespace ngp
+
+using namespace ngp;
+
+extern "C" uint64_t ngp_dp_flags_bytes(void) { return (uint64_t)3 * dp::kMaxBlocks * dp::kMaxWorld * sizeof(uint32_t); }
+
+extern "C" int ngp_enable_peer_access(int peer_device) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (peer_device == dev) return NGP_OK;
+    int can = 0;
+    e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+    if (e != cudaSuccess) return (int)e;
+    if (!can) return NGP_ERR_UNSUPPORTED;
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return NGP_OK; }
+    return e == cudaSuccess ? NGP_OK : (int)e;
+}
+
+extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow,
+                                   uint64_t n, uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1,
+                                   float beta2, float eps, float grad_div, float lr_decay_ln, float lr_decay_steps,
+                                   float growth_factor, float backoff_factor, uint32_t growth_interval, float* state,
+                                   uint32_t* sync, uint32_t rank, uint32_t world, const uint64_t* peer_grads,
+                                   const uint64_t* peer_params, const uint64_t* peer_half, const uint64_t* peer_flags,
+                                   void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !state || !sync || !seg_end || !seg_lr) return NGP_ERR_BAD_ARG;
+    if (n_segments == 0 || n_segments > NGP_ADAM_MAX_SEGMENTS || seg_end[n_segments - 1] != n) return NGP_ERR_BAD_ARG;
+    if (n == 0 || (n & 3) != 0) return NGP_ERR_BAD_ARG;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                         reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
+    if ((al & 15) != 0 || (reinterpret_cast<uintptr_t>(half_shadow) & 7) != 0) return NGP_ERR_BAD_ARG;
+    if (world == 0 || world > dp::kMaxWorld || rank >= world) return NGP_ERR_BAD_ARG;
+    if (world > 1 && (!peer_grads || !peer_params || !peer_flags || (half_shadow && !peer_half))) return NGP_ERR_BAD_ARG;
+    dp::Args a;
+    a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.h = static_cast<__half*>(half_shadow); a.n = n;
+    a.n_seg = n_segments;
+    for (uint32_t s = 0; s < NGP_ADAM_MAX_SEGMENTS; ++s) {
+        a.seg_end[s] = s < n_segments ? seg_end[s] : n;
+        a.seg_lr[s] = s < n_segments ? seg_lr[s] : 0.f;
+    }
+    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_div = grad_div > 0.f ? grad_div : 1.f;
+    a.lr_decay_ln = lr_decay_ln; a.lr_decay_steps = lr_decay_steps;
+    a.growth = growth_factor; a.backoff = backoff_factor; a.growth_interval = growth_interval;
+    a.state = state; a.sync = sync; a.rank = rank; a.world = world;
+    for (uint32_t q = 0; q < dp::kMaxWorld; ++q) {
+        const bool on = world > 1 && q < world;
+        a.peer_g[q] = on ? reinterpret_cast<float*>(peer_grads[q]) : nullptr;
+        a.peer_p[q] = on ? reinterpret_cast<float*>(peer_params[q]) : nullptr;
+        a.peer_h[q] = on && peer_half ? reinterpret_cast<__half*>(peer_half[q]) : nullptr;
+        a.peer_flags[q] = on ? reinterpret_cast<uint32_t*>(peer_flags[q]) : nullptr;
+        if (on && (!a.peer_g[q] || !a.peer_p[q] || !a.peer_flags[q])) return NGP_ERR_BAD_ARG;
+    }
+    int blocks = num_sms();
+    if (blocks > (int)dp::kMaxBlocks) blocks = (int)dp::kMaxBlocks;
+    void* kargs[] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dp::adam_step_fused_kernel), dim3(blocks), dim3(512),
+                                                kargs, 0, as_stream(stream));
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return launch_status();
+}

@@ -262,13 +262,8 @@ NGP_DEVINL uint32_t walk_ray_warp(const MarchParams& p, const Ray& r, float t0, 
 // -------------------------------------------------------------------------------------------------
 // utils
 // -------------------------------------------------------------------------------------------------
-__global__ void near_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                const float* __restrict__ aabb, uint32_t N, float min_near, float* nears,
-                                float* fars) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const Ray r = load_ray(rays_o, rays_d, n);
-    // slab test, axis by axis (raymarching.cu:113-141)
+// slab test, axis by axis (raymarching.cu:113-141); a miss reports FLT_MAX for both
+NGP_DEVINL void near_far_of(const Ray& r, const float* __restrict__ aabb, float min_near, float& near, float& far) {
     float lo = (aabb[0] - r.ox) * r.rdx, hi = (aabb[3] - r.ox) * r.rdx;
     if (lo > hi) { float s = lo; lo = hi; hi = s; }
     float lo_y = (aabb[1] - r.oy) * r.rdy, hi_y = (aabb[4] - r.oy) * r.rdy;
@@ -286,8 +281,38 @@ __global__ void near_far_kernel(const float* __restrict__ rays_o, const float* _
             if (lo < min_near) lo = min_near;
         }
     }
-    nears[n] = miss ? FLT_MAX : lo;
-    fars[n] = miss ? FLT_MAX : hi;
+    near = miss ? FLT_MAX : lo;
+    far = miss ? FLT_MAX : hi;
+}
+
+__global__ void near_far_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                const float* __restrict__ aabb, uint32_t N, float min_near, float* nears,
+                                float* fars) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const Ray r = load_ray(rays_o, rays_d, n);
+    float lo, hi;
+    near_far_of(r, aabb, min_near, lo, hi);
+    nears[n] = lo;
+    fars[n] = hi;
+}
+
+// First kernel of the hand-scheduled train step (ngp_train_prologue): near/far of every ray plus the zero-fill of the
+// step's device-side scalars (sample counter pair, loss accumulator), so no separate fill launches are needed.
+__global__ void train_prologue_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                      const float* __restrict__ aabb, uint32_t N, float min_near, float* nears,
+                                      float* fars, int* counter, float* loss) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0) {
+        if (counter) { counter[0] = 0; counter[1] = 0; }
+        if (loss) *loss = 0.f;
+    }
+    if (n >= N) return;
+    const Ray r = load_ray(rays_o, rays_d, n);
+    float lo, hi;
+    near_far_of(r, aabb, min_near, lo, hi);
+    nears[n] = lo;
+    fars[n] = hi;
 }
 
 __global__ void sph_from_ray_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
@@ -446,38 +471,60 @@ __global__ void __launch_bounds__(256) march_compact_kernel(const float* __restr
 // Single-CTA exclusive scan of the per-ray counts, in ray order.  Writes the (id, offset, count)
 // rows (row n <-> ray n; offsets start at the incoming counter[0], as the reference's atomicAdd
 // would) and bumps the two counters the way the reference's atomics do in aggregate.
+// One pass: thread t owns the `per` consecutive rays [t * per, (t + 1) * per) - local sum, one block-wide scan of the
+// 1024 thread sums, then the rows - so the cost is two barriers whatever N is (it used to be four per 1024 rays).
 __global__ void __launch_bounds__(1024) march_scan_kernel(const int* __restrict__ counts, uint32_t N, int* __restrict__ rays,
                                                           int* __restrict__ counter) {
     __shared__ int s_warp[32];
-    __shared__ int s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = counter[0];
-    __syncthreads();
-    for (uint32_t base = 0; base < N; base += blockDim.x) {
-        const uint32_t n = base + threadIdx.x;
-        const int c = n < N ? counts[n] : 0;
-        int incl = warp_incl_scan_i(c, lane);
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = s_warp[lane];
-            w = warp_incl_scan_i(w, lane);
-            s_warp[lane] = w;
-        }
-        __syncthreads();
-        const int carry = s_carry;
-        const int offset = carry + (warp ? s_warp[warp - 1] : 0) + incl - c;
-        if (n < N) {
-            rays[(size_t)n * 3 + 0] = (int)n;
-            rays[(size_t)n * 3 + 1] = offset;
-            rays[(size_t)n * 3 + 2] = c;
-        }
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) s_carry = carry + s_warp[31];
-        __syncthreads();
+    const uint32_t per = ((N + blockDim.x - 1) / blockDim.x + 3u) & ~3u;  // multiple of 4: 16-byte loads, 48-byte row groups
+    const uint32_t first = threadIdx.x * per;
+    // N % 4 == 0: every group of 4 rays is either fully inside or fully outside [0, N)
+    const bool vec = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(counts) | reinterpret_cast<uintptr_t>(rays)) & 15) == 0;
+    int sum = 0;
+    if (vec) {
+        for (uint32_t i = 0; i < per; i += 4)
+            if (first + i < N) {
+                const int4 c = __ldg(reinterpret_cast<const int4*>(counts + first + i));
+                sum += c.x + c.y + c.z + c.w;
+            }
+    } else {
+        for (uint32_t i = 0; i < per; ++i)
+            if (first + i < N) sum += __ldg(counts + first + i);
     }
-    if (threadIdx.x == 0) {
-        counter[0] = s_carry;
+    int incl = warp_incl_scan_i(sum, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) s_warp[lane] = warp_incl_scan_i(s_warp[lane], lane);
+    __syncthreads();
+    const int carry = counter[0];  // read by every thread BEFORE thread 1023 overwrites it (barrier below)
+    int offset = carry + (warp ? s_warp[warp - 1] : 0) + incl - sum;
+    if (vec) {
+        for (uint32_t i = 0; i < per; i += 4)
+            if (first + i < N) {
+                const uint32_t n = first + i;
+                const int4 c = __ldg(reinterpret_cast<const int4*>(counts + n));
+                const int o0 = offset, o1 = o0 + c.x, o2 = o1 + c.y, o3 = o2 + c.z;
+                int4* row = reinterpret_cast<int4*>(rays + (size_t)n * 3);  // 4 rows = 48 bytes, 16-byte aligned
+                row[0] = make_int4((int)n, o0, c.x, (int)n + 1);
+                row[1] = make_int4(o1, c.y, (int)n + 2, o2);
+                row[2] = make_int4(c.z, (int)n + 3, o3, c.w);
+                offset = o3 + c.w;
+            }
+    } else {
+        for (uint32_t i = 0; i < per; ++i)
+            if (first + i < N) {
+                const uint32_t n = first + i;
+                const int c = __ldg(counts + n);
+                rays[(size_t)n * 3 + 0] = (int)n;
+                rays[(size_t)n * 3 + 1] = offset;
+                rays[(size_t)n * 3 + 2] = c;
+                offset += c;
+            }
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) {
+        counter[0] = carry + s_warp[31];
         counter[1] += (int)N;
     }
 }
@@ -668,6 +715,187 @@ __global__ void __launch_bounds__(256) composite_train_bwd_kernel(
         r_carry = __shfl_sync(0xffffffffu, r_run, 31);
         g_carry = __shfl_sync(0xffffffffu, g_run, 31);
         b_carry = __shfl_sync(0xffffffffu, b_run, 31);
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Hand-scheduled train step: everything between "the field has been evaluated on the marched samples" and "the
+// gradients of sigma / rgb are known" for ONE ray, in one warp, in one launch (ngp_train_ray_loss):
+//   composite forward (raymarching.cu:501-588)  ->  background blend (nerf/renderer.py:541-545)
+//   -> loss gradients at the ray: the guidance gradient G of the blended pixel (nerf/sd.py:115, applied unscaled) and
+//      the opacity-entropy regulariser times the GradScaler scale (nerf/utils.py:389-394,708)
+//   -> composite backward (raymarching.cu:602-693) over the same samples, still hot in L1/L2.
+// The reference spends ~45 launches on this part of a step (two extension kernels + eager elementwise chains either way).
+// Arithmetic of both composite passes is the code of the two kernels above, so results are identical to running them
+// back to back with the same upstream gradients.
+// -------------------------------------------------------------------------------------------------
+struct RayLossArgs {
+    const float *sigmas, *rgbs, *deltas;
+    const int* rays;
+    uint32_t M, N;
+    float T_thresh;
+    const __half* bg;      // [N,3] background colour per ray (bg_net output) or nullptr: the constant bg_const
+    float bg_const;
+    const float* G;        // gradient wrt the blended image: [B,3,hw] (NCHW, hw = H*W pixels per view) or [N,3] if hw == 0
+    uint32_t hw;
+    float lambda;          // entropy weight; the mean runs over the N rays of this launch
+    const float* scale;    // device scalar multiplying the entropy term's gradient (GradScaler scale) or nullptr (1)
+    float *weights_sum, *depth, *image;   // [N], [N], [N,3]: what composite_rays_train returns (image BEFORE the blend)
+    float* d_bg;           // [N,3] gradient wrt the background colour, or nullptr
+    float *grad_sigmas, *grad_rgbs;       // [M], [M,3]
+    float* loss;           // += lambda * mean entropy (zeroed by the prologue)
+    // optional device-side bookkeeping of run_cuda / the bench (done by one thread): samples += counter[0];
+    // step_counter[local_step % 16] = counter; ++local_step
+    const int* counter;
+    long long* samples_total;
+    int* step_counter;
+    int* local_step;
+};
+
+constexpr float kAlphaLoR = 1e-5f, kAlphaHiR = 1.f - 1e-5f;
+
+__global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a) {
+    __shared__ float s_loss[8];
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float entropy = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.counter) {
+        if (a.samples_total) *a.samples_total += (long long)a.counter[0];
+        if (a.step_counter && a.local_step) {
+            const int row = (*a.local_step) & 15;
+            a.step_counter[row * 2] = a.counter[0];
+            a.step_counter[row * 2 + 1] = a.counter[1];
+            *a.local_step += 1;
+        }
+    }
+    if (n < a.N) {
+        const RaySpan s = load_span(a.rays, n, a.M);
+        // ---- pass 1: composite forward ------------------------------------------------------------------------
+        float r = 0, g = 0, b = 0, ws = 0, d = 0;
+        if (s.live) {
+            float T_carry = 1.0f, t_carry = 0.f;
+            for (uint32_t base = 0; base < s.count; base += 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < s.count;
+                float om = 1.0f, d1 = 0.f, alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+                if (valid) {
+                    const size_t m = (size_t)s.offset + i;
+                    const float sigma = a.sigmas[m];
+                    const float2 dl = *(reinterpret_cast<const float2*>(a.deltas) + m);
+                    alpha = 1.0f - __expf(-sigma * dl.x);
+                    om = 1.0f - alpha;
+                    d1 = dl.y;
+                    cr = a.rgbs[m * 3]; cg = a.rgbs[m * 3 + 1]; cb = a.rgbs[m * 3 + 2];
+                }
+                float T_before, t_incl;
+                serial_prefix(om, d1, lane, T_carry, t_carry, T_before, t_incl);
+                const float T_after = T_before * om;
+                const unsigned stop_mask = __ballot_sync(0xffffffffu, valid && (T_after < a.T_thresh));
+                const int stop_lane = stop_mask ? (__ffs(stop_mask) - 1) : 31;
+                if (valid && lane <= stop_lane) {
+                    const float w = alpha * T_before;
+                    r += w * cr; g += w * cg; b += w * cb;
+                    d += w * t_incl;
+                    ws += w;
+                }
+                if (stop_mask) break;
+                T_carry = __shfl_sync(0xffffffffu, T_after, 31);
+                t_carry = __shfl_sync(0xffffffffu, t_incl, 31);
+            }
+            r = warp_sum(r); g = warp_sum(g); b = warp_sum(b); ws = warp_sum(ws); d = warp_sum(d);
+        }
+        // ---- the ray's loss terms (every lane computes the same values) -----------------------------------------
+        const uint32_t id = s.id;
+        float bgc[3] = {a.bg_const, a.bg_const, a.bg_const};
+        if (a.bg) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bgc[c] = __half2float(a.bg[(size_t)id * 3 + c]);
+        }
+        float gi[3];
+        if (a.hw) {
+            const uint32_t view = id / a.hw, pix = id % a.hw;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gi[c] = a.G[((size_t)view * 3 + c) * a.hw + pix];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) gi[c] = a.G[(size_t)id * 3 + c];
+        }
+        // blend backward: d_ws = -sum_c g_c bg_c, d_bg = (1 - ws) g  (train_step.cu blend_backward_kernel)
+        float gws = -(gi[0] * bgc[0] + gi[1] * bgc[1] + gi[2] * bgc[2]);
+        // entropy of the clamped opacity and its gradient (train_step.cu entropy_*_kernel)
+        const float al = fminf(fmaxf(ws, kAlphaLoR), kAlphaHiR);
+        entropy = -al * log2f(al) - (1.f - al) * log2f(1.f - al);
+        if (ws >= kAlphaLoR && ws <= kAlphaHiR) {
+            const float up = a.scale ? *a.scale : 1.f;
+            gws += up * (a.lambda / (float)a.N) * (log2f(1.f - ws) - log2f(ws));
+        }
+        if (lane == 0) {
+            a.weights_sum[id] = ws;
+            a.depth[id] = d;
+            a.image[(size_t)id * 3] = r; a.image[(size_t)id * 3 + 1] = g; a.image[(size_t)id * 3 + 2] = b;
+            if (a.d_bg) {
+                const float one_minus = 1.f - ws;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) a.d_bg[(size_t)id * 3 + c] = one_minus * gi[c];
+            }
+        }
+        // ---- pass 2: composite backward --------------------------------------------------------------------------
+        if (s.live) {
+            const float r_final = r, g_final = g, b_final = b, ws_final = ws;
+            float T_carry = 1.0f, r_carry = 0.f, g_carry = 0.f, b_carry = 0.f;
+            bool stopped = false;
+            for (uint32_t base = 0; base < s.count; base += 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < s.count;
+                const size_t m = (size_t)s.offset + i;
+                if (stopped) {  // warp-uniform: rows behind the early-termination point get zero gradients
+                    if (valid) {
+                        a.grad_sigmas[m] = 0.f;
+                        a.grad_rgbs[m * 3] = 0.f; a.grad_rgbs[m * 3 + 1] = 0.f; a.grad_rgbs[m * 3 + 2] = 0.f;
+                    }
+                    continue;
+                }
+                float om = 1.0f, alpha = 0.f, d0 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+                if (valid) {
+                    const float sigma = a.sigmas[m];
+                    d0 = a.deltas[m * 2];
+                    alpha = 1.0f - __expf(-sigma * d0);
+                    om = 1.0f - alpha;
+                    cr = a.rgbs[m * 3]; cg = a.rgbs[m * 3 + 1]; cb = a.rgbs[m * 3 + 2];
+                }
+                float T_before, unused_t;
+                serial_prefix(om, 0.f, lane, T_carry, 0.f, T_before, unused_t);
+                const float T_after = T_before * om;
+                const unsigned stop_mask = __ballot_sync(0xffffffffu, valid && (T_after < a.T_thresh));
+                const int stop_lane = stop_mask ? (__ffs(stop_mask) - 1) : 31;
+                const bool active = valid && lane <= stop_lane;
+                const float w = active ? alpha * T_before : 0.f;
+                const float r_run = r_carry + warp_incl_scan_f(w * cr, lane);
+                const float g_run = g_carry + warp_incl_scan_f(w * cg, lane);
+                const float b_run = b_carry + warp_incl_scan_f(w * cb, lane);
+                if (active) {
+                    a.grad_rgbs[m * 3] = gi[0] * w; a.grad_rgbs[m * 3 + 1] = gi[1] * w; a.grad_rgbs[m * 3 + 2] = gi[2] * w;
+                    a.grad_sigmas[m] = d0 * (gi[0] * (T_after * cr - (r_final - r_run)) + gi[1] * (T_after * cg - (g_final - g_run)) +
+                                             gi[2] * (T_after * cb - (b_final - b_run)) + gws * (1 - ws_final));
+                } else if (valid) {
+                    a.grad_sigmas[m] = 0.f;
+                    a.grad_rgbs[m * 3] = 0.f; a.grad_rgbs[m * 3 + 1] = 0.f; a.grad_rgbs[m * 3 + 2] = 0.f;
+                }
+                if (stop_mask) { stopped = true; continue; }
+                T_carry = __shfl_sync(0xffffffffu, T_after, 31);
+                r_carry = __shfl_sync(0xffffffffu, r_run, 31);
+                g_carry = __shfl_sync(0xffffffffu, g_run, 31);
+                b_carry = __shfl_sync(0xffffffffu, b_run, 31);
+            }
+        }
+    }
+    // loss: one atomic per block
+    if (lane == 0) s_loss[warp] = entropy;
+    __syncthreads();
+    if (threadIdx.x == 0 && a.loss) {
+        float v = 0.f;
+        for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) v += s_loss[w];
+        atomicAdd(a.loss, v * (a.lambda / (float)a.N));
     }
 }
 
@@ -896,6 +1124,34 @@ extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, 
     march::composite_train_bwd_kernel<true><<<cdiv((uint64_t)N * 32, 256), 256, 0, as_stream(stream)>>>(
         grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image, M, N, T_thresh, grad_sigmas,
         grad_rgbs);
+    return launch_status();
+}
+
+extern "C" int ngp_train_prologue(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
+                                  float* nears, float* fars, int* counter, float* loss, void* stream) {
+    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NGP_ERR_BAD_ARG;
+    march::train_prologue_kernel<<<N ? cdiv(N, 128) : 1, 128, 0, as_stream(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears,
+                                                                                   fars, counter, loss);
+    return launch_status();
+}
+
+extern "C" int ngp_train_ray_loss(const float* sigmas, const float* rgbs, const float* deltas, const int* rays, uint32_t M,
+                                  uint32_t N, float T_thresh, const void* bg_half, float bg_const, const float* grad_pred,
+                                  uint32_t pixels_per_view, float lambda_entropy, const float* scale, float* weights_sum,
+                                  float* depth, float* image, float* grad_bg, float* grad_sigmas, float* grad_rgbs,
+                                  float* loss, const int* counter, long long* samples_total, int* step_counter,
+                                  int* local_step, void* stream) {
+    if (!sigmas || !rgbs || !deltas || !rays || !grad_pred || !weights_sum || !depth || !image || !grad_sigmas || !grad_rgbs)
+        return NGP_ERR_BAD_ARG;
+    if (pixels_per_view && N % pixels_per_view != 0) return NGP_ERR_BAD_ARG;
+    if (N == 0) return NGP_OK;
+    march::RayLossArgs a;
+    a.sigmas = sigmas; a.rgbs = rgbs; a.deltas = deltas; a.rays = rays; a.M = M; a.N = N; a.T_thresh = T_thresh;
+    a.bg = static_cast<const __half*>(bg_half); a.bg_const = bg_const; a.G = grad_pred; a.hw = pixels_per_view;
+    a.lambda = lambda_entropy; a.scale = scale; a.weights_sum = weights_sum; a.depth = depth; a.image = image;
+    a.d_bg = grad_bg; a.grad_sigmas = grad_sigmas; a.grad_rgbs = grad_rgbs; a.loss = loss; a.counter = counter;
+    a.samples_total = samples_total; a.step_counter = step_counter; a.local_step = local_step;
+    march::train_ray_loss_kernel<<<cdiv((uint64_t)N * 32, 256), 256, 0, as_stream(stream)>>>(a);
     return launch_status();
 }
 

@@ -25,9 +25,12 @@ _ALIGN = 8  # elements: every tensor starts 16-byte aligned in the fp16 shadow (
 
 class FusedAdamScaler:
     def __init__(self, param_groups, betas=(0.9, 0.99), eps=1e-15, init_scale=65536.0, growth_factor=2.0,
-                 backoff_factor=0.5, growth_interval=2000, lr_decay=None, grad_div=1.0):
+                 backoff_factor=0.5, growth_interval=2000, lr_decay=None, grad_div=1.0, peer_memory=None):
         """param_groups: [{'params': iterable, 'lr': float}, ...] as NeRFNetwork.get_params returns.
-        lr_decay: None or (factor, iters) for lr * factor ** min(step / iters, 1)."""
+        lr_decay: None or (factor, iters) for lr * factor ** min(step / iters, 1).
+        peer_memory: a parallel.PeerMemory (data parallel): the gradient bucket, the parameters and their fp16 shadow
+        are then placed in memory that every rank of the group can address, and step_fused() all-reduces the
+        gradients itself over NVLink (csrc/dp_step.cu)."""
         groups = []
         for g in param_groups:
             ps = [p for p in g["params"] if p.requires_grad]
@@ -54,8 +57,27 @@ class FusedAdamScaler:
         self.seg_lr = (ctypes.c_float * len(groups))(*self.base_lrs)
         self.n_seg = len(groups)
         f = lambda dt=torch.float32: torch.zeros(off, device=device, dtype=dt)  # noqa: E731
-        self.flat_params, self.flat_grads, self.exp_avg, self.exp_avg_sq = f(), f(), f(), f()
-        self.flat_half = f(torch.half)
+        self.exp_avg, self.exp_avg_sq = f(), f()
+        self.peer = peer_memory
+        self.peer_ptrs = None
+        if peer_memory is None:
+            self.flat_params, self.flat_grads, self.flat_half = f(), f(), f(torch.half)
+        else:
+            # one peer-addressable allocation: [grads f32 | params f32 | shadow f16 | barrier flags], 256-byte aligned parts
+            lib = _cabi.load()
+            al = lambda b: (b + 255) // 256 * 256  # noqa: E731
+            o_g, o_p, o_h = 0, al(4 * off), al(4 * off) * 2
+            o_f = o_h + al(2 * off)
+            total = o_f + int(lib.ngp_dp_flags_bytes())
+            raw, bases = peer_memory.alloc(total)
+            raw.zero_()
+            self._peer_raw = raw
+            self.flat_grads = raw[o_g:o_g + 4 * off].view(torch.float32)
+            self.flat_params = raw[o_p:o_p + 4 * off].view(torch.float32)
+            self.flat_half = raw[o_h:o_h + 2 * off].view(torch.half)
+            mk = lambda o: (ctypes.c_uint64 * len(bases))(*[b + o for b in bases])  # noqa: E731
+            self.peer_ptrs = (mk(o_g), mk(o_p), mk(o_h), mk(o_f))
+            peer_memory.barrier()  # every rank has zeroed its flags before anybody signals
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):
                 view = self.flat_params[o:o + p.numel()].view_as(p)
@@ -69,9 +91,10 @@ class FusedAdamScaler:
         self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
         self.grad_div = float(grad_div)
         self.set_lr_decay(lr_decay)
-        # [scale, growth tracker, steps, found_inf, skipped]
-        self.state = torch.tensor([init_scale, 0.0, 0.0, 0.0, 0.0], device=device, dtype=torch.float32)
+        # [scale, growth tracker, steps, found_inf, skipped, cross-GPU wait timed out, -, -]
+        self.state = torch.tensor([init_scale, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0], device=device, dtype=torch.float32)
         self._blocks_done = torch.zeros(1, device=device, dtype=torch.int32)
+        self._sync = torch.zeros(2, device=device, dtype=torch.int32)  # step_fused: [block election, barrier epoch]
 
     # -- layout helpers ------------------------------------------------------------------------------------------
     def attach_grads(self):
@@ -118,6 +141,43 @@ class FusedAdamScaler:
                    float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,
                    self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
                    int(bool(zero_grads)), _cabi.ptr(self.state), _cabi.ptr(self._blocks_done))
+
+    def step_fused(self):
+        """The same step as ONE cooperative launch (finite check -> grid barrier -> Adam ...), and - with peer
+        memory - the data-parallel gradient all-reduce fused in: reduce-scatter by P2P loads, Adam on this rank's
+        slice, new parameters written to every replica (csrc/dp_step.cu).  Always zero-fills the gradients."""
+        dev = self.device
+        if self.peer_ptrs is None:
+            rank, world, pg, pp, ph, pf = 0, 1, None, None, None, None
+        else:
+            rank, world = self.peer.rank, self.peer.world
+            pg, pp, ph, pf = self.peer_ptrs
+        _cabi.call("ngp_adam_step_fused", dev, _cabi.ptr(self.flat_params), _cabi.ptr(self.flat_grads), _cabi.ptr(self.exp_avg),
+                   _cabi.ptr(self.exp_avg_sq), _cabi.ptr(self.flat_half), self.numel, self.n_seg, self.seg_end, self.seg_lr,
+                   float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,
+                   self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
+                   _cabi.ptr(self.state), _cabi.ptr(self._sync), rank, world, pg, pp, ph, pf)
+
+    def grad_view(self, p):
+        """The slice of the flat gradient bucket that backs `p.grad` (same shape as p)."""
+        o = self.offsets[self._index(p)]
+        return self.flat_grads[o:o + p.numel()].view_as(p)
+
+    def half_view(self, p):
+        """The maintained fp16 shadow of parameter `p`."""
+        o = self.offsets[self._index(p)]
+        return self.flat_half[o:o + p.numel()].view_as(p)
+
+    def _index(self, p):
+        for i, q in enumerate(self.params):
+            if q is p:
+                return i
+        raise KeyError("parameter is not managed by this optimizer")
+
+    @property
+    def comm_error(self):
+        """True if a cross-GPU wait inside step_fused() ever timed out (one device->host read)."""
+        return bool(self.state[5].item() != 0)
 
     # -- checkpointing (nerf/utils.py:847-968 saves optimizer / scaler state next to the model) ----------------------
     def state_dict(self):

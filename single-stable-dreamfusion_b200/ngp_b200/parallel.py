@@ -6,6 +6,8 @@ The reference has no working multi-GPU path (a dormant DDP wrap, nerf/utils.py:2
 all-reduce exactly these parameters.  Parameter .grad tensors are views into the bucket, so autograd
 accumulates straight into it and no flatten / unflatten copies are needed.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -50,3 +52,60 @@ def shard_views(n_views, rank, world_size):
     count = base + (1 if rank < rem else 0)
     first = rank * base + min(rank, rem)
     return first, count
+
+
+def shard_rows(n_rows, rank, world_size):
+    """Row-interleaved split of an image: rank r renders rows r, r + world, ... of EVERY view, so each rank sees the
+    same mix of dense and empty image regions (camera views differ 4x in marched samples; whole-view sharding would
+    leave the step waiting for the rank that drew the densest view).  Returns the row indices of `rank`."""
+    return list(range(rank, n_rows, world_size))
+
+
+class PeerMemory:
+    """Device memory that every rank of the group can address directly (loads / stores / atomics over NVLink).
+
+    alloc(nbytes) -> (local uint8 tensor, [device address of that allocation on every rank, in rank order]).
+    The plumbing is PyTorch's symmetric memory (torch.distributed._symmetric_memory: cuMem allocations whose handles
+    are exchanged through the group's store and mapped into every rank); kernels only ever see raw addresses
+    (csrc/dp_step.cu).  Raises RuntimeError when the box cannot do it; callers then fall back to an NCCL all-reduce.
+    """
+
+    def __init__(self, device, group=None, backend=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerMemory needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.device = torch.device(device)
+        self.backend = backend or os.environ.get("NGP_PEER_BACKEND", "auto")
+        self._keep = []
+        self.used = None
+
+    def alloc(self, nbytes):
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        errors = []
+        for how in ["symm"]:
+            try:
+                out = self._alloc_symm(nbytes)
+                ok = torch.ones(1, device=self.device)
+            except Exception as e:  # noqa: BLE001 - any failure means "this back-end is not available here"
+                errors.append("%s: %r" % (how, e))
+                out, ok = None, torch.zeros(1, device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # all ranks must agree on the back-end
+            if ok.item() > 0:
+                self.used = how
+                return out
+        raise RuntimeError("no peer-addressable memory on this box: " + "; ".join(errors))
+
+    def _alloc_symm(self, nbytes):
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+        hdl = symm.rendezvous(t, self.group)
+        bases = [int(p) for p in hdl.buffer_ptrs]
+        if len(bases) != self.world or bases[self.rank] != t.data_ptr():
+            raise RuntimeError("unexpected symmetric-memory handle layout")
+        self._keep.append((t, hdl))
+        return t, bases
+
+    def barrier(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)

@@ -12,12 +12,13 @@ one ``cudaGraphLaunch``: the training render has static shapes and no host sync 
 optimizer is torch's fused capturable Adam driven by the scaler's device-side found_inf, and NCCL
 all-reduce is graph-capturable.  The occupancy refresh stays outside the graph (it runs every 16th step).
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _cabi
 from .optim import FusedAdamScaler
-from .parallel import FlatGradBucket
+from .parallel import FlatGradBucket, PeerMemory
 from .step_ops import entropy_loss as fused_entropy_loss
 
 
@@ -30,7 +31,11 @@ def entropy_loss(weights_sum, lam=1e-4):
 
 class TrainStep:
     def __init__(self, model, H, W, lr=1e-3, max_steps=1024, lambda_entropy=1e-4, update_interval=16, graph=False,
-                 world_size=1, fused_optimizer=True, lr_decay=None):
+                 world_size=1, fused_optimizer=True, lr_decay=None, manual=None, peer_allreduce=None):
+        """manual: run the step as the hand-scheduled kernel sequence of _body_manual (no autograd, 13 launches) instead
+        of the autograd graph of _body (~58 launches); None = whenever the model has the reference's field shape.
+        peer_allreduce: world_size > 1 only - fuse the gradient all-reduce into the optimizer kernel over NVLink peer
+        memory (csrc/dp_step.cu) instead of calling NCCL; None = if peer-addressable memory is available."""
         self.model, self.H, self.W = model, H, W
         self.max_steps, self.lam, self.update_interval = max_steps, lambda_entropy, update_interval
         self.world = world_size
@@ -39,11 +44,29 @@ class TrainStep:
         device = next(model.parameters()).device
         self.device = device
         self.fused_optimizer = fused_optimizer
+        self.manual = bool(fused_optimizer and self._manual_supported()) if manual is None else bool(manual)
+        if self.manual and not (fused_optimizer and self._manual_supported()):
+            raise RuntimeError("the hand-scheduled step needs the fused optimizer and the reference's field / bg-net shapes")
+        self.peer = None
+        self.peer_error = None
+        if fused_optimizer and self.manual and world_size > 1 and peer_allreduce is not False:
+            try:
+                self.peer = PeerMemory(device)
+            except RuntimeError as e:
+                self.peer_error = repr(e)
         if fused_optimizer:
             # one flat buffer each for params / grads / moments / fp16 shadow; unscale + Adam + scaler.update + shadow
-            # refresh + zero_grad in two launches (optim.py); the all-reduce mean is folded into the unscale
-            self.opt = FusedAdamScaler(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, grad_div=float(world_size),
-                                       lr_decay=lr_decay)
+            # refresh + zero_grad in one (step_fused) or two (step) launches (optim.py); the all-reduce mean is folded
+            # into the unscale
+            try:
+                self.opt = FusedAdamScaler(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, grad_div=float(world_size),
+                                           lr_decay=lr_decay, peer_memory=self.peer)
+            except RuntimeError as e:
+                if self.peer is None or peer_allreduce:
+                    raise
+                self.peer, self.peer_error = None, repr(e)  # no peer-addressable memory here: NCCL all-reduce instead
+                self.opt = FusedAdamScaler(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, grad_div=float(world_size),
+                                           lr_decay=lr_decay)
             self.scaler = self.opt
             self.bucket = None
             self.flat_grads = self.opt.flat_grads
@@ -55,12 +78,23 @@ class TrainStep:
         self.global_step = 0
         self.n_updates = 0
         self.samples = torch.zeros(1, dtype=torch.int64, device=device)  # running count of marched samples
+        self._local_step_dev = torch.zeros(1, dtype=torch.int32, device=device)  # device mirror of model.local_step
+        # background-net branch of the step (default priority: it fills the gaps of the main chain, measured faster than
+        # a high-priority branch that takes SM slots away from the field kernels)
+        self._side = torch.cuda.Stream(device=device) if self.manual else None
+        self.mirror_rng = False  # draw (and drop) the randn(3) run_cuda spends on light_d, to keep torch's RNG stream aligned
+        self._mws = None
+        self._ls_mirror = 0
+        self._static_packed = None
         self._graph = None
         self._graph_launches = 0
         self._static = None
         self.loss = None
 
     # -- one step's device work, shape-static when the fused training render is active ---------------------------
+    def _step_body(self, rays_o, rays_d, G):
+        return self._body_manual(rays_o, rays_d, G) if self.manual else self._body(rays_o, rays_d, G)
+
     def _body(self, rays_o, rays_d, G):
         model = self.model
         B = rays_o.shape[0]
@@ -93,17 +127,152 @@ class TrainStep:
             self.scaler.update()
         return loss
 
+    # -- the same step without autograd: a fixed sequence of our kernels ----------------------------------------------
+    def _manual_supported(self):
+        from . import field as _field
+        m = self.model
+        enc, net = getattr(m, "encoder", None), getattr(m, "sigma_net", None)
+        if enc is None or net is None or not getattr(m, "fused", False) or not getattr(m, "cuda_ray", False):
+            return False
+        try:
+            ok = (enc.num_levels == 16 and enc.level_dim == 2 and enc.input_dim == 3 and net.num_layers == 3
+                  and net.dim_hidden == 64 and net.dim_in == 32 and net.dim_out == 4 and net.net[0].bias is not None
+                  and enc.embeddings.dtype == torch.float32 and enc.embeddings.is_cuda)
+            if m.bg_radius > 0:
+                bg = m.bg_net
+                ok = ok and (m.encoder_bg.input_dim == 3 and m.encoder_bg.degree == 6 and bg.num_layers == 2
+                             and bg.dim_hidden == 64 and bg.dim_out == 3 and bg.net[0].bias is not None)
+            return bool(ok)
+        except AttributeError:
+            return False
+
+    def _manual_workspace(self, N):
+        from .render_train import TrainWorkspace
+        model, dev = self.model, self.device
+        ws = getattr(model, "_train_ws", None)
+        if ws is None or ws.n_rays != N or ws.max_steps != self.max_steps or ws.xyzs.device != dev:
+            ws = TrainWorkspace(N, self.max_steps, dev, getattr(model, "train_capacity_rows", None))
+            model._train_ws = ws
+        m = self._mws
+        if m is None or m["N"] != N:
+            e = lambda *shape, dtype=torch.float32: torch.empty(*shape, device=dev, dtype=dtype)  # noqa: E731
+            m = dict(N=N, nears=e(N), fars=e(N), noises=e(N), weights_sum=e(N), depth=e(N), image=e(N, 3),
+                     bg=e(N, 3, dtype=torch.half), d_bg=e(N, 3), loss=torch.zeros((), device=dev))
+            self._mws = m
+        return ws, m
+
+    def _body_manual(self, rays_o, rays_d, G):
+        """One `-O` train step as 11 launches on the main stream + 2 on a side stream (the background net, which only
+        meets the main chain at the per-ray loss kernel and at the optimizer):
+
+            prologue (near/far + zero counters) . rand . march x3 . field fwd . [bg fwd] . ray loss (composite fwd + blend
+            + both loss gradients + composite bwd) . field bwd . grid scatter . [bg bwd] . all-reduce + Adam + GradScaler
+
+        Same arithmetic as _body (the autograd version of the reference's train_step, nerf/utils.py:337-403,708-713):
+        every kernel is either the one autograd would call or a fusion of such kernels; gradients go straight into the
+        flat bucket (tests/test_gpu_train_step.py compares the two)."""
+        model, opt, dev = self.model, self.opt, self.device
+        B = rays_o.shape[0]
+        ro = rays_o.reshape(-1, 3)
+        rd = rays_d.reshape(-1, 3)
+        N = ro.shape[0]
+        hw = self.H * self.W
+        if N != B * hw or G.shape != (B, 3, self.H, self.W):
+            raise RuntimeError("rays [B, H*W, 3] and G [B, 3, H, W] expected")
+        ws, m = self._manual_workspace(N)
+        enc = model.encoder
+        L = enc.offsets.shape[0] - 1
+        S = float(np.log2(enc.per_level_scale))
+        l0, l1, l2 = model.sigma_net.net
+        field_params = (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+        hw_field = [opt.half_view(t) for t in field_params]
+        g_field = [opt.grad_view(t) for t in field_params]
+        P = _cabi.ptr
+        main = torch.cuda.current_stream(dev)
+        has_bg = model.bg_radius > 0
+        if has_bg:
+            b0, b1 = model.bg_net.net
+            bg_params = (b0.weight, b0.bias, b1.weight, b1.bias)
+            hw_bg = [opt.half_view(t) for t in bg_params]
+            g_bg = [opt.grad_view(t) for t in bg_params]
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                _cabi.call("ngp_bg_forward", dev, P(rd), N, *[P(t) for t in hw_bg], 6, 64, P(m["bg"]))
+
+        _cabi.call("ngp_train_prologue", dev, P(ro), P(rd), P(model.aabb_train), N, 0.2, P(m["nears"]), P(m["fars"]),
+                   P(ws.counter), P(m["loss"]))
+        if self.mirror_rng:
+            torch.randn(3, device=dev)  # nerf/renderer.py:464 (light direction; unused by albedo shading)
+        m["noises"].uniform_()  # the torch.rand(N) of the reference's wrapper (raymarching.py:213-216)
+        _cabi.call("ngp_march_rays_train", dev, P(ro), P(rd), P(model.density_bitfield), float(model.bound), 0.0,
+                   int(self.max_steps), N, int(model.cascade), int(model.grid_size), ws.cap, P(m["nears"]), P(m["fars"]),
+                   P(ws.xyzs), None, P(ws.deltas), P(ws.rays), P(ws.counter), P(m["noises"]), P(ws.march_ws),
+                   ws.march_ws.numel())
+        _cabi.call("ngp_field_forward", dev, P(ws.xyzs), ws.cap, P(ws.counter), P(opt.half_view(enc.embeddings)), P(enc.offsets),
+                   L, 2, S, int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), float(model.bound),
+                   *[P(t) for t in hw_field], 64, 4, P(ws.sigma), P(ws.rgb), P(ws.enc), P(ws.h1), P(ws.h2))
+        if has_bg:
+            main.wait_stream(self._side)
+        _cabi.call("ngp_train_ray_loss", dev, P(ws.sigma), P(ws.rgb), P(ws.deltas), P(ws.rays), ws.cap, N, 1e-4,
+                   P(m["bg"]) if has_bg else None, 1.0, P(G), hw, float(self.lam), opt.state.data_ptr(), P(m["weights_sum"]),
+                   P(m["depth"]), P(m["image"]), P(m["d_bg"]) if has_bg else None, P(ws.d_sigma), P(ws.d_rgb), P(m["loss"]),
+                   P(ws.counter), P(self.samples), P(model.step_counter), P(self._local_step_dev))
+        if has_bg:
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                _cabi.call("ngp_bg_backward", dev, P(rd), P(m["d_bg"]), N, *[P(t) for t in hw_bg], 6, 64,
+                           *[P(t) for t in g_bg])
+        _cabi.call("ngp_field_backward", dev, ws.cap, P(ws.counter), P(hw_field[0]), P(hw_field[2]), P(hw_field[4]), 64, 4,
+                   P(ws.d_sigma), P(ws.d_rgb), P(ws.sigma), P(ws.rgb), P(ws.enc), P(ws.h1), P(ws.h2), P(ws.d_enc),
+                   *[P(t) for t in g_field])
+        _cabi.call("ngp_grid_scatter_samples", dev, P(ws.d_enc), P(ws.xyzs), float(model.bound), P(ws.counter), ws.cap,
+                   P(enc.offsets), L, 2, S, int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)),
+                   P(opt.grad_view(enc.embeddings)))
+        if has_bg:
+            main.wait_stream(self._side)
+        if self.world > 1 and opt.peer_ptrs is None:
+            dist.all_reduce(opt.flat_grads, op=dist.ReduceOp.SUM)
+        opt.step_fused()
+        return m["loss"]
+
     def _bookkeeping_after(self, local_step_before):
         """Python-side effects of run_cuda that a graph replay does not re-execute."""
         model = self.model
-        row = local_step_before % 16
-        ws = getattr(model, "_train_ws", None)
-        if ws is not None:
-            model.step_counter[row].copy_(ws.counter)
+        if not self.manual:  # (the hand-scheduled step writes step_counter and the sample total on the device)
+            row = local_step_before % 16
+            ws = getattr(model, "_train_ws", None)
+            if ws is not None:
+                model.step_counter[row].copy_(ws.counter)
         model.local_step = local_step_before + 1
+        self._ls_mirror = model.local_step
 
-    def __call__(self, rays_o, rays_d, G):
+    # -- inputs --------------------------------------------------------------------------------------------------
+    def pack_inputs(self, rays_o, rays_d, G, pin=False):
+        """One contiguous fp32 buffer [rays_o | rays_d | G] for a step: a packed batch reaches the step's static input
+        buffers with ONE copy (host->device or device->device) instead of three."""
+        parts = [rays_o.reshape(-1), rays_d.reshape(-1), G.reshape(-1)]
+        out = torch.empty(sum(t.numel() for t in parts), dtype=torch.float32, device=rays_o.device)
+        if pin and not out.is_cuda:
+            out = out.pin_memory()
+        torch.cat([t.float() for t in parts], out=out)
+        return out
+
+    def _unpack(self, packed, B):
+        n_ray = B * self.H * self.W * 3
+        ro = packed[:n_ray].view(B, self.H * self.W, 3)
+        rd = packed[n_ray:2 * n_ray].view(B, self.H * self.W, 3)
+        G = packed[2 * n_ray:].view(B, 3, self.H, self.W)
+        return ro, rd, G
+
+    def __call__(self, rays_o, rays_d=None, G=None):
+        """rays_o, rays_d [B, H*W, 3], G [B, 3, H, W] - or a single packed buffer from pack_inputs()."""
         model = self.model
+        packed = None
+        if rays_d is None:
+            packed = rays_o
+            B = packed.numel() // (self.H * self.W * 9)
+            if B * self.H * self.W * 9 != packed.numel():
+                raise RuntimeError("packed inputs do not match H, W of this TrainStep")
         if self.global_step % self.update_interval == 0:
             if self.use_graph and not self.fused_optimizer:
                 from . import field
@@ -113,46 +282,72 @@ class TrainStep:
             self.n_updates += 1
         self.global_step += 1
         (self.opt.attach_grads if self.fused_optimizer else self.bucket.attach)()
+        if self.manual and self._ls_mirror != model.local_step:
+            self._local_step_dev.fill_(model.local_step)  # (update_extra_state restarts the 16-step window)
+            self._ls_mirror = model.local_step
 
         if not self.use_graph:
-            loss = self._body(rays_o, rays_d, G)
-            self.samples.add_(model.step_counter[(model.local_step - 1) % 16, 0].long())
+            if packed is not None:
+                if not packed.is_cuda:
+                    packed = packed.to(self.device, non_blocking=True)
+                rays_o, rays_d, G = self._unpack(packed, B)
+            before = model.local_step
+            loss = self._step_body(rays_o, rays_d, G)
+            if self.manual:
+                self._bookkeeping_after(before)
+            else:
+                self.samples.add_(model.step_counter[(model.local_step - 1) % 16, 0].long())
             self.loss = loss
             return loss
 
         if self._graph is None:
-            self._capture(rays_o, rays_d, G)
-        ro_s, rd_s, g_s = self._static
-        ro_s.copy_(rays_o, non_blocking=True)
-        rd_s.copy_(rays_d, non_blocking=True)
-        g_s.copy_(G, non_blocking=True)
+            if packed is not None:
+                self._capture(*self._unpack(packed, B))
+            else:
+                self._capture(rays_o, rays_d, G)
+        if packed is not None:
+            self._static_packed.copy_(packed, non_blocking=True)
+        else:
+            ro_s, rd_s, g_s = self._static
+            ro_s.copy_(rays_o, non_blocking=True)
+            rd_s.copy_(rays_d, non_blocking=True)
+            g_s.copy_(G, non_blocking=True)
         before = model.local_step
         self._graph.replay()
         _cabi.LAUNCHES += self._graph_launches  # our kernels inside the replayed graph
         self._bookkeeping_after(before)
-        self.samples.add_(model._train_ws.counter[0].long())
+        if not self.manual:
+            self.samples.add_(model._train_ws.counter[0].long())
         return self.loss
 
     def _capture(self, rays_o, rays_d, G):
         model = self.model
-        self._static = (torch.empty_like(rays_o, device=self.device).copy_(rays_o),
-                        torch.empty_like(rays_d, device=self.device).copy_(rays_d),
-                        torch.empty_like(G, device=self.device).copy_(G))
+        B = rays_o.shape[0]
+        self._static_packed = torch.empty(B * self.H * self.W * 9, dtype=torch.float32, device=self.device)
+        self._static = self._unpack(self._static_packed, B)
         ro_s, rd_s, g_s = self._static
+        ro_s.copy_(rays_o)
+        rd_s.copy_(rays_d)
+        g_s.copy_(G)
         # warm up on a side stream (allocator, lazy initialisation, cudaFuncSetAttribute) before capturing
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         saved_step = model.local_step
+        saved_samples = self.samples.clone()
         with torch.cuda.stream(side):
             for _ in range(3):
-                self._body(ro_s, rd_s, g_s)
+                self._step_body(ro_s, rd_s, g_s)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         model.local_step = saved_step
         self._graph = torch.cuda.CUDAGraph()
         launches0 = _cabi.LAUNCHES
         with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
-            self.loss = self._body(ro_s, rd_s, g_s)
+            self.loss = self._step_body(ro_s, rd_s, g_s)
         self._graph_launches = _cabi.LAUNCHES - launches0
         _cabi.LAUNCHES = launches0  # capture launches nothing
         model.local_step = saved_step
+        if self.manual:  # undo the device-side bookkeeping of the warm-up passes
+            self.samples.copy_(saved_samples)
+            self._local_step_dev.fill_(saved_step)
+            self._ls_mirror = saved_step

@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""Multi-GPU check of the fused peer-memory all-reduce + Adam kernel (csrc/dp_step.cu).  Run under torchrun:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/dp_peer_check.py [--n 1816256]
+
+Every rank fills its gradient bucket with different seeded values (one step carries an inf on ONE rank), runs
+FusedAdamScaler.step_fused() over peer memory, and compares parameters / fp16 shadow / scaler state with a
+single-process reference: NCCL all_reduce of the same buckets followed by the two-launch single-GPU optimizer.
+Also times both variants as CUDA-graph replays.  Rank 0 prints one JSON line; exit code 1 on any mismatch.
+(tests/test_gpu_dp.py launches this when the box has >= 2 GPUs.)
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "single-stable-dreamfusion_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--backend", default="auto")
+    ap.add_argument("--n", type=int, default=1816256)
+    ap.add_argument("--steps", type=int, default=6)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from ngp_b200 import _cabi
+    from ngp_b200.optim import FusedAdamScaler
+    from ngp_b200.parallel import PeerMemory
+    _cabi.load()
+
+    n_table = args.n - 8192
+    torch.manual_seed(0)   # identical initial parameters on every rank
+    mk = lambda: [torch.nn.Parameter(torch.randn(n_table // 2, 2, device=dev) * 0.1),  # noqa: E731
+                  torch.nn.Parameter(torch.randn(64, 64, device=dev) * 0.1), torch.nn.Parameter(torch.randn(4096, device=dev) * 0.1)]
+    pa, pb = mk(), None
+    torch.manual_seed(0)
+    pb = mk()
+    groups = lambda ps: [{"params": ps[:1], "lr": 1e-2}, {"params": ps[1:], "lr": 1e-3}]  # noqa: E731
+    result = {"world": world, "n": args.n}
+    try:
+        peer = PeerMemory(dev, backend=args.backend)
+        mine = FusedAdamScaler(groups(pa), growth_interval=3, grad_div=float(world), peer_memory=peer, lr_decay=(0.1, 10))
+        result["backend"] = peer.used
+    except Exception as e:  # noqa: BLE001
+        if rank == 0:
+            print(json.dumps({"ok": False, "error": "peer memory unavailable: %r" % e}))
+        dist.destroy_process_group()
+        sys.exit(2)
+    ref = FusedAdamScaler(groups(pb), growth_interval=3, grad_div=float(world), lr_decay=(0.1, 10))
+    ok = True
+    worst = 0.0
+    for it in range(args.steps):
+        g = torch.Generator(device=dev).manual_seed(1000 * it + rank)
+        raw = torch.randn(mine.numel, device=dev, generator=g) * (10.0 ** (it % 3 - 2))
+        if it == 2 and rank == world - 1:
+            raw[mine.numel - 5] = float("inf")   # found on ONE rank, in the LAST slice: every rank must skip
+        scale = mine.get_scale()
+        assert scale == ref.get_scale()
+        mine.flat_grads.copy_(raw * scale)
+        ref.flat_grads.copy_(raw * scale)
+        torch.cuda.synchronize()
+        dist.barrier()
+        mine.step_fused()
+        dist.all_reduce(ref.flat_grads)
+        ref.step(zero_grads=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        d = (mine.flat_params - ref.flat_params).abs().max().item()
+        worst = max(worst, d)
+        same_half = torch.equal(mine.flat_half, mine.flat_params.half())
+        zeroed = mine.flat_grads.abs().sum().item() == 0
+        st_ok = torch.equal(mine.state[:5], ref.state[:5])
+        if not (d <= 2e-6 and same_half and zeroed and st_ok and not mine.comm_error):
+            ok = False
+            print("rank %d step %d: max|dp| %.3g half %s zeroed %s state %s/%s comm_error %s" % (
+                rank, it, d, same_half, zeroed, mine.state.tolist(), ref.state.tolist(), mine.comm_error), file=sys.stderr)
+    result["max_abs_param_diff"] = worst
+    result["steps_taken"], result["skipped"] = mine.steps_taken, int(mine.state[4].item())
+    ok = ok and result["skipped"] == 1
+
+    # ---- timing: graph replays of (fused) vs (NCCL all_reduce + check_finite + adam) -------------------------------
+    def timed(fn, iters=50):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+            fn()
+        for _ in range(5):
+            gr.replay()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def nccl_path():
+        dist.all_reduce(ref.flat_grads)
+        ref.step(zero_grads=True)
+
+    try:
+        result["fused_us"] = timed(mine.step_fused) * 1e3
+        result["nccl_plus_adam_us"] = timed(nccl_path) * 1e3
+        result["comm_error_after_timing"] = mine.comm_error
+        ok = ok and not mine.comm_error
+    except Exception as e:  # noqa: BLE001
+        result["timing_error"] = repr(e)[:300]
+        ok = False
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    result["ok"] = bool(flag.item() > 0)
+    if rank == 0:
+        print(json.dumps(result))
+    sys.stdout.flush()
+    os._exit(0 if result["ok"] else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -161,8 +161,10 @@ def test_fused_training_render_matches_modular_path(ref_ext):
         assert rel < 2e-2, (n, rel)
 
 
-def test_graphed_train_step_matches_eager(ref_ext):
-    """One CUDA-graph replay per step == the eager step (same seeds): losses and parameters track each other."""
+@pytest.mark.parametrize("manual", [False, True])
+def test_graphed_train_step_matches_eager(ref_ext, manual):
+    """One CUDA-graph replay per step == the eager step (same seeds): losses and parameters track each other.
+    manual: the hand-scheduled kernel sequence instead of the autograd graph (trainer.py)."""
     from ngp_b200.trainer import TrainStep
     from ngp_b200 import provider
     ro, rd = provider.make_training_views(6 * 2, 64, 64, seed=3, pin=False)
@@ -171,7 +173,7 @@ def test_graphed_train_step_matches_eager(ref_ext):
     finals = []
     for graph in (False, True):
         m, _ = _models(ref_ext)
-        step = TrainStep(m, 64, 64, graph=graph)
+        step = TrainStep(m, 64, 64, graph=graph, manual=manual)
         torch.manual_seed(5)
         losses = []
         for i in range(6):

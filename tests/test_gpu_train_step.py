@@ -17,7 +17,9 @@ def _two_models():
     return a, b
 
 
-def test_fused_adam_scaler_matches_torch_adam_and_gradscaler():
+@pytest.mark.parametrize("one_launch", [False, True])
+def test_fused_adam_scaler_matches_torch_adam_and_gradscaler(one_launch):
+    """one_launch: the cooperative finite-check + Adam kernel (csrc/dp_step.cu, world 1) instead of the two launches."""
     from ngp_b200.optim import FusedAdamScaler
     from ngp_b200 import field
     a, b = _two_models()
@@ -40,7 +42,7 @@ def test_fused_adam_scaler_matches_torch_adam_and_gradscaler():
         for p, q, r in zip(a, b, raw):
             p.grad.copy_(r * s_mine * 2.0)      # "all-reduced sum over 2 ranks" of scaled grads
             q.grad = r * s_ref
-        mine.step(zero_grads=True)
+        mine.step_fused() if one_launch else mine.step(zero_grads=True)
         scaler.step(opt)
         scaler.update()
         if it not in (5, 8):
@@ -128,7 +130,7 @@ def test_train_step_fused_optimizer_tracks_torch_optimizer(ref_ext):
         opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)
         torch.manual_seed(0)
         m = NeRFNetwork(opt).to(DEV).train()
-        step = TrainStep(m, 64, 64, lr=1e-3, graph=False, fused_optimizer=fused)
+        step = TrainStep(m, 64, 64, lr=1e-3, graph=False, fused_optimizer=fused, manual=False)
         torch.manual_seed(5)
         losses = [step(ro[i], rd[i], G[i]).item() for i in range(4)]
         finals.append((losses, {n: p.detach().clone() for n, p in m.named_parameters()}))
@@ -168,3 +170,81 @@ def test_fused_background_net_matches_torch_modules():
             a, b = res[0][1][n].float(), res[1][1][n].float()
             rel = ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
             assert rel < 2e-2, (N, n, rel)       # the torch path rounds weight gradients (and their split-K partials) to fp16
+
+
+def _bench_like_model():
+    import argparse
+    from ngp_b200.network_grid import NeRFNetwork
+    opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)
+    torch.manual_seed(0)
+    return NeRFNetwork(opt).to(DEV).train()
+
+
+@pytest.mark.parametrize("views", [1, 2])
+def test_hand_scheduled_step_matches_autograd_step(views):
+    """TrainStep(manual=True) - 13 launches, no autograd - must produce the gradients, loss and bookkeeping of the
+    autograd version of the same step (which tests/test_gpu_pipeline.py pins to the reference pipeline)."""
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    ro, rd = provider.make_training_views(views, 64, 64, seed=3, pin=False)
+    ro, rd = ro.to(DEV), rd.to(DEV)
+    G = torch.randn(views, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 1e-2
+    got = {}
+    for manual in (True, False):
+        m = _bench_like_model()
+        step = TrainStep(m, 64, 64, lr=1e-3, graph=False, manual=manual)
+        assert step.manual == manual
+        step.mirror_rng = True   # same torch RNG consumption as run_cuda, so both draw the same ray noise
+        grads = []
+
+        def capture(*a, _s=step, _g=grads, **k):
+            _g.append(_s.opt.flat_grads.clone())
+            _s.opt.flat_grads.zero_()
+        step.opt.step = capture
+        step.opt.step_fused = capture
+        torch.manual_seed(5)
+        loss = step(ro, rd, G)
+        torch.cuda.synchronize()
+        got[manual] = dict(loss=loss.item(), g=grads[0], opt=step.opt, counter=m.step_counter.clone(), samples=step.samples.item(),
+                           local_step=m.local_step, model=m)
+    a, b = got[True], got[False]
+    assert a["samples"] == b["samples"] > 0
+    assert torch.equal(a["counter"], b["counter"]) and a["local_step"] == b["local_step"] == 1
+    assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(b["loss"])
+    for (name, p), (_, q) in zip(a["model"].named_parameters(), b["model"].named_parameters()):
+        oa, ob = a["opt"].offsets[a["opt"]._index(p)], b["opt"].offsets[b["opt"]._index(q)]
+        ga, gb = a["g"][oa:oa + p.numel()], b["g"][ob:ob + q.numel()]
+        assert gb.abs().max() > 0, name
+        rel = ((ga - gb).norm() / gb.norm()).item()
+        assert rel < 1e-3, (name, rel)   # fp32 atomics order is the only difference
+
+
+def test_hand_scheduled_step_graph_replay_and_packed_inputs():
+    """Graph replays of the hand-scheduled step (cooperative optimizer kernel + side-stream branch inside the graph)
+    follow the eager step; packed inputs reach the static buffers with one copy."""
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    ro, rd = provider.make_training_views(6, 64, 64, seed=4, pin=False)
+    ro, rd = ro.view(6, 1, 4096, 3).to(DEV), rd.view(6, 1, 4096, 3).to(DEV)
+    G = torch.randn(6, 1, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2)) * 1e-2
+    out = []
+    for graph in (False, True):
+        m = _bench_like_model()
+        step = TrainStep(m, 64, 64, lr=1e-4, graph=graph, manual=True)
+        torch.manual_seed(7)
+        losses = []
+        for i in range(6):
+            if graph and i % 2 == 1:
+                losses.append(step(step.pack_inputs(ro[i], rd[i], G[i])).item())
+            else:
+                losses.append(step(ro[i], rd[i], G[i]).item())
+        torch.cuda.synchronize()
+        assert not step.opt.comm_error
+        assert step.opt.steps_taken == (6 + 3 if graph else 6)   # the capture warms up with three real steps
+        out.append((losses, step.samples.item(), m.step_counter.clone(), m.local_step))
+    (la, sa, ca, lsa), (lb, sb, cb, lsb) = out
+    assert lsa == lsb == 6 and sa > 0 and sb > 0
+    # different noise draws / three extra optimizer steps in the graphed run: the loss stays in the same range
+    np.testing.assert_allclose(la, lb, rtol=0.2)
+    assert (ca[:6, 1] == 4096).all() and (cb[:6, 1] == 4096).all()
+    assert abs(sa - sb) < 0.2 * sa
