@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--lr", type=float, default=1e-5)
     ap.add_argument("--no-graph", action="store_true", help="run the train step eagerly instead of as one CUDA graph")
     ap.add_argument("--autograd", action="store_true", help="autograd version of the step instead of the hand-scheduled kernels")
+    ap.add_argument("--ray-order", default="tiles", choices=["tiles", "rows"], help="order / sharding of a view's rays")
+    ap.add_argument("--no-pipeline", action="store_true", help="apply the optimizer update at the end of its own step")
     ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce instead of the fused peer-memory all-reduce + Adam")
     ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
@@ -189,7 +191,7 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
     from ngp_b200 import _cabi, provider
-    from ngp_b200.parallel import shard_rows
+    from ngp_b200.parallel import shard_pixels, shard_rows
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -201,24 +203,32 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=device)
     _cabi.load()
 
-    # Data-parallel sharding: every rank renders image rows rank, rank + world, ... of ALL views of the step (an even
-    # split of the step's 8 x 4096 rays whose per-rank sample counts stay balanced; whole views differ 4x in samples)
-    if H % world != 0:
-        raise SystemExit("--gpus must divide the image height %d" % H)
-    rows = shard_rows(H, rank, world)
-    Hl = len(rows)
+    # Data-parallel sharding of the step's 8 x 4096 rays: every rank renders its share of EVERY view - 8x8-pixel blocks
+    # dealt round-robin along the block diagonals (parallel.shard_pixels; --ray-order rows: interleaved image rows).
+    # Per-rank sample counts stay balanced (whole views differ 4x in samples) and a rank's rays stay spatially coherent.
+    if (H * W) % world != 0:
+        raise SystemExit("--gpus must divide the ray count of a view")
+    if args.ray_order == "tiles":
+        pix = shard_pixels(H, W, rank, world)
+    else:
+        pix = [r * W + c for r in shard_rows(H, rank, world) for c in range(W)]
+    pix_t = torch.tensor(pix, dtype=torch.long)
+    Hl = len(pix) // W
     n_pool = 64
     ro_all, rd_all = provider.make_training_views(n_pool * args.views, H, W, seed=0, pin=False)
-    ro_all = ro_all.view(n_pool, args.views, H, W, 3)[:, :, rows].reshape(n_pool, args.views, Hl * W, 3)
-    rd_all = rd_all.view(n_pool, args.views, H, W, 3)[:, :, rows].reshape(n_pool, args.views, Hl * W, 3)
-    g_all = (torch.randn(n_pool, args.views, 3, H, W, generator=torch.Generator().manual_seed(2)) * 1e-2)[:, :, :, rows]
+    ro_all = ro_all.view(n_pool, args.views, H * W, 3)[:, :, pix_t].contiguous()
+    rd_all = rd_all.view(n_pool, args.views, H * W, 3)[:, :, pix_t].contiguous()
+    # the guidance gradient of the rendered pixels, in the same ray order ([views, 3, rays of this rank])
+    g_all = (torch.randn(n_pool, args.views, 3, H * W, generator=torch.Generator().manual_seed(2)) * 1e-2)[:, :, :, pix_t]
+    g_all = g_all.reshape(n_pool, args.views, 3, Hl, W).contiguous()
 
     from ngp_b200.trainer import TrainStep
     model = build_model(device)
     # lr: the optimizer step runs in full, but a small step keeps the synthetic (random-gradient) scene at its
     # random-init occupancy so that every timed pass sees the same ~3.4 M samples per step
     step_fn = TrainStep(model, Hl, W, lr=args.lr, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world,
-                        manual=False if args.autograd else None, peer_allreduce=False if args.nccl else None)
+                        manual=False if args.autograd else None, peer_allreduce=False if args.nccl else None,
+                        pipelined=not (args.no_pipeline or args.autograd))
     # one packed, pinned host buffer per batch [rays_o | rays_d | G]: a step's inputs are ONE copy
     host_pool = torch.stack([step_fn.pack_inputs(ro_all[k], rd_all[k], g_all[k].contiguous()) for k in range(n_pool)]).pin_memory()
 
@@ -268,6 +278,7 @@ def run_b200_arm(args):
     barrier()
     e0.record()
     run_steps(args.steps, False, 1000, record=True)
+    step_fn.flush()  # pipelined optimizer: the last step's update belongs to the timed work
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -283,6 +294,7 @@ def run_b200_arm(args):
     barrier()
     f0.record()
     run_steps(args.steps, True, 2000)
+    step_fn.flush()
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
@@ -383,7 +395,9 @@ def run_b200_arm(args):
                 "views_per_step": args.views, "rays_per_step": args.views * H * W,
                 "samples_per_step": samples / args.steps, "cuda_graph": not args.no_graph, "lr": args.lr,
                 "hand_scheduled_step": step_fn.manual, "comm_error": bool(step_fn.fused_optimizer and step_fn.opt.comm_error),
-                "sharding": "image rows interleaved over ranks (every rank renders rows r::N of all views)",
+                "sharding": ("8x8-pixel blocks of every view dealt along the block diagonals" if args.ray_order == "tiles"
+                             else "image rows interleaved over ranks"),
+                "pipelined_optimizer": step_fn.pipelined,
                 "grad_allreduce": ("none (1 GPU)" if world == 1 else
                                    ("fused into the optimizer kernel over NVLink peer memory (%s)" % step_fn.peer.used
                                     if step_fn.opt.peer_ptrs is not None else "NCCL all_reduce (%s)" % (step_fn.peer_error or "requested"))),

@@ -163,6 +163,10 @@ int ngp_freq_encode_backward(const float* grad, const float* outputs, uint32_t B
  * in density_grid order (renderer.py:597). */
 int ngp_occupancy_cell_points(uint32_t H, float cell_scale, float half_cell, const float* noise, float* xyzs,
                               void* stream);
+/* One rank's share of a data-parallel refresh: the query points of Morton cells [first, first + count) only, jitter from
+ * noise f32[count,3] indexed by (cell - first); xyzs f32[count,3]. */
+int ngp_occupancy_cell_points_range(uint32_t H, float cell_scale, float half_cell, const float* noise, uint32_t first,
+                                    uint32_t count, float* xyzs, void* stream);
 
 /* EMA-max + mean + bitfield (renderer.py:600-607).  grid f32[n_cells] updated in place where
  * grid >= 0: grid = max(grid*decay, tmp).  mean_out f32[1] = mean over valid cells.  bitfield
@@ -257,14 +261,17 @@ int ngp_bg_backward(const float* dirs, const float* grad_rgb, uint32_t N, const 
  *   every rank's gradient bucket, parameter buffer, fp16 shadow and flag pad (ngp_dp_flags_bytes() bytes, zeroed once),
  *   all mapped into this process (symmetric memory / CUDA IPC).  Each rank reduces and updates slice `rank` and writes
  *   the new parameters to every replica; exp_avg / exp_avg_sq are maintained for that slice only.  The gradient bucket
- *   is zero-filled on the way out.  All ranks must launch the same sequence of calls. */
+ *   is zero-filled on the way out.  All ranks must launch the same sequence of calls.
+ *   deferred != 0: for a trainer that applies step k's update at the START of step k+1 (overlapped with that step's ray
+ *   marching): a launch that finds state[6] == 0 applies nothing and sets state[6] = 1 ("gradients will be pending next
+ *   time"); the caller clears state[6] after flushing the last pending update. */
 #define NGP_DP_MAX_WORLD 8
 #define NGP_DP_MAX_BLOCKS 256
 int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow, uint64_t n,
                         uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1, float beta2,
                         float eps, float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor,
-                        float backoff_factor, uint32_t growth_interval, float* state, uint32_t* sync, uint32_t rank,
-                        uint32_t world, const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half,
+                        float backoff_factor, uint32_t growth_interval, int deferred, float* state, uint32_t* sync,
+                        uint32_t rank, uint32_t world, const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half,
                         const uint64_t* peer_flags, void* stream);
 uint64_t ngp_dp_flags_bytes(void);
 /* cudaDeviceEnablePeerAccess(peer_device) from the current device (idempotent). */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "ngp_freq_encode_forward": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp, _vp]),
     "ngp_freq_encode_backward": (_i32, [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp]),
     "ngp_occupancy_cell_points": (_i32, [_u32, _f32, _f32, _vp, _vp, _vp]),
+    "ngp_occupancy_cell_points_range": (_i32, [_u32, _f32, _f32, _vp, _u32, _u32, _vp, _vp]),
     "ngp_update_density_grid": (_i32, [_vp, _vp, _u32, _f32, _f32, _vp, _vp, _vp, _u64, _vp]),
     "ngp_bench_gather4": (_i32, [_vp, _u32, _vp, _u32, _u32, _u32, _vp]),
     "ngp_bench_red8": (_i32, [_vp, _u32, _u32, _u32, _u32, _vp]),
@@ -59,7 +60,7 @@ SIGNATURES = {
     "ngp_adam_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64), C.POINTER(_f32), _f32, _f32, _f32, _f32,
                              _f32, _f32, _f32, _f32, _u32, _i32, _vp, _vp, _vp]),
     "ngp_adam_step_fused": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64), C.POINTER(_f32), _f32, _f32, _f32, _f32,
-                                   _f32, _f32, _f32, _f32, _u32, _vp, _vp, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64),
+                                   _f32, _f32, _f32, _f32, _u32, _i32, _vp, _vp, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64),
                                    C.POINTER(_u64), C.POINTER(_u64), _vp]),
     "ngp_dp_flags_bytes": (_u64, []),
     "ngp_enable_peer_access": (_i32, [_i32]),

@@ -50,7 +50,8 @@ struct Args {
     float lr_decay_ln, lr_decay_steps;
     float growth, backoff;
     uint32_t growth_interval;
-    float* state;          // [0] scale [1] growth tracker [2] steps [3] found_inf [4] skipped [5] error flag
+    float* state;          // [0] scale [1] growth tracker [2] steps [3] found_inf [4] skipped [5] error flag [6] armed
+    int deferred;          // 1: a launch with state[6] == 0 only arms (sets state[6] = 1) and applies nothing
     uint32_t* sync;        // [0] blocks_done [1] epoch
     // data parallel
     uint32_t rank, world;
@@ -103,6 +104,13 @@ NGP_DEVINL uint32_t xrank_barrier(const Args& a, uint32_t barrier, uint32_t bloc
 
 __global__ void __launch_bounds__(512) adam_step_fused_kernel(const Args a) {
     cg::grid_group grid = cg::this_grid();
+    if (a.deferred && *(volatile float*)(a.state + 6) == 0.f) {
+        // deferred mode (the step is applied at the START of the next train step, overlapped with its ray marching):
+        // nothing is pending yet - every block has read the flag before block 0 raises it
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.state[6] = 1.f;
+        return;
+    }
     const float scale = a.state[0];
     const float step0 = a.state[2];
     const uint32_t epoch = a.sync[1] + 1;
@@ -267,8 +275,8 @@ extern "C" int ngp_enable_peer_access(int peer_device) {
 extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow,
                                    uint64_t n, uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1,
                                    float beta2, float eps, float grad_div, float lr_decay_ln, float lr_decay_steps,
-                                   float growth_factor, float backoff_factor, uint32_t growth_interval, float* state,
-                                   uint32_t* sync, uint32_t rank, uint32_t world, const uint64_t* peer_grads,
+                                   float growth_factor, float backoff_factor, uint32_t growth_interval, int deferred,
+                                   float* state, uint32_t* sync, uint32_t rank, uint32_t world, const uint64_t* peer_grads,
                                    const uint64_t* peer_params, const uint64_t* peer_half, const uint64_t* peer_flags,
                                    void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !state || !sync || !seg_end || !seg_lr) return NGP_ERR_BAD_ARG;
@@ -289,7 +297,7 @@ extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, 
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_div = grad_div > 0.f ? grad_div : 1.f;
     a.lr_decay_ln = lr_decay_ln; a.lr_decay_steps = lr_decay_steps;
     a.growth = growth_factor; a.backoff = backoff_factor; a.growth_interval = growth_interval;
-    a.state = state; a.sync = sync; a.rank = rank; a.world = world;
+    a.state = state; a.sync = sync; a.rank = rank; a.world = world; a.deferred = deferred;
     for (uint32_t q = 0; q < dp::kMaxWorld; ++q) {
         const bool on = world > 1 && q < world;
         a.peer_g[q] = on ? reinterpret_cast<float*>(peer_grads[q]) : nullptr;

@@ -38,6 +38,25 @@ __global__ void __launch_bounds__(256) cell_points_kernel(uint32_t H, float cell
     }
 }
 
+// The same query points for the Morton cells [first, first + count) only, jitter taken from noise[count, 3] indexed by
+// m - first: one rank's share of a data-parallel occupancy refresh (every rank draws its own jitter for its own cells).
+__global__ void __launch_bounds__(256) cell_points_range_kernel(uint32_t H, float cell_scale, float half_cell,
+                                                                const float* __restrict__ noise, uint32_t first, uint32_t count,
+                                                                float* __restrict__ xyzs) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const uint32_t m = first + k;
+    const uint32_t c[3] = {compact3(m), compact3(m >> 1), compact3(m >> 2)};
+    const float inv_hm1 = __fdiv_rn(1.0f, (float)(H - 1));
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float centre = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, (float)c[a]), inv_hm1), 1.0f);
+        const float scaled = __fmul_rn(centre, cell_scale);
+        const float jitter = __fmul_rn(__fsub_rn(__fmul_rn(noise[(size_t)k * 3 + a], 2.0f), 1.0f), half_cell);
+        xyzs[(size_t)k * 3 + a] = __fadd_rn(scaled, jitter);
+    }
+}
+
 struct Accum {
     double sum;
     unsigned long long count;
@@ -107,6 +126,15 @@ extern "C" int ngp_occupancy_cell_points(uint32_t H, float cell_scale, float hal
     if (!noise || !xyzs || H < 2 || H > 1024) return NGP_ERR_BAD_ARG;
     const uint32_t n = H * H * H;
     occ::cell_points_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(H, cell_scale, half_cell, noise, xyzs);
+    return launch_status();
+}
+
+extern "C" int ngp_occupancy_cell_points_range(uint32_t H, float cell_scale, float half_cell, const float* noise, uint32_t first,
+                                               uint32_t count, float* xyzs, void* stream) {
+    if (!noise || !xyzs || H < 2 || H > 1024) return NGP_ERR_BAD_ARG;
+    if ((uint64_t)first + count > (uint64_t)H * H * H) return NGP_ERR_BAD_ARG;
+    if (count == 0) return NGP_OK;
+    occ::cell_points_range_kernel<<<cdiv(count, 256), 256, 0, as_stream(stream)>>>(H, cell_scale, half_cell, noise, first, count, xyzs);
     return launch_status();
 }
 

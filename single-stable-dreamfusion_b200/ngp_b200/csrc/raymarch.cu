@@ -754,6 +754,20 @@ struct RayLossArgs {
 
 constexpr float kAlphaLoR = 1e-5f, kAlphaHiR = 1.f - 1e-5f;
 
+struct RaySample { float sigma, d0, d1, r, g, b; };
+// sample i of the ray's span (zeros past its end)
+NGP_DEVINL RaySample load_ray_sample(const RayLossArgs& a, const RaySpan& s, uint32_t i) {
+    RaySample v = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (i < s.count) {
+        const size_t m = (size_t)s.offset + i;
+        v.sigma = a.sigmas[m];
+        const float2 dl = *(reinterpret_cast<const float2*>(a.deltas) + m);
+        v.d0 = dl.x; v.d1 = dl.y;
+        v.r = a.rgbs[m * 3]; v.g = a.rgbs[m * 3 + 1]; v.b = a.rgbs[m * 3 + 2];
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a) {
     __shared__ float s_loss[8];
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -774,18 +788,19 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
         float r = 0, g = 0, b = 0, ws = 0, d = 0;
         if (s.live) {
             float T_carry = 1.0f, t_carry = 0.f;
+            // the ray's samples are walked 32 at a time and each chunk depends on the previous one (transmittance), so the
+            // loads of chunk k+1 are issued before chunk k is processed: the walk is bound by load latency otherwise
+            RaySample nxt = load_ray_sample(a, s, lane);
             for (uint32_t base = 0; base < s.count; base += 32) {
-                const uint32_t i = base + lane;
-                const bool valid = i < s.count;
+                const RaySample cur = nxt;
+                if (base + 32 < s.count) nxt = load_ray_sample(a, s, base + 32 + lane);
+                const bool valid = base + lane < s.count;
                 float om = 1.0f, d1 = 0.f, alpha = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
                 if (valid) {
-                    const size_t m = (size_t)s.offset + i;
-                    const float sigma = a.sigmas[m];
-                    const float2 dl = *(reinterpret_cast<const float2*>(a.deltas) + m);
-                    alpha = 1.0f - __expf(-sigma * dl.x);
+                    alpha = 1.0f - __expf(-cur.sigma * cur.d0);
                     om = 1.0f - alpha;
-                    d1 = dl.y;
-                    cr = a.rgbs[m * 3]; cg = a.rgbs[m * 3 + 1]; cb = a.rgbs[m * 3 + 2];
+                    d1 = cur.d1;
+                    cr = cur.r; cg = cur.g; cb = cur.b;
                 }
                 float T_before, t_incl;
                 serial_prefix(om, d1, lane, T_carry, t_carry, T_before, t_incl);
@@ -844,6 +859,7 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
             const float r_final = r, g_final = g, b_final = b, ws_final = ws;
             float T_carry = 1.0f, r_carry = 0.f, g_carry = 0.f, b_carry = 0.f;
             bool stopped = false;
+            RaySample nxt = load_ray_sample(a, s, lane);
             for (uint32_t base = 0; base < s.count; base += 32) {
                 const uint32_t i = base + lane;
                 const bool valid = i < s.count;
@@ -855,13 +871,14 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
                     }
                     continue;
                 }
+                const RaySample cur = nxt;
+                if (base + 32 < s.count) nxt = load_ray_sample(a, s, base + 32 + lane);
                 float om = 1.0f, alpha = 0.f, d0 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
                 if (valid) {
-                    const float sigma = a.sigmas[m];
-                    d0 = a.deltas[m * 2];
-                    alpha = 1.0f - __expf(-sigma * d0);
+                    d0 = cur.d0;
+                    alpha = 1.0f - __expf(-cur.sigma * d0);
                     om = 1.0f - alpha;
-                    cr = a.rgbs[m * 3]; cg = a.rgbs[m * 3 + 1]; cb = a.rgbs[m * 3 + 2];
+                    cr = cur.r; cg = cur.g; cb = cur.b;
                 }
                 float T_before, unused_t;
                 serial_prefix(om, 0.f, lane, T_carry, 0.f, T_before, unused_t);

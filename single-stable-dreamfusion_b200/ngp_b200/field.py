@@ -125,6 +125,23 @@ def fused_field(xyzs, encoder, sigma_net, bound, count=None):
                              encoder.gridtype_id, encoder.align_corners, bound, count)
 
 
+@torch.no_grad()
+def fused_field_into(xyzs, encoder, sigma_net, bound, sigma_out, rgb_out):
+    """Inference-only fused field: writes sigma [M] / albedo [M,3] (fp32) into caller-owned buffers, allocates nothing."""
+    M = xyzs.shape[0]
+    if sigma_out.shape[0] < M or rgb_out.shape[0] < M or not xyzs.is_contiguous() or xyzs.dtype != torch.float32:
+        raise RuntimeError("fused_field_into: contiguous fp32 xyzs and output buffers of at least M rows expected")
+    l0, l1, l2 = sigma_net.net
+    dev = xyzs.device
+    hw = [cached_half(t) for t in (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)]
+    table = cached_half(encoder.embeddings)
+    _cabi.call("ngp_field_forward", dev, _cabi.ptr(xyzs), M, None, _cabi.ptr(table), _cabi.ptr(encoder.offsets),
+               encoder.offsets.shape[0] - 1, encoder.embeddings.shape[1], float(np.log2(encoder.per_level_scale)),
+               int(encoder.base_resolution), int(encoder.gridtype_id), int(bool(encoder.align_corners)), float(bound),
+               *[_cabi.ptr(t) for t in hw], l0.weight.shape[0], l2.weight.shape[0], _cabi.ptr(sigma_out), _cabi.ptr(rgb_out),
+               None, None, None)
+
+
 def can_fuse(x, encoder, sigma_net):
     """The fused kernels are built for the reference's own field shape under fp16 autocast on a CUDA tensor."""
     try:

@@ -142,10 +142,11 @@ class FusedAdamScaler:
                    self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
                    int(bool(zero_grads)), _cabi.ptr(self.state), _cabi.ptr(self._blocks_done))
 
-    def step_fused(self):
+    def step_fused(self, deferred=False):
         """The same step as ONE cooperative launch (finite check -> grid barrier -> Adam ...), and - with peer
         memory - the data-parallel gradient all-reduce fused in: reduce-scatter by P2P loads, Adam on this rank's
-        slice, new parameters written to every replica (csrc/dp_step.cu).  Always zero-fills the gradients."""
+        slice, new parameters written to every replica (csrc/dp_step.cu).  Always zero-fills the gradients.
+        deferred: the launch only arms (state[6] = 1) when nothing is pending yet - see TrainStep(pipelined=True)."""
         dev = self.device
         if self.peer_ptrs is None:
             rank, world, pg, pp, ph, pf = 0, 1, None, None, None, None
@@ -156,7 +157,7 @@ class FusedAdamScaler:
                    _cabi.ptr(self.exp_avg_sq), _cabi.ptr(self.flat_half), self.numel, self.n_seg, self.seg_end, self.seg_lr,
                    float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,
                    self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
-                   _cabi.ptr(self.state), _cabi.ptr(self._sync), rank, world, pg, pp, ph, pf)
+                   int(bool(deferred)), _cabi.ptr(self.state), _cabi.ptr(self._sync), rank, world, pg, pp, ph, pf)
 
     def grad_view(self, p):
         """The slice of the flat gradient bucket that backs `p.grad` (same shape as p)."""

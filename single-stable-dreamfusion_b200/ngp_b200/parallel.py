@@ -61,6 +61,25 @@ def shard_rows(n_rows, rank, world_size):
     return list(range(rank, n_rows, world_size))
 
 
+def shard_pixels(H, W, rank, world_size, tile=8):
+    """Pixel indices (row-major ids, as a list) of `rank`'s share of an H x W view, in the order the rays are rendered:
+    the image is cut into tile x tile blocks, block (ty, tx) belongs to rank (ty + tx) % world (one block per block-row
+    and block-column for every rank: the same mix of object and background as the whole image), and the rays of a
+    block are contiguous, so neighbouring rays - which touch the same coarse grid cells - are processed together.
+    Falls back to interleaved rows when the tiling does not divide evenly."""
+    ty_n, tx_n = H // tile, W // tile
+    if H % tile or W % tile or (ty_n * tx_n) % world_size or tx_n % world_size:
+        return [r * W + c for r in shard_rows(H, rank, world_size) for c in range(W)]
+    out = []
+    for ty in range(ty_n):
+        for tx in range(tx_n):
+            if (ty + tx) % world_size == rank:
+                for y in range(tile):
+                    base = (ty * tile + y) * W + tx * tile
+                    out.extend(range(base, base + tile))
+    return out
+
+
 class PeerMemory:
     """Device memory that every rank of the group can address directly (loads / stores / atomics over NVLink).
 

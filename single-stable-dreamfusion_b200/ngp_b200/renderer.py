@@ -39,6 +39,18 @@ class _LazyScalar:
         return self.value
 
 
+class _LazyCount:
+    """mean_count = int(sum(step_counter[:n, 0]) / n), evaluated (one reduction + sync) on first use."""
+
+    def __init__(self, snapshot, n):
+        self.snapshot, self.n, self.value = snapshot, n, None
+
+    def get(self):
+        if self.value is None:
+            self.value = int(int(self.snapshot[:self.n].sum().item()) / self.n)
+        return self.value
+
+
 class NeRFRenderer(nn.Module):
     def __init__(self, opt):
         super().__init__()
@@ -229,32 +241,69 @@ class NeRFRenderer(nn.Module):
         H = self.grid_size
         device = self.density_bitfield.device
         n_cells = H ** 3
-        tmp_grid = torch.empty_like(self.density_grid)
+        shard = getattr(self, "dp_shard", None)  # (rank, world[, group]): data-parallel refresh, see below
+        sharded = shard is not None and noise is None and shard[1] > 1 and n_cells % shard[1] == 0
+        n_query = n_cells // shard[1] if sharded else n_cells
+        # persistent scratch: the refresh allocates nothing after its first call (an allocation after a CUDA graph has
+        # been captured costs tens of milliseconds of cudaMalloc on the step it lands on)
+        ws = getattr(self, "_occ_ws", None)
+        if ws is None or ws["n"] != n_query or ws["u"].device != device:
+            e = lambda *shape, dtype=torch.float32: torch.empty(*shape, device=device, dtype=dtype)  # noqa: E731
+            ws = dict(n=n_query, u=e(n_query, 3), xyzs=e(n_query, 3), sigma=e(n_query), rgb=e(n_query, 3),
+                      tmp=torch.empty_like(self.density_grid), mean=e(1), acc=e(16, dtype=torch.uint8))
+            self._occ_ws = ws
+        tmp_grid = ws["tmp"]
 
         for cas in range(self.cascade):
             bound = min(2 ** cas, self.bound)
             half_cell = bound / H
-            u = torch.rand(n_cells, 3, device=device) if noise is None else noise[cas].to(device, torch.float32).contiguous()
-            xyzs = torch.empty(n_cells, 3, device=device, dtype=torch.float32)
-            _cabi.call("ngp_occupancy_cell_points", device, H, float(bound - half_cell), float(half_cell), _cabi.ptr(u),
-                       _cabi.ptr(xyzs))
-            # Morton-ordered queries: the densities land in density_grid order, no index scatter needed
-            tmp_grid[cas] = self.density(xyzs)['sigma'].reshape(-1).detach().float()
+            if noise is None:
+                u = ws["u"].uniform_()  # the torch.rand of renderer.py:586, drawn in place
+            else:
+                u = noise[cas].to(device, torch.float32).contiguous()
+            xyzs = ws["xyzs"]
+            if sharded:
+                # every rank evaluates the density of 1/world of the cells (a contiguous Morton range, with its own
+                # jitter) and the ranges are all-gathered: identical grids on all ranks at 1/world of the field work
+                import torch.distributed as dist
+                _cabi.call("ngp_occupancy_cell_points_range", device, H, float(bound - half_cell), float(half_cell),
+                           _cabi.ptr(u), shard[0] * n_query, n_query, _cabi.ptr(xyzs))
+                dist.all_gather_into_tensor(tmp_grid[cas], self._density_into(xyzs, ws),
+                                            group=shard[2] if len(shard) > 2 else None)
+            else:
+                _cabi.call("ngp_occupancy_cell_points", device, H, float(bound - half_cell), float(half_cell), _cabi.ptr(u),
+                           _cabi.ptr(xyzs))
+                # Morton-ordered queries: the densities land in density_grid order, no index scatter needed
+                sig = self._density_into(xyzs, ws)
+                if self.cascade == 1:
+                    tmp_grid = sig.view(1, -1)  # the scratch itself: no copy
+                else:
+                    tmp_grid[cas].copy_(sig)
 
-        mean = torch.empty(1, device=device, dtype=torch.float32)
-        ws = torch.empty(16, device=device, dtype=torch.uint8)
+        mean = ws["mean"]
         _cabi.call("ngp_update_density_grid", device, _cabi.ptr(self.density_grid), _cabi.ptr(tmp_grid),
                    self.cascade * n_cells, float(decay), float(self.density_thresh), _cabi.ptr(mean),
-                   _cabi.ptr(self.density_bitfield), _cabi.ptr(ws), ws.numel())
+                   _cabi.ptr(self.density_bitfield), _cabi.ptr(ws["acc"]), ws["acc"].numel())
         self._mean_density = _LazyScalar(tensor=mean)
         self.iter_density += 1
 
-        # mean sample count of the last (up to 16) steps (renderer.py:610-613)
+        # mean sample count of the last (up to 16) steps (renderer.py:610-613): a snapshot of the counters now, the
+        # sum and the device->host read only if somebody asks for the value (nobody does with force_all_rays)
         total_step = min(16, self.local_step)
         if total_step > 0:
-            s = self.step_counter[:total_step, 0].sum()
-            self._mean_count = _LazyScalar(tensor=s, fn=lambda v, n=total_step: int(v / n))
+            snap = ws.setdefault("count_snap", torch.zeros(16, dtype=torch.int32, device=device))
+            snap.copy_(self.step_counter[:, 0])
+            self._mean_count = _LazyCount(snap, total_step)
         self.local_step = 0
+
+    def _density_into(self, xyzs, ws):
+        """sigma (fp32 [n]) of the query points, written into the refresh scratch when the fused field applies."""
+        from . import field as _field
+        enc, net = getattr(self, "encoder", None), getattr(self, "sigma_net", None)
+        if getattr(self, "fused", False) and enc is not None and net is not None and _field.can_fuse(xyzs, enc, net):
+            _field.fused_field_into(xyzs, enc, net, self.bound, ws["sigma"], ws["rgb"])
+            return ws["sigma"]
+        return self.density(xyzs)['sigma'].reshape(-1).detach().float().contiguous()
 
     def render(self, rays_o, rays_d, staged=False, max_ray_batch=4096, **kwargs):
         # rays_o, rays_d: [B, N, 3]; never staged in cuda_ray mode (renderer.py:630-652)

@@ -31,12 +31,18 @@ def entropy_loss(weights_sum, lam=1e-4):
 
 class TrainStep:
     def __init__(self, model, H, W, lr=1e-3, max_steps=1024, lambda_entropy=1e-4, update_interval=16, graph=False,
-                 world_size=1, fused_optimizer=True, lr_decay=None, manual=None, peer_allreduce=None):
+                 world_size=1, fused_optimizer=True, lr_decay=None, manual=None, peer_allreduce=None, pipelined=False):
         """manual: run the step as the hand-scheduled kernel sequence of _body_manual (no autograd, 13 launches) instead
         of the autograd graph of _body (~58 launches); None = whenever the model has the reference's field shape.
         peer_allreduce: world_size > 1 only - fuse the gradient all-reduce into the optimizer kernel over NVLink peer
-        memory (csrc/dp_step.cu) instead of calling NCCL; None = if peer-addressable memory is available."""
+        memory (csrc/dp_step.cu) instead of calling NCCL; None = if peer-addressable memory is available.
+        pipelined (hand-scheduled step only): apply step k's optimizer update (and gradient all-reduce) at the START of
+        step k+1, on the side stream, overlapped with that step's ray marching (which reads no parameters).  Same
+        arithmetic in the same order; the parameters lag one update behind until flush() - called automatically before
+        every occupancy refresh, and by the user before reading the parameters."""
         self.model, self.H, self.W = model, H, W
+        self.pipelined = bool(pipelined)
+        self._pending = False
         self.max_steps, self.lam, self.update_interval = max_steps, lambda_entropy, update_interval
         self.world = world_size
         self.use_graph = graph
@@ -75,6 +81,8 @@ class TrainStep:
             self.scaler = torch.amp.GradScaler("cuda")
             self.bucket = FlatGradBucket(list(model.parameters()), device)
             self.flat_grads = self.bucket.flat
+        if world_size > 1 and dist.is_available() and dist.is_initialized() and not hasattr(model, "dp_shard"):
+            model.dp_shard = (dist.get_rank(), world_size)  # occupancy refresh: 1/world of the cells per rank + all-gather
         self.global_step = 0
         self.n_updates = 0
         self.samples = torch.zeros(1, dtype=torch.int64, device=device)  # running count of marched samples
@@ -82,6 +90,9 @@ class TrainStep:
         # background-net branch of the step (default priority: it fills the gaps of the main chain, measured faster than
         # a high-priority branch that takes SM slots away from the field kernels)
         self._side = torch.cuda.Stream(device=device) if self.manual else None
+        # pipelined optimizer launch: its own HIGH-priority stream, so that its 148 cooperative CTAs are placed ahead of the
+        # thousands of ray-marching CTAs it runs beside (otherwise it only starts when the marcher's last wave does)
+        self._side_opt = torch.cuda.Stream(device=device, priority=-1) if (self.manual and self.pipelined) else None
         self.mirror_rng = False  # draw (and drop) the randn(3) run_cuda spends on light_d, to keep torch's RNG stream aligned
         self._mws = None
         self._ls_mirror = 0
@@ -195,7 +206,12 @@ class TrainStep:
             bg_params = (b0.weight, b0.bias, b1.weight, b1.bias)
             hw_bg = [opt.half_view(t) for t in bg_params]
             g_bg = [opt.grad_view(t) for t in bg_params]
-            self._side.wait_stream(main)
+        if self.pipelined:
+            self._side_opt.wait_stream(main)
+            with torch.cuda.stream(self._side_opt):
+                self._apply_update(deferred=True)  # the PREVIOUS step's update, beside this step's ray marching
+        if has_bg:
+            self._side.wait_stream(self._side_opt if self.pipelined else main)  # (the bg net reads the updated parameters)
             with torch.cuda.stream(self._side):
                 _cabi.call("ngp_bg_forward", dev, P(rd), N, *[P(t) for t in hw_bg], 6, 64, P(m["bg"]))
 
@@ -208,6 +224,8 @@ class TrainStep:
                    int(self.max_steps), N, int(model.cascade), int(model.grid_size), ws.cap, P(m["nears"]), P(m["fars"]),
                    P(ws.xyzs), None, P(ws.deltas), P(ws.rays), P(ws.counter), P(m["noises"]), P(ws.march_ws),
                    ws.march_ws.numel())
+        if self.pipelined:
+            main.wait_stream(self._side_opt)  # the field reads the updated parameters
         _cabi.call("ngp_field_forward", dev, P(ws.xyzs), ws.cap, P(ws.counter), P(opt.half_view(enc.embeddings)), P(enc.offsets),
                    L, 2, S, int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), float(model.bound),
                    *[P(t) for t in hw_field], 64, 4, P(ws.sigma), P(ws.rgb), P(ws.enc), P(ws.h1), P(ws.h2))
@@ -230,10 +248,23 @@ class TrainStep:
                    P(opt.grad_view(enc.embeddings)))
         if has_bg:
             main.wait_stream(self._side)
-        if self.world > 1 and opt.peer_ptrs is None:
-            dist.all_reduce(opt.flat_grads, op=dist.ReduceOp.SUM)
-        opt.step_fused()
+        if not self.pipelined:
+            self._apply_update(deferred=False)
+        self._pending = True
         return m["loss"]
+
+    def _apply_update(self, deferred):
+        if self.world > 1 and self.opt.peer_ptrs is None:
+            dist.all_reduce(self.opt.flat_grads, op=dist.ReduceOp.SUM)
+        self.opt.step_fused(deferred=deferred)
+
+    def flush(self):
+        """Pipelined mode: apply the update that is still pending (no-op otherwise).  After it the parameters are what
+        the un-pipelined step would have left."""
+        if self.manual and self.pipelined and self._pending:
+            self._apply_update(deferred=True)
+            self.opt.state[6:7].zero_()  # nothing pending: the next step's leading launch only re-arms
+            self._pending = False
 
     def _bookkeeping_after(self, local_step_before):
         """Python-side effects of run_cuda that a graph replay does not re-execute."""
@@ -274,6 +305,7 @@ class TrainStep:
             if B * self.H * self.W * 9 != packed.numel():
                 raise RuntimeError("packed inputs do not match H, W of this TrainStep")
         if self.global_step % self.update_interval == 0:
+            self.flush()  # (pipelined mode) the refresh must see the parameters of the completed previous step
             if self.use_graph and not self.fused_optimizer:
                 from . import field
                 field.invalidate_half_cache()  # graph replays update the parameters without bumping ._version

@@ -89,6 +89,25 @@ def main():
     result["steps_taken"], result["skipped"] = mine.steps_taken, int(mine.state[4].item())
     ok = ok and result["skipped"] == 1
 
+    # ---- data-parallel occupancy refresh: 1/world of the cells per rank + all-gather -> identical grids everywhere -----
+    import argparse as _ap
+    from ngp_b200.network_grid import NeRFNetwork
+    torch.manual_seed(0)
+    model = NeRFNetwork(_ap.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)).to(dev).train()
+    torch.manual_seed(100 + rank)   # different jitter streams per rank, as in training
+    model.dp_shard = (rank, world)
+    with torch.autocast("cuda", torch.float16):
+        model.update_extra_state()
+        model.update_extra_state()
+    grids = [torch.empty_like(model.density_grid) for _ in range(world)]
+    dist.all_gather(grids, model.density_grid)
+    bits = [torch.empty_like(model.density_bitfield) for _ in range(world)]
+    dist.all_gather(bits, model.density_bitfield)
+    same = all(torch.equal(g, grids[0]) for g in grids) and all(torch.equal(b, bits[0]) for b in bits)
+    occ = float(torch.tensor([bin(int(v)).count("1") for v in bits[0].cpu().tolist()]).sum()) / (model.density_bitfield.numel() * 8)
+    result["sharded_refresh_identical"], result["sharded_refresh_occupancy"] = bool(same), occ
+    ok = ok and same and 0.02 < occ < 0.15   # the random-init density blob occupies ~5.6 % of the grid
+
     # ---- timing: graph replays of (fused) vs (NCCL all_reduce + check_finite + adam) -------------------------------
     def timed(fn, iters=50):
         side = torch.cuda.Stream()

@@ -68,3 +68,17 @@ def test_flat_bucket_allreduce_equals_single_process_gradient():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_shard_pixels_partitions_every_view_evenly():
+    from ngp_b200.parallel import shard_pixels, shard_rows
+    for world in (1, 2, 4, 8):
+        parts = [shard_pixels(64, 64, r, world) for r in range(world)]
+        assert sorted(p for part in parts for p in part) == list(range(64 * 64))
+        assert all(len(part) == 64 * 64 // world for part in parts)
+        # every rank owns one 8x8 block per block-row: the same mix of image centre and border
+        for part in parts:
+            rows = sorted({p // 64 for p in part})
+            assert rows == list(range(64))
+    # tiling that does not divide: interleaved rows
+    assert shard_pixels(6, 4, 1, 3) == [r * 4 + c for r in shard_rows(6, 1, 3) for c in range(4)]

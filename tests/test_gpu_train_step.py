@@ -248,3 +248,32 @@ def test_hand_scheduled_step_graph_replay_and_packed_inputs():
     np.testing.assert_allclose(la, lb, rtol=0.2)
     assert (ca[:6, 1] == 4096).all() and (cb[:6, 1] == 4096).all()
     assert abs(sa - sb) < 0.2 * sa
+
+
+def test_pipelined_optimizer_applies_the_same_updates_one_step_later():
+    """pipelined=True defers step k's optimizer launch to the start of step k+1 (beside the ray marching); after
+    flush() the same number of updates has been applied and the parameters agree with the un-pipelined run."""
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    ro, rd = provider.make_training_views(5, 64, 64, seed=4, pin=False)
+    ro, rd = ro.view(5, 1, 4096, 3).to(DEV), rd.view(5, 1, 4096, 3).to(DEV)
+    G = torch.randn(5, 1, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2)) * 1e-2
+    finals = []
+    for pipelined in (False, True):
+        m = _bench_like_model()
+        step = TrainStep(m, 64, 64, lr=1e-4, graph=False, manual=True, pipelined=pipelined)
+        torch.manual_seed(7)
+        losses = [step(ro[i], rd[i], G[i]).item() for i in range(5)]
+        if pipelined:
+            assert step.opt.steps_taken == 4            # the fifth update is still pending
+            step.flush()
+            step.flush()                                # idempotent
+        assert step.opt.steps_taken == 5 and step.opt.state[4].item() == 0
+        assert step.opt.flat_grads.abs().sum().item() == 0
+        finals.append((losses, {n: p.detach().clone() for n, p in m.named_parameters()}))
+    # step 1 sees identical parameters in both runs; afterwards only the atomics' summation order differs
+    assert abs(finals[0][0][0] - finals[1][0][0]) <= 1e-6 * abs(finals[0][0][0])
+    np.testing.assert_allclose(finals[0][0], finals[1][0], rtol=2e-2)
+    for n in finals[0][1]:
+        a, b = finals[0][1][n], finals[1][1][n]
+        assert ((a - b).norm() / (b.norm() + 1e-12)).item() < 0.05, n
