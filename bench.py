@@ -29,6 +29,7 @@ for _p in (ROOT, PKG):
         sys.path.insert(0, _p)
 
 METRIC = "NeRF train-step samples/s (march+hashgrid+MLP+composite fwd/bwd)"
+NCU_SCATTER_DRAM_BYTES_PER_LAUNCH = 313.4e6  # profiles/ncu_full_r1_v7.md: 0.3095 GB read + 0.0039 GB written
 UNIT = "samples/s"
 VIEWS_PER_STEP = 8
 H = W = 64
@@ -48,8 +49,11 @@ def parse():
     ap.add_argument("--lr", type=float, default=1e-5)
     ap.add_argument("--no-graph", action="store_true", help="run the train step eagerly instead of as one CUDA graph")
     ap.add_argument("--autograd", action="store_true", help="autograd version of the step instead of the hand-scheduled kernels")
-    ap.add_argument("--ray-order", default="tiles", choices=["tiles", "rows"], help="order / sharding of a view's rays")
-    ap.add_argument("--no-pipeline", action="store_true", help="apply the optimizer update at the end of its own step")
+    ap.add_argument("--ray-order", default="rows", choices=["tiles", "rows"], help="sharding of a view's rays over the ranks "
+                    "(rows: interleaved image rows, measured 9 %% faster at 8 GPUs than 8x8 blocks dealt along diagonals)")
+    ap.add_argument("--pipeline", action="store_true", help="apply step k's optimizer update at the start of step k+1 "
+                    "(beside the ray marching); measured: no gain, the marcher slows down by what the optimizer takes")
+    ap.add_argument("--chunks", type=int, default=0, help="ray chunks run as parallel chains (0 = the default, 2)")
     ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce instead of the fused peer-memory all-reduce + Adam")
     ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
@@ -228,7 +232,7 @@ def run_b200_arm(args):
     # random-init occupancy so that every timed pass sees the same ~3.4 M samples per step
     step_fn = TrainStep(model, Hl, W, lr=args.lr, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world,
                         manual=False if args.autograd else None, peer_allreduce=False if args.nccl else None,
-                        pipelined=not (args.no_pipeline or args.autograd))
+                        pipelined=args.pipeline and not args.autograd, n_chunks=args.chunks or None)
     # one packed, pinned host buffer per batch [rays_o | rays_d | G]: a step's inputs are ONE copy
     host_pool = torch.stack([step_fn.pack_inputs(ro_all[k], rd_all[k], g_all[k].contiguous()) for k in range(n_pool)]).pin_memory()
 
@@ -319,6 +323,11 @@ def run_b200_arm(args):
     if True:  # every rank runs the same eager steps (they contain the gradient all-reduce); rank 0 reports
         was_graph = step_fn.use_graph
         step_fn.use_graph = False
+        # one serial chain for the per-kernel timings (concurrent chains inflate each other's event-to-event times);
+        # the step's own workspace (referenced by the captured graph) is kept aside and restored afterwards
+        saved_ws = (step_fn.n_chunks, step_fn._mws, step_fn._chain, getattr(model, "_train_ws", None))
+        if step_fn.manual:
+            step_fn.n_chunks, step_fn._mws = 1, None
         names = ["ngp_grid_scatter_samples", "ngp_grid_encode_backward", "ngp_field_forward", "ngp_field_backward",
                  "ngp_march_rays_train", "ngp_composite_rays_train_forward", "ngp_composite_rays_train_backward",
                  "ngp_grid_encode_forward", "ngp_train_prologue", "ngp_train_ray_loss", "ngp_bg_forward", "ngp_bg_backward",
@@ -337,6 +346,10 @@ def run_b200_arm(args):
             if evs:
                 kern[name] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
         step_fn.use_graph = was_graph
+        if step_fn.manual:
+            step_fn.flush()
+            torch.cuda.synchronize()
+            step_fn.n_chunks, step_fn._mws, step_fn._chain, model._train_ws = saved_ws
     if world > 1:
         dist.barrier()
 
@@ -363,7 +376,7 @@ def run_b200_arm(args):
         # algorithmic L2 bytes per encoded point: 16 levels x 8 corners x 4 B (SURVEY 8d / BASELINE.md 4); the profiled
         # eager steps processed prof_samples points in total, one forward and two backward launches per step
         launches_per_step = n_calls / max(args.profile_steps, 1)
-        points_per_launch = prof_samples / max(args.profile_steps, 1)
+        points_per_launch = prof_samples / max(n_calls, 1)
         is_gather = dom in ("ngp_field_forward", "ngp_grid_encode_forward")
         is_scatter = dom in ("ngp_grid_scatter_samples", "ngp_grid_encode_backward")
         achieved = 512.0 * points_per_launch / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
@@ -371,7 +384,15 @@ def run_b200_arm(args):
         step_kernel_ms = sum(v[0] for v in kern.values()) / max(args.profile_steps, 1)
         roofline = {
             "bound": "l2", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak if (peak and (is_gather or is_scatter)) else None, "traffic": None,
+            "frac": achieved / peak if (peak and (is_gather or is_scatter)) else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of the grid scatter kernel per launch, from the ncu --set full
+            # capture profiles/ncu_full_r1_v8.md (3.4 M samples per launch): the table gradient lives in L2, HBM only sees
+            # the d_enc / xyzs streams (76 B per sample algorithmic = 0.26 GB)
+            "traffic": NCU_SCATTER_DRAM_BYTES_PER_LAUNCH if is_scatter else None,
+            "hbm": {"algorithmic_bytes_per_sample": 144, "achieved_gbs": 144.0 * samples / (ms * 1e-3) / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"),
+                    "frac": (144.0 * samples / (ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                    "note": "whole-step HBM view (SURVEY 8d: 144 B per marched sample); the step is L2 / issue bound, not HBM bound"},
             "avg_launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
             "share_of_step": (tot_ms / max(args.profile_steps, 1)) / (ms / args.steps),
             "how": "CUDA events around the entry point over %d eager (non-graph) steps after the timed region; "
@@ -398,6 +419,7 @@ def run_b200_arm(args):
                 "sharding": ("8x8-pixel blocks of every view dealt along the block diagonals" if args.ray_order == "tiles"
                              else "image rows interleaved over ranks"),
                 "pipelined_optimizer": step_fn.pipelined,
+                "ray_chunks": len(step_fn._mws["chunks"]) if step_fn._mws else 1,
                 "grad_allreduce": ("none (1 GPU)" if world == 1 else
                                    ("fused into the optimizer kernel over NVLink peer memory (%s)" % step_fn.peer.used
                                     if step_fn.opt.peer_ptrs is not None else "NCCL all_reduce (%s)" % (step_fn.peer_error or "requested"))),

@@ -262,6 +262,9 @@ int ngp_bg_backward(const float* dirs, const float* grad_rgb, uint32_t N, const 
  *   all mapped into this process (symmetric memory / CUDA IPC).  Each rank reduces and updates slice `rank` and writes
  *   the new parameters to every replica; exp_avg / exp_avg_sq are maintained for that slice only.  The gradient bucket
  *   is zero-filled on the way out.  All ranks must launch the same sequence of calls.
+ *   multicast: NULL, or a HOST array of 3 NVLS multicast addresses of the gradient bucket, the parameters and the shadow
+ *   (the same symmetric allocation mapped through the NVSwitch): the reduce-scatter then is one multimem.ld_reduce per
+ *   element (summed inside the switch) and the parameter broadcast one multimem.st instead of `world` P2P stores.
  *   deferred != 0: for a trainer that applies step k's update at the START of step k+1 (overlapped with that step's ray
  *   marching): a launch that finds state[6] == 0 applies nothing and sets state[6] = 1 ("gradients will be pending next
  *   time"); the caller clears state[6] after flushing the last pending update. */
@@ -272,29 +275,33 @@ int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_
                         float eps, float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor,
                         float backoff_factor, uint32_t growth_interval, int deferred, float* state, uint32_t* sync,
                         uint32_t rank, uint32_t world, const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half,
-                        const uint64_t* peer_flags, void* stream);
+                        const uint64_t* peer_flags, const uint64_t* multicast, void* stream);
 uint64_t ngp_dp_flags_bytes(void);
 /* cudaDeviceEnablePeerAccess(peer_device) from the current device (idempotent). */
 int ngp_enable_peer_access(int peer_device);
 
 /* First and middle kernels of the hand-scheduled train step (ngp_b200/trainer.py).
- * ngp_train_prologue: near_far_from_aabb (raymarching.cu:92-156) for N rays + zero-fill of counter i32[2] and loss f32[1]
- * (either may be NULL).
+ * ngp_train_prologue: near_far_from_aabb (raymarching.cu:92-156) for N rays + the step's device-side bookkeeping: zero-fill
+ * of counters i32[n_counters] and loss f32[1]; opens the step's row of run_cuda's 16-step window (nerf/renderer.py:466-467):
+ * *cur_row = *local_step % 16, step_counter[*cur_row] = (0, 0), ++*local_step.  Each pointer group may be NULL.
  * ngp_train_ray_loss: per ray, in one launch: composite_rays_train forward (raymarching.cu:501-588), the background blend
  * (nerf/renderer.py:541-545), the gradients of the two losses of Trainer.train_step at the ray - grad_pred (the guidance
  * gradient wrt the blended image, [B,3,pixels_per_view] NCHW as nerf/sd.py:115 passes it, or [N,3] if pixels_per_view is
  * 0) and lambda * mean opacity entropy times *scale (nerf/utils.py:389-394,708) - and composite_rays_train backward
- * (raymarching.cu:602-693).  Outputs: weights_sum[N], depth[N], image[N,3] (before the blend), grad_bg[N,3] (optional),
- * grad_sigmas[M], grad_rgbs[M,3]; *loss += the entropy loss.  bg_half: f16[N,3] or NULL (then the colour bg_const).
- * Optional device-side bookkeeping when counter != NULL: *samples_total += counter[0];
- * step_counter[*local_step % 16] = counter; ++*local_step (nerf/renderer.py:466-467). */
+ * (raymarching.cu:602-693).  The launch may cover a chunk of the step's rays: its N rays are rays ray_base .. ray_base+N-1
+ * of n_rays_total (0 = N); all per-ray pointers are the chunk's.  Outputs: weights_sum[N], depth[N], image[N,3] (before the
+ * blend), grad_bg[N,3] (optional), grad_sigmas[M], grad_rgbs[M,3]; *loss += the chunk's share of the entropy loss.
+ * bg_half: f16[N,3] or NULL (then the colour bg_const).  Optional bookkeeping when counter != NULL (atomic):
+ * *samples_total += counter[0]; step_counter[*cur_row] += counter. */
 int ngp_train_prologue(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near, float* nears,
-                       float* fars, int* counter, float* loss, void* stream);
+                       float* fars, int* counters, uint32_t n_counters, float* loss, int* step_counter, int* local_step,
+                       int* cur_row, void* stream);
 int ngp_train_ray_loss(const float* sigmas, const float* rgbs, const float* deltas, const int* rays, uint32_t M, uint32_t N,
                        float T_thresh, const void* bg_half, float bg_const, const float* grad_pred, uint32_t pixels_per_view,
-                       float lambda_entropy, const float* scale, float* weights_sum, float* depth, float* image,
-                       float* grad_bg, float* grad_sigmas, float* grad_rgbs, float* loss, const int* counter,
-                       long long* samples_total, int* step_counter, int* local_step, void* stream);
+                       uint32_t ray_base, uint32_t n_rays_total, float lambda_entropy, const float* scale, float* weights_sum,
+                       float* depth, float* image, float* grad_bg, float* grad_sigmas, float* grad_rgbs, float* loss,
+                       const int* counter, unsigned long long* samples_total, int* step_counter, const int* cur_row,
+                       void* stream);
 
 /* End of run_cuda (nerf/renderer.py:535-557): image_out = image + (1 - weights_sum) * bg, depth_out =
  * clamp(depth - nears, 0) / (fars - nears) (NaN where the ray misses the box, as the reference), mask = nears < fars.

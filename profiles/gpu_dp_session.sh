@@ -14,6 +14,8 @@ for N in $NS; do
   if [ "$FIRST" = 1 ] && [ "$N" != 1 ]; then
     timeout 300 $TR --master-port 29511 tests/dp_peer_check.py > $O/dp_check_${TAG}_n$N.json 2> $O/dp_check_${TAG}_n$N.err
     echo "dp_check N=$N exit $?"; tail -1 $O/dp_check_${TAG}_n$N.json | cut -c1-500; grep -v "^\*\*\*\|OMP_NUM\|^$" $O/dp_check_${TAG}_n$N.err | tail -3 | cut -c1-300
+    NGP_DP_MULTICAST=0 timeout 300 $TR --master-port 29514 tests/dp_peer_check.py > $O/dp_check_${TAG}_n${N}_p2p.json 2> $O/dp_check_${TAG}_n${N}_p2p.err
+    echo "dp_check (P2P only) N=$N exit $?"; tail -1 $O/dp_check_${TAG}_n${N}_p2p.json | cut -c1-500
   fi
   PORT=$((29520 + N))
   if [ "$N" = 1 ]; then

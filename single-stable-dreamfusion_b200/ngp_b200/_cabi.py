@@ -61,12 +61,12 @@ SIGNATURES = {
                              _f32, _f32, _f32, _f32, _u32, _i32, _vp, _vp, _vp]),
     "ngp_adam_step_fused": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64), C.POINTER(_f32), _f32, _f32, _f32, _f32,
                                    _f32, _f32, _f32, _f32, _u32, _i32, _vp, _vp, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64),
-                                   C.POINTER(_u64), C.POINTER(_u64), _vp]),
+                                   C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _vp]),
     "ngp_dp_flags_bytes": (_u64, []),
     "ngp_enable_peer_access": (_i32, [_i32]),
-    "ngp_train_prologue": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp]),
-    "ngp_train_ray_loss": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _f32, _vp, _u32, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
-                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_train_prologue": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_train_ray_loss": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _f32, _vp, _u32, _u32, _u32, _f32, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ngp_blend_background_forward": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
     "ngp_blend_background_backward": (_i32, [_vp, _vp, _vp, _i32, _u32, _vp, _vp, _vp]),
     "ngp_entropy_loss_forward": (_i32, [_vp, _u32, _f32, _vp, _vp]),

@@ -59,6 +59,11 @@ struct Args {
     float* peer_p[kMaxWorld];
     __half* peer_h[kMaxWorld];
     uint32_t* peer_flags[kMaxWorld];  // each: [3][kMaxBlocks][kMaxWorld] uint32, zero-initialised
+    // optional NVLink SHARP (NVLS) multicast views of the same three buffers: one multimem.ld_reduce returns the sum of an
+    // element over all replicas (added inside the switch), one multimem.st writes an element to every replica
+    float* mc_g;
+    float* mc_p;
+    __half* mc_h;
 };
 
 NGP_DEVINL void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -71,6 +76,18 @@ NGP_DEVINL float4 ld_relaxed_sys_f4(const float* p) {
     float4 v;
     asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
+}
+NGP_DEVINL float4 multimem_ld_reduce_add_f4(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+NGP_DEVINL void multimem_st_f4(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+NGP_DEVINL void multimem_st_b64(void* mc, uint2 v) {  // 8 bytes moved as two f32 lanes (a store: the bit patterns pass through)
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
 }
 NGP_DEVINL uint64_t now_ns() {
     uint64_t t;
@@ -130,12 +147,19 @@ __global__ void __launch_bounds__(512) adam_step_fused_kernel(const Args a) {
     bool bad = false;
     for (uint64_t i = lo + tid; i < hi; i += nthreads) {
         float4 s;
-        if (a.world > 1) {
-            s = ld_relaxed_sys_f4(a.peer_g[0] + i * 4);
-            for (uint32_t q = 1; q < a.world; ++q) {
-                const float4 t = ld_relaxed_sys_f4(a.peer_g[q] + i * 4);
-                s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
-            }
+        if (a.world > 1 && a.mc_g) {
+            s = multimem_ld_reduce_add_f4(a.mc_g + i * 4);   // summed in the NVSwitch: 1/world of the P2P ingress
+            *reinterpret_cast<float4*>(a.g + i * 4) = s;
+        } else if (a.world > 1) {
+            // all `world` loads are issued before the first add: one NVLink round trip per element, not `world` of them
+            float4 v[kMaxWorld];
+#pragma unroll
+            for (uint32_t q = 0; q < kMaxWorld; ++q)
+                if (q < a.world) v[q] = ld_relaxed_sys_f4(a.peer_g[q] + i * 4);
+            s = v[0];
+#pragma unroll
+            for (uint32_t q = 1; q < kMaxWorld; ++q)
+                if (q < a.world) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }   // fixed rank order
             *reinterpret_cast<float4*>(a.g + i * 4) = s;  // nobody else reads slice `rank` of this rank's bucket
         } else {
             s = *reinterpret_cast<const float4*>(a.g + i * 4);
@@ -197,7 +221,10 @@ __global__ void __launch_bounds__(512) adam_step_fused_kernel(const Args a) {
             __half2 h0 = __floats2half2_rn(p[0], p[1]), h1 = __floats2half2_rn(p[2], p[3]);
             uint2 raw;
             raw.x = *reinterpret_cast<uint32_t*>(&h0); raw.y = *reinterpret_cast<uint32_t*>(&h1);
-            if (a.world > 1) {
+            if (a.world > 1 && a.mc_p) {
+                multimem_st_f4(a.mc_p + e0, pn);             // one store, replicated by the switch to every rank
+                if (a.h) multimem_st_b64(a.mc_h + e0, raw);
+            } else if (a.world > 1) {
                 for (uint32_t q = 0; q < a.world; ++q) {
                     const uint32_t dst = (a.rank + q) % a.world;   // start with the own replica, spread the link load
                     *reinterpret_cast<float4*>(a.peer_p[dst] + e0) = pn;
@@ -278,7 +305,7 @@ extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, 
                                    float growth_factor, float backoff_factor, uint32_t growth_interval, int deferred,
                                    float* state, uint32_t* sync, uint32_t rank, uint32_t world, const uint64_t* peer_grads,
                                    const uint64_t* peer_params, const uint64_t* peer_half, const uint64_t* peer_flags,
-                                   void* stream) {
+                                   const uint64_t* multicast, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !state || !sync || !seg_end || !seg_lr) return NGP_ERR_BAD_ARG;
     if (n_segments == 0 || n_segments > NGP_ADAM_MAX_SEGMENTS || seg_end[n_segments - 1] != n) return NGP_ERR_BAD_ARG;
     if (n == 0 || (n & 3) != 0) return NGP_ERR_BAD_ARG;
@@ -306,6 +333,10 @@ extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, 
         a.peer_flags[q] = on ? reinterpret_cast<uint32_t*>(peer_flags[q]) : nullptr;
         if (on && (!a.peer_g[q] || !a.peer_p[q] || !a.peer_flags[q])) return NGP_ERR_BAD_ARG;
     }
+    const bool mc = world > 1 && multicast && multicast[0] && multicast[1] && (!half_shadow || multicast[2]);
+    a.mc_g = mc ? reinterpret_cast<float*>(multicast[0]) : nullptr;
+    a.mc_p = mc ? reinterpret_cast<float*>(multicast[1]) : nullptr;
+    a.mc_h = mc && half_shadow ? reinterpret_cast<__half*>(multicast[2]) : nullptr;
     int blocks = num_sms();
     if (blocks > (int)dp::kMaxBlocks) blocks = (int)dp::kMaxBlocks;
     void* kargs[] = {&a};

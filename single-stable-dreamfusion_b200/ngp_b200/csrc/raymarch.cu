@@ -297,15 +297,25 @@ __global__ void near_far_kernel(const float* __restrict__ rays_o, const float* _
     fars[n] = hi;
 }
 
-// First kernel of the hand-scheduled train step (ngp_train_prologue): near/far of every ray plus the zero-fill of the
-// step's device-side scalars (sample counter pair, loss accumulator), so no separate fill launches are needed.
+// First kernel of the hand-scheduled train step (ngp_train_prologue): near/far of every ray plus the step's device-side
+// bookkeeping, so no separate fill launches are needed: zero the sample-counter pairs and the loss accumulator; open the
+// step's row of run_cuda's 16-step counter window (nerf/renderer.py:466-467): *cur_row = *local_step % 16,
+// step_counter[*cur_row] = 0, ++*local_step.
 __global__ void train_prologue_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                       const float* __restrict__ aabb, uint32_t N, float min_near, float* nears,
-                                      float* fars, int* counter, float* loss) {
+                                      float* fars, int* counters, uint32_t n_counters, float* loss, int* step_counter,
+                                      int* local_step, int* cur_row) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n == 0) {
-        if (counter) { counter[0] = 0; counter[1] = 0; }
+        for (uint32_t i = 0; counters && i < n_counters; ++i) counters[i] = 0;
         if (loss) *loss = 0.f;
+        if (step_counter && local_step && cur_row) {
+            const int row = (*local_step) & 15;
+            *cur_row = row;
+            step_counter[row * 2] = 0;
+            step_counter[row * 2 + 1] = 0;
+            *local_step += 1;
+        }
     }
     if (n >= N) return;
     const Ray r = load_ray(rays_o, rays_d, n);
@@ -744,12 +754,15 @@ struct RayLossArgs {
     float* d_bg;           // [N,3] gradient wrt the background colour, or nullptr
     float *grad_sigmas, *grad_rgbs;       // [M], [M,3]
     float* loss;           // += lambda * mean entropy (zeroed by the prologue)
-    // optional device-side bookkeeping of run_cuda / the bench (done by one thread): samples += counter[0];
-    // step_counter[local_step % 16] = counter; ++local_step
+    // A launch may cover a CHUNK of the step's rays (chunks run on parallel streams): ray_base = index of its first ray
+    // among all rays of the step (for the NCHW lookup of G), n_total = rays of the whole step (the entropy mean)
+    uint32_t ray_base, n_total;
+    // optional device-side bookkeeping of run_cuda / the bench (done by one thread, atomically - chunks run concurrently):
+    // samples_total += counter[0]; step_counter[*cur_row] += counter   (row opened by the prologue)
     const int* counter;
-    long long* samples_total;
+    unsigned long long* samples_total;
     int* step_counter;
-    int* local_step;
+    const int* cur_row;
 };
 
 constexpr float kAlphaLoR = 1e-5f, kAlphaHiR = 1.f - 1e-5f;
@@ -774,12 +787,11 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float entropy = 0.f;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.counter) {
-        if (a.samples_total) *a.samples_total += (long long)a.counter[0];
-        if (a.step_counter && a.local_step) {
-            const int row = (*a.local_step) & 15;
-            a.step_counter[row * 2] = a.counter[0];
-            a.step_counter[row * 2 + 1] = a.counter[1];
-            *a.local_step += 1;
+        if (a.samples_total) atomicAdd(a.samples_total, (unsigned long long)a.counter[0]);
+        if (a.step_counter && a.cur_row) {
+            const int row = (*a.cur_row) & 15;
+            atomicAdd(a.step_counter + row * 2, a.counter[0]);
+            atomicAdd(a.step_counter + row * 2 + 1, a.counter[1]);
         }
     }
     if (n < a.N) {
@@ -828,7 +840,8 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
         }
         float gi[3];
         if (a.hw) {
-            const uint32_t view = id / a.hw, pix = id % a.hw;
+            const uint32_t gid = id + a.ray_base;
+            const uint32_t view = gid / a.hw, pix = gid % a.hw;
 #pragma unroll
             for (int c = 0; c < 3; ++c) gi[c] = a.G[((size_t)view * 3 + c) * a.hw + pix];
         } else {
@@ -842,7 +855,7 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
         entropy = -al * log2f(al) - (1.f - al) * log2f(1.f - al);
         if (ws >= kAlphaLoR && ws <= kAlphaHiR) {
             const float up = a.scale ? *a.scale : 1.f;
-            gws += up * (a.lambda / (float)a.N) * (log2f(1.f - ws) - log2f(ws));
+            gws += up * (a.lambda / (float)a.n_total) * (log2f(1.f - ws) - log2f(ws));
         }
         if (lane == 0) {
             a.weights_sum[id] = ws;
@@ -912,7 +925,7 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
     if (threadIdx.x == 0 && a.loss) {
         float v = 0.f;
         for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) v += s_loss[w];
-        atomicAdd(a.loss, v * (a.lambda / (float)a.N));
+        atomicAdd(a.loss, v * (a.lambda / (float)a.n_total));
     }
 }
 
@@ -1145,29 +1158,33 @@ extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, 
 }
 
 extern "C" int ngp_train_prologue(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
-                                  float* nears, float* fars, int* counter, float* loss, void* stream) {
+                                  float* nears, float* fars, int* counters, uint32_t n_counters, float* loss,
+                                  int* step_counter, int* local_step, int* cur_row, void* stream) {
     if (!rays_o || !rays_d || !aabb || !nears || !fars) return NGP_ERR_BAD_ARG;
-    march::train_prologue_kernel<<<N ? cdiv(N, 128) : 1, 128, 0, as_stream(stream)>>>(rays_o, rays_d, aabb, N, min_near, nears,
-                                                                                   fars, counter, loss);
+    march::train_prologue_kernel<<<N ? cdiv(N, 128) : 1, 128, 0, as_stream(stream)>>>(
+        rays_o, rays_d, aabb, N, min_near, nears, fars, counters, n_counters, loss, step_counter, local_step, cur_row);
     return launch_status();
 }
 
 extern "C" int ngp_train_ray_loss(const float* sigmas, const float* rgbs, const float* deltas, const int* rays, uint32_t M,
                                   uint32_t N, float T_thresh, const void* bg_half, float bg_const, const float* grad_pred,
-                                  uint32_t pixels_per_view, float lambda_entropy, const float* scale, float* weights_sum,
-                                  float* depth, float* image, float* grad_bg, float* grad_sigmas, float* grad_rgbs,
-                                  float* loss, const int* counter, long long* samples_total, int* step_counter,
-                                  int* local_step, void* stream) {
+                                  uint32_t pixels_per_view, uint32_t ray_base, uint32_t n_rays_total, float lambda_entropy,
+                                  const float* scale, float* weights_sum, float* depth, float* image, float* grad_bg,
+                                  float* grad_sigmas, float* grad_rgbs, float* loss, const int* counter,
+                                  unsigned long long* samples_total, int* step_counter, const int* cur_row, void* stream) {
     if (!sigmas || !rgbs || !deltas || !rays || !grad_pred || !weights_sum || !depth || !image || !grad_sigmas || !grad_rgbs)
         return NGP_ERR_BAD_ARG;
-    if (pixels_per_view && N % pixels_per_view != 0) return NGP_ERR_BAD_ARG;
+    if (n_rays_total == 0) n_rays_total = N;
+    if ((uint64_t)ray_base + N > n_rays_total) return NGP_ERR_BAD_ARG;
+    if (pixels_per_view && n_rays_total % pixels_per_view != 0) return NGP_ERR_BAD_ARG;
     if (N == 0) return NGP_OK;
     march::RayLossArgs a;
     a.sigmas = sigmas; a.rgbs = rgbs; a.deltas = deltas; a.rays = rays; a.M = M; a.N = N; a.T_thresh = T_thresh;
     a.bg = static_cast<const __half*>(bg_half); a.bg_const = bg_const; a.G = grad_pred; a.hw = pixels_per_view;
+    a.ray_base = ray_base; a.n_total = n_rays_total;
     a.lambda = lambda_entropy; a.scale = scale; a.weights_sum = weights_sum; a.depth = depth; a.image = image;
     a.d_bg = grad_bg; a.grad_sigmas = grad_sigmas; a.grad_rgbs = grad_rgbs; a.loss = loss; a.counter = counter;
-    a.samples_total = samples_total; a.step_counter = step_counter; a.local_step = local_step;
+    a.samples_total = samples_total; a.step_counter = step_counter; a.cur_row = cur_row;
     march::train_ray_loss_kernel<<<cdiv((uint64_t)N * 32, 256), 256, 0, as_stream(stream)>>>(a);
     return launch_status();
 }

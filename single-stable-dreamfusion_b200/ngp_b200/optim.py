@@ -15,6 +15,7 @@ All state (loss scale, growth tracker, step count) stays on the device: the step
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -60,6 +61,11 @@ class FusedAdamScaler:
         self.exp_avg, self.exp_avg_sq = f(), f()
         self.peer = peer_memory
         self.peer_ptrs = None
+        self.multicast = None
+        # measured (profiles/dp_check_*): the switch-side reduction wins from 8 ranks on (64 vs 67 us per step), plain P2P
+        # at 2 ranks (52 vs 64 us) - the multimem instructions cost latency and only pay once the fan-out is large
+        env = os.environ.get("NGP_DP_MULTICAST", "auto")
+        self.use_multicast = (peer_memory is not None and peer_memory.world > 4) if env == "auto" else env != "0"
         if peer_memory is None:
             self.flat_params, self.flat_grads, self.flat_half = f(), f(), f(torch.half)
         else:
@@ -69,7 +75,7 @@ class FusedAdamScaler:
             o_g, o_p, o_h = 0, al(4 * off), al(4 * off) * 2
             o_f = o_h + al(2 * off)
             total = o_f + int(lib.ngp_dp_flags_bytes())
-            raw, bases = peer_memory.alloc(total)
+            raw, bases, mc_base = peer_memory.alloc(total)
             raw.zero_()
             self._peer_raw = raw
             self.flat_grads = raw[o_g:o_g + 4 * off].view(torch.float32)
@@ -77,6 +83,8 @@ class FusedAdamScaler:
             self.flat_half = raw[o_h:o_h + 2 * off].view(torch.half)
             mk = lambda o: (ctypes.c_uint64 * len(bases))(*[b + o for b in bases])  # noqa: E731
             self.peer_ptrs = (mk(o_g), mk(o_p), mk(o_h), mk(o_f))
+            # NVLS multicast view of the same allocation (0 when the box has none): switch-side reduction / broadcast
+            self.multicast = (ctypes.c_uint64 * 3)(mc_base + o_g, mc_base + o_p, mc_base + o_h) if mc_base else None
             peer_memory.barrier()  # every rank has zeroed its flags before anybody signals
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):
@@ -149,15 +157,16 @@ class FusedAdamScaler:
         deferred: the launch only arms (state[6] = 1) when nothing is pending yet - see TrainStep(pipelined=True)."""
         dev = self.device
         if self.peer_ptrs is None:
-            rank, world, pg, pp, ph, pf = 0, 1, None, None, None, None
+            rank, world, pg, pp, ph, pf, mc = 0, 1, None, None, None, None, None
         else:
             rank, world = self.peer.rank, self.peer.world
             pg, pp, ph, pf = self.peer_ptrs
+            mc = self.multicast if self.use_multicast else None
         _cabi.call("ngp_adam_step_fused", dev, _cabi.ptr(self.flat_params), _cabi.ptr(self.flat_grads), _cabi.ptr(self.exp_avg),
                    _cabi.ptr(self.exp_avg_sq), _cabi.ptr(self.flat_half), self.numel, self.n_seg, self.seg_end, self.seg_lr,
                    float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,
                    self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
-                   int(bool(deferred)), _cabi.ptr(self.state), _cabi.ptr(self._sync), rank, world, pg, pp, ph, pf)
+                   int(bool(deferred)), _cabi.ptr(self.state), _cabi.ptr(self._sync), rank, world, pg, pp, ph, pf, mc)
 
     def grad_view(self, p):
         """The slice of the flat gradient bucket that backs `p.grad` (same shape as p)."""

@@ -6,8 +6,6 @@ The reference has no working multi-GPU path (a dormant DDP wrap, nerf/utils.py:2
 all-reduce exactly these parameters.  Parameter .grad tensors are views into the bucket, so autograd
 accumulates straight into it and no flatten / unflatten copies are needed.
 """
-import os
-
 import torch
 import torch.distributed as dist
 
@@ -83,37 +81,34 @@ def shard_pixels(H, W, rank, world_size, tile=8):
 class PeerMemory:
     """Device memory that every rank of the group can address directly (loads / stores / atomics over NVLink).
 
-    alloc(nbytes) -> (local uint8 tensor, [device address of that allocation on every rank, in rank order]).
+    alloc(nbytes) -> (local uint8 tensor, [device address of that allocation on every rank, in rank order],
+                      NVLS multicast address of the allocation or 0).
     The plumbing is PyTorch's symmetric memory (torch.distributed._symmetric_memory: cuMem allocations whose handles
     are exchanged through the group's store and mapped into every rank); kernels only ever see raw addresses
     (csrc/dp_step.cu).  Raises RuntimeError when the box cannot do it; callers then fall back to an NCCL all-reduce.
     """
 
-    def __init__(self, device, group=None, backend=None):
+    def __init__(self, device, group=None):
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerMemory needs an initialised process group")
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.device = torch.device(device)
-        self.backend = backend or os.environ.get("NGP_PEER_BACKEND", "auto")
         self._keep = []
         self.used = None
 
     def alloc(self, nbytes):
         nbytes = (int(nbytes) + 255) // 256 * 256
-        errors = []
-        for how in ["symm"]:
-            try:
-                out = self._alloc_symm(nbytes)
-                ok = torch.ones(1, device=self.device)
-            except Exception as e:  # noqa: BLE001 - any failure means "this back-end is not available here"
-                errors.append("%s: %r" % (how, e))
-                out, ok = None, torch.zeros(1, device=self.device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # all ranks must agree on the back-end
-            if ok.item() > 0:
-                self.used = how
-                return out
-        raise RuntimeError("no peer-addressable memory on this box: " + "; ".join(errors))
+        try:
+            out, err = self._alloc_symm(nbytes), None
+        except Exception as e:  # noqa: BLE001 - any failure means "not available on this box"
+            out, err = None, repr(e)
+        ok = torch.tensor([0.0 if out is None else 1.0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)  # every rank takes the same path
+        if ok.item() > 0:
+            self.used = "symm"
+            return out
+        raise RuntimeError("no peer-addressable memory on this box: %s" % (err or "another rank failed"))
 
     def _alloc_symm(self, nbytes):
         import torch.distributed._symmetric_memory as symm
@@ -123,7 +118,12 @@ class PeerMemory:
         if len(bases) != self.world or bases[self.rank] != t.data_ptr():
             raise RuntimeError("unexpected symmetric-memory handle layout")
         self._keep.append((t, hdl))
-        return t, bases
+        mc = 0
+        try:
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        except Exception:  # noqa: BLE001 - no multicast on this box / torch build
+            mc = 0
+        return t, bases, mc
 
     def barrier(self):
         torch.cuda.synchronize(self.device)

@@ -21,7 +21,7 @@ _BYTES_PER_ROW = 12 + 8 + 4 + 12 + 64 + 128 + 128 + 4 + 12 + 64  # xyzs deltas s
 class TrainWorkspace:
     """Static per-(N, max_steps) buffers of the training render."""
 
-    def __init__(self, n_rays, max_steps, device, cap_rows=None):
+    def __init__(self, n_rays, max_steps, device, cap_rows=None, counter=None):
         cap = n_rays * max_steps if cap_rows is None else min(int(cap_rows), n_rays * max_steps)
         cap = (cap + 127) // 128 * 128  # the field kernels save / restore whole 128-sample tiles
         self.n_rays, self.max_steps, self.cap = n_rays, max_steps, cap
@@ -34,7 +34,7 @@ class TrainWorkspace:
         self.rays = torch.empty(n_rays, 3, device=device, dtype=torch.int32)
         lib = _cabi.load()
         self.march_ws = torch.empty(int(lib.ngp_march_rays_train_workspace(n_rays, int(max_steps))), device=device, dtype=torch.uint8)
-        self.counter = torch.zeros(2, device=device, dtype=torch.int32)
+        self.counter = torch.zeros(2, device=device, dtype=torch.int32) if counter is None else counter
 
     @property
     def nbytes(self):

@@ -26,7 +26,6 @@ import torch.distributed as dist  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--backend", default="auto")
     ap.add_argument("--n", type=int, default=1816256)
     ap.add_argument("--steps", type=int, default=6)
     args = ap.parse_args()
@@ -49,9 +48,10 @@ def main():
     groups = lambda ps: [{"params": ps[:1], "lr": 1e-2}, {"params": ps[1:], "lr": 1e-3}]  # noqa: E731
     result = {"world": world, "n": args.n}
     try:
-        peer = PeerMemory(dev, backend=args.backend)
+        peer = PeerMemory(dev)
         mine = FusedAdamScaler(groups(pa), growth_interval=3, grad_div=float(world), peer_memory=peer, lr_decay=(0.1, 10))
         result["backend"] = peer.used
+        result["multicast"] = bool(mine.multicast is not None and mine.use_multicast)   # NGP_DP_MULTICAST=0 forces P2P
     except Exception as e:  # noqa: BLE001
         if rank == 0:
             print(json.dumps({"ok": False, "error": "peer memory unavailable: %r" % e}))

@@ -180,8 +180,8 @@ def _bench_like_model():
     return NeRFNetwork(opt).to(DEV).train()
 
 
-@pytest.mark.parametrize("views", [1, 2])
-def test_hand_scheduled_step_matches_autograd_step(views):
+@pytest.mark.parametrize("views,n_chunks", [(1, 1), (1, 2), (2, 1), (2, 3)])
+def test_hand_scheduled_step_matches_autograd_step(views, n_chunks):
     """TrainStep(manual=True) - 13 launches, no autograd - must produce the gradients, loss and bookkeeping of the
     autograd version of the same step (which tests/test_gpu_pipeline.py pins to the reference pipeline)."""
     from ngp_b200 import provider
@@ -192,7 +192,7 @@ def test_hand_scheduled_step_matches_autograd_step(views):
     got = {}
     for manual in (True, False):
         m = _bench_like_model()
-        step = TrainStep(m, 64, 64, lr=1e-3, graph=False, manual=manual)
+        step = TrainStep(m, 64, 64, lr=1e-3, graph=False, manual=manual, n_chunks=n_chunks)   # chunks: parallel ray chains
         assert step.manual == manual
         step.mirror_rng = True   # same torch RNG consumption as run_cuda, so both draw the same ray noise
         grads = []
@@ -210,7 +210,7 @@ def test_hand_scheduled_step_matches_autograd_step(views):
     a, b = got[True], got[False]
     assert a["samples"] == b["samples"] > 0
     assert torch.equal(a["counter"], b["counter"]) and a["local_step"] == b["local_step"] == 1
-    assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(b["loss"])
+    assert abs(a["loss"] - b["loss"]) <= 1e-5 * abs(b["loss"])   # (per-block atomics: summation order differs)
     for (name, p), (_, q) in zip(a["model"].named_parameters(), b["model"].named_parameters()):
         oa, ob = a["opt"].offsets[a["opt"]._index(p)], b["opt"].offsets[b["opt"]._index(q)]
         ga, gb = a["g"][oa:oa + p.numel()], b["g"][ob:ob + q.numel()]
