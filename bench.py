@@ -29,7 +29,7 @@ for _p in (ROOT, PKG):
         sys.path.insert(0, _p)
 
 METRIC = "NeRF train-step samples/s (march+hashgrid+MLP+composite fwd/bwd)"
-NCU_SCATTER_DRAM_BYTES_PER_LAUNCH = 313.4e6  # profiles/ncu_full_r1_v7.md: 0.3095 GB read + 0.0039 GB written
+NCU_SCATTER_DRAM_BYTES_PER_LAUNCH = 250.2e6  # profiles/ncu_full_r1_v8.md: 0.2448 GB read + 0.0054 GB written (3.4 M samples)
 UNIT = "samples/s"
 VIEWS_PER_STEP = 8
 H = W = 64
