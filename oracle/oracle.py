@@ -296,3 +296,41 @@ def f2h(x):
     out = np.empty(x.shape, np.uint16)
     lib().oracle_f2h(_p(x), _p(out), C.c_uint64(x.size))
     return out.view(np.float16)
+
+
+def train_ray_loss(sigmas, rgbs, deltas, rays, bg, grad_pred_nchw, pixels_per_view, lambda_entropy, scale, T_thresh=1e-4):
+    """TEST INFRASTRUCTURE - restatement of what the reference's train_step does between "the field has been evaluated"
+    and "the gradients of sigma / rgb are known" for rays in ray order (row n <-> ray n), fp32:
+
+      composite_rays_train forward (raymarching.cu:501-588)                    -> weights_sum, depth, image
+      image + (1 - weights_sum) * bg  (nerf/renderer.py:541-545)               -> the blended prediction
+      d(pred) = G (nerf/sd.py:115, unscaled), loss = lambda * mean(H2(clamp(ws, 1e-5, 1 - 1e-5))) (nerf/utils.py:389-394)
+      back-propagated with the GradScaler scale on the entropy term only (nerf/utils.py:708)
+      composite_rays_train backward (raymarching.cu:602-693)                   -> grad_sigmas, grad_rgbs
+
+    bg: [N,3] fp32 (already rounded to half if it came from the bg net); grad_pred_nchw: [B,3,pixels_per_view].
+    Returns dict(weights_sum, depth, image, loss, grad_ws, grad_bg, grad_sigmas, grad_rgbs)."""
+    rays = _c(rays, np.int32)
+    N = rays.shape[0]
+    bg = _c(bg, np.float32).reshape(N, 3)
+    G = _c(grad_pred_nchw, np.float32)
+    Bv = N // pixels_per_view
+    g_ray = np.ascontiguousarray(G.reshape(Bv, 3, pixels_per_view).transpose(0, 2, 1).reshape(N, 3))
+    ws, depth, image = composite_rays_train_forward(sigmas, rgbs, deltas, rays, T_thresh)
+    f32 = np.float32
+    # blend backward
+    grad_ws = -(g_ray[:, 0] * bg[:, 0] + g_ray[:, 1] * bg[:, 1] + g_ray[:, 2] * bg[:, 2]).astype(f32)
+    grad_bg = ((f32(1) - ws)[:, None] * g_ray).astype(f32)
+    # entropy of the clamped opacity and its (sub)gradient
+    lo, hi = f32(1e-5), f32(1) - f32(1e-5)
+    a = np.clip(ws, lo, hi)
+    ent = (-a * np.log2(a) - (f32(1) - a) * np.log2(f32(1) - a)).astype(f32)
+    loss = f32(lambda_entropy) * f32(ent.astype(np.float64).mean())
+    inside = (ws >= lo) & (ws <= hi)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dent = (np.log2(f32(1) - ws) - np.log2(ws)).astype(f32)
+    grad_ws = grad_ws + np.where(inside, f32(scale) * (f32(lambda_entropy) / f32(N)) * dent, f32(0)).astype(f32)
+    # rays in ray order: id == row, so the per-ray gradients index directly
+    gs, gc = composite_rays_train_backward(grad_ws, g_ray, sigmas, rgbs, deltas, rays, ws, image, T_thresh)
+    return dict(weights_sum=ws, depth=depth, image=image, loss=loss, grad_ws=grad_ws, grad_bg=grad_bg, grad_sigmas=gs,
+                grad_rgbs=gc)

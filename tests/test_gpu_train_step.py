@@ -277,3 +277,64 @@ def test_pipelined_optimizer_applies_the_same_updates_one_step_later():
     for n in finals[0][1]:
         a, b = finals[0][1][n], finals[1][1][n]
         assert ((a - b).norm() / (b.norm() + 1e-12)).item() < 0.05, n
+
+
+@pytest.mark.parametrize("split", [1, 2])
+def test_train_ray_loss_kernel_vs_oracle(split):
+    """ngp_train_ray_loss (composite fwd + blend + loss gradients + composite bwd, one launch) through the C ABI against
+    the oracle restatement (oracle.train_ray_loss: C composite kernels + numpy blend / entropy), on marched samples of a
+    blob scene; split = 2 runs it as two ray chunks (ray_base / n_rays_total), as the two-chain train step does."""
+    import ngp_testutil as util
+    from ngp_b200 import _cabi
+    from oracle import oracle as O
+    side, views = 16, 2
+    rays_o, rays_d = [], []
+    for v in range(views):
+        ro, rd = util.look_at_rays(side, phi_deg=30.0 + 100.0 * v)
+        rays_o.append(ro); rays_d.append(rd)
+    rays_o, rays_d = np.concatenate(rays_o), np.concatenate(rays_d)
+    N, hw = rays_o.shape[0], side * side
+    grid = util.blob_density_grid(1, 128, 1.0, 0)
+    bits = O.packbits(grid, 10.0)
+    nears, fars = O.near_far_from_aabb(rays_o, rays_d, np.array([-1, -1, -1, 1, 1, 1], np.float32), 0.2)
+    noises = np.random.default_rng(1).random(N).astype(np.float32)
+    ox, _, ol, orays, ocnt = O.march_rays_train(rays_o, rays_d, 1.0, bits, 1, 128, nears, fars, noises, 0.0, 256)
+    total = int(ocnt[0])
+    assert total > 1000 and np.array_equal(orays[:, 0], np.arange(N))
+    sig, rgb = util.pseudo_field(ox[:total])
+    rng = np.random.default_rng(2)
+    bg = rng.uniform(0, 1, (N, 3)).astype(np.float16)
+    G = (rng.standard_normal((views, 3, hw)) * 1e-2).astype(np.float32)
+    lam, scale = 1e-4, 65536.0
+    want = O.train_ray_loss(sig, rgb, ol[:total], orays, bg.astype(np.float32), G, hw, lam, scale, 1e-4)
+
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)  # noqa: E731
+    sig_t, rgb_t, dl_t, bg_t, G_t = T(sig), T(rgb), T(ol[:total]), T(bg), T(G)
+    scale_t = torch.tensor([scale], device=DEV)
+    ws = torch.full((N,), -1.0, device=DEV); depth = torch.empty(N, device=DEV); image = torch.empty(N, 3, device=DEV)
+    d_bg = torch.empty(N, 3, device=DEV)
+    gs = torch.full((total,), 7.0, device=DEV); gc = torch.full((total, 3), 7.0, device=DEV)
+    loss = torch.zeros((), device=DEV)
+    samples = torch.zeros(1, dtype=torch.int64, device=DEV)
+    step_counter = torch.zeros(16, 2, dtype=torch.int32, device=DEV)
+    cur_row = torch.full((1,), 3, dtype=torch.int32, device=DEV)
+    P = _cabi.ptr
+    bounds = [0, N] if split == 1 else [0, N // 2 + 5, N]
+    for lo, hi in zip(bounds, bounds[1:]):
+        rays_c = orays[lo:hi].copy()
+        rays_c[:, 0] -= lo                       # ray ids are local to the chunk; offsets stay global rows of the buffers
+        cnt = torch.tensor([int(rays_c[:, 2].sum()), hi - lo], dtype=torch.int32, device=DEV)
+        rays_t = T(rays_c)
+        _cabi.call("ngp_train_ray_loss", torch.device(DEV), P(sig_t), P(rgb_t), P(dl_t), P(rays_t), total, hi - lo, 1e-4,
+                   P(bg_t[lo:hi]), 1.0, P(G_t), hw, lo, N, lam, P(scale_t), P(ws[lo:hi]), P(depth[lo:hi]), P(image[lo:hi]),
+                   P(d_bg[lo:hi]), P(gs), P(gc), P(loss), P(cnt), P(samples), P(step_counter), P(cur_row))
+    torch.cuda.synchronize()
+    N_ = lambda t: t.detach().cpu().numpy()  # noqa: E731
+    for got, name in ((ws, "weights_sum"), (depth, "depth"), (image, "image"), (d_bg, "grad_bg")):
+        np.testing.assert_allclose(N_(got), want[name], rtol=1e-5, atol=1e-6, err_msg=name)
+    assert abs(loss.item() - want["loss"]) <= 1e-5 * abs(want["loss"])
+    sc = max(np.abs(want["grad_sigmas"]).max(), 1e-6)
+    assert np.abs(N_(gs) - want["grad_sigmas"]).max() < 1e-4 * sc + 1e-6
+    np.testing.assert_allclose(N_(gc), want["grad_rgbs"], rtol=1e-5, atol=1e-7)
+    assert samples.item() == total
+    assert step_counter[3].tolist() == [total, N] and step_counter.sum().item() == total + N

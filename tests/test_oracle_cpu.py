@@ -353,3 +353,44 @@ def test_occupancy_update_matches_numpy():
     assert np.array_equal(new, want_g)
     assert abs(mean - want_g[valid].mean()) < 1e-4
     assert np.array_equal(bits, O.packbits(want_g, min(mean, 10.0)))
+
+
+def test_train_ray_loss_restatement_is_consistent():
+    """oracle.train_ray_loss (the checker of the fused per-ray kernel): its sigma / rgb gradients are the finite-difference
+    gradients of  sum(G * blend(image, ws, bg)) + scale * lambda * mean entropy(ws)  built from the composite forward."""
+    rng = np.random.default_rng(0)
+    n_rays, per = 12, 9
+    M = n_rays * per
+    rays = np.stack([np.arange(n_rays), np.arange(n_rays) * per, np.full(n_rays, per)], -1).astype(np.int32)
+    sig = rng.uniform(0.5, 6.0, M).astype(np.float32)
+    rgb = rng.uniform(0, 1, (M, 3)).astype(np.float32)
+    deltas = np.stack([np.full(M, 0.05), np.full(M, 0.05)], -1).astype(np.float32)
+    bg = rng.uniform(0, 1, (n_rays, 3)).astype(np.float32)
+    G = rng.standard_normal((2, 3, n_rays // 2)).astype(np.float32)
+    lam, scale = 0.3, 8.0
+    out = O.train_ray_loss(sig, rgb, deltas, rays, bg, G, n_rays // 2, lam, scale, 1e-4)
+    g_ray = G.transpose(0, 2, 1).reshape(n_rays, 3)
+
+    def objective(s64, c64):
+        total = 0.0
+        for n in range(n_rays):
+            T, ws, img = 1.0, 0.0, np.zeros(3)
+            for i in range(n * per, (n + 1) * per):
+                alpha = 1 - np.exp(-s64[i] * 0.05)
+                w = alpha * T
+                ws += w; img += w * c64[i]; T *= 1 - alpha
+            a = min(max(ws, 1e-5), 1 - 1e-5)
+            ent = -a * np.log2(a) - (1 - a) * np.log2(1 - a)
+            total += (g_ray[n] * (img + (1 - ws) * bg[n])).sum() + scale * lam * ent / n_rays
+        return total
+
+    s64, c64 = sig.astype(np.float64), rgb.astype(np.float64)
+    for idx in rng.choice(M, 10, replace=False):
+        e = np.zeros(M); e[idx] = 1e-5
+        fd = (objective(s64 + e, c64) - objective(s64 - e, c64)) / 2e-5
+        assert abs(fd - out["grad_sigmas"][idx]) < 2e-3 * max(1.0, abs(fd)), (idx, fd, out["grad_sigmas"][idx])
+        e3 = np.zeros((M, 3)); e3[idx, 1] = 1e-5
+        fd = (objective(s64, c64 + e3) - objective(s64, c64 - e3)) / 2e-5
+        assert abs(fd - out["grad_rgbs"][idx, 1]) < 2e-3 * max(1.0, abs(fd))
+    assert abs(out["loss"] - lam * np.mean([-a * np.log2(a) - (1 - a) * np.log2(1 - a) for a in np.clip(out["weights_sum"], 1e-5, 1 - 1e-5).astype(np.float64)])) < 1e-6
+    np.testing.assert_allclose(out["grad_bg"], (1 - out["weights_sum"])[:, None] * g_ray, rtol=1e-6)
