@@ -191,8 +191,14 @@ class FusedAdamScaler:
 
     # -- checkpointing (nerf/utils.py:847-968 saves optimizer / scaler state next to the model) ----------------------
     def state_dict(self):
-        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "state": self.state.clone(),
-                "base_lrs": list(self.base_lrs), "offsets": list(self.offsets), "numel": self.numel}
+        """Collective when the moments are sharded (fused data-parallel step): every rank must call it."""
+        if self.peer_ptrs is not None:
+            from .parallel import gather_owner_slices
+            m, v = gather_owner_slices(self.exp_avg, self.peer.group), gather_owner_slices(self.exp_avg_sq, self.peer.group)
+        else:
+            m, v = self.exp_avg.clone(), self.exp_avg_sq.clone()
+        return {"exp_avg": m, "exp_avg_sq": v, "state": self.state.clone(), "base_lrs": list(self.base_lrs),
+                "offsets": list(self.offsets), "numel": self.numel}
 
     def load_state_dict(self, sd):
         if sd["numel"] != self.numel or list(sd["offsets"]) != list(self.offsets):

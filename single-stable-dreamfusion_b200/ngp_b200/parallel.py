@@ -78,6 +78,34 @@ def shard_pixels(H, W, rank, world_size, tile=8):
     return out
 
 
+def owner_slice(numel, rank, world_size):
+    """[lo, hi) element range of the flat optimizer buffers that `rank` owns in the fused data-parallel step: the
+    partition csrc/dp_step.cu uses (float4 granularity, ceil(n4 / world) float4s per rank, the tail ranks may own less)."""
+    n4 = numel // 4
+    per = (n4 + world_size - 1) // world_size
+    lo = min(per * rank, n4)
+    hi = min(lo + per, n4)
+    return 4 * lo, 4 * hi
+
+
+def gather_owner_slices(flat, group=None):
+    """Every rank holds the valid values of `flat` only inside its owner_slice (sharded Adam moments); returns the fully
+    valid buffer on every rank (one all_gather of equal, padded chunks).  Works on any backend / device."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat.clone()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1:
+        return flat.clone()
+    numel = flat.numel()
+    per = 4 * ((numel // 4 + world - 1) // world)
+    lo, hi = owner_slice(numel, rank, world)
+    mine = torch.zeros(per, dtype=flat.dtype, device=flat.device)
+    mine[:hi - lo] = flat[lo:hi]
+    out = torch.empty(per * world, dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out[:numel].clone()
+
+
 class PeerMemory:
     """Device memory that every rank of the group can address directly (loads / stores / atomics over NVLink).
 

@@ -82,3 +82,66 @@ def test_shard_pixels_partitions_every_view_evenly():
             assert rows == list(range(64))
     # tiling that does not divide: interleaved rows
     assert shard_pixels(6, 4, 1, 3) == [r * 4 + c for r in shard_rows(6, 1, 3) for c in range(4)]
+
+
+def test_owner_slice_partitions_the_flat_buffer():
+    from ngp_b200.parallel import owner_slice
+    for numel in (8, 1816256, 4 * 1001, 4 * 7):
+        for world in (1, 2, 3, 4, 8):
+            spans = [owner_slice(numel, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == numel
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(lo % 4 == 0 and hi % 4 == 0 and lo <= hi for lo, hi in spans)
+
+
+def _sharded_adam_worker(rank, world, port, out):
+    """Host-side model of csrc/dp_step.cu on CPU tensors: reduce-scatter by reading every rank's bucket, Adam on the owned
+    slice with sharded moments, parameters broadcast from their owner - against single-process Adam on the summed grads."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ngp_b200.parallel import gather_owner_slices, owner_slice
+        numel, lr, b1, b2, eps = 4 * 53, 1e-2, 0.9, 0.99, 1e-15
+        torch.manual_seed(0)
+        p = torch.randn(numel)
+        p_ref = p.clone()
+        m, v = torch.zeros(numel), torch.zeros(numel)           # only [lo, hi) is maintained on this rank
+        m_ref, v_ref = torch.zeros(numel), torch.zeros(numel)
+        lo, hi = owner_slice(numel, rank, world)
+        for t in range(1, 4):
+            g_all = [torch.randn(numel, generator=torch.Generator().manual_seed(100 * t + r)) for r in range(world)]
+            # P1: rank r sums slice r of every bucket, in rank order
+            s = g_all[0][lo:hi].clone()
+            for q in range(1, world):
+                s += g_all[q][lo:hi]
+            gr = s / world
+            # P2: Adam on the slice
+            m[lo:hi] = m[lo:hi] + (1 - b1) * (gr - m[lo:hi])
+            v[lo:hi] = b2 * v[lo:hi] + (1 - b2) * gr * gr
+            step = lr / (1 - b1 ** t)
+            new = p[lo:hi] - step * m[lo:hi] / (v[lo:hi].sqrt() / (1 - b2 ** t) ** 0.5 + eps)
+            # ... written to every replica: here an all_gather of the (padded) slices
+            stale = torch.full((numel,), float("nan"))
+            stale[lo:hi] = new
+            p = gather_owner_slices(stale)
+            # single-process reference on the summed gradients
+            g = sum(g_all) / world
+            m_ref = m_ref + (1 - b1) * (g - m_ref)
+            v_ref = b2 * v_ref + (1 - b2) * g * g
+            p_ref = p_ref - (lr / (1 - b1 ** t)) * m_ref / (v_ref.sqrt() / (1 - b2 ** t) ** 0.5 + eps)
+        ok = torch.isfinite(p).all() and torch.allclose(p, p_ref, rtol=1e-5, atol=1e-6)
+        # checkpointing: the sharded moments reassemble to the full ones
+        ok = ok and torch.allclose(gather_owner_slices(m), m_ref, rtol=1e-5, atol=1e-7)
+        ok = ok and torch.allclose(gather_owner_slices(v), v_ref, rtol=1e-5, atol=1e-9)
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_adam_with_owner_broadcast_equals_single_process_adam(world):
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sharded_adam_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {r: True for r in range(world)}
