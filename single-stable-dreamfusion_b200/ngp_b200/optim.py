@@ -95,6 +95,7 @@ class FusedAdamScaler:
         self.flat_half.copy_(self.flat_params)
         for p, o in zip(self.params, self.offsets):
             field.register_half_shadow(p, self.flat_half[o:o + p.numel()].view_as(p))
+        self._seen_versions = [p._version for p in self.params]
         self.betas, self.eps = betas, eps
         self.growth_factor, self.backoff_factor, self.growth_interval = growth_factor, backoff_factor, growth_interval
         self.grad_div = float(grad_div)
@@ -167,6 +168,20 @@ class FusedAdamScaler:
                    float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,
                    self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
                    int(bool(deferred)), _cabi.ptr(self.state), _cabi.ptr(self._sync), rank, world, pg, pp, ph, pf, mc)
+
+    def sync_shadow_if_changed(self):
+        """Refresh the fp16 shadow if a parameter was edited through torch (load_state_dict, manual init) since the
+        last look: such in-place edits land in the flat fp32 buffer and bump ``param._version``; the kernels read the
+        shadow.  Host-side version compare, one copy kernel only when something changed."""
+        versions = [p._version for p in self.params]
+        if versions != self._seen_versions:
+            with torch.no_grad():
+                self.flat_half.copy_(self.flat_params)
+            self._seen_versions = versions
+            for p in self.params:       # keep field.cached_half's bookkeeping in step (same shadow tensors)
+                s = field._shadows.get(id(p))
+                if s is not None:
+                    s[2][0] = p._version
 
     def grad_view(self, p):
         """The slice of the flat gradient bucket that backs `p.grad` (same shape as p)."""

@@ -302,6 +302,29 @@ class TrainStep:
             dist.all_reduce(self.opt.flat_grads, op=dist.ReduceOp.SUM)
         self.opt.step_fused(deferred=deferred)
 
+    # -- checkpoints in the reference Trainer's layout (nerf/utils.py:847-968) -------------------------------------------
+    def save_checkpoint(self, path, epoch=0, full=True):
+        """Collective under the fused data-parallel optimizer (its moments are sharded); write from one rank."""
+        from . import checkpoint as ck
+        self.flush()
+        state = ck.checkpoint_dict(self.model, epoch=epoch, global_step=self.global_step, optimizer=self.opt,
+                                   scaler=self.scaler, full=full)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0:
+            torch.save(state, path)
+
+    def load_checkpoint(self, path, model_only=False):
+        """Reference-written and own checkpoints alike; optimizer state is restored only if it has this trainer's layout
+        (a reference Adam state is reported in the returned `warnings`, as the reference itself does)."""
+        from . import checkpoint as ck
+        self.flush()
+        info = ck.load_checkpoint(path, self.model, optimizer=self.opt if self.fused_optimizer else None,
+                                  model_only=model_only, map_location=self.device)
+        if not model_only:
+            self.global_step = int(info["global_step"])
+        if self.fused_optimizer:
+            self.opt.sync_shadow_if_changed()
+        return info
+
     def flush(self):
         """Pipelined mode: apply the update that is still pending (no-op otherwise).  After it the parameters are what
         the un-pipelined step would have left."""
@@ -358,6 +381,8 @@ class TrainStep:
             self.n_updates += 1
         self.global_step += 1
         (self.opt.attach_grads if self.fused_optimizer else self.bucket.attach)()
+        if self.fused_optimizer:
+            self.opt.sync_shadow_if_changed()   # parameters edited through torch since the last step (load_state_dict ...)
         if self.manual and self._ls_mirror != model.local_step:
             self._local_step_dev.fill_(model.local_step)  # (update_extra_state restarts the 16-step window)
             self._ls_mirror = model.local_step
