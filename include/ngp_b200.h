@@ -69,8 +69,11 @@ int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* 
                              int align_corners, int dtype, int grad_layout, int grad_emb_dtype, void* stream);
 
 /* Tuning / test switches.  option 0: value != 0 disables the warp-aggregated scatter of the backward (every
- * sample then issues its own atomics, like the reference). */
+ * sample then issues its own atomics, like the reference).  option 1: value != 0 makes ngp_grid_scatter_samples run
+ * its counting build (measurement only): every red instruction a lane issues AFTER warp aggregation is counted. */
 int ngp_grid_set_option(int option, int value);
+/* Reads (and optionally resets) that counter into *lane_ops (HOST pointer); synchronises the device. */
+int ngp_grid_red_count(uint64_t* lane_ops, int reset);
 
 /* Device-computed per-level (scale, resolution) exactly as gridencoder.cu:125-126 evaluates them
  * (exp2f on the device).  scales f32[L], resolutions u32[L] are DEVICE buffers. */
@@ -255,7 +258,8 @@ int ngp_bg_backward(const float* dirs, const float* grad_rgb, uint32_t N, const 
 /* The optimisation step as ONE cooperative launch, with the data-parallel gradient all-reduce fused in over NVLink
  * peer memory (csrc/dp_step.cu): replaces ngp_check_finite + ngp_adam_step (world == 1) and, for world > 1, the
  * all_reduce DistributedDataParallel would issue for the reference's dormant wrap (nerf/utils.py:200-202) as well.
- *   state f32[8]: as ngp_adam_step, plus [5] = 1 if a cross-GPU wait timed out.  sync u32[2], zero-initialised:
+ *   state f32[8]: as ngp_adam_step, plus [5] = 1 if a cross-GPU wait timed out (sticky: from then on the step is a no-op
+ *   on every rank that saw the flag - nothing is reduced, updated, broadcast or cleared).  sync u32[2], zero-initialised:
  *   [0] block election, [1] barrier epoch.  n must be a multiple of 4.
  *   world > 1: peer_* are HOST arrays of `world` device addresses (this rank's own buffers included, in rank order) of
  *   every rank's gradient bucket, parameter buffer, fp16 shadow and flag pad (ngp_dp_flags_bytes() bytes, zeroed once),
@@ -277,6 +281,9 @@ int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_
                         uint32_t rank, uint32_t world, const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half,
                         const uint64_t* peer_flags, const uint64_t* multicast, void* stream);
 uint64_t ngp_dp_flags_bytes(void);
+/* option 0: timeout of the cross-GPU waits in milliseconds (default 20000); option 1: blocks of the cooperative launch
+ * (0 = one per SM). */
+int ngp_dp_set_option(int option, int value);
 /* cudaDeviceEnablePeerAccess(peer_device) from the current device (idempotent). */
 int ngp_enable_peer_access(int peer_device);
 

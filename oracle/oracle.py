@@ -334,3 +334,90 @@ def train_ray_loss(sigmas, rgbs, deltas, rays, bg, grad_pred_nchw, pixels_per_vi
     gs, gc = composite_rays_train_backward(grad_ws, g_ray, sigmas, rgbs, deltas, rays, ws, image, T_thresh)
     return dict(weights_sum=ws, depth=depth, image=image, loss=loss, grad_ws=grad_ws, grad_bg=grad_bg, grad_sigmas=gs,
                 grad_rgbs=gc)
+
+
+# ------------------------------------------------------------------ the field network (nerf/network_grid.py)
+def _h16(a):
+    """Round to fp16 and come back as float64 (what a half tensor holds)."""
+    return np.asarray(a, np.float64).astype(np.float16).astype(np.float64)
+
+
+def field_forward(xyzs, table, offsets, S, H, weights, biases, bound=1.0, gridtype=1, align_corners=False,
+                  scale_override=None, round_hidden=True):
+    """TEST INFRASTRUCTURE - fp64 restatement of ``NeRFNetwork.common_forward`` under fp16 autocast
+    (nerf/network_grid.py:76-87: GridEncoder -> Linear/ReLU x2 -> Linear -> trunc_exp(h0 + blob), sigmoid(h1..3);
+    blob = 5 exp(-|x|^2 / (2 * 0.2^2)), :66-74; trunc_exp = exp in fp32, activation.py:8).
+
+    table / weights / biases are quantised to fp16 first (autocast feeds half operands to the encoder and to cuBLAS);
+    the encoding is the bit-exact C restatement of the half kernel; everything after it is float64.
+    round_hidden=True additionally rounds every Linear output to fp16 (a half GEMM returns half) - the arithmetic the
+    reference and the fused kernel both implement; False gives the un-rounded fp64 value of the same network.
+    Returns dict(enc [M,32] f16, h1, h2 (post-ReLU), out [M,4] (pre-activation), sigma [M], albedo [M,3]) in float64."""
+    xyzs = _c(xyzs, np.float32)
+    x01 = ((xyzs + np.float32(bound)) * (np.float32(1.0) / np.float32(2 * bound))).astype(np.float32)   # grid.py:142
+    enc, _ = grid_encode_forward(x01, np.asarray(table).astype(np.float16), offsets, S, H, gridtype=gridtype,
+                                 align_corners=align_corners, scale_override=scale_override)
+    W = [_h16(w) for w in weights]
+    b = [_h16(v) for v in biases]
+    rnd = _h16 if round_hidden else (lambda a: a)
+    e = enc.astype(np.float64)
+    h1 = np.maximum(rnd(e @ W[0].T + b[0]), 0.0)
+    h2 = np.maximum(rnd(h1 @ W[1].T + b[1]), 0.0)
+    out = rnd(h2 @ W[2].T + b[2])
+    x64 = xyzs.astype(np.float64)
+    blob = 5.0 * np.exp(-(x64 ** 2).sum(-1) / (2 * 0.2 ** 2))
+    sigma = np.exp(out[:, 0] + blob)
+    albedo = 1.0 / (1.0 + np.exp(-out[:, 1:]))
+    return dict(enc=enc, x01=x01, h1=h1, h2=h2, out=out, sigma=sigma, albedo=albedo, W=W, b=b)
+
+
+def field_backward(fwd, d_sigma, d_albedo, offsets, n_rows, S, H, gridtype=1, align_corners=False, scale_override=None):
+    """TEST INFRASTRUCTURE - exact (float64, no intermediate rounding) gradients of ``field_forward``'s outputs wrt the
+    table and the MLP parameters, by the chain rule of nerf/network_grid.py:76-87 with trunc_exp's backward
+    g * exp(clamp(x, -15, 15)) (activation.py:13-15).  `fwd` is field_forward's dict (either rounding mode: the ReLU masks
+    and activations are taken from it).  Returns dict(table [n_rows,2], w1, b1, w2, b2, w3, b3, d_enc [M,32])."""
+    d_sigma = np.asarray(d_sigma, np.float64)
+    d_albedo = np.asarray(d_albedo, np.float64)
+    W = fwd["W"]
+    arg = np.log(fwd["sigma"])                                        # h0 + blob
+    dout = np.empty_like(fwd["out"])
+    dout[:, 0] = d_sigma * np.exp(np.clip(arg, -15.0, 15.0))
+    dout[:, 1:] = d_albedo * fwd["albedo"] * (1.0 - fwd["albedo"])
+    h2, h1, e = fwd["h2"], fwd["h1"], fwd["enc"].astype(np.float64)
+    g = {}
+    g["w3"], g["b3"] = dout.T @ h2, dout.sum(0)
+    dh2 = (dout @ W[2]) * (h2 > 0)
+    g["w2"], g["b2"] = dh2.T @ h1, dh2.sum(0)
+    dh1 = (dh2 @ W[1]) * (h1 > 0)
+    g["w1"], g["b1"] = dh1.T @ e, dh1.sum(0)
+    d_enc = dh1 @ W[0]
+    g["d_enc"] = d_enc
+    # the encoder's backward with exact accumulation; gradients handed over in fp32 (nothing is rounded to half here)
+    g["table"] = grid_encode_backward(d_enc.astype(np.float32), fwd["x01"], offsets, n_rows, 2, S, H, gridtype=gridtype,
+                                      align_corners=align_corners, scale_override=scale_override)
+    return g
+
+
+def bg_forward(dirs, weights, biases, degree=6):
+    """TEST INFRASTRUCTURE - fp64 restatement of ``NeRFNetwork.background`` under fp16 autocast (nerf/network_grid.py:
+    158-167: FreqEncoder(degree 6) -> Linear(39,64)+ReLU -> Linear(64,3) -> sigmoid), fp16-quantised parameters, Linear
+    outputs rounded to fp16 as a half GEMM returns them, encoder input rounded to half as autocast feeds it."""
+    enc = freq_encode_forward(_c(dirs, np.float32), degree)            # fp32, bit-exact restatement of kernel_freq
+    e = _h16(enc)                                                      # autocast casts the Linear's input to half
+    W = [_h16(w) for w in weights]
+    b = [_h16(v) for v in biases]
+    h = np.maximum(_h16(e @ W[0].T + b[0]), 0.0)
+    out = _h16(h @ W[1].T + b[1])
+    rgb = _h16(1.0 / (1.0 + np.exp(-out)))
+    return dict(e=e, h=h, out=out, rgb=rgb, W=W)
+
+
+def bg_backward(fwd, d_rgb):
+    """Exact float64 parameter gradients of bg_forward's rgb (chain rule, no intermediate rounding)."""
+    d_rgb = np.asarray(d_rgb, np.float64)
+    y = 1.0 / (1.0 + np.exp(-fwd["out"]))
+    dout = d_rgb * y * (1.0 - y)
+    g = {"w2": dout.T @ fwd["h"], "b2": dout.sum(0)}
+    dh = (dout @ fwd["W"][1]) * (fwd["h"] > 0)
+    g["w1"], g["b1"] = dh.T @ fwd["e"], dh.sum(0)
+    return g

@@ -163,6 +163,40 @@ class RefGridNeRF(nn.Module):
     def background(self, d):
         return torch.sigmoid(_run_mlp(self.bg_net, _RefFreq.apply(d.reshape(-1, 3), 6, 39, self.ns)))
 
+    # -- shading (nerf/network_grid.py:90-144) ---------------------------------------------------------------------
+    def finite_difference_normal(self, x, epsilon=1e-2):
+        vals = []
+        for axis in range(3):
+            for sign in (1.0, -1.0):
+                off = torch.zeros(1, 3, device=x.device)
+                off[0, axis] = sign * epsilon
+                vals.append(self.common_forward((x + off).clamp(-self.bound, self.bound))[0])
+        dx_pos, dx_neg, dy_pos, dy_neg, dz_pos, dz_neg = vals
+        normal = torch.stack([0.5 * (dx_pos - dx_neg) / epsilon, 0.5 * (dy_pos - dy_neg) / epsilon,
+                              0.5 * (dz_pos - dz_neg) / epsilon], dim=-1)
+        return -normal
+
+    def normal(self, x):
+        normal = self.finite_difference_normal(x)
+        normal = normal / torch.sqrt(torch.clamp(torch.sum(normal * normal, -1, keepdim=True), min=1e-20))  # safe_normalize
+        normal[torch.isnan(normal)] = 0
+        return normal
+
+    def forward(self, x, d, l=None, ratio=1, shading="albedo"):
+        if shading == "albedo":
+            sigma, color = self.common_forward(x)
+            return sigma, color, None
+        sigma, albedo = self.common_forward(x)
+        normal = self.normal(x)
+        lambertian = ratio + (1 - ratio) * (normal @ l).clamp(min=0)
+        if shading == "textureless":
+            color = lambertian.unsqueeze(-1).repeat(1, 3)
+        elif shading == "normal":
+            color = (normal + 1) / 2
+        else:
+            color = albedo * lambertian.unsqueeze(-1)
+        return sigma, color, normal
+
     def march_train(self, rays_o, rays_d, nears, fars, counter, max_steps, perturb=True):
         ns = self.ns
         N = rays_o.shape[0]
@@ -180,22 +214,74 @@ class RefGridNeRF(nn.Module):
         torch.cuda.empty_cache()                         # allocator flush every step (raymarching.py:231)
         return xyzs[:m], dirs[:m], deltas[:m], rays
 
-    def render_train(self, rays_o, rays_d, max_steps=1024, T_thresh=1e-4):
+    def render_train(self, rays_o, rays_d, max_steps=1024, T_thresh=1e-4, shading="albedo", ambient_ratio=1.0):
+        """run_cuda, training branch (nerf/renderer.py:446-494,535-557)."""
         prefix = rays_o.shape[:-1]
         rays_o = rays_o.contiguous().view(-1, 3)
         rays_d = rays_d.contiguous().view(-1, 3)
         nears, fars = ref_ext.near_far_from_aabb(self.ns, rays_o, rays_d, self.aabb, 0.2)
-        _ = rays_o[0] + torch.randn(3, device=rays_o.device)   # light_d is drawn even for albedo shading
+        light_d = rays_o[0] + torch.randn(3, device=rays_o.device)   # drawn even for albedo shading (:461-464)
+        light_d = light_d / torch.sqrt(torch.clamp(torch.sum(light_d * light_d, -1, keepdim=True), min=1e-20))
         counter = self.step_counter[self.local_step % 16]
         counter.zero_()
         self.local_step += 1
         xyzs, dirs, deltas, rays = self.march_train(rays_o, rays_d, nears, fars, counter, max_steps)
-        sigmas, rgbs = self.common_forward(xyzs)
+        sigmas, rgbs, normals = self(xyzs, dirs, light_d, ratio=ambient_ratio, shading=shading)
         ws, depth, image = _RefCompositeTrain.apply(sigmas, rgbs, deltas, rays, T_thresh, self.ns)
+        results = {}
+        if normals is not None:   # orientation + smoothness regularisers (:485-494)
+            weights = 1 - torch.exp(-sigmas)
+            results["loss_orient"] = (weights.detach() * (normals * dirs).sum(-1).clamp(min=0) ** 2).mean()
+            normals_perturb = self.normal(xyzs + torch.randn_like(xyzs) * 1e-2)
+            results["loss_smooth"] = (normals - normals_perturb).abs().mean()
         bg = self.background(rays_d)
         image = image + (1 - ws).unsqueeze(-1) * bg
         depth = torch.clamp(depth - nears, min=0) / (fars - nears)
-        return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": ws.reshape(*prefix)}
+        results.update({"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": ws.reshape(*prefix)})
+        return results
+
+    @torch.no_grad()
+    def render_eval(self, rays_o, rays_d, max_steps=1024, T_thresh=1e-4, perturb=False, bg_color=None, use_bg_net=True):
+        """run_cuda, inference branch (nerf/renderer.py:496-557) on the reference's march_rays / composite_rays, with the
+        reference's boolean-mask compaction and one host sync per iteration."""
+        ns = self.ns
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3).float()
+        rays_d = rays_d.contiguous().view(-1, 3).float()
+        N, dev = rays_o.shape[0], rays_o.device
+        nears, fars = ref_ext.near_far_from_aabb(ns, rays_o, rays_d, self.aabb, 0.2)
+        _ = torch.randn(3, device=dev)
+        weights_sum = torch.zeros(N, device=dev)
+        depth = torch.zeros(N, device=dev)
+        image = torch.zeros(N, 3, device=dev)
+        rays_alive = torch.arange(N, dtype=torch.int32, device=dev)
+        rays_t = nears.clone()
+        step = 0
+        iters = 0
+        while step < max_steps:
+            n_alive = rays_alive.shape[0]
+            if n_alive <= 0:
+                break
+            n_step = max(min(N // n_alive, 8), 1)
+            M = n_alive * n_step
+            M += 128 - (M % 128)
+            xyzs = torch.zeros(M, 3, device=dev)
+            dirs = torch.zeros(M, 3, device=dev)
+            deltas = torch.zeros(M, 2, device=dev)
+            noises = torch.rand(n_alive, device=dev) if (perturb and step == 0) else torch.zeros(n_alive, device=dev)
+            ns.march.march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, self.bound, 0.0, max_steps, self.cascade, 128,
+                                self.density_bitfield, nears, fars, xyzs, dirs, deltas, noises)
+            sigmas, rgbs = self.common_forward(xyzs)
+            ns.march.composite_rays(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas.float().contiguous(),
+                                    rgbs.float().contiguous(), deltas, weights_sum, depth, image)
+            rays_alive = rays_alive[rays_alive >= 0]
+            step += n_step
+            iters += 1
+        bg = self.background(rays_d) if use_bg_net else (1 if bg_color is None else bg_color)
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg
+        depth = torch.clamp(depth - nears, min=0) / (fars - nears)
+        return {"image": image.view(*prefix, 3), "depth": depth.view(*prefix), "weights_sum": weights_sum.reshape(*prefix),
+                "mask": (nears < fars).reshape(*prefix), "iterations": iters}
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95, noise=None):
@@ -278,15 +364,19 @@ def time_reference_train_step(device, views=1, steps=20, warmup=5, Hh=64, Ww=64,
         one(i)
     torch.cuda.synchronize()
     samples = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    evs[0].record()
     for i in range(steps):
         one(100 + i)
-    e1.record()
+        evs[i + 1].record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    return {"value": samples / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms / steps, "views_per_step": views,
-            "samples_per_step": samples / steps, "steps": steps,
+    ms = evs[0].elapsed_time(evs[-1])
+    per = sorted(a.elapsed_time(b) for a, b in zip(evs, evs[1:]))
+    med = per[len(per) // 2]
+    return {"value": samples / (ms * 1e-3), "value_median": (samples / steps) / (med * 1e-3), "unit": "samples/s",
+            "ms_per_step": ms / steps, "ms_per_step_median": med, "ms_per_step_p10": per[len(per) // 10],
+            "ms_per_step_p90": per[(len(per) * 9) // 10], "views_per_step": views,
+            "samples_per_step": samples / steps, "steps": steps, "warmup": warmup,
             "what": "reference CUDA extensions (gridencoder/raymarching/freqencoder rebuilt unmodified for sm_100) "
                     "+ the reference's host call pattern, same -O train step, 1 GPU"}
 
@@ -296,7 +386,7 @@ if __name__ == "__main__":
     # step (raymarching.py:231), which must not be charged for another workload's cached blocks
     import json
     import sys
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-    warm = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    warm = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     res = time_reference_train_step(torch.device("cuda", 0), views=1, steps=steps, warmup=warm)
     print("REF_PIPELINE_JSON " + json.dumps(res), flush=True)

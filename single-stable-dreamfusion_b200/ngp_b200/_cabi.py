@@ -24,6 +24,7 @@ SIGNATURES = {
     "ngp_grid_encode_forward": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _vp, _u32, _i32, _i32, _i32, _vp]),
     "ngp_grid_encode_backward": (_i32, [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _u32, _f32, _u32, _vp, _vp, _u32, _i32, _i32, _i32, _i32, _vp]),
     "ngp_grid_set_option": (_i32, [_i32, _i32]),
+    "ngp_grid_red_count": (_i32, [C.POINTER(_u64), _i32]),
     "ngp_grid_level_params": (_i32, [_u32, _f32, _u32, _vp, _vp, _vp]),
     "ngp_near_far_from_aabb": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp]),
     "ngp_sph_from_ray": (_i32, [_vp, _vp, _f32, _u32, _vp, _vp]),
@@ -63,6 +64,7 @@ SIGNATURES = {
                                    _f32, _f32, _f32, _f32, _u32, _i32, _vp, _vp, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64),
                                    C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _vp]),
     "ngp_dp_flags_bytes": (_u64, []),
+    "ngp_dp_set_option": (_i32, [_i32, _i32]),
     "ngp_enable_peer_access": (_i32, [_i32]),
     "ngp_train_prologue": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
     "ngp_train_ray_loss": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _f32, _vp, _u32, _u32, _u32, _f32, _vp, _vp, _vp,

@@ -248,11 +248,9 @@ extern "C" int ngp_bg_backward(const float* dirs, const float* grad_rgb, uint32_
     if (N == 0) return NGP_OK;
     const bg::Weights w = {static_cast<const __half*>(w1), static_cast<const __half*>(b1), static_cast<const __half*>(w2),
                            static_cast<const __half*>(b2)};
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(bg::bg_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bg::SmemB::total);
-        attr_set = true;
-    }
+    static PerDeviceAttr attr;
+    const int arc = set_kernel_smem(&attr, reinterpret_cast<const void*>(bg::bg_backward_kernel), (int)bg::SmemB::total);
+    if (arc != NGP_OK) return arc;
     // one CTA per SM at most: in the train step this kernel runs beside the (persistent, shared-memory hungry) field
     // kernels on a side stream and should fill their gaps, not evict them
     const int blocks = min(cdiv(N, bg::kRays), num_sms());

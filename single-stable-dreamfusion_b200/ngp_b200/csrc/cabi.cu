@@ -1,6 +1,8 @@
 // Library-level entry points of the C ABI (version, error strings, device info).
 #include <string.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace ngp {
@@ -14,6 +16,24 @@ int num_sms() {
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+int set_kernel_smem(PerDeviceAttr* slot, const void* func, int smem_bytes, int carveout_percent) {
+    static std::mutex mu;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    std::lock_guard<std::mutex> lock(mu);
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && slot->smem[dev] == smem_bytes && slot->carveout[dev] == carveout_percent + 2) return NGP_OK;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    if (carveout_percent >= 0) {
+        e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, carveout_percent);
+        if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    }
+    if (tracked) { slot->smem[dev] = smem_bytes; slot->carveout[dev] = carveout_percent + 2; }
+    return NGP_OK;
 }
 }  // namespace ngp
 

@@ -25,6 +25,14 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device (cabi.cu)
 
+// Kernel attributes (dynamic shared memory limit, carve-out) are per device: a per-kernel cache of "what was last set
+// on device d" (cabi.cu), thread-safe, errors returned.  `slot` = one static PerDeviceAttr per kernel.
+struct PerDeviceAttr {
+    int smem[64];      // 0 = never set on that device
+    int carveout[64];  // -2 = never set
+};
+int set_kernel_smem(PerDeviceAttr* slot, const void* func, int smem_bytes, int carveout_percent = -1);
+
 // ---- warp primitives -------------------------------------------------------------------------
 NGP_DEVINL float warp_sum(float v) {
 #pragma unroll

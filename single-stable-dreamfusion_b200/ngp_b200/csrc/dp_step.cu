@@ -19,8 +19,10 @@
 //
 // Cross-GPU barriers are flag exchanges in peer memory (st.release.sys / ld.acquire.sys), one slot per (barrier, block,
 // source rank), carrying a monotonically increasing epoch kept on the device, so the kernel is CUDA-graph replayable.
-// Every spin is bounded by a wall-clock timeout (kSpinTimeoutNs): a lost peer raises the error flag instead of hanging
-// the GPU.
+// Every spin is bounded by a wall-clock timeout (default 20 s, ngp_dp_set_option(0, milliseconds)): a lost peer raises
+// the sticky error flag state[5] instead of hanging the GPU, and the step becomes a NO-OP: the flag travels with the
+// found_inf exchange of B1, a rank that saw it (locally or from a peer) neither runs Adam, nor writes to any replica,
+// nor clears its bucket, and every later launch returns at once.  TrainStep polls the flag and raises.
 #include <cooperative_groups.h>
 #include <math.h>
 
@@ -33,7 +35,8 @@ namespace dp {
 
 constexpr uint32_t kMaxWorld = NGP_DP_MAX_WORLD;
 constexpr uint32_t kMaxBlocks = NGP_DP_MAX_BLOCKS;
-constexpr uint64_t kSpinTimeoutNs = 20ull * 1000 * 1000 * 1000;  // 20 s
+uint64_t g_spin_timeout_ns = 20ull * 1000 * 1000 * 1000;  // 20 s; ngp_dp_set_option(0, ms)
+int g_blocks = 0;                                          // 0 = one block per SM; ngp_dp_set_option(1, blocks)
 
 struct Args {
     float* p;          // parameters (flat fp32), this rank's replica
@@ -64,6 +67,7 @@ struct Args {
     float* mc_g;
     float* mc_p;
     __half* mc_h;
+    uint64_t timeout_ns;
 };
 
 NGP_DEVINL void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -99,28 +103,39 @@ NGP_DEVINL uint32_t* flag_slot(uint32_t* pad, uint32_t barrier, uint32_t block, 
     return pad + ((size_t)barrier * kMaxBlocks + block) * kMaxWorld + src;
 }
 
-// Block-level barrier across ranks: block b of every rank meets block b of every other rank.  `payload` (0/1) is OR-ed
-// over the ranks and returned (to thread 0..world-1; callers combine with __syncthreads_or).
+// Block-level barrier across ranks: block b of every rank meets block b of every other rank.  `payload` (2 bits) is
+// OR-ed over the ranks and returned to every thread of the block.  A timed-out wait sets the sticky error flag state[5]
+// and reports payload bit 1 (kPayloadError).
+constexpr uint32_t kPayloadInf = 1u, kPayloadError = 2u;
 NGP_DEVINL uint32_t xrank_barrier(const Args& a, uint32_t barrier, uint32_t block, uint32_t epoch, uint32_t payload) {
-    uint32_t got = 0;
+    __shared__ uint32_t s_or;
+    if (threadIdx.x == 0) s_or = 0u;
     __syncthreads();
     if (threadIdx.x < a.world) {
         const uint32_t q = threadIdx.x;
+        uint32_t got = 0;
         __threadfence_system();
-        st_release_sys(flag_slot(a.peer_flags[q], barrier, block, a.rank), epoch * 2 + payload);
+        st_release_sys(flag_slot(a.peer_flags[q], barrier, block, a.rank), epoch * 4 + (payload & 3u));
         const uint32_t* mine = flag_slot(a.peer_flags[a.rank], barrier, block, q);
         const uint64_t t0 = now_ns();
         for (;;) {
             const uint32_t f = ld_acquire_sys(mine);
-            if ((int32_t)((f >> 1) - epoch) >= 0) { got = f & 1u; break; }
-            if (now_ns() - t0 > kSpinTimeoutNs) { a.state[5] = 1.f; break; }
+            if ((int32_t)((f >> 2) - epoch) >= 0) { got = f & 3u; break; }
+            if (now_ns() - t0 > a.timeout_ns) { *(volatile float*)(a.state + 5) = 1.f; got = kPayloadError; break; }
         }
+        if (got) atomicOr(&s_or, got);
     }
-    return __syncthreads_or((int)got) ? 1u : 0u;
+    __syncthreads();
+    const uint32_t r = s_or;
+    __syncthreads();   // s_or may be re-initialised by the next barrier of this block
+    return r;
 }
 
 __global__ void __launch_bounds__(512) adam_step_fused_kernel(const Args a) {
     cg::grid_group grid = cg::this_grid();
+    // a cross-GPU wait timed out in an earlier launch: the data-parallel job is broken, apply nothing (sticky; read by
+    // every block before any barrier of this launch could set it)
+    if (a.world > 1 && *(volatile float*)(a.state + 5) != 0.f) return;
     if (a.deferred && *(volatile float*)(a.state + 6) == 0.f) {
         // deferred mode (the step is applied at the START of the next train step, overlapped with its ray marching):
         // nothing is pending yet - every block has read the flag before block 0 raises it
@@ -172,11 +187,20 @@ __global__ void __launch_bounds__(512) adam_step_fused_kernel(const Args a) {
     grid.sync();
     if (a.world > 1) {   // B1: OR the flags of all ranks (block 0 talks to the peers, the grid barrier spreads the result)
         if (blockIdx.x == 0) {
-            const uint32_t any = xrank_barrier(a, 1, 0, epoch, *(volatile float*)(a.state + 3) != 0.f ? 1u : 0u);
-            if (threadIdx.x == 0 && any) a.state[3] = 1.0f;
+            // bit 0: found_inf; bit 1: a B0 wait of this rank timed out (any block) - then NOBODY may apply the step
+            const uint32_t mine = (*(volatile float*)(a.state + 3) != 0.f ? kPayloadInf : 0u) |
+                                  (*(volatile float*)(a.state + 5) != 0.f ? kPayloadError : 0u);
+            const uint32_t any = xrank_barrier(a, 1, 0, epoch, mine);
+            if (threadIdx.x == 0) {
+                if (any & kPayloadInf) a.state[3] = 1.0f;
+                if (any & kPayloadError) a.state[5] = 1.0f;
+            }
             __threadfence();
         }
         grid.sync();
+        // broken exchange: leave parameters, moments, buckets and the scaler state exactly as they are (on every rank
+        // that learned of it); all blocks take this branch together, nobody waits in B2 or the election below
+        if (*(volatile float*)(a.state + 5) != 0.f) return;
     }
     const bool skip = *(volatile float*)(a.state + 3) != 0.f;
 
@@ -299,6 +323,13 @@ extern "C" int ngp_enable_peer_access(int peer_device) {
     return e == cudaSuccess ? NGP_OK : (int)e;
 }
 
+// 0: spin timeout of the cross-GPU waits in milliseconds (>= 1); 1: blocks of the cooperative launch (0 = one per SM)
+extern "C" int ngp_dp_set_option(int option, int value) {
+    if (option == 0 && value >= 1) { dp::g_spin_timeout_ns = (uint64_t)value * 1000000ull; return NGP_OK; }
+    if (option == 1 && value >= 0 && value <= (int)dp::kMaxBlocks) { dp::g_blocks = value; return NGP_OK; }
+    return NGP_ERR_BAD_ARG;
+}
+
 extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow,
                                    uint64_t n, uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1,
                                    float beta2, float eps, float grad_div, float lr_decay_ln, float lr_decay_steps,
@@ -337,7 +368,9 @@ extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, 
     a.mc_g = mc ? reinterpret_cast<float*>(multicast[0]) : nullptr;
     a.mc_p = mc ? reinterpret_cast<float*>(multicast[1]) : nullptr;
     a.mc_h = mc && half_shadow ? reinterpret_cast<__half*>(multicast[2]) : nullptr;
-    int blocks = num_sms();
+    a.timeout_ns = dp::g_spin_timeout_ns;
+    int blocks = dp::g_blocks > 0 ? dp::g_blocks : num_sms();
+    if (blocks > num_sms()) blocks = num_sms();
     if (blocks > (int)dp::kMaxBlocks) blocks = (int)dp::kMaxBlocks;
     void* kargs[] = {&a};
     cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dp::adam_step_fused_kernel), dim3(blocks), dim3(512),

@@ -605,13 +605,10 @@ extern "C" int ngp_field_forward(const float* xyzs, uint32_t M, const int* count
            static_cast<const __half*>(b2), static_cast<const __half*>(w3), static_cast<const __half*>(b3)};
     a.sigma = sigma; a.rgb = rgb;
     a.enc = static_cast<__half*>(enc_save); a.h1 = static_cast<__half*>(h1_save); a.h2 = static_cast<__half*>(h2_save);
-    static int attr_set = -1;
-    if (attr_set != field::g_fwd_carveout) {
-        cudaFuncSetAttribute(field::field_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)field::FwdSmem::total);
-        if (field::g_fwd_carveout >= 0)
-            cudaFuncSetAttribute(field::field_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, field::g_fwd_carveout);
-        attr_set = field::g_fwd_carveout;
-    }
+    static PerDeviceAttr attr;
+    rc = set_kernel_smem(&attr, reinterpret_cast<const void*>(field::field_forward_kernel), (int)field::FwdSmem::total,
+                         field::g_fwd_carveout);
+    if (rc != NGP_OK) return rc;
     const int tiles = cdiv(M, field::kTile);
     const int grid = min(tiles, num_sms() * field::g_fwd_ctas_per_sm);
     field::field_forward_kernel<<<grid, field::kTile, field::FwdSmem::total, as_stream(stream)>>>(a);
@@ -644,11 +641,9 @@ extern "C" int ngp_field_backward(uint32_t M, const int* count_ptr, const void* 
     a.enc = static_cast<const __half*>(enc_save); a.h1 = static_cast<const __half*>(h1_save); a.h2 = static_cast<const __half*>(h2_save);
     a.d_enc = static_cast<__half*>(d_enc);
     a.gw1 = gw1; a.gb1 = gb1; a.gw2 = gw2; a.gb2 = gb2; a.gw3 = gw3; a.gb3 = gb3;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(field::field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)field::BwdSmem::total);
-        attr_set = true;
-    }
+    static PerDeviceAttr attr;
+    rc = set_kernel_smem(&attr, reinterpret_cast<const void*>(field::field_backward_kernel), (int)field::BwdSmem::total);
+    if (rc != NGP_OK) return rc;
     const int tiles = cdiv(M, field::kTile);
     const int grid = min(tiles, num_sms() * 2);
     field::field_backward_kernel<<<grid, field::kTile, field::BwdSmem::total, as_stream(stream)>>>(a);

@@ -3,11 +3,30 @@
 
 using namespace ngp;
 
-namespace ngp { namespace grid { bool g_disable_warpagg = false; } }
+namespace ngp { namespace grid {
+bool g_disable_warpagg = false;
+bool g_count_reds = false;                          // ngp_grid_set_option(1, x): the counting build of the scatter
+__device__ unsigned long long g_red_lane_ops = 0;   // post-aggregation red instructions x active lanes, ngp_grid_red_count
+} }
 
 extern "C" int ngp_grid_set_option(int option, int value) {
     if (option == 0) { grid::g_disable_warpagg = (value != 0); return NGP_OK; }
+    if (option == 1) { grid::g_count_reds = (value != 0); return NGP_OK; }
     return NGP_ERR_BAD_ARG;
+}
+
+extern "C" int ngp_grid_red_count(uint64_t* lane_ops, int reset) {
+    if (!lane_ops) return NGP_ERR_BAD_ARG;
+    unsigned long long v = 0;
+    cudaError_t e = cudaMemcpyFromSymbol(&v, grid::g_red_lane_ops, sizeof(v));   // synchronises the device
+    if (e != cudaSuccess) return (int)e;
+    *lane_ops = v;
+    if (reset) {
+        v = 0;
+        e = cudaMemcpyToSymbol(grid::g_red_lane_ops, &v, sizeof(v));
+        if (e != cudaSuccess) return (int)e;
+    }
+    return NGP_OK;
 }
 
 extern "C" int ngp_grid_encode_forward(const float* inputs, const void* embeddings, const int* offsets, void* outputs,
@@ -70,6 +89,14 @@ extern "C" int ngp_grid_scatter_samples(const void* d_enc, const float* xyzs, fl
     if (L == 0 || L > grid::kMaxLevels || gridtype > 1 || C != 2) return NGP_ERR_UNSUPPORTED;
     if (M_cap == 0) return NGP_OK;
     const int blocks = min(cdiv(M_cap, 256), num_sms() * 16);
+    if (grid::g_count_reds) {   // measurement only (bench.py's roofline pass): same kernel, plus one counter per lane
+        unsigned long long* ctr = nullptr;
+        if (cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), grid::g_red_lane_ops) != cudaSuccess) return launch_status();
+        grid::encode_backward_warpagg_kernel<__half, 2, true><<<blocks, 256, 0, as_stream(stream)>>>(
+            static_cast<const __half*>(d_enc), xyzs, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners != 0, count_ptr,
+            bound, ctr);
+        return launch_status();
+    }
     grid::encode_backward_warpagg_kernel<__half, 2><<<blocks, 256, 0, as_stream(stream)>>>(
         static_cast<const __half*>(d_enc), xyzs, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners != 0, count_ptr, bound);
     return launch_status();

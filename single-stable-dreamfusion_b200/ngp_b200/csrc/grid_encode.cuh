@@ -509,9 +509,11 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
 // USED = axes that enter the row index (a 'tiled' level whose table is smaller than (res+1)^2 drops z: 4 distinct
 // rows per cell, and since the weights of the two z corners sum to 1 only the (x, y) bilinear weights are needed),
 // HASHED = spatial hash of all three axes.
-template <uint32_t USED, bool HASHED, uint32_t C>
+// COUNT (measurement builds of the kernel only): `reds` accumulates the red instructions THIS lane issued, i.e. the
+// post-aggregation atomic lane-ops that bench.py's roofline divides by the measured red issue ceiling.
+template <uint32_t USED, bool HASHED, uint32_t C, bool COUNT = false>
 NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool align_corners, bool valid, const float (&g)[C],
-                              uint32_t lane, float* __restrict__ grad_table) {
+                              uint32_t lane, float* __restrict__ grad_table, uint32_t* reds = nullptr) {
     constexpr uint32_t NC = 1u << USED;  // distinct rows per cell
     float frac[USED];
     uint32_t base[USED];
@@ -597,9 +599,11 @@ NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool 
             float* dst = tbl + (size_t)lo * 2;
             if (hi == lo + 1 && (((lp.offset + lo) & 1u) == 0)) {
                 red_add_f32x4(dst, v[corner][0], v[corner][1], v[corner + 1][0], v[corner + 1][1]);
+                if constexpr (COUNT) *reds += 1u;
             } else {
                 red_add_f32x2(dst, v[corner][0], v[corner][1]);
                 red_add_f32x2(tbl + (size_t)hi * 2, v[corner + 1][0], v[corner + 1][1]);
+                if constexpr (COUNT) *reds += 2u;
             }
         }
     } else {
@@ -612,16 +616,17 @@ NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool 
 #pragma unroll
                 for (uint32_t c = 0; c < C; c += 4) red_add_f32x4(dst + c, v[corner][c], v[corner][c + 1], v[corner][c + 2], v[corner][c + 3]);
             }
+            if constexpr (COUNT) *reds += (C <= 2 ? 1u : C / 4);
         }
     }
     }  // head && valid
 }
 
-template <typename T, uint32_t C>
+template <typename T, uint32_t C, bool COUNT = false>
 __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
     const T* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
     float* __restrict__ grad_table, uint32_t B_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-    bool align_corners, const int* __restrict__ count_ptr, float bound) {
+    bool align_corners, const int* __restrict__ count_ptr, float bound, unsigned long long* red_lane_ops = nullptr) {
     constexpr uint32_t D = 3;
     __shared__ FastLevel<D> s_levels[kMaxLevels];
     for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_fast_level<D>(offsets, l, S, H, gridtype, align_corners);
@@ -632,6 +637,7 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
     const float inv_2b = bound > 0.f ? __fdiv_rn(1.0f, 2 * bound) : 1.0f;
     const uint32_t lane = threadIdx.x & 31;
     constexpr bool kPacked = (sizeof(T) == 2 && C == 2);
+    uint32_t reds = 0;
 
     for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; (b & ~31u) < B; b += gridDim.x * blockDim.x) {
         // whole warps stay alive (shuffles below); out-of-range / out-of-cube samples just contribute nothing
@@ -675,12 +681,16 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
                     if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
                 }
                 // warp-uniform dispatch on the level's addressing class
-                if (lp.hashed)          warpagg_level<3, true, C>(lp, x, align_corners, valid, g, lane, grad_table);
-                else if (lp.used == 3)  warpagg_level<3, false, C>(lp, x, align_corners, valid, g, lane, grad_table);
-                else if (lp.used == 2)  warpagg_level<2, false, C>(lp, x, align_corners, valid, g, lane, grad_table);
-                else                    warpagg_level<1, false, C>(lp, x, align_corners, valid, g, lane, grad_table);
+                if (lp.hashed)          warpagg_level<3, true, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
+                else if (lp.used == 3)  warpagg_level<3, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
+                else if (lp.used == 2)  warpagg_level<2, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
+                else                    warpagg_level<1, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
             }
         }
+    }
+    if constexpr (COUNT) {
+        const int total = warp_sum_i((int)reds);
+        if (lane == 0 && red_lane_ops && total) atomicAdd(red_lane_ops, (unsigned long long)total);
     }
 }
 

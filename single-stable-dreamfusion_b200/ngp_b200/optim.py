@@ -66,6 +66,8 @@ class FusedAdamScaler:
         # at 2 ranks (52 vs 64 us) - the multimem instructions cost latency and only pay once the fan-out is large
         env = os.environ.get("NGP_DP_MULTICAST", "auto")
         self.use_multicast = (peer_memory is not None and peer_memory.world > 4) if env == "auto" else env != "0"
+        if os.environ.get("NGP_DP_TIMEOUT_MS"):
+            _cabi.check(_cabi.load().ngp_dp_set_option(0, int(os.environ["NGP_DP_TIMEOUT_MS"])), "ngp_dp_set_option")
         if peer_memory is None:
             self.flat_params, self.flat_grads, self.flat_half = f(), f(), f(torch.half)
         else:

@@ -21,8 +21,10 @@ _BYTES_PER_ROW = 12 + 8 + 4 + 12 + 64 + 128 + 128 + 4 + 12 + 64  # xyzs deltas s
 class TrainWorkspace:
     """Static per-(N, max_steps) buffers of the training render."""
 
-    def __init__(self, n_rays, max_steps, device, cap_rows=None, counter=None):
-        cap = n_rays * max_steps if cap_rows is None else min(int(cap_rows), n_rays * max_steps)
+    def __init__(self, n_rays, max_steps, device, counter=None):
+        # always the worst case (every ray emits max_steps samples): the marcher can then never overflow, so no ray is
+        # ever dropped and rows >= counter[0] are never read
+        cap = n_rays * max_steps
         cap = (cap + 127) // 128 * 128  # the field kernels save / restore whole 128-sample tiles
         self.n_rays, self.max_steps, self.cap = n_rays, max_steps, cap
         f32, f16 = torch.float32, torch.half
@@ -108,7 +110,7 @@ def render_train(model, rays_o, rays_d, nears, fars, noises, dt_gamma, max_steps
     N = rays_o.shape[0]
     ws = getattr(model, "_train_ws", None)
     if ws is None or ws.n_rays != N or ws.max_steps != max_steps or ws.xyzs.device != rays_o.device:
-        ws = TrainWorkspace(N, max_steps, rays_o.device, getattr(model, "train_capacity_rows", None))
+        ws = TrainWorkspace(N, max_steps, rays_o.device)
         model._train_ws = ws
     cfg = dict(encoder=model.encoder, bitfield=model.density_bitfield, bound=model.bound, dt_gamma=dt_gamma,
                max_steps=max_steps, cascade=model.cascade, grid_size=model.grid_size, T_thresh=T_thresh)

@@ -49,6 +49,13 @@ class TrainStep:
         self._chain = []
         self.max_steps, self.lam, self.update_interval = max_steps, lambda_entropy, update_interval
         self.world = world_size
+        # Data parallel = the SAME step as one GPU rendering all rays: the guidance term is a per-pixel SUM (nerf/sd.py:115
+        # `latents.backward(gradient=grad)`, un-normalised), so rank gradients are reduced with SUM and never divided; the
+        # entropy term is a MEAN over all rays of the job, so each rank's local mean is weighted 1 / world.
+        self.lam_local = float(lambda_entropy) / float(world_size)
+        self.fixed_noises = None  # tests: per-ray perturbation noise [N] used instead of a fresh torch.rand draw
+        self.keep_grads = False   # tests: copy the gradient bucket to self.grad_snapshot right before the optimizer
+        self.grad_snapshot = None  # (a device-to-device copy inside the step, so it also works in a graph replay)
         self.use_graph = graph
         self.single_backward = True  # one engine pass for both roots (see _body); False = the reference's two passes
         device = next(model.parameters()).device
@@ -66,16 +73,15 @@ class TrainStep:
                 self.peer_error = repr(e)
         if fused_optimizer:
             # one flat buffer each for params / grads / moments / fp16 shadow; unscale + Adam + scaler.update + shadow
-            # refresh + zero_grad in one (step_fused) or two (step) launches (optim.py); the all-reduce mean is folded
-            # into the unscale
+            # refresh + zero_grad in one (step_fused) or two (step) launches (optim.py); gradients are SUMMED over ranks
             try:
-                self.opt = FusedAdamScaler(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, grad_div=float(world_size),
+                self.opt = FusedAdamScaler(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, grad_div=1.0,
                                            lr_decay=lr_decay, peer_memory=self.peer)
             except RuntimeError as e:
                 if self.peer is None or peer_allreduce:
                     raise
                 self.peer, self.peer_error = None, repr(e)  # no peer-addressable memory here: NCCL all-reduce instead
-                self.opt = FusedAdamScaler(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, grad_div=float(world_size),
+                self.opt = FusedAdamScaler(model.get_params(lr), betas=(0.9, 0.99), eps=1e-15, grad_div=1.0,
                                            lr_decay=lr_decay)
             self.scaler = self.opt
             self.bucket = None
@@ -120,7 +126,7 @@ class TrainStep:
                                shading="albedo", force_all_rays=True, max_steps=self.max_steps, dt_gamma=0)
             pred_rgb = out["image"].reshape(B, self.H, self.W, 3).permute(0, 3, 1, 2).contiguous()
             ws = out["weights_sum"].reshape(B, 1, self.H, self.W)
-            loss = fused_entropy_loss(ws, self.lam) if self.fused_optimizer else entropy_loss(ws, self.lam)
+            loss = fused_entropy_loss(ws, self.lam_local) if self.fused_optimizer else entropy_loss(ws, self.lam_local)
         # The reference runs TWO backward passes over the render graph per step: the guidance's manual
         # `pred_rgb.backward(gradient=G, retain_graph=True)` (nerf/sd.py:115) and `scaler.scale(loss).backward()`
         # (nerf/utils.py:708).  Back-propagation is linear in the upstream gradient, so both roots are handed to the
@@ -136,8 +142,6 @@ class TrainStep:
         if self.fused_optimizer:
             self.opt.step(zero_grads=True)
         else:
-            if self.world > 1:
-                self.bucket.flat.div_(self.world)
             self.scaler.step(self.opt)
             self.scaler.update()
         return loss
@@ -175,12 +179,10 @@ class TrainStep:
                  bg=e(N, 3, dtype=torch.half), d_bg=e(N, 3), loss=torch.zeros((), device=dev),
                  counters=torch.zeros(n_chunks, 2, dtype=torch.int32, device=dev),
                  cur_row=torch.zeros(1, dtype=torch.int32, device=dev), chunks=[])
-        cap_rows = getattr(self.model, "train_capacity_rows", None)
         base = 0
         for c in range(n_chunks):
             n_c = N // n_chunks + (1 if c < N % n_chunks else 0)
-            ws = TrainWorkspace(n_c, self.max_steps, dev, None if cap_rows is None else max(128, int(cap_rows) * n_c // N),
-                                counter=m["counters"][c])
+            ws = TrainWorkspace(n_c, self.max_steps, dev, counter=m["counters"][c])
             m["chunks"].append((base, n_c, ws))
             base += n_c
         self.model._train_ws = m["chunks"][0][2]  # (what run_cuda's own fused path would allocate; kept for introspection)
@@ -242,7 +244,10 @@ class TrainStep:
                    P(m["cur_row"]))
         if self.mirror_rng:
             torch.randn(3, device=dev)  # nerf/renderer.py:464 (light direction; unused by albedo shading)
-        m["noises"].uniform_()  # the torch.rand(N) of the reference's wrapper (raymarching.py:213-216)
+        if self.fixed_noises is not None:
+            m["noises"].copy_(self.fixed_noises)
+        else:
+            m["noises"].uniform_()  # the torch.rand(N) of the reference's wrapper (raymarching.py:213-216)
 
         chunks = m["chunks"]
         streams = [main] + self._chain[:len(chunks) - 1]
@@ -263,7 +268,7 @@ class TrainStep:
             if has_bg:
                 torch.cuda.current_stream(dev).wait_stream(self._side)
             _cabi.call("ngp_train_ray_loss", dev, P(ws.sigma), P(ws.rgb), P(ws.deltas), P(ws.rays), ws.cap, n_c, 1e-4,
-                       P(m["bg"][sl]) if has_bg else None, 1.0, P(G), hw, base, N, float(self.lam), opt.state.data_ptr(),
+                       P(m["bg"][sl]) if has_bg else None, 1.0, P(G), hw, base, N, float(self.lam_local), opt.state.data_ptr(),
                        P(m["weights_sum"][sl]), P(m["depth"][sl]), P(m["image"][sl]), P(m["d_bg"][sl]) if has_bg else None,
                        P(ws.d_sigma), P(ws.d_rgb), P(m["loss"]), P(ws.counter), P(self.samples), P(model.step_counter),
                        P(m["cur_row"]))
@@ -292,6 +297,10 @@ class TrainStep:
             main.wait_stream(st)
         if has_bg:
             main.wait_stream(self._side)
+        if self.keep_grads:
+            if self.grad_snapshot is None:
+                self.grad_snapshot = torch.empty_like(opt.flat_grads)
+            self.grad_snapshot.copy_(opt.flat_grads)
         if not self.pipelined:
             self._apply_update(deferred=False)
         self._pending = True
@@ -373,6 +382,12 @@ class TrainStep:
                 raise RuntimeError("packed inputs do not match H, W of this TrainStep")
         if self.global_step % self.update_interval == 0:
             self.flush()  # (pipelined mode) the refresh must see the parameters of the completed previous step
+            if self.fused_optimizer and self.world > 1 and self.opt.peer_ptrs is not None and self.global_step > 0 \
+                    and self.opt.comm_error:
+                # a cross-GPU wait inside the fused all-reduce + Adam kernel timed out: from that launch on the kernel
+                # applies nothing on any rank that saw the flag (csrc/dp_step.cu) - stop instead of training on
+                raise RuntimeError("data-parallel step: a peer did not reach the gradient exchange in time (see "
+                                   "NGP_DP_TIMEOUT_MS); parameters were left untouched from that step on")
             if self.use_graph and not self.fused_optimizer:
                 from . import field
                 field.invalidate_half_cache()  # graph replays update the parameters without bumping ._version
@@ -415,6 +430,7 @@ class TrainStep:
             g_s.copy_(G, non_blocking=True)
         before = model.local_step
         self._graph.replay()
+        self._pending = True
         _cabi.LAUNCHES += self._graph_launches  # our kernels inside the replayed graph
         self._bookkeeping_after(before)
         if not self.manual:
@@ -430,17 +446,25 @@ class TrainStep:
         ro_s.copy_(rays_o)
         rd_s.copy_(rays_d)
         g_s.copy_(G)
-        # warm up on a side stream (allocator, lazy initialisation, cudaFuncSetAttribute) before capturing
+        # warm up on a side stream (allocator, lazy initialisation, cudaFuncSetAttribute) before capturing.  The warm-up
+        # passes are REAL steps (they must touch every code path the capture will); everything they change - parameters,
+        # fp16 shadow, Adam moments, step count / loss scale / growth tracker, step_counter rows, sample total - is
+        # snapshotted first and restored afterwards, so graph=True trains exactly like graph=False.
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         saved_step = model.local_step
-        saved_samples = self.samples.clone()
+        snap = self._snapshot_training_state()
         with torch.cuda.stream(side):
             for _ in range(3):
                 self._step_body(ro_s, rd_s, g_s)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._restore_training_state(snap)
         model.local_step = saved_step
+        if self.manual:
+            self._local_step_dev.fill_(saved_step)
+            self._ls_mirror = saved_step
+        torch.cuda.synchronize()
         self._graph = torch.cuda.CUDAGraph()
         launches0 = _cabi.LAUNCHES
         with torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
@@ -448,7 +472,46 @@ class TrainStep:
         self._graph_launches = _cabi.LAUNCHES - launches0
         _cabi.LAUNCHES = launches0  # capture launches nothing
         model.local_step = saved_step
-        if self.manual:  # undo the device-side bookkeeping of the warm-up passes
-            self.samples.copy_(saved_samples)
-            self._local_step_dev.fill_(saved_step)
-            self._ls_mirror = saved_step
+        self._pending = snap["pending"]
+
+    def _snapshot_training_state(self):
+        """Everything a train step mutates besides its own scratch (see _capture)."""
+        snap = dict(step_counter=self.model.step_counter.clone(), samples=self.samples.clone(), pending=self._pending)
+        if self.fused_optimizer:
+            o = self.opt
+            snap["opt"] = [t.clone() for t in (o.flat_params, o.flat_half, o.exp_avg, o.exp_avg_sq, o.state)]
+        else:
+            snap["params"] = [p.detach().clone() for p in self.model.parameters()]
+            snap["adam"] = {id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                            for p, st in self.opt.state.items()}
+            sc = self.scaler
+            snap["scaler"] = None if sc._scale is None else (sc._scale.clone(), sc._growth_tracker.clone())
+        return snap
+
+    def _restore_training_state(self, snap):
+        with torch.no_grad():
+            self.model.step_counter.copy_(snap["step_counter"])
+            self.samples.copy_(snap["samples"])
+            if self.fused_optimizer:
+                o = self.opt
+                err = o.state[5].clone()   # a cross-GPU timeout during the warm-up must stay visible
+                for dst, src in zip((o.flat_params, o.flat_half, o.exp_avg, o.exp_avg_sq, o.state), snap["opt"]):
+                    dst.copy_(src)
+                o.state[5].copy_(torch.maximum(err, o.state[5]))
+                o.flat_grads.zero_()
+                # (o._sync - the cross-GPU barrier epoch - keeps counting: the peers' flags carry it)
+            else:
+                for p, q in zip(self.model.parameters(), snap["params"]):
+                    p.copy_(q)
+                for p, st in self.opt.state.items():   # in place: a capturable Adam's state tensors must keep their addresses
+                    old = snap["adam"].get(id(p))
+                    for k, v in st.items():
+                        if torch.is_tensor(v):
+                            v.copy_(old[k]) if old is not None and k in old else v.zero_()
+                if snap["scaler"] is not None:
+                    self.scaler._scale.copy_(snap["scaler"][0])
+                    self.scaler._growth_tracker.copy_(snap["scaler"][1])
+                elif self.scaler._scale is not None:
+                    self.scaler._scale.fill_(self.scaler._init_scale)
+                    self.scaler._growth_tracker.zero_()
+                self.bucket.zero()

@@ -34,60 +34,19 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     from ngp_b200 import _cabi
-    from ngp_b200.optim import FusedAdamScaler
-    from ngp_b200.parallel import PeerMemory
     _cabi.load()
 
-    n_table = args.n - 8192
-    torch.manual_seed(0)   # identical initial parameters on every rank
-    mk = lambda: [torch.nn.Parameter(torch.randn(n_table // 2, 2, device=dev) * 0.1),  # noqa: E731
-                  torch.nn.Parameter(torch.randn(64, 64, device=dev) * 0.1), torch.nn.Parameter(torch.randn(4096, device=dev) * 0.1)]
-    pa, pb = mk(), None
-    torch.manual_seed(0)
-    pb = mk()
-    groups = lambda ps: [{"params": ps[:1], "lr": 1e-2}, {"params": ps[1:], "lr": 1e-3}]  # noqa: E731
-    result = {"world": world, "n": args.n}
-    try:
-        peer = PeerMemory(dev)
-        mine = FusedAdamScaler(groups(pa), growth_interval=3, grad_div=float(world), peer_memory=peer, lr_decay=(0.1, 10))
-        result["backend"] = peer.used
-        result["multicast"] = bool(mine.multicast is not None and mine.use_multicast)   # NGP_DP_MULTICAST=0 forces P2P
-    except Exception as e:  # noqa: BLE001
+    from ngp_b200 import dp_check
+    result = dp_check.run(dev, n=args.n, steps=args.steps, grad_div=float(world))
+    if "error" in result:
         if rank == 0:
-            print(json.dumps({"ok": False, "error": "peer memory unavailable: %r" % e}))
+            print(json.dumps({"ok": False, "error": result["error"]}))
         dist.destroy_process_group()
         sys.exit(2)
-    ref = FusedAdamScaler(groups(pb), growth_interval=3, grad_div=float(world), lr_decay=(0.1, 10))
-    ok = True
-    worst = 0.0
-    for it in range(args.steps):
-        g = torch.Generator(device=dev).manual_seed(1000 * it + rank)
-        raw = torch.randn(mine.numel, device=dev, generator=g) * (10.0 ** (it % 3 - 2))
-        if it == 2 and rank == world - 1:
-            raw[mine.numel - 5] = float("inf")   # found on ONE rank, in the LAST slice: every rank must skip
-        scale = mine.get_scale()
-        assert scale == ref.get_scale()
-        mine.flat_grads.copy_(raw * scale)
-        ref.flat_grads.copy_(raw * scale)
-        torch.cuda.synchronize()
-        dist.barrier()
-        mine.step_fused()
-        dist.all_reduce(ref.flat_grads)
-        ref.step(zero_grads=True)
-        torch.cuda.synchronize()
-        dist.barrier()
-        d = (mine.flat_params - ref.flat_params).abs().max().item()
-        worst = max(worst, d)
-        same_half = torch.equal(mine.flat_half, mine.flat_params.half())
-        zeroed = mine.flat_grads.abs().sum().item() == 0
-        st_ok = torch.equal(mine.state[:5], ref.state[:5])
-        if not (d <= 2e-6 and same_half and zeroed and st_ok and not mine.comm_error):
-            ok = False
-            print("rank %d step %d: max|dp| %.3g half %s zeroed %s state %s/%s comm_error %s" % (
-                rank, it, d, same_half, zeroed, mine.state.tolist(), ref.state.tolist(), mine.comm_error), file=sys.stderr)
-    result["max_abs_param_diff"] = worst
-    result["steps_taken"], result["skipped"] = mine.steps_taken, int(mine.state[4].item())
-    ok = ok and result["skipped"] == 1
+    mine, ref = result.pop("_objects")
+    ok = result["ok"]
+    if not ok:
+        print("rank %d: %r" % (rank, result.get("first_failure")), file=sys.stderr)
 
     # ---- data-parallel occupancy refresh: 1/world of the cells per rank + all-gather -> identical grids everywhere -----
     import argparse as _ap

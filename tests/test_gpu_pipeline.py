@@ -182,8 +182,8 @@ def test_graphed_train_step_matches_eager(ref_ext, manual):
         finals.append((losses, m.encoder.embeddings.detach().clone(), int(step.samples.item()), m.local_step))
     assert finals[0][3] == finals[1][3] == 6
     assert finals[1][2] > 0
-    # the graphed run executes 3 extra warm-up optimizer steps on the first batch before capture, so the two runs
-    # are not step-for-step identical; they must stay statistically close
+    # the graphed run draws different ray noise (its rolled-back warm-up steps consumed torch RNG), so the two runs are
+    # not step-for-step identical; they must stay statistically close
     assert abs(np.mean(finals[0][0]) - np.mean(finals[1][0])) < 0.2 * abs(np.mean(finals[0][0])) + 1e-6
 
 

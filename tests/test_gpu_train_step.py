@@ -240,14 +240,74 @@ def test_hand_scheduled_step_graph_replay_and_packed_inputs():
                 losses.append(step(ro[i], rd[i], G[i]).item())
         torch.cuda.synchronize()
         assert not step.opt.comm_error
-        assert step.opt.steps_taken == (6 + 3 if graph else 6)   # the capture warms up with three real steps
+        assert step.opt.steps_taken == 6   # the capture's warm-up steps are rolled back (trainer._capture)
         out.append((losses, step.samples.item(), m.step_counter.clone(), m.local_step))
     (la, sa, ca, lsa), (lb, sb, cb, lsb) = out
     assert lsa == lsb == 6 and sa > 0 and sb > 0
-    # different noise draws / three extra optimizer steps in the graphed run: the loss stays in the same range
+    # different noise draws in the graphed run (its warm-up consumed torch RNG): the loss stays in the same range
     np.testing.assert_allclose(la, lb, rtol=0.2)
     assert (ca[:6, 1] == 4096).all() and (cb[:6, 1] == 4096).all()
     assert abs(sa - sb) < 0.2 * sa
+
+
+def test_graph_capture_leaves_no_training_side_effects():
+    """The three warm-up steps before capture are REAL steps; parameters, fp16 shadow, Adam moments, step count, loss
+    scale, step_counter and the sample total must be exactly what they were before the capture."""
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    ro, rd = provider.make_training_views(1, 64, 64, seed=4, pin=False)
+    ro, rd = ro.to(DEV), rd.to(DEV)
+    G = torch.randn(1, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2)) * 1e-2
+    for manual in (True, False):
+        m = _bench_like_model()
+        step = TrainStep(m, 64, 64, lr=1e-3, graph=True, manual=manual)
+        with torch.autocast("cuda", torch.float16):
+            m.update_extra_state()
+        o = step.opt
+        before = [t.clone() for t in (o.flat_params, o.flat_half, o.exp_avg, o.exp_avg_sq, o.state, m.step_counter, step.samples)]
+        step._capture(ro, rd, G)
+        torch.cuda.synchronize()
+        after = (o.flat_params, o.flat_half, o.exp_avg, o.exp_avg_sq, o.state, m.step_counter, step.samples)
+        for a, b in zip(before, after):
+            assert torch.equal(a, b)
+        assert o.flat_grads.abs().sum().item() == 0 and m.local_step == 0 and o.steps_taken == 0
+
+
+def test_pixel_sharded_ranks_sum_to_the_one_gpu_step():
+    """Data parallel = the same step: two virtual ranks, each rendering its interleaved rows of every view (bench.py's
+    sharding), must produce gradient buckets whose SUM is the bucket of one GPU rendering all rays - guidance summed per
+    pixel, entropy averaged over ALL rays of the job (nerf/sd.py:115, nerf/utils.py:389-394)."""
+    from ngp_b200 import provider
+    from ngp_b200.parallel import shard_rows
+    from ngp_b200.trainer import TrainStep
+    views, Hh, Ww, world = 2, 64, 64, 2
+    ro, rd = provider.make_training_views(views, Hh, Ww, seed=3, pin=False)
+    ro, rd = ro.to(DEV), rd.to(DEV)
+    G = torch.randn(views, 3, Hh, Ww, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 1e-2
+    noises = torch.rand(views * Hh * Ww, device=DEV, generator=torch.Generator(device=DEV).manual_seed(9))
+
+    def one(rows, world_size):
+        m = _bench_like_model()
+        Hl = len(rows)
+        step = TrainStep(m, Hl, Ww, lr=1e-3, graph=False, manual=True, world_size=world_size, peer_allreduce=False, lambda_entropy=1e-2)
+        idx = torch.tensor(rows, device=DEV)
+        sel = lambda t: t.view(views, Hh, Ww, 3)[:, idx].reshape(views, Hl * Ww, 3).contiguous()  # noqa: E731
+        step.fixed_noises = noises.view(views, Hh, Ww)[:, idx].reshape(-1).contiguous()
+        grads = []
+        step._apply_update = lambda deferred=False, _s=step, _g=grads: (_g.append(_s.opt.flat_grads.clone()), _s.opt.flat_grads.zero_())
+        loss = step(sel(ro), sel(rd), G[:, :, idx].contiguous())
+        torch.cuda.synchronize()
+        return grads[0], loss.item(), step.opt.get_scale(), int(step.samples.item())
+
+    g_full, l_full, scale, n_full = one(list(range(Hh)), 1)
+    parts = [one(shard_rows(Hh, r, world), world) for r in range(world)]
+    assert sum(p[3] for p in parts) == n_full            # the same samples, split
+    g_sum = sum(p[0] for p in parts)
+    assert abs(sum(p[1] for p in parts) - l_full) <= 1e-5 * abs(l_full)
+    rel = ((g_sum - g_full).norm() / g_full.norm()).item()
+    assert rel < 1e-3, rel
+    # and the entropy term really is in there at a visible weight: dropping the 1/world would be caught
+    assert l_full > 0 and scale == 65536.0
 
 
 def test_pipelined_optimizer_applies_the_same_updates_one_step_later():
