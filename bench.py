@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce instead of the fused peer-memory all-reduce + Adam")
     ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
+    ap.add_argument("--host-rays", action="store_true", help="feed pre-generated rays (1.18 MB / step) instead of camera poses; "
+                    "default: the step's input is 8 poses + intrinsics + the guidance gradient, rays are generated on the device")
     ap.add_argument("--ref-steps", type=int, default=200, help="timed steps of the reference CUDA-extension pipeline")
     ap.add_argument("--ref-warmup", type=int, default=50)
     return ap.parse_args()
@@ -224,9 +226,14 @@ def run_b200_arm(args):
     pix_t = torch.tensor(pix, dtype=torch.long)
     Hl = len(pix) // W
     n_pool = 64
-    ro_all, rd_all = provider.make_training_views(n_pool * args.views, H, W, seed=0, pin=False)
-    ro_all = ro_all.view(n_pool, args.views, H * W, 3)[:, :, pix_t].contiguous()
-    rd_all = rd_all.view(n_pool, args.views, H * W, 3)[:, :, pix_t].contiguous()
+    device_rays = not args.host_rays and not args.autograd and args.ray_order == "rows"
+    if device_rays:
+        poses_all, intr_all = provider.make_training_poses(n_pool * args.views, H, W, seed=0)
+        poses_all, intr_all = poses_all.view(n_pool, args.views, 4, 4), intr_all.view(n_pool, args.views, 4)
+    else:
+        ro_all, rd_all = provider.make_training_views(n_pool * args.views, H, W, seed=0, pin=False)
+        ro_all = ro_all.view(n_pool, args.views, H * W, 3)[:, :, pix_t].contiguous()
+        rd_all = rd_all.view(n_pool, args.views, H * W, 3)[:, :, pix_t].contiguous()
     # the guidance gradient of the rendered pixels, in the same ray order ([views, 3, rays of this rank])
     g_all = (torch.randn(n_pool, args.views, 3, H * W, generator=torch.Generator().manual_seed(2)) * 1e-2)[:, :, :, pix_t]
     g_all = g_all.reshape(n_pool, args.views, 3, Hl, W).contiguous()
@@ -237,9 +244,15 @@ def run_b200_arm(args):
     # random-init occupancy so that every timed pass sees the same ~3.4 M samples per step
     step_fn = TrainStep(model, Hl, W, lr=args.lr, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world,
                         manual=False if args.autograd else None, peer_allreduce=False if args.nccl else None,
-                        pipelined=args.pipeline and not args.autograd, n_chunks=args.chunks or None)
-    # one packed, pinned host buffer per batch [rays_o | rays_d | G]: a step's inputs are ONE copy
-    host_pool = torch.stack([step_fn.pack_inputs(ro_all[k], rd_all[k], g_all[k].contiguous()) for k in range(n_pool)]).pin_memory()
+                        pipelined=args.pipeline and not args.autograd, n_chunks=args.chunks or None,
+                        device_rays=(H, rank, world) if device_rays else None)
+    # one packed, pinned host buffer per batch: a step's inputs are ONE copy - [poses | intrinsics | G] (the rays of this
+    # rank's interleaved image rows are generated by the step's prologue kernel), or [rays_o | rays_d | G] with --host-rays
+    if device_rays:
+        host_pool = torch.stack([step_fn.pack_pose_inputs(poses_all[k], intr_all[k], g_all[k].contiguous())
+                                 for k in range(n_pool)]).pin_memory()
+    else:
+        host_pool = torch.stack([step_fn.pack_inputs(ro_all[k], rd_all[k], g_all[k].contiguous()) for k in range(n_pool)]).pin_memory()
 
     def host_batch(i):
         return host_pool[i % n_pool]
@@ -475,6 +488,8 @@ def run_b200_arm(args):
                 "sharding": ("8x8-pixel blocks of every view dealt along the block diagonals" if args.ray_order == "tiles"
                              else "image rows interleaved over ranks"),
                 "pipelined_optimizer": step_fn.pipelined,
+                "step_inputs": ("camera poses + intrinsics + guidance gradient; rays generated on the device (nerf/utils.py:get_rays)"
+                                if device_rays else "pre-generated rays + guidance gradient"),
                 "ray_chunks": len(step_fn._mws["chunks"]) if step_fn._mws else 1,
                 "grad_allreduce": ("none (1 GPU)" if world == 1 else
                                    ("fused into the optimizer kernel over NVLink peer memory (%s)" % step_fn.peer.used
@@ -505,7 +520,7 @@ def run_b200_arm(args):
                            if os.environ.get("CUDA_VISIBLE_DEVICES") else str(local_rank))
                 for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
                     env.pop(k, None)
-                out = subprocess.run([sys.executable, "-m", "oracle.ref_pipeline", str(args.ref_steps), str(args.ref_warmup)],
+                out = subprocess.run([sys.executable, "-m", "oracle.ref_pipeline", str(args.ref_steps), str(args.ref_warmup), repr(args.lr)],
                                      cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
                 tag = [l for l in out.stdout.splitlines() if l.startswith("REF_PIPELINE_JSON ")]
                 line["ref_cuda_ext"] = json.loads(tag[-1][len("REF_PIPELINE_JSON "):]) if tag else {

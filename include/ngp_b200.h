@@ -310,6 +310,19 @@ int ngp_train_ray_loss(const float* sigmas, const float* rgbs, const float* delt
                        const int* counter, unsigned long long* samples_total, int* step_counter, const int* cur_row,
                        void* stream);
 
+/* Ray generation on the device: nerf/utils.py:43-106 get_rays (the N = -1 full-image branch, as nerf/provider.py:227 calls
+ * it).  poses f32[B,4,4] row-major cam2world; intrinsics f32[4] = (fx, fy, cx, cy), or f32[B,4] when intrinsics_per_view
+ * != 0 (one random focal per training view, provider.py:209-213).  Produces image rows row0, row0 + row_stride, ...
+ * (n_rows of them; 0 = all that fit; row_stride 0 = 1) of every view: rays_o, rays_d f32[B, n_rows * W, 3].
+ * ngp_train_prologue_rays = ngp_train_prologue with the rays generated instead of loaded (one launch; the rays are also
+ * written out, the marcher and the background net read them). */
+int ngp_get_rays(const float* poses, const float* intrinsics, int intrinsics_per_view, uint32_t B, uint32_t H, uint32_t W,
+                 uint32_t row0, uint32_t row_stride, uint32_t n_rows, float* rays_o, float* rays_d, void* stream);
+int ngp_train_prologue_rays(const float* poses, const float* intrinsics, int intrinsics_per_view, uint32_t B, uint32_t H,
+                            uint32_t W, uint32_t row0, uint32_t row_stride, uint32_t n_rows, float* rays_o, float* rays_d,
+                            const float* aabb, float min_near, float* nears, float* fars, int* counters, uint32_t n_counters,
+                            float* loss, int* step_counter, int* local_step, int* cur_row, void* stream);
+
 /* End of run_cuda (nerf/renderer.py:535-557): image_out = image + (1 - weights_sum) * bg, depth_out =
  * clamp(depth - nears, 0) / (fars - nears) (NaN where the ray misses the box, as the reference), mask = nears < fars.
  * bg is f32[N,3] (bg_per_ray != 0) or one f32[3] colour.  depth_out / mask may be NULL. */

@@ -421,3 +421,23 @@ def bg_backward(fwd, d_rgb):
     dh = (dout @ fwd["W"][1]) * (fwd["h"] > 0)
     g["w1"], g["b1"] = dh.T @ fwd["e"], dh.sum(0)
     return g
+
+
+def get_rays(poses, intrinsics, H, W):
+    """TEST INFRASTRUCTURE - numpy restatement of nerf/utils.py:43-106 get_rays for the full image (N = -1): pixel centres
+    at +0.5 (:60-61), directions ((i - cx) / fx, (j - cy) / fy, 1) (:93-96) normalised by safe_normalize (:33-36, clamp of
+    the squared norm at 1e-20), rays_d = directions @ R^T (:98), rays_o = translation (:100-101).  fp32 like torch.
+    poses [B,4,4]; intrinsics [4] or [B,4].  Returns rays_o, rays_d [B, H*W, 3]."""
+    poses = _c(poses, np.float32)
+    K = np.broadcast_to(_c(intrinsics, np.float32).reshape(-1, 4), (poses.shape[0], 4))
+    f32 = np.float32
+    j, i = np.meshgrid(np.arange(H, dtype=f32), np.arange(W, dtype=f32), indexing="ij")   # i: column, j: row
+    i = i.reshape(1, H * W) + f32(0.5)
+    j = j.reshape(1, H * W) + f32(0.5)
+    xs = ((i - K[:, 2:3]) / K[:, 0:1]).astype(f32)
+    ys = ((j - K[:, 3:4]) / K[:, 1:2]).astype(f32)
+    d = np.stack([xs, ys, np.ones_like(xs)], -1)
+    d = (d / np.sqrt(np.maximum((d * d).sum(-1, keepdims=True), f32(1e-20)))).astype(f32)
+    rays_d = np.einsum("bnc,bkc->bnk", d, poses[:, :3, :3]).astype(f32)
+    rays_o = np.broadcast_to(poses[:, None, :3, 3], rays_d.shape).astype(f32).copy()
+    return rays_o, rays_d

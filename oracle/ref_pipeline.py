@@ -319,9 +319,11 @@ class RefGridNeRF(nn.Module):
                 {"params": self.bg_net.parameters(), "lr": lr}]
 
 
-def time_reference_train_step(device, views=1, steps=20, warmup=5, Hh=64, Ww=64, max_steps=1024):
+def time_reference_train_step(device, views=1, steps=200, warmup=50, Hh=64, Ww=64, max_steps=1024, lr=1e-5):
     """Times the reference's -O train step (reference kernels + reference call pattern) on `device`.
-    The reference renders one view per step (provider.py:240 batch_size=1)."""
+    The reference renders one view per step (provider.py:240 batch_size=1).  lr: as in bench.py a SMALL step, so that the
+    synthetic random-gradient "training" leaves the scene at its random-init occupancy and every timed step marches the
+    same ~0.4 M samples per view on both sides of the comparison."""
     import sys, os
     ns = ref_ext.load()
     if ns is None:
@@ -332,7 +334,7 @@ def time_reference_train_step(device, views=1, steps=20, warmup=5, Hh=64, Ww=64,
     torch.manual_seed(0)
     model = RefGridNeRF(ns).to(device)
     model.train()
-    opt = torch.optim.Adam(model.param_groups(1e-3), betas=(0.9, 0.99), eps=1e-15)
+    opt = torch.optim.Adam(model.param_groups(lr), betas=(0.9, 0.99), eps=1e-15)
     scaler = torch.amp.GradScaler("cuda")
     ro_all, rd_all = provider.make_training_views(32 * views, Hh, Ww, seed=0)
     ro_all = ro_all.view(32, views, Hh * Ww, 3).to(device)
@@ -376,7 +378,7 @@ def time_reference_train_step(device, views=1, steps=20, warmup=5, Hh=64, Ww=64,
     return {"value": samples / (ms * 1e-3), "value_median": (samples / steps) / (med * 1e-3), "unit": "samples/s",
             "ms_per_step": ms / steps, "ms_per_step_median": med, "ms_per_step_p10": per[len(per) // 10],
             "ms_per_step_p90": per[(len(per) * 9) // 10], "views_per_step": views,
-            "samples_per_step": samples / steps, "steps": steps, "warmup": warmup,
+            "samples_per_step": samples / steps, "steps": steps, "warmup": warmup, "lr": lr,
             "what": "reference CUDA extensions (gridencoder/raymarching/freqencoder rebuilt unmodified for sm_100) "
                     "+ the reference's host call pattern, same -O train step, 1 GPU"}
 
@@ -388,5 +390,6 @@ if __name__ == "__main__":
     import sys
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     warm = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-    res = time_reference_train_step(torch.device("cuda", 0), views=1, steps=steps, warmup=warm)
+    lr = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-5
+    res = time_reference_train_step(torch.device("cuda", 0), views=1, steps=steps, warmup=warm, lr=lr)
     print("REF_PIPELINE_JSON " + json.dumps(res), flush=True)

@@ -325,6 +325,74 @@ __global__ void train_prologue_kernel(const float* __restrict__ rays_o, const fl
     fars[n] = hi;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Ray generation on the device (nerf/utils.py:43-106 get_rays, the N = -1 branch the dataset uses, provider.py:227): pixel
+// centres at +0.5, camera-space direction ((i - cx) / fx, (j - cy) / fy, 1) normalised with safe_normalize (clamp of the
+// squared norm at 1e-20, :33-36), rotated by the pose's 3x3 block (rays_d = directions @ R^T), origin = the pose's
+// translation.  Sharded views: this launch produces `n_rows` image rows  row0, row0 + row_stride, ...  of every view
+// (parallel.shard_rows), rows of one view contiguous.
+// -------------------------------------------------------------------------------------------------
+struct RayGen {
+    const float* poses;        // [B, 4, 4] row-major cam2world
+    const float* intrinsics;   // [B, 4] or [1, 4]: fx, fy, cx, cy
+    uint32_t B, W, n_rows, row0, row_stride, intr_per_view;
+};
+NGP_DEVINL Ray generate_ray(const RayGen& g, uint32_t n) {
+    const uint32_t per_view = g.n_rows * g.W;
+    const uint32_t b = n / per_view, p = n - b * per_view;
+    const uint32_t rl = p / g.W, col = p - rl * g.W;
+    const uint32_t row = g.row0 + rl * g.row_stride;
+    const float* K = g.intrinsics + (g.intr_per_view ? (size_t)b * 4 : 0);
+    const float* P = g.poses + (size_t)b * 16;
+    const float x = __fdiv_rn(__fsub_rn(__fadd_rn((float)col, 0.5f), K[2]), K[0]);
+    const float y = __fdiv_rn(__fsub_rn(__fadd_rn((float)row, 0.5f), K[3]), K[1]);
+    const float z = 1.0f;
+    const float nrm = sqrtf(fmaxf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)), 1e-20f));
+    const float dx = __fdiv_rn(x, nrm), dy = __fdiv_rn(y, nrm), dz = __fdiv_rn(z, nrm);
+    Ray r;
+    r.dx = dx * P[0] + dy * P[1] + dz * P[2];
+    r.dy = dx * P[4] + dy * P[5] + dz * P[6];
+    r.dz = dx * P[8] + dy * P[9] + dz * P[10];
+    r.ox = P[3]; r.oy = P[7]; r.oz = P[11];
+    r.rdx = 1 / r.dx; r.rdy = 1 / r.dy; r.rdz = 1 / r.dz;
+    return r;
+}
+
+__global__ void get_rays_kernel(const RayGen g, float* __restrict__ rays_o, float* __restrict__ rays_d) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= g.B * g.n_rows * g.W) return;
+    const Ray r = generate_ray(g, n);
+    rays_o[n * 3] = r.ox; rays_o[n * 3 + 1] = r.oy; rays_o[n * 3 + 2] = r.oz;
+    rays_d[n * 3] = r.dx; rays_d[n * 3 + 1] = r.dy; rays_d[n * 3 + 2] = r.dz;
+}
+
+// train_prologue_kernel with the rays generated in place of loaded: a step's input is B poses + intrinsics (+ G)
+__global__ void train_prologue_rays_kernel(const RayGen g, float* __restrict__ rays_o, float* __restrict__ rays_d,
+                                           const float* __restrict__ aabb, float min_near, float* nears, float* fars,
+                                           int* counters, uint32_t n_counters, float* loss, int* step_counter, int* local_step,
+                                           int* cur_row) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0) {
+        for (uint32_t i = 0; counters && i < n_counters; ++i) counters[i] = 0;
+        if (loss) *loss = 0.f;
+        if (step_counter && local_step && cur_row) {
+            const int row = (*local_step) & 15;
+            *cur_row = row;
+            step_counter[row * 2] = 0;
+            step_counter[row * 2 + 1] = 0;
+            *local_step += 1;
+        }
+    }
+    if (n >= g.B * g.n_rows * g.W) return;
+    const Ray r = generate_ray(g, n);
+    rays_o[n * 3] = r.ox; rays_o[n * 3 + 1] = r.oy; rays_o[n * 3 + 2] = r.oz;
+    rays_d[n * 3] = r.dx; rays_d[n * 3 + 1] = r.dy; rays_d[n * 3 + 2] = r.dz;
+    float lo, hi;
+    near_far_of(r, aabb, min_near, lo, hi);
+    nears[n] = lo;
+    fars[n] = hi;
+}
+
 __global__ void sph_from_ray_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
                                     uint32_t N, float* coords) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1163,6 +1231,45 @@ extern "C" int ngp_train_prologue(const float* rays_o, const float* rays_d, cons
     if (!rays_o || !rays_d || !aabb || !nears || !fars) return NGP_ERR_BAD_ARG;
     march::train_prologue_kernel<<<N ? cdiv(N, 128) : 1, 128, 0, as_stream(stream)>>>(
         rays_o, rays_d, aabb, N, min_near, nears, fars, counters, n_counters, loss, step_counter, local_step, cur_row);
+    return launch_status();
+}
+
+static int make_raygen(march::RayGen& g, const float* poses, const float* intrinsics, uint32_t B, uint32_t H, uint32_t W,
+                       uint32_t row0, uint32_t row_stride, uint32_t n_rows, int intrinsics_per_view) {
+    if (!poses || !intrinsics) return NGP_ERR_BAD_ARG;
+    if (row_stride == 0) row_stride = 1;
+    if (n_rows == 0) n_rows = (H - row0 + row_stride - 1) / row_stride;
+    if (B == 0 || W == 0 || row0 >= H || row0 + (uint64_t)(n_rows - 1) * row_stride >= H) return NGP_ERR_BAD_ARG;
+    if ((uint64_t)B * n_rows * W > 0x7fffffffull) return NGP_ERR_BAD_ARG;
+    g.poses = poses; g.intrinsics = intrinsics; g.B = B; g.W = W; g.n_rows = n_rows; g.row0 = row0; g.row_stride = row_stride;
+    g.intr_per_view = intrinsics_per_view ? 1u : 0u;
+    return NGP_OK;
+}
+
+extern "C" int ngp_get_rays(const float* poses, const float* intrinsics, int intrinsics_per_view, uint32_t B, uint32_t H,
+                            uint32_t W, uint32_t row0, uint32_t row_stride, uint32_t n_rows, float* rays_o, float* rays_d,
+                            void* stream) {
+    if (!rays_o || !rays_d) return NGP_ERR_BAD_ARG;
+    march::RayGen g;
+    const int rc = make_raygen(g, poses, intrinsics, B, H, W, row0, row_stride, n_rows, intrinsics_per_view);
+    if (rc != NGP_OK) return rc;
+    const uint32_t N = g.B * g.n_rows * g.W;
+    march::get_rays_kernel<<<cdiv(N, 256), 256, 0, as_stream(stream)>>>(g, rays_o, rays_d);
+    return launch_status();
+}
+
+extern "C" int ngp_train_prologue_rays(const float* poses, const float* intrinsics, int intrinsics_per_view, uint32_t B,
+                                       uint32_t H, uint32_t W, uint32_t row0, uint32_t row_stride, uint32_t n_rows,
+                                       float* rays_o, float* rays_d, const float* aabb, float min_near, float* nears,
+                                       float* fars, int* counters, uint32_t n_counters, float* loss, int* step_counter,
+                                       int* local_step, int* cur_row, void* stream) {
+    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NGP_ERR_BAD_ARG;
+    march::RayGen g;
+    const int rc = make_raygen(g, poses, intrinsics, B, H, W, row0, row_stride, n_rows, intrinsics_per_view);
+    if (rc != NGP_OK) return rc;
+    const uint32_t N = g.B * g.n_rows * g.W;
+    march::train_prologue_rays_kernel<<<cdiv(N, 128), 128, 0, as_stream(stream)>>>(
+        g, rays_o, rays_d, aabb, min_near, nears, fars, counters, n_counters, loss, step_counter, local_step, cur_row);
     return launch_status();
 }
 

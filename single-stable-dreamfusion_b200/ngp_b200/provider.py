@@ -55,6 +55,47 @@ def get_rays(pose, H, W, fovy_deg):
     return rays_o, rays_d
 
 
+def intrinsics_of(H, W, fovy_deg):
+    """(fx, fy, cx, cy) as the reference's dataset builds them (nerf/provider.py:188-189,212-213: focal from the image
+    HEIGHT, cx = H / 2, cy = W / 2)."""
+    focal = H / (2 * np.tan(np.deg2rad(fovy_deg) / 2))
+    return np.array([focal, focal, H / 2, W / 2], np.float32)
+
+
+def make_training_poses(n_views, H=64, W=64, seed=0, fovy_range=(40.0, 70.0)):
+    """The seeded training views as CAMERAS: poses float32 [n_views, 4, 4] (cam2world) and intrinsics [n_views, 4] -
+    what a train step needs when the rays are generated on the device (get_rays_device / TrainStep(device_rays=...)).
+    Same random stream as make_training_views, so both describe the same views."""
+    rng = np.random.default_rng(seed)
+    poses = np.empty((n_views, 4, 4), np.float32)
+    intr = np.empty((n_views, 4), np.float32)
+    for v in range(n_views):
+        poses[v] = rand_pose(rng)
+        intr[v] = intrinsics_of(H, W, rng.uniform(*fovy_range))
+    return torch.from_numpy(poses), torch.from_numpy(intr)
+
+
+def get_rays_device(poses, intrinsics, H, W, row0=0, row_stride=1, n_rows=None):
+    """nerf/utils.py:43-106 get_rays (full image, N = -1) as one kernel on the device: poses [B,4,4] (CUDA, fp32),
+    intrinsics [4] or [B,4] -> rays_o, rays_d [B, n_rows * W, 3].  row0 / row_stride / n_rows select the interleaved image
+    rows a data-parallel rank renders (parallel.shard_rows)."""
+    from . import _cabi
+    _cabi.require_cuda(poses, intrinsics)
+    poses = poses.contiguous().float()
+    intrinsics = intrinsics.contiguous().float()
+    B = poses.shape[0]
+    if n_rows is None:
+        n_rows = (H - row0 + row_stride - 1) // row_stride
+    per_view = 1 if intrinsics.dim() == 2 else 0
+    if per_view and intrinsics.shape != (B, 4) or (not per_view and intrinsics.shape != (4,)):
+        raise RuntimeError("intrinsics [4] or [B, 4] expected")
+    rays_o = torch.empty(B, n_rows * W, 3, device=poses.device)
+    rays_d = torch.empty(B, n_rows * W, 3, device=poses.device)
+    _cabi.call("ngp_get_rays", poses.device, _cabi.ptr(poses), _cabi.ptr(intrinsics), per_view, B, H, W, row0, row_stride, n_rows,
+               _cabi.ptr(rays_o), _cabi.ptr(rays_d))
+    return rays_o, rays_d
+
+
 def make_training_views(n_views, H=64, W=64, seed=0, fovy_range=(40.0, 70.0), pin=True):
     """Returns rays_o, rays_d as float32 tensors [n_views, H*W, 3] (pinned when a GPU is present)."""
     rng = np.random.default_rng(seed)

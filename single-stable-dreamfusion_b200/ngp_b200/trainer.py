@@ -32,8 +32,11 @@ def entropy_loss(weights_sum, lam=1e-4):
 class TrainStep:
     def __init__(self, model, H, W, lr=1e-3, max_steps=1024, lambda_entropy=1e-4, update_interval=16, graph=False,
                  world_size=1, fused_optimizer=True, lr_decay=None, manual=None, peer_allreduce=None, pipelined=False,
-                 n_chunks=None):
-        """manual: run the step as the hand-scheduled kernel sequence of _body_manual (no autograd, 13 launches) instead
+                 n_chunks=None, device_rays=None):
+        """device_rays: None, or (H_full, row0, row_stride): the step's inputs are then camera POSES [B,4,4] and intrinsics
+        [B,4] (fx, fy, cx, cy) instead of rays - the prologue kernel generates the rays of image rows row0, row0 + stride, ...
+        (this TrainStep's H of them) of every view on the device (nerf/utils.py:43-106 get_rays; hand-scheduled step only).
+        manual: run the step as the hand-scheduled kernel sequence of _body_manual (no autograd, 13 launches) instead
         of the autograd graph of _body (~58 launches); None = whenever the model has the reference's field shape.
         peer_allreduce: world_size > 1 only - fuse the gradient all-reduce into the optimizer kernel over NVLink peer
         memory (csrc/dp_step.cu) instead of calling NCCL; None = if peer-addressable memory is available.
@@ -43,6 +46,7 @@ class TrainStep:
         every occupancy refresh, and by the user before reading the parameters."""
         self.model, self.H, self.W = model, H, W
         self.pipelined = bool(pipelined)
+        self.device_rays = None if device_rays is None else tuple(int(v) for v in device_rays)
         self._pending = False
         self.n_chunks = n_chunks            # ray chunks run as parallel chains; None = 2 (measured: -6 % step time at 32768
         #                                     rays, -2.5 % at 4096; 3 chains are slower than 2)
@@ -64,6 +68,8 @@ class TrainStep:
         self.manual = bool(fused_optimizer and self._manual_supported()) if manual is None else bool(manual)
         if self.manual and not (fused_optimizer and self._manual_supported()):
             raise RuntimeError("the hand-scheduled step needs the fused optimizer and the reference's field / bg-net shapes")
+        if self.device_rays is not None and not self.manual:
+            raise RuntimeError("device-side ray generation is part of the hand-scheduled step (manual=True)")
         self.peer = None
         self.peer_error = None
         if fused_optimizer and self.manual and world_size > 1 and peer_allreduce is not False:
@@ -205,15 +211,29 @@ class TrainStep:
         flat bucket (tests/test_gpu_train_step.py compares the two)."""
         model, opt, dev = self.model, self.opt, self.device
         B = rays_o.shape[0]
-        ro = rays_o.reshape(-1, 3)
-        rd = rays_d.reshape(-1, 3)
-        N = ro.shape[0]
         hw = self.H * self.W
-        if N != B * hw or G.shape != (B, 3, self.H, self.W):
-            raise RuntimeError("rays [B, H*W, 3] and G [B, 3, H, W] expected")
-        if not (ro.is_contiguous() and rd.is_contiguous() and G.is_contiguous() and ro.dtype == rd.dtype == G.dtype == torch.float32):
-            raise RuntimeError("contiguous fp32 rays and G expected")
-        m = self._manual_workspace(N)
+        poses = intr = None
+        if self.device_rays is not None:
+            # (rays_o, rays_d) carry (poses [B,4,4], intrinsics [B,4]); the rays live in the step's workspace
+            poses, intr = rays_o, rays_d
+            N = B * hw
+            if poses.shape != (B, 4, 4) or intr.shape != (B, 4) or G.shape != (B, 3, self.H, self.W):
+                raise RuntimeError("poses [B, 4, 4], intrinsics [B, 4] and G [B, 3, H, W] expected")
+            if not (poses.is_contiguous() and intr.is_contiguous() and G.is_contiguous() and poses.dtype == intr.dtype == G.dtype == torch.float32):
+                raise RuntimeError("contiguous fp32 poses, intrinsics and G expected")
+            m = self._manual_workspace(N)
+            if "ro" not in m:
+                m["ro"], m["rd"] = torch.empty(N, 3, device=dev), torch.empty(N, 3, device=dev)
+            ro, rd = m["ro"], m["rd"]
+        else:
+            ro = rays_o.reshape(-1, 3)
+            rd = rays_d.reshape(-1, 3)
+            N = ro.shape[0]
+            if N != B * hw or G.shape != (B, 3, self.H, self.W):
+                raise RuntimeError("rays [B, H*W, 3] and G [B, 3, H, W] expected")
+            if not (ro.is_contiguous() and rd.is_contiguous() and G.is_contiguous() and ro.dtype == rd.dtype == G.dtype == torch.float32):
+                raise RuntimeError("contiguous fp32 rays and G expected")
+            m = self._manual_workspace(N)
         enc = model.encoder
         L = enc.offsets.shape[0] - 1
         S = float(np.log2(enc.per_level_scale))
@@ -234,14 +254,24 @@ class TrainStep:
             self._side_opt.wait_stream(main)
             with torch.cuda.stream(self._side_opt):
                 self._apply_update(deferred=True)  # the PREVIOUS step's update, beside this step's ray marching
-        if has_bg:
+        def bg_forward():
             self._side.wait_stream(self._side_opt if self.pipelined else main)  # (the bg net reads the updated parameters)
             with torch.cuda.stream(self._side):
                 _cabi.call("ngp_bg_forward", dev, P(rd), N, *[P(t) for t in hw_bg], 6, 64, P(m["bg"]))
 
-        _cabi.call("ngp_train_prologue", dev, P(ro), P(rd), P(model.aabb_train), N, 0.2, P(m["nears"]), P(m["fars"]),
-                   P(m["counters"]), m["counters"].numel(), P(m["loss"]), P(model.step_counter), P(self._local_step_dev),
-                   P(m["cur_row"]))
+        if poses is None:
+            if has_bg:
+                bg_forward()
+            _cabi.call("ngp_train_prologue", dev, P(ro), P(rd), P(model.aabb_train), N, 0.2, P(m["nears"]), P(m["fars"]),
+                       P(m["counters"]), m["counters"].numel(), P(m["loss"]), P(model.step_counter), P(self._local_step_dev),
+                       P(m["cur_row"]))
+        else:
+            h_full, row0, row_stride = self.device_rays
+            _cabi.call("ngp_train_prologue_rays", dev, P(poses), P(intr), 1, B, h_full, self.W, row0, row_stride, self.H, P(ro),
+                       P(rd), P(model.aabb_train), 0.2, P(m["nears"]), P(m["fars"]), P(m["counters"]), m["counters"].numel(),
+                       P(m["loss"]), P(model.step_counter), P(self._local_step_dev), P(m["cur_row"]))
+            if has_bg:
+                bg_forward()    # (reads the generated ray directions)
         if self.mirror_rng:
             torch.randn(3, device=dev)  # nerf/renderer.py:464 (light direction; unused by albedo shading)
         if self.fixed_noises is not None:
@@ -364,7 +394,20 @@ class TrainStep:
         torch.cat([t.float() for t in parts], out=out)
         return out
 
+    def pack_pose_inputs(self, poses, intrinsics, G, pin=False):
+        """device_rays mode: one contiguous fp32 buffer [poses (B x 16) | intrinsics (B x 4) | G] for a step."""
+        return self.pack_inputs(poses, intrinsics, G, pin)
+
+    def _batch_of(self, packed):
+        per = (20 + 3 * self.H * self.W) if self.device_rays is not None else 9 * self.H * self.W
+        B = packed.numel() // per
+        if B * per != packed.numel():
+            raise RuntimeError("packed inputs do not match H, W of this TrainStep")
+        return B
+
     def _unpack(self, packed, B):
+        if self.device_rays is not None:
+            return (packed[:B * 16].view(B, 4, 4), packed[B * 16:B * 20].view(B, 4), packed[B * 20:].view(B, 3, self.H, self.W))
         n_ray = B * self.H * self.W * 3
         ro = packed[:n_ray].view(B, self.H * self.W, 3)
         rd = packed[n_ray:2 * n_ray].view(B, self.H * self.W, 3)
@@ -372,14 +415,13 @@ class TrainStep:
         return ro, rd, G
 
     def __call__(self, rays_o, rays_d=None, G=None):
-        """rays_o, rays_d [B, H*W, 3], G [B, 3, H, W] - or a single packed buffer from pack_inputs()."""
+        """rays_o, rays_d [B, H*W, 3], G [B, 3, H, W] - or a single packed buffer from pack_inputs().
+        device_rays mode: poses [B, 4, 4], intrinsics [B, 4], G - or a packed buffer from pack_pose_inputs()."""
         model = self.model
         packed = None
         if rays_d is None:
             packed = rays_o
-            B = packed.numel() // (self.H * self.W * 9)
-            if B * self.H * self.W * 9 != packed.numel():
-                raise RuntimeError("packed inputs do not match H, W of this TrainStep")
+            B = self._batch_of(packed)
         if self.global_step % self.update_interval == 0:
             self.flush()  # (pipelined mode) the refresh must see the parameters of the completed previous step
             if self.fused_optimizer and self.world > 1 and self.opt.peer_ptrs is not None and self.global_step > 0 \
@@ -440,7 +482,8 @@ class TrainStep:
     def _capture(self, rays_o, rays_d, G):
         model = self.model
         B = rays_o.shape[0]
-        self._static_packed = torch.empty(B * self.H * self.W * 9, dtype=torch.float32, device=self.device)
+        per = (20 + 3 * self.H * self.W) if self.device_rays is not None else 9 * self.H * self.W
+        self._static_packed = torch.empty(B * per, dtype=torch.float32, device=self.device)
         self._static = self._unpack(self._static_packed, B)
         ro_s, rd_s, g_s = self._static
         ro_s.copy_(rays_o)

@@ -73,3 +73,80 @@ def test_reference_shaped_files_load():
             raise RuntimeError("layout mismatch")
     info = ck.load_checkpoint(ref_file, b, optimizer=_Opt())
     assert info["epoch"] == 3 and any("optimizer" in w for w in info["warnings"])
+
+
+def _manifest():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "ref_state_dict_manifest.json")) as f:
+        return json.load(f)
+
+
+def test_state_dict_matches_the_real_reference_models_manifest():
+    """tests/golden/ref_state_dict_manifest.json = keys / shapes / dtypes of the REAL nerf/network_grid.NeRFNetwork's
+    state_dict(), written by oracle/make_golden_host.py (which imports the reference); ours must be identical, key for
+    key, in the same order of parameter groups."""
+    man = _manifest()
+    m = _model(0)
+    sd = m.state_dict()
+    assert sorted(sd) == sorted(man["keys"])
+    for k, meta in man["keys"].items():
+        assert list(sd[k].shape) == meta["shape"], k
+        assert str(sd[k].dtype).replace("torch.", "") == meta["dtype"], k
+    assert sum(p.numel() for p in m.parameters()) == man["n_parameters"]
+    assert sd["encoder.offsets"].tolist() == man["offsets"]
+    groups = [{"n_tensors": len(list(g["params"])), "lr_mult": g["lr"] / 1e-3} for g in m.get_params(1e-3)]
+    assert groups == man["param_groups"]
+
+
+def test_cross_load_with_the_real_reference_model():
+    """With /root/reference present (this container; not the GPU box): build the REAL reference model, load its
+    state_dict into ours and ours into it with strict=True, and round-trip a reference-Trainer-shaped checkpoint file."""
+    import pytest
+    if not os.path.isdir("/root/reference/nerf") or not os.path.isdir(os.path.join(ROOT, "oracle", "_ref")):
+        pytest.skip("the reference tree / its built extension modules are not available here")
+    import subprocess
+    code = r'''
+import argparse, os, sys, tempfile, torch
+ROOT = %r
+sys.path.insert(0, ROOT)
+from oracle.make_golden_host import import_reference_grid_model
+RefNet, _, _ = import_reference_grid_model()
+opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)
+torch.manual_seed(1)
+ref = RefNet(opt)
+with torch.no_grad():
+    ref.density_grid.uniform_(0, 20); ref.density_bitfield.random_(0, 255); ref.step_counter.random_(0, 1000)
+ref_sd = {k: v.clone() for k, v in ref.state_dict().items()}
+# the product package shadows the reference's top-level module names: import it in a clean module table
+for name in [n for n in sys.modules if n.split(".")[0] in ("gridencoder", "raymarching", "freqencoder", "encoding", "activation", "nerf")]:
+    del sys.modules[name]
+sys.path = [p for p in sys.path if not p.startswith("/root/reference") and not p.endswith("oracle/_ref")]
+sys.path.insert(0, os.path.join(ROOT, "single-stable-dreamfusion_b200"))
+from ngp_b200.network_grid import NeRFNetwork
+from ngp_b200 import checkpoint as ck
+torch.manual_seed(2)
+mine = NeRFNetwork(opt)
+res = mine.load_state_dict(ref_sd, strict=True)
+for k, v in mine.state_dict().items():
+    assert torch.equal(v, ref_sd[k]), k
+torch.manual_seed(3)
+mine2 = NeRFNetwork(opt)
+ref.load_state_dict(mine2.state_dict(), strict=True)          # and the other way round
+for k, v in ref.state_dict().items():
+    assert torch.equal(v, mine2.state_dict()[k]), k
+# a file as the reference Trainer writes it (nerf/utils.py:847-902)
+state = {"epoch": 5, "global_step": 500, "stats": {"loss": [], "valid_loss": [], "results": [], "checkpoints": [], "best_result": None},
+         "mean_count": 321, "mean_density": 1.25, "model": ref_sd}
+with tempfile.TemporaryDirectory() as d:
+    path = os.path.join(d, "df_ep0005.pth")
+    torch.save(state, path)
+    torch.manual_seed(4)
+    mine3 = NeRFNetwork(opt)
+    info = ck.load_checkpoint(path, mine3)
+assert info["epoch"] == 5 and not info["missing_keys"] and not info["unexpected_keys"]
+assert mine3.mean_count == 321 and mine3.mean_density == 1.25
+assert torch.equal(mine3.encoder.embeddings, ref_sd["encoder.embeddings"])
+print("CROSS_LOAD_OK")
+''' % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert "CROSS_LOAD_OK" in out.stdout, out.stderr[-3000:]

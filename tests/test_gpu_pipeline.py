@@ -242,3 +242,22 @@ def test_single_backward_pass_equals_the_two_reference_passes(ref_ext, g_scale, 
     assert torch.isfinite(a).all() and b.abs().sum() > 0
     rel = ((a - b).norm() / b.norm()).item()
     assert rel < tol, rel
+
+
+def test_orbit_test_mode_writes_videos(tmp_path):
+    """ngp_b200.orbit.test = the reference's --test mode (nerf/utils.py:507-555): eval-mode frames of the camera ring,
+    uint8 conversion, two video files."""
+    import os
+    from ngp_b200 import orbit
+    from ngp_b200.network_grid import NeRFNetwork
+    opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=0)
+    torch.manual_seed(0)
+    m = NeRFNetwork(opt).to(DEV).train()
+    with torch.autocast("cuda", torch.float16):
+        m.update_extra_state()
+    rgb, depth, paths = orbit.test(m, str(tmp_path), name="df_ep0001", n_frames=4, H=48, W=48, max_steps=256)
+    assert rgb.shape == (4, 48, 48, 3) and rgb.dtype == np.uint8 and depth.shape == (4, 48, 48)
+    assert m.training and len(paths) == 2 and all(os.path.getsize(p) > 0 for p in paths)
+    centre, corner = rgb[:, 24, 24].astype(int), rgb[:, 0, 0].astype(int)
+    assert (corner == 255).all()                      # white background where the ray misses the blob
+    assert (centre.sum(-1) < 3 * 250).all()           # the density blob in the middle is not white

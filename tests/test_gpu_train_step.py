@@ -398,3 +398,54 @@ def test_train_ray_loss_kernel_vs_oracle(split):
     np.testing.assert_allclose(N_(gc), want["grad_rgbs"], rtol=1e-5, atol=1e-7)
     assert samples.item() == total
     assert step_counter[3].tolist() == [total, N] and step_counter.sum().item() == total + N
+
+
+def test_device_get_rays_matches_the_reference_golden():
+    """ngp_get_rays (nerf/utils.py:43-106 on the device) against rays the REAL reference generated
+    (tests/golden/rays_golden.npz, oracle/make_golden_host.py), full images and a rank's interleaved rows."""
+    import os
+    from ngp_b200 import provider
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rays_golden.npz"))
+    H, W = int(gold["H"]), int(gold["W"])
+    poses = torch.from_numpy(gold["poses"]).to(DEV)
+    for tag in ("a", "b"):
+        intr = torch.from_numpy(gold["intrinsics_" + tag]).to(DEV)
+        ro, rd = provider.get_rays_device(poses, intr, H, W)
+        assert np.array_equal(ro.cpu().numpy(), gold["rays_o_" + tag])
+        np.testing.assert_allclose(rd.cpu().numpy(), gold["rays_d_" + tag], rtol=0, atol=2e-7)
+        # per-view intrinsics + row sharding: rank 1 of 3 renders rows 1, 4, 7, ...
+        rows = list(range(1, H, 3))
+        ro_s, rd_s = provider.get_rays_device(poses, intr[None].repeat(poses.shape[0], 1).contiguous(), H, W, row0=1, row_stride=3)
+        want = rd.view(-1, H, W, 3)[:, rows].reshape(poses.shape[0], -1, 3)
+        assert torch.equal(rd_s, want) and ro_s.shape == want.shape
+
+
+def test_device_rays_step_equals_the_host_rays_step():
+    """TrainStep(device_rays=...): poses + intrinsics in, rays generated by the prologue kernel - the same step as feeding
+    the (identical) rays from outside: bit-equal sample counts, gradients equal up to atomics order."""
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    views = 2
+    poses, intr = provider.make_training_poses(views, 64, 64, seed=3)
+    poses, intr = poses.to(DEV), intr.to(DEV)
+    ro, rd = provider.get_rays_device(poses, intr, 64, 64)
+    G = torch.randn(views, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 1e-2
+    noises = torch.rand(views * 4096, device=DEV, generator=torch.Generator(device=DEV).manual_seed(9))
+    got = []
+    for device_rays, graph in ((None, False), ((64, 0, 1), False), ((64, 0, 1), True)):
+        m = _bench_like_model()
+        step = TrainStep(m, 64, 64, lr=0.0, graph=graph, manual=True, device_rays=device_rays)
+        step.fixed_noises, step.keep_grads = noises, True
+        if device_rays is None:
+            loss = step(ro, rd, G)
+        elif graph:
+            loss = step(step.pack_pose_inputs(poses, intr, G))
+        else:
+            loss = step(poses, intr, G)
+        torch.cuda.synchronize()
+        got.append((loss.item(), step.grad_snapshot.clone(), int(step.samples.item()), m.step_counter[0].clone()))
+    for other in got[1:]:
+        assert other[2] == got[0][2] > 0 and torch.equal(other[3], got[0][3])
+        assert abs(other[0] - got[0][0]) <= 1e-6 * abs(got[0][0])
+        rel = ((other[1] - got[0][1]).norm() / got[0][1].norm()).item()
+        assert rel < 1e-4, rel
