@@ -350,7 +350,7 @@ def run_b200_arm(args):
         step_fn._side = torch.cuda.current_stream(device)
     names = ["ngp_grid_scatter_samples", "ngp_grid_encode_backward", "ngp_field_forward", "ngp_field_backward",
              "ngp_march_rays_train", "ngp_composite_rays_train_forward", "ngp_composite_rays_train_backward",
-             "ngp_grid_encode_forward", "ngp_train_prologue", "ngp_train_ray_loss", "ngp_bg_forward", "ngp_bg_backward",
+             "ngp_grid_encode_forward", "ngp_train_prologue", "ngp_train_prologue_rays", "ngp_train_ray_loss", "ngp_bg_forward", "ngp_bg_backward",
              "ngp_adam_step_fused"]
     step_fn.global_step = 1  # keep the occupancy refresh out of the profiled steps
     run_steps(2, False, 3000)

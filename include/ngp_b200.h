@@ -310,6 +310,25 @@ int ngp_train_ray_loss(const float* sigmas, const float* rgbs, const float* delt
                        const int* counter, unsigned long long* samples_total, int* step_counter, const int* cur_row,
                        void* stream);
 
+/* The inference branch of run_cuda (nerf/renderer.py:496-532) as ONE launch: the reference's host loop - count alive rays
+ * (a device->host sync per iteration), n_step = clamp(N / n_alive, 1, 8), march_rays, field, composite_rays, mask-compact -
+ * becomes a CUDA-graph conditional WHILE node whose body is march -> fused field (ngp_field_forward) -> composite ->
+ * device compaction -> a one-thread kernel that advances the loop state and sets the loop condition.  Same kernels'
+ * arithmetic as ngp_march_rays / ngp_composite_rays (albedo shading), so weights_sum[N] / depth[N] / image[N,3] (zeroed
+ * here, BEFORE the background blend and depth normalisation) equal the host loop's.  noises: f32[N] perturbation of the
+ * first iteration, or NULL.  workspace: ngp_render_infer_workspace(N) bytes of device memory the caller keeps alive; the
+ * executable graph is cached per argument set (keep pointers stable across frames).  Returns NGP_ERR_UNSUPPORTED if the
+ * driver cannot build the conditional graph (callers then run the host loop).
+ * ngp_render_infer_state copies the final loop state (int[8]: n_alive, n_step, step, cur, iterations, rows, -, -) to the host. */
+uint64_t ngp_render_infer_workspace(uint32_t N);
+int ngp_render_infer_loop(const float* rays_o, const float* rays_d, const float* nears, const float* fars, uint32_t N, float bound,
+                          float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, float T_thresh,
+                          const float* noises, const void* table, const int* offsets, uint32_t L, uint32_t Cfeat, float S,
+                          uint32_t Hres, uint32_t gridtype, int align_corners, const void* w1, const void* b1, const void* w2,
+                          const void* b2, const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* weights_sum,
+                          float* depth, float* image, void* workspace, uint64_t workspace_bytes, void* stream);
+int ngp_render_infer_state(const void* workspace, int* state_host, void* stream);
+
 /* Ray generation on the device: nerf/utils.py:43-106 get_rays (the N = -1 full-image branch, as nerf/provider.py:227 calls
  * it).  poses f32[B,4,4] row-major cam2world; intrinsics f32[4] = (fx, fy, cx, cy), or f32[B,4] when intrinsics_per_view
  * != 0 (one random focal per training view, provider.py:209-213).  Produces image rows row0, row0 + row_stride, ...

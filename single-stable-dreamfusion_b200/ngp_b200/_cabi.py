@@ -67,6 +67,10 @@ SIGNATURES = {
     "ngp_dp_set_option": (_i32, [_i32, _i32]),
     "ngp_enable_peer_access": (_i32, [_i32]),
     "ngp_train_prologue": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_render_infer_workspace": (_u64, [_u32]),
+    "ngp_render_infer_loop": (_i32, [_vp, _vp, _vp, _vp, _u32, _f32, _f32, _u32, _u32, _u32, _vp, _f32, _vp, _vp, _vp, _u32, _u32, _f32,
+                                     _u32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "ngp_render_infer_state": (_i32, [_vp, C.POINTER(_i32), _vp]),
     "ngp_get_rays": (_i32, [_vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "ngp_train_prologue_rays": (_i32, [_vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _u32,
                                        _vp, _vp, _vp, _vp, _vp]),
@@ -152,6 +156,17 @@ def call(name, device, *args):
             rc = getattr(lib, name)(*args, stream())
     LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
+
+
+def call_rc(name, device, *args, launches=1):
+    """Like call(), but returns the status code instead of raising (for entry points with a documented fallback)."""
+    global LAUNCHES
+    lib = load()
+    with torch.cuda.device(device):
+        rc = getattr(lib, name)(*args, stream())
+    if rc == 0:
+        LAUNCHES += launches
+    return rc
 
 
 def dtype_code(dtype):

@@ -11,6 +11,8 @@
 //     transmittance chain rebuilt with warp shuffles in the reference's multiplication order (so
 //     the early-termination decision is the reference's), colour/weight sums by warp reduction.
 #include <float.h>
+#include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -1116,6 +1118,183 @@ __global__ void __launch_bounds__(kCompactBlock) compact_scatter_kernel(const in
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) *n_out = base + s_warp[31];
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// Device-driven inference loop.  The reference's eval branch (nerf/renderer.py:496-532) is a HOST while-loop: count
+// the alive rays (a device->host sync), pick n_step = clamp(N / n_alive, 1, 8), march, evaluate the field, composite,
+// compact.  Here the loop state lives on the device and the loop itself is a CUDA-graph conditional WHILE node
+// (ngp_render_infer_loop): the kernels below read n_alive / n_step from `InferState`, the last kernel of the body
+// advances the state and sets the loop condition - no host round trip per iteration.  Arithmetic and visiting order
+// are those of march_infer_kernel / composite_infer_kernel above (so results equal the host loop's bit for bit).
+// -------------------------------------------------------------------------------------------------
+struct InferState {
+    int n_alive;      // rays in alive[cur]
+    int n_step;       // samples marched per alive ray this iteration
+    int step;         // sum of the n_step of completed iterations (the reference's `step`)
+    int cur;          // which of the two alive buffers is current
+    int iters;        // completed iterations
+    int rows;         // n_alive * n_step: field rows of this iteration
+    int n_next;       // compaction output count
+    int pad;
+};
+
+NGP_DEVINL int plan_n_step(int N, int n_alive) { return max(min(N / max(n_alive, 1), 8), 1); }  // renderer.py:521
+
+__global__ void infer_init_kernel(uint32_t N, const float* __restrict__ nears, int* __restrict__ alive0, float* __restrict__ rays_t,
+                                  float* __restrict__ weights_sum, float* __restrict__ depth, float* __restrict__ image,
+                                  InferState* st) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n == 0) {
+        st->n_alive = (int)N; st->n_step = plan_n_step((int)N, (int)N); st->step = 0; st->cur = 0; st->iters = 0;
+        st->rows = (int)N * st->n_step; st->n_next = 0;
+    }
+    if (n >= N) return;
+    alive0[n] = (int)n;              // rays_alive = arange(N), rays_t = nears.clone()  (renderer.py:505-507)
+    rays_t[n] = nears[n];
+    weights_sum[n] = 0.f; depth[n] = 0.f;
+    image[n * 3] = 0.f; image[n * 3 + 1] = 0.f; image[n * 3 + 2] = 0.f;
+}
+
+__global__ void __launch_bounds__(128) infer_march_kernel(const InferState* __restrict__ st, uint32_t N, int* __restrict__ alive_buf,
+                                                          const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                                                          const float* __restrict__ rays_d, float bound, float dt_gamma,
+                                                          uint32_t max_steps, uint32_t C, uint32_t H,
+                                                          const uint8_t* __restrict__ grid, const float* __restrict__ fars,
+                                                          float* __restrict__ xyzs, float* __restrict__ deltas,
+                                                          const float* __restrict__ noises) {
+    const uint32_t n_alive = (uint32_t)st->n_alive, n_step = (uint32_t)st->n_step;
+    const int* __restrict__ rays_alive = alive_buf + (size_t)st->cur * N;
+    const bool first = st->step == 0;
+    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < n_alive; n += gridDim.x * blockDim.x) {
+        const int id = rays_alive[n];
+        const Ray r = load_ray(rays_o, rays_d, (uint32_t)id);
+        const float far = fars[id];
+        float t = rays_t[id];
+        const float noise = (first && noises) ? noises[n] : 0.f;      // perturb only on the first call (renderer.py:523)
+        t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * noise;
+        float last_t = t;
+        float* px = xyzs + (size_t)n * n_step * 3;
+        float* pl = deltas + (size_t)n * n_step * 2;
+        uint32_t step = 0;
+        float x, y, z, dt;
+        while (t < far && step < n_step) {
+            if (probe(p, r, t, x, y, z, dt)) {
+                px[0] = x; px[1] = y; px[2] = z;
+                t += dt;
+                pl[0] = dt;
+                pl[1] = t - last_t;
+                last_t = t;
+                px += 3; pl += 2;
+                ++step;
+            }
+        }
+        // unused slots: what the reference's zero-filled buffers hold (delta 0 terminates the composite, :858)
+        for (; step < n_step; ++step) { px[0] = 0.f; px[1] = 0.f; px[2] = 0.f; pl[0] = 0.f; pl[1] = 0.f; px += 3; pl += 2; }
+    }
+}
+
+__global__ void __launch_bounds__(128) infer_composite_kernel(const InferState* __restrict__ st, uint32_t N, float T_thresh,
+                                                              int* __restrict__ alive_buf, float* __restrict__ rays_t,
+                                                              const float* __restrict__ sigmas, const float* __restrict__ rgbs,
+                                                              const float* __restrict__ deltas, float* weights_sum, float* depth,
+                                                              float* image) {
+    const uint32_t n_alive = (uint32_t)st->n_alive, n_step = (uint32_t)st->n_step;
+    int* __restrict__ rays_alive = alive_buf + (size_t)st->cur * N;
+    for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < n_alive; n += gridDim.x * blockDim.x) {
+        const int id = rays_alive[n];
+        const float* ps = sigmas + (size_t)n * n_step;
+        const float* pc = rgbs + (size_t)n * n_step * 3;
+        const float* pl = deltas + (size_t)n * n_step * 2;
+        float t = rays_t[id];
+        float wsum = weights_sum[id], d = depth[id];
+        float r = image[id * 3], g = image[id * 3 + 1], b = image[id * 3 + 2];
+        uint32_t step = 0;
+        while (step < n_step) {
+            if (pl[0] == 0) break;
+            const float alpha = 1.0f - __expf(-ps[0] * pl[0]);
+            const float T = 1 - wsum;
+            const float w = alpha * T;
+            wsum += w;
+            t += pl[1];
+            d += w * t;
+            r += w * pc[0]; g += w * pc[1]; b += w * pc[2];
+            if (T < T_thresh) break;
+            ++ps; pc += 3; pl += 2; ++step;
+        }
+        if (step < n_step) rays_alive[n] = -1; else rays_t[id] = t;
+        weights_sum[id] = wsum;
+        depth[id] = d;
+        image[id * 3] = r; image[id * 3 + 1] = g; image[id * 3 + 2] = b;
+    }
+}
+
+// stable compaction alive[cur] -> alive[cur ^ 1] with a device-side length: per-block counts, then scatter
+__global__ void __launch_bounds__(kCompactBlock) infer_compact_count_kernel(const InferState* __restrict__ st, uint32_t N,
+                                                                            const int* __restrict__ alive_buf,
+                                                                            int* __restrict__ block_counts) {
+    const uint32_t n_alive = (uint32_t)st->n_alive;
+    const int* __restrict__ rays_alive = alive_buf + (size_t)st->cur * N;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int keep = (i < n_alive && rays_alive[i] >= 0) ? 1 : 0;
+    const int total = __syncthreads_count(keep);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kCompactBlock) infer_compact_scatter_kernel(InferState* st, uint32_t N, int* __restrict__ alive_buf,
+                                                                              const int* __restrict__ block_counts) {
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    const uint32_t n_alive = (uint32_t)st->n_alive;
+    const int* __restrict__ rays_alive = alive_buf + (size_t)st->cur * N;
+    int* __restrict__ out = alive_buf + (size_t)(st->cur ^ 1) * N;
+    if (blockIdx.x * blockDim.x >= n_alive && blockIdx.x != 0) return;   // (block 0 always runs: it publishes an empty result)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (uint32_t j = threadIdx.x; j < blockIdx.x; j += blockDim.x) part += block_counts[j];
+    part = warp_sum_i(part);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_warp[lane];
+        v = warp_sum_i(v);
+        if (lane == 0) s_base = v;
+    }
+    __syncthreads();
+    const int base = s_base;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = i < n_alive ? rays_alive[i] : -1;
+    const int keep = v >= 0 ? 1 : 0;
+    const int incl = warp_incl_scan_i(keep, lane);
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        w = warp_incl_scan_i(w, lane);
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int pos = base + (warp ? s_warp[warp - 1] : 0) + incl - keep;
+    if (keep) out[pos] = v;
+    // the block holding the last alive slot publishes the total
+    const uint32_t last_block = n_alive ? (n_alive - 1) / blockDim.x : 0u;
+    if (blockIdx.x == last_block && threadIdx.x == blockDim.x - 1) st->n_next = base + s_warp[31];
+}
+
+// last kernel of the loop body: advance the loop state and decide whether the body runs again
+__global__ void infer_plan_kernel(InferState* st, uint32_t N, uint32_t max_steps, cudaGraphConditionalHandle handle,
+                                  int use_handle) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    st->step += st->n_step;                         // renderer.py:532
+    st->n_alive = st->n_next;                       // rays_alive = rays_alive[rays_alive >= 0]  (:529)
+    st->cur ^= 1;
+    st->iters += 1;
+    st->n_step = plan_n_step((int)N, st->n_alive);
+    st->rows = st->n_alive * st->n_step;
+    const bool again = st->n_alive > 0 && st->step < (int)max_steps;   // `while step < max_steps` / `if n_alive <= 0: break`
+    if (use_handle) cudaGraphSetConditional(handle, again ? 1u : 0u);
+}
+
 }  // namespace march
 }  // namespace ngp
 
@@ -1336,4 +1515,175 @@ extern "C" int ngp_compact_alive(const int* rays_alive, uint32_t n_alive, int* o
     march::compact_count_kernel<<<blocks, march::kCompactBlock, 0, st>>>(rays_alive, n_alive, block_counts);
     march::compact_scatter_kernel<<<blocks, march::kCompactBlock, 0, st>>>(rays_alive, n_alive, block_counts, out, n_out);
     return launch_status();
+}
+
+// -------------------------------------------------------------------------------------------------
+// ngp_render_infer_loop: the whole inference loop of run_cuda as ONE graph launch (init node -> conditional WHILE node
+// whose body is march -> fused field -> composite -> compaction -> plan).  The executable graph is cached per argument
+// set (pointers and scalars are baked into its nodes), so callers keep their buffers in a persistent workspace.
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct InferLoopKey {
+    const void* p[20];
+    uint32_t u[10];
+    float f[4];
+    int dev;
+    bool operator==(const InferLoopKey& o) const { return memcmp(this, &o, sizeof(InferLoopKey)) == 0; }
+};
+struct InferLoopEntry {
+    InferLoopKey key;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t stamp = 0;
+    bool valid = false;
+};
+constexpr int kInferCache = 8;
+InferLoopEntry g_infer_cache[kInferCache];
+uint64_t g_infer_stamp = 0;
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+struct InferLayout {
+    uint64_t state, alive, rays_t, xyzs, deltas, sigma, rgb, blocks, total;
+};
+inline InferLayout infer_layout(uint32_t N) {
+    InferLayout l;
+    const uint64_t cap = align_up((uint64_t)N, 128) + 128;   // field tiles are 128 rows
+    uint64_t o = 0;
+    l.state = o; o += 256;
+    l.alive = o; o += align_up((uint64_t)2 * N * 4, 256);
+    l.rays_t = o; o += align_up((uint64_t)N * 4, 256);
+    l.xyzs = o; o += align_up(cap * 12, 256);
+    l.deltas = o; o += align_up(cap * 8, 256);
+    l.sigma = o; o += align_up(cap * 4, 256);
+    l.rgb = o; o += align_up(cap * 12, 256);
+    l.blocks = o; o += align_up((uint64_t)cdiv(N ? N : 1, march::kCompactBlock) * 4, 256);
+    l.total = o;
+    return l;
+}
+}  // namespace
+
+extern "C" uint64_t ngp_render_infer_workspace(uint32_t N) { return infer_layout(N).total; }
+
+extern "C" int ngp_render_infer_loop(const float* rays_o, const float* rays_d, const float* nears, const float* fars, uint32_t N,
+                                     float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                                     const uint8_t* grid, float T_thresh, const float* noises, const void* table,
+                                     const int* offsets, uint32_t L, uint32_t Cfeat, float S, uint32_t Hres, uint32_t gridtype,
+                                     int align_corners, const void* w1, const void* b1, const void* w2, const void* b2,
+                                     const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* weights_sum,
+                                     float* depth, float* image, void* workspace, uint64_t workspace_bytes, void* stream) {
+    if (!rays_o || !rays_d || !nears || !fars || !grid || !table || !offsets || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 ||
+        !weights_sum || !depth || !image)
+        return NGP_ERR_BAD_ARG;
+    if (C == 0 || H == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
+    if (L != 16 || Cfeat != 2 || hidden != 64 || out_dim != 4) return NGP_ERR_UNSUPPORTED;
+    if (N == 0) return NGP_OK;
+    const InferLayout lay = infer_layout(N);
+    if (!workspace || workspace_bytes < lay.total) return NGP_ERR_WORKSPACE;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    march::InferState* st = reinterpret_cast<march::InferState*>(ws + lay.state);
+    int* alive = reinterpret_cast<int*>(ws + lay.alive);
+    float* rays_t = reinterpret_cast<float*>(ws + lay.rays_t);
+    float* xyzs = reinterpret_cast<float*>(ws + lay.xyzs);
+    float* deltas = reinterpret_cast<float*>(ws + lay.deltas);
+    float* sigma = reinterpret_cast<float*>(ws + lay.sigma);
+    float* rgb = reinterpret_cast<float*>(ws + lay.rgb);
+    int* blocks = reinterpret_cast<int*>(ws + lay.blocks);
+
+    InferLoopKey key;
+    memset(&key, 0, sizeof(key));
+    const void* ptrs[] = {rays_o, rays_d, nears, fars, grid, noises, table, offsets, w1, b1, w2, b2, w3, b3, weights_sum, depth,
+                          image, workspace};
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.p[i] = ptrs[i];
+    const uint32_t us[] = {N, max_steps, C, H, L, Cfeat, Hres, gridtype, (uint32_t)(align_corners != 0), 0u};
+    for (size_t i = 0; i < 10; ++i) key.u[i] = us[i];
+    key.f[0] = bound; key.f[1] = dt_gamma; key.f[2] = T_thresh; key.f[3] = S;
+    if (cudaGetDevice(&key.dev) != cudaSuccess) return launch_status();
+
+    InferLoopEntry* hit = nullptr;
+    InferLoopEntry* victim = &g_infer_cache[0];
+    for (int i = 0; i < kInferCache; ++i) {
+        InferLoopEntry& e = g_infer_cache[i];
+        if (e.valid && e.key == key) { hit = &e; break; }
+        if (!e.valid || e.stamp < victim->stamp || (victim->valid && !e.valid)) victim = &e;
+    }
+    if (!hit) {
+        if (victim->valid) {
+            cudaGraphExecDestroy(victim->exec);
+            cudaGraphDestroy(victim->graph);
+            victim->valid = false;
+        }
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t cs = nullptr;
+        cudaError_t e = cudaGraphCreate(&graph, 0);
+        int rc = NGP_OK;
+        do {
+            if (e != cudaSuccess) break;
+            // node 1: loop state + accumulators
+            cudaGraphNode_t init_node;
+            {
+                cudaKernelNodeParams kp;
+                memset(&kp, 0, sizeof(kp));
+                void* args[] = {(void*)&N, (void*)&nears, (void*)&alive, (void*)&rays_t, (void*)&weights_sum, (void*)&depth,
+                                (void*)&image, (void*)&st};
+                kp.func = reinterpret_cast<void*>(march::infer_init_kernel);
+                kp.gridDim = dim3(cdiv(N, 256));
+                kp.blockDim = dim3(256);
+                kp.kernelParams = args;
+                if ((e = cudaGraphAddKernelNode(&init_node, graph, nullptr, 0, &kp)) != cudaSuccess) break;
+            }
+            // node 2: WHILE (condition defaults to 1 at every launch; infer_plan_kernel sets it at the end of each pass)
+            cudaGraphConditionalHandle handle;
+            if ((e = cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault)) != cudaSuccess) break;
+            cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+            cp.conditional.handle = handle;
+            cp.conditional.type = cudaGraphCondTypeWhile;
+            cp.conditional.size = 1;
+            cudaGraphNode_t while_node;
+            if ((e = cudaGraphAddNode(&while_node, graph, &init_node, 1, &cp)) != cudaSuccess) break;
+            cudaGraph_t body = cp.conditional.phGraph_out[0];
+            if ((e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking)) != cudaSuccess) break;
+            if ((e = cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) break;
+            const int persistent = num_sms() * 8;
+            const int g128 = min(cdiv(N, 128), persistent);
+            march::infer_march_kernel<<<g128, 128, 0, cs>>>(st, N, alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                                                            fars, xyzs, deltas, noises);
+            rc = ngp_field_forward(xyzs, (uint32_t)(align_up((uint64_t)N, 128)), &st->rows, table, offsets, L, Cfeat, S, Hres, gridtype,
+                                   align_corners, bound, w1, b1, w2, b2, w3, b3, hidden, out_dim, sigma, rgb, nullptr, nullptr, nullptr,
+                                   cs);
+            march::infer_composite_kernel<<<g128, 128, 0, cs>>>(st, N, T_thresh, alive, rays_t, sigma, rgb, deltas, weights_sum, depth,
+                                                                image);
+            const int cblocks = cdiv(N, march::kCompactBlock);
+            march::infer_compact_count_kernel<<<cblocks, march::kCompactBlock, 0, cs>>>(st, N, alive, blocks);
+            march::infer_compact_scatter_kernel<<<cblocks, march::kCompactBlock, 0, cs>>>(st, N, alive, blocks);
+            march::infer_plan_kernel<<<1, 32, 0, cs>>>(st, N, max_steps, handle, 1);
+            cudaGraph_t captured = nullptr;
+            e = cudaStreamEndCapture(cs, &captured);
+            if (e != cudaSuccess || rc != NGP_OK) break;
+            if ((e = cudaGraphInstantiate(&exec, graph, 0)) != cudaSuccess) break;
+        } while (false);
+        if (cs) cudaStreamDestroy(cs);
+        if (e != cudaSuccess || rc != NGP_OK || !exec) {
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            fprintf(stderr, "[ngp_b200] ngp_render_infer_loop: conditional graph not built (%s, rc %d); the caller runs the host loop\n",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "no error", rc);
+            return NGP_ERR_UNSUPPORTED;
+        }
+        victim->key = key; victim->graph = graph; victim->exec = exec; victim->valid = true;
+        hit = victim;
+    }
+    hit->stamp = ++g_infer_stamp;
+    const cudaError_t le = cudaGraphLaunch(hit->exec, as_stream(stream));
+    if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
+    return launch_status();
+}
+
+// device int[8] view of the loop state after the last launch on this workspace: n_alive, n_step, step, cur, iters, ...
+extern "C" int ngp_render_infer_state(const void* workspace, int* state_host, void* stream) {
+    if (!workspace || !state_host) return NGP_ERR_BAD_ARG;
+    cudaError_t e = cudaMemcpyAsync(state_host, workspace, sizeof(march::InferState), cudaMemcpyDeviceToHost, as_stream(stream));
+    if (e == cudaSuccess) e = cudaStreamSynchronize(as_stream(stream));
+    return e == cudaSuccess ? NGP_OK : (int)e;
 }

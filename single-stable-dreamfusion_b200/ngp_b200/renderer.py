@@ -192,7 +192,15 @@ class NeRFRenderer(nn.Module):
             depth = torch.zeros(N, dtype=dtype, device=device)
             image = torch.zeros(N, 3, dtype=dtype, device=device)
 
-            n_alive = N
+            done = False
+            if shading == 'albedo' and self.infer_loop == 'graph' and self._fused_training_path(rays_o):
+                # the whole loop as one CUDA-graph launch with a conditional WHILE node: no host sync per iteration
+                res = self._run_infer_loop(rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh)
+                if res is not None:
+                    weights_sum, depth, image = res
+                    done = True
+
+            n_alive = 0 if done else N
             rays_alive = torch.arange(n_alive, dtype=torch.int32, device=device)
             rays_t = nears.clone()
 
@@ -229,6 +237,56 @@ class NeRFRenderer(nn.Module):
         results['weights_sum'] = weights_sum
         results['mask'] = mask
         return results
+
+    # 'graph': the inference loop runs on the device (csrc/raymarch.cu ngp_render_infer_loop); 'host': the reference's
+    # host loop with one 4-byte read per iteration (also the fallback for shaded renders and non-fusable fields)
+    infer_loop = 'graph'
+
+    @torch.no_grad()
+    def _run_infer_loop(self, rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh):
+        import numpy as np
+        from .field import cached_half
+        N, device = rays_o.shape[0], rays_o.device
+        lib = _cabi.load()
+        ws = getattr(self, "_infer_ws", None)
+        if ws is None or ws["N"] != N or ws["work"].device != device:
+            e = lambda *shape: torch.empty(*shape, device=device, dtype=torch.float32)  # noqa: E731
+            ws = dict(N=N, rays_o=e(N, 3), rays_d=e(N, 3), nears=e(N), fars=e(N), noises=e(N), weights_sum=e(N), depth=e(N),
+                      image=e(N, 3), work=torch.empty(int(lib.ngp_render_infer_workspace(N)), device=device, dtype=torch.uint8))
+            self._infer_ws = ws
+        # the graph bakes its pointers in: inputs are staged in the persistent workspace (one graph per resolution)
+        ws["rays_o"].copy_(rays_o); ws["rays_d"].copy_(rays_d); ws["nears"].copy_(nears); ws["fars"].copy_(fars)
+        if perturb:
+            ws["noises"].uniform_()          # the torch.rand(n_alive) of the first march_rays call (raymarching.py:337-339)
+        enc = self.encoder
+        l0, l1, l2 = self.sigma_net.net
+        hw = [cached_half(t) for t in (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)]
+        table = cached_half(enc.embeddings)
+        P = _cabi.ptr
+        rc = _cabi.call_rc("ngp_render_infer_loop", device, P(ws["rays_o"]), P(ws["rays_d"]), P(ws["nears"]), P(ws["fars"]), N,
+                           float(self.bound), float(dt_gamma), int(max_steps), int(self.cascade), int(self.grid_size),
+                           P(self.density_bitfield), float(T_thresh), P(ws["noises"]) if perturb else None, P(table),
+                           P(enc.offsets), enc.offsets.shape[0] - 1, 2, float(np.log2(enc.per_level_scale)),
+                           int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), *[P(t) for t in hw],
+                           64, 4, P(ws["weights_sum"]), P(ws["depth"]), P(ws["image"]), P(ws["work"]), ws["work"].numel(),
+                           launches=1)
+        if rc != 0:
+            if rc == -2:   # NGP_ERR_UNSUPPORTED: this driver cannot build the conditional graph - host loop from now on
+                type(self).infer_loop = 'host'
+                return None
+            _cabi.check(rc, "ngp_render_infer_loop")
+        return ws["weights_sum"].clone(), ws["depth"], ws["image"]
+
+    def infer_loop_iterations(self):
+        """Iterations the last device-driven inference loop ran (one device->host read; diagnostics / bench only)."""
+        import ctypes
+        ws = getattr(self, "_infer_ws", None)
+        if ws is None:
+            return None
+        st = (ctypes.c_int * 8)()
+        _cabi.check(_cabi.load().ngp_render_infer_state(_cabi.ptr(ws["work"]), st, torch.cuda.current_stream().cuda_stream),
+                    "ngp_render_infer_state")
+        return int(st[4])
 
     # --------------------------------------------------------------------------------------------
     @torch.no_grad()
