@@ -261,3 +261,38 @@ def test_orbit_test_mode_writes_videos(tmp_path):
     centre, corner = rgb[:, 24, 24].astype(int), rgb[:, 0, 0].astype(int)
     assert (corner == 255).all()                      # white background where the ray misses the blob
     assert (centre.sum(-1) < 3 * 250).all()           # the density blob in the middle is not white
+
+
+@pytest.mark.parametrize("side,perturb", [(96, False), (200, True)])
+def test_device_driven_inference_loop_equals_the_host_loop(side, perturb):
+    """run_cuda's eval branch as ONE graph launch (conditional WHILE node: march -> field -> composite -> compact -> plan,
+    csrc/raymarch.cu ngp_render_infer_loop) against the reference-shaped host loop (one .item() per iteration): same
+    kernels' arithmetic, same visiting order - bit-equal accumulators."""
+    from ngp_b200.network_grid import NeRFNetwork
+    opt = argparse.Namespace(bound=1, cuda_ray=True, min_near=0.1, density_thresh=10, bg_radius=1.4)
+    torch.manual_seed(0)
+    m = NeRFNetwork(opt).to(DEV).train()
+    with torch.no_grad():
+        m.encoder.embeddings.uniform_(-0.5, 0.5)
+    with torch.autocast("cuda", torch.float16):
+        m.update_extra_state()
+    m.eval()
+    rays_o, rays_d = util.look_at_rays(side, radius=1.8, theta_deg=60, phi_deg=40)
+    ro, rd = torch.from_numpy(rays_o).to(DEV)[None], torch.from_numpy(rays_d).to(DEV)[None]
+    outs = {}
+    for mode in ("host", "graph", "graph"):     # the second graph call replays the cached executable graph
+        m.infer_loop = mode
+        torch.manual_seed(77)
+        with torch.no_grad(), torch.autocast("cuda", torch.float16):
+            outs[mode] = m.render(ro, rd, staged=True, perturb=perturb, max_steps=1024, T_thresh=1e-4)
+        if mode == "graph":
+            assert type(m).infer_loop == "graph", "the conditional graph could not be built on this driver"
+            iters = m.infer_loop_iterations()
+            assert 1 <= iters <= 1024
+    a, b = outs["host"], outs["graph"]
+    assert torch.equal(a["mask"], b["mask"])
+    for k in ("image", "weights_sum"):
+        assert torch.equal(a[k], b[k]), (k, (a[k].float() - b[k].float()).abs().max().item())
+    ok = torch.isfinite(a["depth"])
+    assert torch.equal(torch.isfinite(b["depth"]), ok) and torch.equal(a["depth"][ok], b["depth"][ok])
+    assert b["weights_sum"].max() > 0.5 and 0 < iters
