@@ -43,6 +43,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="train", choices=["train", "infer"], help="train: the -O train step (the headline "
+                    "metric, BASELINE configs[2]/[3]); infer: BASELINE configs[4], the 100-frame 800x800 test orbit through "
+                    "the inference branch of run_cuda (1 GPU; a secondary line with its own metric)")
+    ap.add_argument("--frames", type=int, default=100, help="--config infer: frames of the orbit")
+    ap.add_argument("--res", type=int, default=800, help="--config infer: image side")
     ap.add_argument("--views", type=int, default=VIEWS_PER_STEP, help="camera views per step, whole job")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's CUDA extensions")
@@ -599,6 +604,128 @@ def teardown(step_fn, world):
         pass
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: inference render, 800x800, 100-frame 360-degree orbit
+# ---------------------------------------------------------------------------------------------------
+def run_infer_config(args):
+    """Frames/s of the reference's --test orbit (nerf/provider.py:214-222, nerf/utils.py:435-456,507-555) through
+    NeRFRenderer.run_cuda's inference branch: per frame one pose -> rays on the device -> ONE graph launch (conditional
+    WHILE loop of march / fused field / composite / compaction) -> blend.  `value`: frames stay on the device;
+    `e2e`: pose from pinned host memory in, the rendered RGB + depth frame read back to the host (what Trainer.test does)."""
+    import torch
+    from ngp_b200 import _cabi, orbit, provider
+    assert torch.cuda.is_available(), "the B200 arm needs a GPU; there is no CPU fallback"
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    _cabi.load()
+    R, n_frames = args.res, args.frames
+    model = build_model(device)
+    with torch.autocast("cuda", torch.float16):
+        model.update_extra_state()       # the random-init scene: the density blob, ~5.6 % of the grid occupied
+    model.eval()
+    poses, intr = orbit.orbit_cameras(n_frames, R, R, device="cpu")
+    poses_pinned = poses.pin_memory()
+    poses_dev, intr_dev = poses.to(device), intr.to(device)
+    rgb_host = torch.empty(R, R, 3).pin_memory()
+    depth_host = torch.empty(R, R).pin_memory()
+
+    def frame(i, e2e):
+        pose = poses_pinned[i % n_frames].to(device, non_blocking=True) if e2e else poses_dev[i % n_frames]
+        rgb, depth = orbit.render_frame(model, pose, intr_dev, R, R, max_steps=MAX_STEPS)
+        if e2e:
+            rgb_host.copy_(rgb, non_blocking=True)
+            depth_host.copy_(depth, non_blocking=True)
+            torch.cuda.current_stream().synchronize()      # Trainer.test converts every frame on the host
+        return rgb
+
+    clocks = ClockSampler(device.index)
+    clocks.start()
+    time.sleep(1.0)
+    for i in range(max(args.warmup, 3)):
+        frame(i, False)
+    torch.cuda.synchronize()
+    iters = []
+    launches0 = _cabi.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n_frames):
+        frame(i, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _cabi.LAUNCHES - launches0
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(n_frames):
+        frame(i, True)
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1)
+    clk = clocks.stop()
+    # loop shape + samples of a few frames (diagnostics, untimed): iterations of the device loop, and the per-kernel times
+    # of the same frames through the host loop (CUDA events around the entry points)
+    for i in range(0, n_frames, max(1, n_frames // 5)):
+        frame(i, False)
+        iters.append(model.infer_loop_iterations())
+    model.infer_loop = "host"
+    names = ["ngp_march_rays", "ngp_field_forward", "ngp_composite_rays", "ngp_compact_alive", "ngp_get_rays", "ngp_bg_forward",
+             "ngp_near_far_from_aabb", "ngp_blend_background_forward"]
+    frame(0, False)
+    torch.cuda.synchronize()
+    _cabi.PROFILE = {n: [] for n in names}
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for i in range(3):
+        frame(i * 7, False)
+    h1.record()
+    torch.cuda.synchronize()
+    prof, _cabi.PROFILE = _cabi.PROFILE, None
+    host_loop_ms = h0.elapsed_time(h1) / 3
+    kern = {n: (sum(a.elapsed_time(b) for a, b in ev) / 3, len(ev) / 3) for n, ev in prof.items() if ev}
+    model.infer_loop = "graph"
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = peaks.get("hbm_gbs") or 6650.0
+    gathers_s, _ = measure_l2_peaks(device)
+    dom = max(kern, key=lambda k: kern[k][0]) if kern else None
+    line = {
+        "metric": "NeRF inference frames/s (800x800, 100-frame orbit, march_rays/composite_rays)", "value": n_frames / (ms * 1e-3),
+        "unit": "frames/s", "n_gpus": 1, "steps": n_frames, "warmup": max(args.warmup, 3), "ms_per_step": ms / n_frames,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[4]: inference render %dx%d via march_rays / composite_rays with the occupancy "
+                               "grid, %d-frame 360-degree orbit (circle poses r 1.8, theta 60, fov 55), random-init scene "
+                               "(density blob), max_steps 1024, T_thresh 1e-4, white background" % (R, R, n_frames),
+                   "rays_per_frame": R * R, "rays_per_s": R * R * n_frames / (ms * 1e-3),
+                   "inference_loop": type(model).infer_loop + " (one cudaGraphLaunch per frame, conditional WHILE node)",
+                   "loop_iterations_per_frame": iters, "host_loop_ms_per_frame": host_loop_ms,
+                   "timing": "every frame renders a different camera; a frame's sample / accumulator buffers (>60 MB) are "
+                             "rewritten every loop iteration"},
+        "e2e": {"value": n_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 64,
+                "d2h_bytes_per_step": R * R * 16, "ms_per_step": ms_e2e / n_frames},
+        "gpu_launches": launches, "clocks": clk,
+        "roofline": {"kernel": dom, "bound": "l2-gather" if dom == "ngp_field_forward" else "latency", "unit": "GB/s",
+                     "achieved": None, "peak": gathers_s * 4 / 1e9, "frac": None, "traffic": None,
+                     "kernels_ms_per_frame_host_loop": {k: v[0] for k, v in kern.items()},
+                     "kernel_calls_per_frame_host_loop": {k: v[1] for k, v in kern.items()}, "hbm_peak_gbs": hbm_peak,
+                     "note": "per-kernel times from the host-loop variant of the same frames (events cannot be recorded inside "
+                             "the graph's WHILE body); the loop is a chain of short launches bound by latency, not bandwidth"},
+    }
+    if not args.no_ref_cuda:
+        try:
+            env = dict(os.environ)
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(k, None)
+            out = subprocess.run([sys.executable, "-m", "oracle.ref_pipeline", "infer", str(min(n_frames, 20)), str(R)], cwd=ROOT,
+                                 env=env, capture_output=True, text=True, timeout=900)
+            tag = [l for l in out.stdout.splitlines() if l.startswith("REF_PIPELINE_JSON ")]
+            line["ref_cuda_ext"] = json.loads(tag[-1][len("REF_PIPELINE_JSON "):]) if tag else {"unavailable": (out.stderr or out.stdout)[-300:]}
+            if "ms_per_frame_median" in line["ref_cuda_ext"]:
+                line["ref_cuda_ext"]["speedup_e2e_vs_ref_median"] = line["ref_cuda_ext"]["ms_per_frame_median"] / (ms_e2e / n_frames)
+        except Exception as e:  # noqa: BLE001
+            line["ref_cuda_ext"] = {"unavailable": repr(e)[:200]}
+    emit(line)
+    sys.stdout.flush()
+
+
 _REAL_STDOUT = None
 
 
@@ -620,6 +747,9 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.config == "infer":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_infer_config(args)
     else:
         run_b200_arm(args)
 

@@ -383,11 +383,59 @@ def time_reference_train_step(device, views=1, steps=200, warmup=50, Hh=64, Ww=6
                     "+ the reference's host call pattern, same -O train step, 1 GPU"}
 
 
+def time_reference_inference(device, frames=20, res=800, max_steps=1024):
+    """Times the reference's inference loop (reference kernels + its host loop with boolean-mask compaction and a
+    per-iteration sync, nerf/renderer.py:496-557) on the test orbit's cameras, plus the per-frame device->host read and uint8
+    conversion of Trainer.test (nerf/utils.py:526-537)."""
+    import sys, os
+    ns = ref_ext.load()
+    if ns is None:
+        return {"unavailable": "oracle/_ref not built"}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "single-stable-dreamfusion_b200"))
+    from ngp_b200 import provider
+    torch.manual_seed(0)
+    model = RefGridNeRF(ns).to(device)
+    with torch.autocast("cuda", torch.float16):
+        model.update_extra_state()
+    model.eval()
+    views = provider.make_orbit_views(frames, res, res)
+    rays = [(torch.from_numpy(o).to(device)[None], torch.from_numpy(d).to(device)[None]) for o, d in views]
+
+    def one(i):
+        with torch.no_grad(), torch.autocast("cuda", torch.float16):
+            out = model.render_eval(rays[i][0], rays[i][1], max_steps=max_steps, T_thresh=1e-4, perturb=False)
+        pred = (out["image"].reshape(res, res, 3).detach().cpu().numpy() * 255).astype(np.uint8)
+        with np.errstate(invalid="ignore"):
+            (out["depth"].reshape(res, res).detach().cpu().numpy() * 255).astype(np.uint8)
+        return out["iterations"], pred
+
+    one(0); one(1)
+    torch.cuda.synchronize()
+    import time
+    per, its = [], []
+    for i in range(frames):
+        t0 = time.perf_counter()
+        it, _ = one(i)
+        torch.cuda.synchronize()
+        per.append((time.perf_counter() - t0) * 1e3)
+        its.append(it)
+    per_s = sorted(per)
+    return {"ms_per_frame": sum(per) / len(per), "ms_per_frame_median": per_s[len(per_s) // 2], "frames": frames,
+            "frames_per_s_median": 1e3 / per_s[len(per_s) // 2], "loop_iterations_per_frame": its[:: max(1, frames // 5)],
+            "what": "reference CUDA extensions + the reference's host inference loop and per-frame host conversion, %dx%d" % (res, res)}
+
+
 if __name__ == "__main__":
     # run in a fresh process (own CUDA context / caching allocator): the reference empties the allocator cache every
     # step (raymarching.py:231), which must not be charged for another workload's cached blocks
     import json
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "infer":
+        res = time_reference_inference(torch.device("cuda", 0), frames=int(sys.argv[2]) if len(sys.argv) > 2 else 20,
+                                       res=int(sys.argv[3]) if len(sys.argv) > 3 else 800)
+        print("REF_PIPELINE_JSON " + json.dumps(res), flush=True)
+        sys.exit(0)
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     warm = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     lr = float(sys.argv[3]) if len(sys.argv) > 3 else 1e-5
