@@ -310,6 +310,20 @@ int ngp_train_ray_loss(const float* sigmas, const float* rgbs, const float* delt
                        const int* counter, unsigned long long* samples_total, int* step_counter, const int* cur_row,
                        void* stream);
 
+/* Shading path as a 7-point stencil (nerf/network_grid.py:90-144; csrc/shading.cu).  ngp_stencil_points: xyzs f32[M,3] ->
+ * out f32[M*K,3], K = 7 (x, x+eps e_x, x-eps e_x, x+eps e_y, ...) or 6 (with_centre == 0), shifted points clamped to
+ * [-bound, bound] (:93-98): the K points of a sample are K consecutive rows of ONE field batch.  ngp_shade_forward: the K
+ * densities (sigma_all f32[M*K]) -> normal f32[M,3] = safe_normalize(-0.5 (s+ - s-) / eps), NaN -> 0 (:100-114) and, for
+ * K = 7 and color_out != NULL, the colour of mode 0 lambertian (albedo * (ratio + (1 - ratio) max(n.l, 0)), albedo = the
+ * centre row of rgb_all f32[M*K,3]), 1 textureless, 2 normal ((n + 1) / 2) with autocast's half roundings (:126-140).
+ * ngp_shade_backward: d_normal f32[M,3] and / or d_color f32[M,3] -> d_sigma_all f32[M*K] (0 for the centre row) and
+ * d_rgb_all f32[M*K,3] (centre row only; may be NULL). */
+int ngp_stencil_points(const float* xyzs, uint32_t M, float eps, float bound, int with_centre, float* out, void* stream);
+int ngp_shade_forward(const float* sigma_all, const float* rgb_all, uint32_t M, uint32_t K, const float* light, float ratio, int mode,
+                      float* normal_out, float* color_out, void* stream);
+int ngp_shade_backward(const float* sigma_all, const float* rgb_all, uint32_t M, uint32_t K, const float* light, float ratio, int mode,
+                       const float* d_normal, const float* d_color, float* d_sigma_all, float* d_rgb_all, void* stream);
+
 /* The inference branch of run_cuda (nerf/renderer.py:496-532) as ONE launch: the reference's host loop - count alive rays
  * (a device->host sync per iteration), n_step = clamp(N / n_alive, 1, 8), march_rays, field, composite_rays, mask-compact -
  * becomes a CUDA-graph conditional WHILE node whose body is march -> fused field (ngp_field_forward) -> composite ->

@@ -78,7 +78,16 @@ class NeRFNetwork(NeRFRenderer):
             grads.append(0.5 * (pos - neg) / epsilon)
         return -torch.stack(grads, dim=-1)
 
+    def _stencil_fusable(self, x):
+        return self.fused and _field.can_fuse(x.detach() if x.requires_grad else x, self.encoder, self.sigma_net) and not x.requires_grad
+
     def normal(self, x):
+        if self._stencil_fusable(x):
+            # the six shifted points of every sample as six consecutive rows of ONE fused-field batch (csrc/shading.cu)
+            from . import step_ops
+            sigma6, _ = _field.fused_field(step_ops.stencil_points(x, 1e-2, self.bound, with_centre=False), self.encoder,
+                                           self.sigma_net, self.bound)
+            return step_ops.stencil_normal(sigma6)
         normal = safe_normalize(self.finite_difference_normal(x))
         normal[torch.isnan(normal)] = 0
         return normal
@@ -88,6 +97,15 @@ class NeRFNetwork(NeRFRenderer):
         if shading == 'albedo':
             sigma, color = self.common_forward(x)
             normal = None
+        elif self._stencil_fusable(x):
+            # 7-point stencil: centre + six shifted points per sample in one fused-field launch, then one kernel for
+            # normal + lambertian / textureless / normal colouring (csrc/shading.cu)
+            from . import step_ops
+            M = x.shape[0]
+            sigma_all, rgb_all = _field.fused_field(step_ops.stencil_points(x, 1e-2, self.bound, with_centre=True), self.encoder,
+                                                    self.sigma_net, self.bound)
+            normal, color = step_ops.shade(sigma_all, rgb_all, l, ratio, shading)
+            sigma = sigma_all.view(M, 7)[:, 0]
         else:
             sigma, albedo = self.common_forward(x)
             normal = self.normal(x)

@@ -129,3 +129,66 @@ def background_net(d, bg_net):
     """sigmoid(bg_net(freq_encode(d))) as a half tensor [N,3] (what NeRFNetwork.background returns under autocast)."""
     l0, l1 = bg_net.net
     return _BackgroundNet.apply(d.contiguous().float(), l0.weight, l0.bias, l1.weight, l1.bias)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Shading stencil (csrc/shading.cu; nerf/network_grid.py:90-144): the K stencil points of a sample are K consecutive rows
+# of one field batch; these ops build the points and turn the K densities into normal / colour, forward and backward.
+# ---------------------------------------------------------------------------------------------------------------------
+SHADING_MODES = {"lambertian": 0, "textureless": 1, "normal": 2}
+
+
+def stencil_points(x, eps, bound, with_centre=True):
+    """x [M,3] -> [M*K, 3] rows (K = 7: x, x+eps e_x, x-eps e_x, x+eps e_y, ...; K = 6 without the centre), every shifted
+    point clamped to [-bound, bound] as network_grid.py:93-98 does.  No gradient flows to x (the reference's xyzs carry none)."""
+    _cabi.require_cuda(x)
+    x = x.detach().contiguous().float()
+    M = x.shape[0]
+    K = 7 if with_centre else 6
+    out = torch.empty(M * K, 3, device=x.device, dtype=torch.float32)
+    _cabi.call("ngp_stencil_points", x.device, _cabi.ptr(x), M, float(eps), float(bound), int(with_centre), _cabi.ptr(out))
+    return out
+
+
+class _Shade(Function):
+    @staticmethod
+    def forward(ctx, sigma_all, rgb_all, K, light, ratio, mode):
+        dev = sigma_all.device
+        sigma_all = sigma_all.contiguous().float()
+        M = sigma_all.shape[0] // K
+        want_color = mode is not None
+        rgb_c = rgb_all.contiguous().float() if (want_color and rgb_all is not None) else None
+        light_c = light.detach().contiguous().float() if light is not None else None
+        normal = torch.empty(M, 3, device=dev, dtype=torch.float32)
+        color = torch.empty(M, 3, device=dev, dtype=torch.float32) if want_color else None
+        _cabi.call("ngp_shade_forward", dev, _cabi.ptr(sigma_all), _cabi.ptr(rgb_c), M, K, _cabi.ptr(light_c), float(ratio),
+                   int(mode or 0), _cabi.ptr(normal), _cabi.ptr(color))
+        ctx.save_for_backward(sigma_all, rgb_c, light_c)
+        ctx.meta = (M, K, float(ratio), mode, bool(ctx.needs_input_grad[1]))
+        if want_color:
+            return normal, color
+        return normal
+
+    @staticmethod
+    def backward(ctx, d_normal, d_color=None):
+        sigma_all, rgb_c, light_c = ctx.saved_tensors
+        M, K, ratio, mode, need_rgb = ctx.meta
+        dev = sigma_all.device
+        d_normal = d_normal.contiguous().float() if d_normal is not None else None
+        d_color = d_color.contiguous().float() if (d_color is not None and mode is not None) else None
+        d_sigma = torch.empty(M * K, device=dev, dtype=torch.float32)
+        d_rgb = torch.empty(M * K, 3, device=dev, dtype=torch.float32) if (need_rgb and mode == 0 and d_color is not None) else None
+        _cabi.call("ngp_shade_backward", dev, _cabi.ptr(sigma_all), _cabi.ptr(rgb_c), M, K, _cabi.ptr(light_c), ratio, int(mode or 0),
+                   _cabi.ptr(d_normal), _cabi.ptr(d_color), _cabi.ptr(d_sigma), _cabi.ptr(d_rgb))
+        return d_sigma, d_rgb, None, None, None, None
+
+
+def shade(sigma_all, rgb_all, light, ratio, shading):
+    """sigma_all [7M] / rgb_all [7M,3] of stencil_points(x, with_centre=True) -> (normal [M,3] fp32, color [M,3] fp32 holding
+    the reference's half values) for shading in {'lambertian', 'textureless', 'normal'} (network_grid.py:126-140)."""
+    return _Shade.apply(sigma_all, rgb_all, 7, light, ratio, SHADING_MODES[shading])
+
+
+def stencil_normal(sigma6):
+    """sigma6 [6M] of stencil_points(x, with_centre=False) -> NeRFNetwork.normal(x) [M,3] (network_grid.py:108-114)."""
+    return _Shade.apply(sigma6, None, 6, None, 1.0, None)

@@ -375,3 +375,60 @@ def test_lambertian_training_render_vs_reference(ref_ext, fused):
     res["table_grad_vs_ref"] = ((ge - rge).norm() / rge.norm()).item()
     _report("lambertian_%s" % ("fused" if fused else "modular"), res)
     assert res["table_grad_vs_ref"] < 5e-2, res         # the reference's table gradient is accumulated in fp16 here
+
+
+@pytest.mark.parametrize("shading", ["lambertian", "textureless", "normal"])
+def test_shading_stencil_ops_vs_torch_restatement(shading):
+    """csrc/shading.cu (stencil points, normal + colour forward / backward) against the reference's own torch expressions
+    (nerf/network_grid.py:90-144) evaluated under autocast on the same K densities."""
+    from ngp_b200 import step_ops
+    g = torch.Generator(device=DEV).manual_seed(4)
+    M = 5000
+    x = (torch.rand(M, 3, device=DEV, generator=g) * 2 - 1)
+    x[:50] = x[:50].sign()                                   # on the boundary: the shifted points are clamped
+    pts = step_ops.stencil_points(x, 1e-2, 1.0, True).view(M, 7, 3)
+    want = [x]
+    for axis in range(3):
+        for sgn in (1.0, -1.0):
+            off = torch.zeros(1, 3, device=DEV); off[0, axis] = sgn * 1e-2
+            want.append((x + off).clamp(-1.0, 1.0))
+    assert torch.equal(pts, torch.stack(want, 1))
+    assert torch.equal(step_ops.stencil_points(x, 1e-2, 1.0, False).view(M, 6, 3), pts[:, 1:])
+
+    sigma_all = (torch.rand(M, 7, device=DEV, generator=g) * 3).requires_grad_()
+    with torch.no_grad():
+        sigma_all[7, 1:] = 1.0                               # zero gradient: safe_normalize's clamp branch
+    albedo = torch.rand(M, 7, 3, device=DEV, generator=g).half().float().requires_grad_()
+    light = torch.nn.functional.normalize(torch.randn(3, device=DEV, generator=g), dim=0)
+    up_c = torch.randn(M, 3, device=DEV, generator=g)
+    up_n = torch.randn(M, 3, device=DEV, generator=g) * 0.1
+    ratio = 0.1
+
+    normal, color = step_ops.shade(sigma_all.reshape(-1), albedo.reshape(-1, 3), light, ratio, shading)
+    got = torch.autograd.grad([color, normal], [sigma_all, albedo], [up_c, up_n], allow_unused=True)
+
+    s = sigma_all
+    with torch.autocast("cuda", torch.float16):
+        grad = torch.stack([0.5 * (s[:, 1] - s[:, 2]) / 1e-2, 0.5 * (s[:, 3] - s[:, 4]) / 1e-2, 0.5 * (s[:, 5] - s[:, 6]) / 1e-2], -1)
+        n = -grad
+        n = n / torch.sqrt(torch.clamp(torch.sum(n * n, -1, keepdim=True), min=1e-20))
+        n = torch.where(torch.isnan(n), torch.zeros_like(n), n)
+        lam = ratio + (1 - ratio) * (n @ light).clamp(min=0)
+        if shading == "textureless":
+            c = lam.unsqueeze(-1).repeat(1, 3)
+        elif shading == "normal":
+            c = (n + 1) / 2
+        else:
+            c = albedo[:, 0].half() * lam.unsqueeze(-1)
+    ref = torch.autograd.grad([c.float(), n], [sigma_all, albedo], [up_c, up_n], allow_unused=True)
+    assert torch.allclose(normal, n.float(), atol=1e-6)
+    assert torch.allclose(color, c.float(), atol=1e-3 if shading != "normal" else 1e-6)      # one half ulp of a value in [0, 1]
+    rel = ((got[0] - ref[0]).norm() / ref[0].norm()).item()
+    assert rel < 2e-3, rel        # the torch chain runs its backward partly in half
+    assert got[0][:, 0].abs().max().item() == 0
+    if shading == "lambertian":
+        assert torch.allclose(got[1][:, 0], ref[1][:, 0], atol=2e-3 * up_c.abs().max().item())
+        assert got[1][:, 1:].abs().max().item() == 0
+    # normal-only variant (K = 6)
+    n6 = step_ops.stencil_normal(sigma_all[:, 1:].reshape(-1))
+    assert torch.equal(n6, normal)
