@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
     ap.add_argument("--host-rays", action="store_true", help="feed pre-generated rays (1.18 MB / step) instead of camera poses; "
                     "default: the step's input is 8 poses + intrinsics + the guidance gradient, rays are generated on the device")
+    ap.add_argument("--no-shading", action="store_true", help="skip the secondary lambertian-vs-albedo step timing")
     ap.add_argument("--ref-steps", type=int, default=200, help="timed steps of the reference CUDA-extension pipeline")
     ap.add_argument("--ref-warmup", type=int, default=50)
     return ap.parse_args()
@@ -540,8 +541,48 @@ def run_b200_arm(args):
                         line["one_view_per_step"]["value_median"] / line["ref_cuda_ext"]["value_median"])
                 except Exception as e:  # noqa: BLE001
                     line["one_view_per_step"] = {"error": repr(e)[:200]}
+        if world == 1 and not args.no_shading:
+            try:   # secondary: the shaded step of the reference's schedule after albedo_iters (nerf/utils.py:345-356)
+                line["shading"] = shading_run(device, args)
+            except Exception as e:  # noqa: BLE001
+                line["shading"] = {"error": repr(e)[:300]}
         emit(line)
     teardown(step_fn, world)
+
+
+def shading_run(device, args, steps=12, warmup=4):
+    """ONE view per step (the reference's batch) through the autograd step: albedo vs lambertian shading (7 field
+    evaluations per sample for the normals + 6 for the smoothness normals, nerf/network_grid.py:90-144, nerf/renderer.py:
+    485-494) with the 7-point stencil kernels (csrc/shading.cu).  Eager steps, CUDA events, median."""
+    import torch
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    ro, rd = provider.make_training_views(16, H, W, seed=0, pin=False)
+    ro, rd = ro.to(device), rd.to(device)
+    g = (torch.randn(1, 3, H, W, generator=torch.Generator().manual_seed(2)) * 1e-2).to(device)
+    out = {}
+    for shading in ("albedo", "lambertian"):
+        model = build_model(device)
+        step_fn = TrainStep(model, H, W, lr=args.lr, max_steps=MAX_STEPS, graph=False, manual=False, shading=shading)
+        for i in range(warmup):
+            step_fn(ro[i % 16:i % 16 + 1], rd[i % 16:i % 16 + 1], g)
+        torch.cuda.synchronize()
+        step_fn.samples.zero_()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record()
+        for i in range(steps):
+            k = (warmup + i) % 16
+            step_fn(ro[k:k + 1], rd[k:k + 1], g)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        per = sorted(a.elapsed_time(b) for a, b in zip(evs, evs[1:]))
+        out[shading] = {"ms_per_step_median": per[len(per) // 2], "samples_per_step": int(step_fn.samples.item()) / steps}
+        del step_fn, model
+        torch.cuda.empty_cache()
+    out["lambertian_over_albedo"] = out["lambertian"]["ms_per_step_median"] / out["albedo"]["ms_per_step_median"]
+    out["what"] = ("autograd train step, 1 view of 64x64 rays, eager; lambertian = 13 field evaluations per sample forward (7-point "
+                   "stencil + 6 smoothness normals) and 7 backward, each stencil ONE fused-field launch")
+    return out
 
 
 def one_view_run(device, args, steps=200, warmup=50):

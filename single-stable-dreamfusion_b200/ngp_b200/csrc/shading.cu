@@ -137,7 +137,7 @@ __global__ void shade_backward_kernel(const float* __restrict__ sigma_all, const
 #pragma unroll
                 for (int a = 0; a < 3; ++a) d_alb[a] = dc[a] * lam;
             }
-            if (dh > 0.f) {                   // clamp(min=0) passes the gradient where the input is positive
+            if (dh >= 0.f) {                  // clamp(min=0) passes the gradient where input >= 0 (torch: grad * (x >= min))
                 const float d_dot = d_lam * (1.0f - ratio);
 #pragma unroll
                 for (int a = 0; a < 3; ++a) dn[a] += d_dot * light[a];

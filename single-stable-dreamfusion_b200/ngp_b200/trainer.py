@@ -32,7 +32,7 @@ def entropy_loss(weights_sum, lam=1e-4):
 class TrainStep:
     def __init__(self, model, H, W, lr=1e-3, max_steps=1024, lambda_entropy=1e-4, update_interval=16, graph=False,
                  world_size=1, fused_optimizer=True, lr_decay=None, manual=None, peer_allreduce=None, pipelined=False,
-                 n_chunks=None, device_rays=None):
+                 n_chunks=None, device_rays=None, shading="albedo", ambient_ratio=None, lambda_orient=1e-2, lambda_smooth=0.0):
         """device_rays: None, or (H_full, row0, row_stride): the step's inputs are then camera POSES [B,4,4] and intrinsics
         [B,4] (fx, fy, cx, cy) instead of rays - the prologue kernel generates the rays of image rows row0, row0 + stride, ...
         (this TrainStep's H of them) of every view on the device (nerf/utils.py:43-106 get_rays; hand-scheduled step only).
@@ -45,6 +45,16 @@ class TrainStep:
         arithmetic in the same order; the parameters lag one update behind until flush() - called automatically before
         every occupancy refresh, and by the user before reading the parameters."""
         self.model, self.H, self.W = model, H, W
+        # shading != 'albedo' (after albedo_iters the reference draws 'textureless' / 'lambertian' with ambient_ratio 0.1,
+        # nerf/utils.py:345-356, and adds lambda_orient * loss_orient [+ lambda_smooth * loss_smooth], :396-402): runs
+        # through the autograd step (the 7-point stencil kernels of csrc/shading.cu under run_cuda)
+        self.shading = shading
+        self.ambient_ratio = (1.0 if shading == "albedo" else 0.1) if ambient_ratio is None else float(ambient_ratio)
+        self.lambda_orient, self.lambda_smooth = float(lambda_orient), float(lambda_smooth)
+        if shading != "albedo":
+            if manual:
+                raise RuntimeError("the hand-scheduled step implements albedo shading; use manual=False for shaded steps")
+            manual = False
         self.pipelined = bool(pipelined)
         self.device_rays = None if device_rays is None else tuple(int(v) for v in device_rays)
         self._pending = False
@@ -128,11 +138,15 @@ class TrainStep:
         if not self.fused_optimizer:
             self.bucket.zero()  # (the fused optimizer kernel leaves the gradient buffer zeroed)
         with torch.autocast("cuda", torch.float16):
-            out = model.render(rays_o, rays_d, staged=False, perturb=True, bg_color=None, ambient_ratio=1.0,
-                               shading="albedo", force_all_rays=True, max_steps=self.max_steps, dt_gamma=0)
+            out = model.render(rays_o, rays_d, staged=False, perturb=True, bg_color=None, ambient_ratio=self.ambient_ratio,
+                               shading=self.shading, force_all_rays=True, max_steps=self.max_steps, dt_gamma=0)
             pred_rgb = out["image"].reshape(B, self.H, self.W, 3).permute(0, 3, 1, 2).contiguous()
             ws = out["weights_sum"].reshape(B, 1, self.H, self.W)
             loss = fused_entropy_loss(ws, self.lam_local) if self.fused_optimizer else entropy_loss(ws, self.lam_local)
+            if self.lambda_orient > 0 and "loss_orient" in out:       # nerf/utils.py:396-398
+                loss = loss + (self.lambda_orient / self.world) * out["loss_orient"]
+            if self.lambda_smooth > 0 and "loss_smooth" in out:       # :400-402
+                loss = loss + (self.lambda_smooth / self.world) * out["loss_smooth"]
         # The reference runs TWO backward passes over the render graph per step: the guidance's manual
         # `pred_rgb.backward(gradient=G, retain_graph=True)` (nerf/sd.py:115) and `scaler.scale(loss).backward()`
         # (nerf/utils.py:708).  Back-propagation is linear in the upstream gradient, so both roots are handed to the
