@@ -280,6 +280,18 @@ int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_
                         float backoff_factor, uint32_t growth_interval, int deferred, float* state, uint32_t* sync,
                         uint32_t rank, uint32_t world, const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half,
                         const uint64_t* peer_flags, const uint64_t* multicast, void* stream);
+/* world > 1, second generation: the same data-parallel step WITHOUT grid-wide barriers, as a plain launch of independent
+ * blocks (block b owns sub-slice b of its rank's slice: flag exchange - P2P / multimem reduce - Adam - parameter broadcast -
+ * flag exchange - clear).  The GradScaler verdict comes from each rank's OWN bucket (the caller runs ngp_check_finite(grads, n,
+ * state + 3) on the same stream first; a sum of <= 8 finite fp32 gradients is finite) and travels with the first flag exchange.
+ * Same arguments and state layout as ngp_adam_step_fused; a lost peer (timeout) makes the blocks that notice it apply nothing
+ * and every later launch a no-op (state[5], sticky). */
+int ngp_adam_step_dp(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow, uint64_t n,
+                     uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1, float beta2, float eps,
+                     float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor, float backoff_factor,
+                     uint32_t growth_interval, int deferred, float* state, uint32_t* sync, uint32_t rank, uint32_t world,
+                     const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half, const uint64_t* peer_flags,
+                     const uint64_t* multicast, void* stream);
 uint64_t ngp_dp_flags_bytes(void);
 /* option 0: timeout of the cross-GPU waits in milliseconds (default 20000); option 1: blocks of the cooperative launch
  * (0 = one per SM). */

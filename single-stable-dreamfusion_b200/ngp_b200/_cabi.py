@@ -63,6 +63,9 @@ SIGNATURES = {
     "ngp_adam_step_fused": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64), C.POINTER(_f32), _f32, _f32, _f32, _f32,
                                    _f32, _f32, _f32, _f32, _u32, _i32, _vp, _vp, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64),
                                    C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _vp]),
+    "ngp_adam_step_dp": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64), C.POINTER(_f32), _f32, _f32, _f32, _f32,
+                                _f32, _f32, _f32, _f32, _u32, _i32, _vp, _vp, _u32, _u32, C.POINTER(_u64), C.POINTER(_u64),
+                                C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64), _vp]),
     "ngp_dp_flags_bytes": (_u64, []),
     "ngp_dp_set_option": (_i32, [_i32, _i32]),
     "ngp_enable_peer_access": (_i32, [_i32]),
@@ -137,7 +140,7 @@ def require_contiguous(*tensors):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
-KERNELS_PER_CALL = {"ngp_march_rays_train": 3, "ngp_update_density_grid": 2, "ngp_compact_alive": 2}
+KERNELS_PER_CALL = {"ngp_march_rays_train": 2, "ngp_update_density_grid": 2, "ngp_compact_alive": 2}
 LAUNCHES = 0       # running count of our kernels launched through this module
 PROFILE = None     # optional {entry point name: [(start_event, end_event), ...]} filled while set (bench.py)
 

@@ -302,6 +302,155 @@ __global__ void __launch_bounds__(512) adam_step_fused_kernel(const Args a) {
     }
 }
 
+
+// -------------------------------------------------------------------------------------------------------------------
+// world > 1, second generation (ngp_adam_step_dp): the same step WITHOUT grid-wide barriers, as a plain (non-cooperative)
+// launch of independent blocks.  What made the cooperative kernel need two grid barriers and the B1 exchange was the
+// GradScaler's inf / nan check on the REDUCED gradient.  A sum is non-finite iff an addend is (finite fp32 gradients cannot
+// overflow a sum of <= 8), so every rank checks its OWN bucket first (ngp_check_finite, one small launch before this one)
+// and the verdict rides on B0's flag exchange: after B0 every block of every rank knows the global found_inf.  Block b then
+// owns sub-slice b of its rank's slice end to end:
+//     B0(b)  flags of block b of all ranks (payload: local found_inf | error)
+//     P      per element: `world` P2P loads (or one multimem.ld_reduce) -> sum -> Adam -> new parameter + fp16 shadow
+//            stored to every replica (or one multimem.st each)
+//     B2(b)  every rank's block b is done: its reads of MY bucket and its writes to MY replica have completed
+//     Z      zero sub-slice b of ALL `world` slices of my bucket (exactly what the peers' blocks b have finished reading)
+// No block ever waits for another block of its own grid, so the grid can be small (it runs beside the next step's ray
+// marching in pipelined mode) and needs no co-residency guarantee.
+// -------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) adam_dp_kernel(const Args a) {
+    __shared__ bool s_last;
+    if (*(volatile float*)(a.state + 5) != 0.f) return;                 // sticky: a peer was lost in an earlier launch
+    const bool arm_only = a.deferred && *(volatile float*)(a.state + 6) == 0.f;   // deferred mode, nothing pending yet
+    const float scale = a.state[0];
+    const float step0 = a.state[2];
+    const uint32_t epoch = a.sync[1] + 1;
+    bool skip = false, broken = false;
+    if (!arm_only) {
+        const uint64_t n4 = a.n / 4;
+        const uint64_t per = (n4 + a.world - 1) / a.world;
+        const uint64_t lo = per * a.rank < n4 ? per * a.rank : n4;
+        const uint64_t hi = lo + per < n4 ? lo + per : n4;
+        const uint64_t chunk = (per + gridDim.x - 1) / gridDim.x;       // float4s of a slice that one block owns
+        const uint64_t b_lo = lo + chunk * blockIdx.x < hi ? lo + chunk * blockIdx.x : hi;
+        const uint64_t b_hi = b_lo + chunk < hi ? b_lo + chunk : hi;
+
+        const uint32_t mine = (*(volatile float*)(a.state + 3) != 0.f ? kPayloadInf : 0u);
+        const uint32_t any = xrank_barrier(a, 0, blockIdx.x, epoch, mine);      // B0
+        broken = (any & kPayloadError) != 0u;
+        skip = (any & kPayloadInf) != 0u;
+        if (!broken) {
+            if (!skip) {
+                const float t = step0 + 1.f;
+                __shared__ float s_coef[3];
+                if (threadIdx.x == 0) {
+                    s_coef[0] = (float)(1.0 - pow((double)a.beta1, (double)t));
+                    s_coef[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)t));
+                    s_coef[2] = a.lr_decay_ln != 0.f ? expf(a.lr_decay_ln * fminf(step0, a.lr_decay_steps)) : 1.f;
+                }
+                __syncthreads();
+                const float bc1 = s_coef[0], bc2_sqrt = s_coef[1], lr_mult = s_coef[2];
+                const float inv = 1.0f / (scale * a.grad_div);
+                const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
+                for (uint64_t i = b_lo + threadIdx.x; i < b_hi; i += blockDim.x) {
+                    const uint64_t e0 = i * 4;
+                    float4 s;
+                    if (a.mc_g) {
+                        s = multimem_ld_reduce_add_f4(a.mc_g + e0);
+                    } else {
+                        float4 v[kMaxWorld];
+#pragma unroll
+                        for (uint32_t q = 0; q < kMaxWorld; ++q)
+                            if (q < a.world) v[q] = ld_relaxed_sys_f4(a.peer_g[q] + e0);
+                        s = v[0];
+#pragma unroll
+                        for (uint32_t q = 1; q < kMaxWorld; ++q)
+                            if (q < a.world) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }   // fixed rank order
+                    }
+                    const float4 p4 = *reinterpret_cast<const float4*>(a.p + e0);
+                    const float4 m4 = *reinterpret_cast<const float4*>(a.m + e0);
+                    const float4 v4 = *reinterpret_cast<const float4*>(a.v + e0);
+                    float g[4] = {s.x, s.y, s.z, s.w}, p[4] = {p4.x, p4.y, p4.z, p4.w};
+                    float m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                    for (uint32_t j = 0; j < 4; ++j) {
+                        float lr = a.seg_lr[0];
+#pragma unroll
+                        for (uint32_t sg = 1; sg < NGP_ADAM_MAX_SEGMENTS; ++sg)
+                            if (sg < a.n_seg && e0 + j >= a.seg_end[sg - 1]) lr = a.seg_lr[sg];
+                        const float step_size = lr * lr_mult / bc1;
+                        const float gr = g[j] * inv;
+                        m[j] = fmaf(w1, gr - m[j], m[j]);
+                        v[j] = a.beta2 * v[j] + w2 * gr * gr;
+                        const float denom = sqrtf(v[j]) / bc2_sqrt + a.eps;
+                        p[j] -= step_size * m[j] / denom;
+                    }
+                    *reinterpret_cast<float4*>(a.m + e0) = make_float4(m[0], m[1], m[2], m[3]);
+                    *reinterpret_cast<float4*>(a.v + e0) = make_float4(v[0], v[1], v[2], v[3]);
+                    const float4 pn = make_float4(p[0], p[1], p[2], p[3]);
+                    __half2 h0 = __floats2half2_rn(p[0], p[1]), h1 = __floats2half2_rn(p[2], p[3]);
+                    uint2 raw;
+                    raw.x = *reinterpret_cast<uint32_t*>(&h0); raw.y = *reinterpret_cast<uint32_t*>(&h1);
+                    if (a.mc_p) {
+                        multimem_st_f4(a.mc_p + e0, pn);
+                        if (a.h) multimem_st_b64(a.mc_h + e0, raw);
+                    } else {
+                        for (uint32_t q = 0; q < a.world; ++q) {
+                            const uint32_t dst = (a.rank + q) % a.world;
+                            *reinterpret_cast<float4*>(a.peer_p[dst] + e0) = pn;
+                            if (a.h) *reinterpret_cast<uint2*>(a.peer_h[dst] + e0) = raw;
+                        }
+                    }
+                }
+            }
+            const uint32_t late = xrank_barrier(a, 2, blockIdx.x, epoch, 0);     // B2
+            broken = (late & kPayloadError) != 0u;
+            if (!broken) {
+                // every rank's block b has finished reading sub-slice b of "its" slice of my bucket: clear those
+                for (uint32_t q = 0; q < a.world; ++q) {
+                    const uint64_t q_lo = per * q < n4 ? per * q : n4;
+                    const uint64_t q_hi = q_lo + per < n4 ? q_lo + per : n4;
+                    const uint64_t z_lo = q_lo + chunk * blockIdx.x < q_hi ? q_lo + chunk * blockIdx.x : q_hi;
+                    const uint64_t z_hi = z_lo + chunk < q_hi ? z_lo + chunk : q_hi;
+                    for (uint64_t i = z_lo + threadIdx.x; i < z_hi; i += blockDim.x)
+                        *reinterpret_cast<float4*>(a.g + i * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    // ---- last block: GradScaler.update() + step count + epoch (or: arm the deferred mode) ---------------------------------
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&a.sync[0], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        a.sync[0] = 0u;
+        if (arm_only) { a.state[6] = 1.f; return; }
+        if (*(volatile float*)(a.state + 5) != 0.f) return;      // broken exchange: scaler state and epoch stay as they are
+        float tracker = a.state[1];
+        float new_scale = scale;
+        if (skip) {
+            new_scale = scale * a.backoff;
+            tracker = 0.f;
+            a.state[4] += 1.f;
+        } else {
+            a.state[2] = step0 + 1.f;
+            tracker += 1.f;
+            if (tracker >= (float)a.growth_interval) {
+                const float grown = scale * a.growth;
+                if (isfinite(grown)) new_scale = grown;
+                tracker = 0.f;
+            }
+        }
+        a.state[0] = new_scale;
+        a.state[1] = tracker;
+        a.state[3] = 0.f;
+        a.sync[1] = epoch;
+    }
+}
+
 }  // namespace dp
 }  // namespace ngp
 
@@ -330,6 +479,37 @@ extern "C" int ngp_dp_set_option(int option, int value) {
     return NGP_ERR_BAD_ARG;
 }
 
+static int fill_dp_args(dp::Args& a, float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow, uint64_t n,
+                        uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1, float beta2, float eps,
+                        float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor, float backoff_factor,
+                        uint32_t growth_interval, int deferred, float* state, uint32_t* sync, uint32_t rank, uint32_t world,
+                        const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half,
+                        const uint64_t* peer_flags, const uint64_t* multicast);
+
+// The data-parallel step without grid-wide barriers (see adam_dp_kernel): world > 1 only, and the caller must have run
+// ngp_check_finite(grads, n, state + 3) on the same stream first.  Same arguments as ngp_adam_step_fused.
+extern "C" int ngp_adam_step_dp(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow, uint64_t n,
+                                uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1, float beta2,
+                                float eps, float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor,
+                                float backoff_factor, uint32_t growth_interval, int deferred, float* state, uint32_t* sync,
+                                uint32_t rank, uint32_t world, const uint64_t* peer_grads, const uint64_t* peer_params,
+                                const uint64_t* peer_half, const uint64_t* peer_flags, const uint64_t* multicast, void* stream) {
+    if (world < 2) return NGP_ERR_BAD_ARG;
+    dp::Args a;
+    const int rc = fill_dp_args(a, params, grads, exp_avg, exp_avg_sq, half_shadow, n, n_segments, seg_end, seg_lr, beta1, beta2, eps,
+                                grad_div, lr_decay_ln, lr_decay_steps, growth_factor, backoff_factor, growth_interval, deferred, state,
+                                sync, rank, world, peer_grads, peer_params, peer_half, peer_flags, multicast);
+    if (rc != NGP_OK) return rc;
+    // a rank's slice is n / (4 world) float4s; ~4 per thread keeps `world` x 4 peer loads in flight per thread
+    const uint64_t per = (n / 4 + world - 1) / world;
+    int blocks = dp::g_blocks > 0 ? dp::g_blocks : (int)((per + 512 * 4 - 1) / (512 * 4));
+    if (blocks < 8) blocks = 8;
+    if (blocks > num_sms()) blocks = num_sms();
+    if (blocks > (int)dp::kMaxBlocks) blocks = (int)dp::kMaxBlocks;
+    dp::adam_dp_kernel<<<blocks, 512, 0, as_stream(stream)>>>(a);
+    return launch_status();
+}
+
 extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow,
                                    uint64_t n, uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1,
                                    float beta2, float eps, float grad_div, float lr_decay_ln, float lr_decay_steps,
@@ -337,6 +517,27 @@ extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, 
                                    float* state, uint32_t* sync, uint32_t rank, uint32_t world, const uint64_t* peer_grads,
                                    const uint64_t* peer_params, const uint64_t* peer_half, const uint64_t* peer_flags,
                                    const uint64_t* multicast, void* stream) {
+    dp::Args a;
+    const int frc = fill_dp_args(a, params, grads, exp_avg, exp_avg_sq, half_shadow, n, n_segments, seg_end, seg_lr, beta1, beta2, eps,
+                                 grad_div, lr_decay_ln, lr_decay_steps, growth_factor, backoff_factor, growth_interval, deferred, state,
+                                 sync, rank, world, peer_grads, peer_params, peer_half, peer_flags, multicast);
+    if (frc != NGP_OK) return frc;
+    int blocks = dp::g_blocks > 0 ? dp::g_blocks : num_sms();
+    if (blocks > num_sms()) blocks = num_sms();
+    if (blocks > (int)dp::kMaxBlocks) blocks = (int)dp::kMaxBlocks;
+    void* kargs[] = {&a};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dp::adam_step_fused_kernel), dim3(blocks), dim3(512),
+                                                kargs, 0, as_stream(stream));
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return launch_status();
+}
+
+static int fill_dp_args(dp::Args& a, float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow, uint64_t n,
+                        uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1, float beta2, float eps,
+                        float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor, float backoff_factor,
+                        uint32_t growth_interval, int deferred, float* state, uint32_t* sync, uint32_t rank, uint32_t world,
+                        const uint64_t* peer_grads, const uint64_t* peer_params, const uint64_t* peer_half,
+                        const uint64_t* peer_flags, const uint64_t* multicast) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !state || !sync || !seg_end || !seg_lr) return NGP_ERR_BAD_ARG;
     if (n_segments == 0 || n_segments > NGP_ADAM_MAX_SEGMENTS || seg_end[n_segments - 1] != n) return NGP_ERR_BAD_ARG;
     if (n == 0 || (n & 3) != 0) return NGP_ERR_BAD_ARG;
@@ -345,7 +546,6 @@ extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, 
     if ((al & 15) != 0 || (reinterpret_cast<uintptr_t>(half_shadow) & 7) != 0) return NGP_ERR_BAD_ARG;
     if (world == 0 || world > dp::kMaxWorld || rank >= world) return NGP_ERR_BAD_ARG;
     if (world > 1 && (!peer_grads || !peer_params || !peer_flags || (half_shadow && !peer_half))) return NGP_ERR_BAD_ARG;
-    dp::Args a;
     a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.h = static_cast<__half*>(half_shadow); a.n = n;
     a.n_seg = n_segments;
     for (uint32_t s = 0; s < NGP_ADAM_MAX_SEGMENTS; ++s) {
@@ -369,12 +569,5 @@ extern "C" int ngp_adam_step_fused(float* params, float* grads, float* exp_avg, 
     a.mc_p = mc ? reinterpret_cast<float*>(multicast[1]) : nullptr;
     a.mc_h = mc && half_shadow ? reinterpret_cast<__half*>(multicast[2]) : nullptr;
     a.timeout_ns = dp::g_spin_timeout_ns;
-    int blocks = dp::g_blocks > 0 ? dp::g_blocks : num_sms();
-    if (blocks > num_sms()) blocks = num_sms();
-    if (blocks > (int)dp::kMaxBlocks) blocks = (int)dp::kMaxBlocks;
-    void* kargs[] = {&a};
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(dp::adam_step_fused_kernel), dim3(blocks), dim3(512),
-                                                kargs, 0, as_stream(stream));
-    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
-    return launch_status();
+    return NGP_OK;
 }

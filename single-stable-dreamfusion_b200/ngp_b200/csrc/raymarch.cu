@@ -507,6 +507,9 @@ __global__ void __launch_bounds__(128) march_write_warp_kernel(const float* __re
                         deltas + (size_t)offset * 2);
 }
 
+__device__ void scan_ray_counts(const int* __restrict__ counts, uint32_t N, int* __restrict__ rays, int* __restrict__ counter,
+                                int* s_warp);
+
 // Single-pass variant: walk every ray ONCE, writing its samples into a private slab of max_steps rows, then (after
 // the scan has assigned the final offsets) copy the slabs to their packed positions.
 __global__ void __launch_bounds__(128) march_slab_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -514,16 +517,34 @@ __global__ void __launch_bounds__(128) march_slab_kernel(const float* __restrict
                                                          uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                                                          const float* __restrict__ nears, const float* __restrict__ fars,
                                                          const float* __restrict__ noises, int* __restrict__ counts,
-                                                         float* __restrict__ slab_xyz, float* __restrict__ slab_delta) {
+                                                         float* __restrict__ slab_xyz, float* __restrict__ slab_delta,
+                                                         unsigned int* __restrict__ blocks_done, int* __restrict__ rays,
+                                                         int* __restrict__ counter) {
+    __shared__ int s_warp[32];
+    __shared__ bool s_last;
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (n >= N) return;
-    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
-    const Ray r = load_ray(rays_o, rays_d, n);
-    const float t0 = perturbed_start(p, nears[n], noises[n]);
-    const uint32_t steps = walk_ray_warp<true>(p, r, t0, fars[n], max_steps, lane, slab_xyz + (size_t)n * max_steps * 3, nullptr,
-                                               slab_delta + (size_t)n * max_steps * 2);
-    if (lane == 0) counts[n] = (int)steps;
+    if (n < N) {
+        const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+        const Ray r = load_ray(rays_o, rays_d, n);
+        const float t0 = perturbed_start(p, nears[n], noises[n]);
+        const uint32_t steps = walk_ray_warp<true>(p, r, t0, fars[n], max_steps, lane, slab_xyz + (size_t)n * max_steps * 3, nullptr,
+                                                   slab_delta + (size_t)n * max_steps * 2);
+        if (lane == 0) counts[n] = (int)steps;
+    }
+    if (!blocks_done) return;
+    // the LAST block to finish scans the counts (it used to be a separate single-CTA launch): a release / acquire pair
+    // on the election counter makes every block's counts visible to it
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(blocks_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    scan_ray_counts(counts, N, rays, counter, s_warp);
+    if (threadIdx.x == 0) *blocks_done = 0u;     // ready for the next launch on this workspace
 }
 
 __global__ void __launch_bounds__(256) march_compact_kernel(const float* __restrict__ rays_d, const int* __restrict__ rays,
@@ -548,15 +569,14 @@ __global__ void __launch_bounds__(256) march_compact_kernel(const float* __restr
     }
 }
 
-// Single-CTA exclusive scan of the per-ray counts, in ray order.  Writes the (id, offset, count)
-// rows (row n <-> ray n; offsets start at the incoming counter[0], as the reference's atomicAdd
+// Block-wide exclusive scan of the per-ray counts, in ray order (any block size that is a multiple of 32, <= 1024).  Writes
+// the (id, offset, count) rows (row n <-> ray n; offsets start at the incoming counter[0], as the reference's atomicAdd
 // would) and bumps the two counters the way the reference's atomics do in aggregate.
 // One pass: thread t owns the `per` consecutive rays [t * per, (t + 1) * per) - local sum, one block-wide scan of the
-// 1024 thread sums, then the rows - so the cost is two barriers whatever N is (it used to be four per 1024 rays).
-__global__ void __launch_bounds__(1024) march_scan_kernel(const int* __restrict__ counts, uint32_t N, int* __restrict__ rays,
-                                                          int* __restrict__ counter) {
-    __shared__ int s_warp[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// thread sums, then the rows - so the cost is two barriers whatever N is.
+__device__ void scan_ray_counts(const int* __restrict__ counts, uint32_t N, int* __restrict__ rays, int* __restrict__ counter,
+                                int* s_warp /* [32] shared */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint32_t per = ((N + blockDim.x - 1) / blockDim.x + 3u) & ~3u;  // multiple of 4: 16-byte loads, 48-byte row groups
     const uint32_t first = threadIdx.x * per;
     // N % 4 == 0: every group of 4 rays is either fully inside or fully outside [0, N)
@@ -565,25 +585,28 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(const int* __restrict_
     if (vec) {
         for (uint32_t i = 0; i < per; i += 4)
             if (first + i < N) {
-                const int4 c = __ldg(reinterpret_cast<const int4*>(counts + first + i));
+                const int4 c = __ldcg(reinterpret_cast<const int4*>(counts + first + i));   // L2: written by other blocks
                 sum += c.x + c.y + c.z + c.w;
             }
     } else {
         for (uint32_t i = 0; i < per; ++i)
-            if (first + i < N) sum += __ldg(counts + first + i);
+            if (first + i < N) sum += __ldcg(counts + first + i);
     }
     int incl = warp_incl_scan_i(sum, lane);
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (warp == 0) s_warp[lane] = warp_incl_scan_i(s_warp[lane], lane);
+    if (warp == 0) {
+        const int v = lane < n_warps ? s_warp[lane] : 0;
+        s_warp[lane] = warp_incl_scan_i(v, lane);
+    }
     __syncthreads();
-    const int carry = counter[0];  // read by every thread BEFORE thread 1023 overwrites it (barrier below)
+    const int carry = counter[0];  // read by every thread BEFORE the last thread overwrites it (barrier below)
     int offset = carry + (warp ? s_warp[warp - 1] : 0) + incl - sum;
     if (vec) {
         for (uint32_t i = 0; i < per; i += 4)
             if (first + i < N) {
                 const uint32_t n = first + i;
-                const int4 c = __ldg(reinterpret_cast<const int4*>(counts + n));
+                const int4 c = __ldcg(reinterpret_cast<const int4*>(counts + n));
                 const int o0 = offset, o1 = o0 + c.x, o2 = o1 + c.y, o3 = o2 + c.z;
                 int4* row = reinterpret_cast<int4*>(rays + (size_t)n * 3);  // 4 rows = 48 bytes, 16-byte aligned
                 row[0] = make_int4((int)n, o0, c.x, (int)n + 1);
@@ -595,7 +618,7 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(const int* __restrict_
         for (uint32_t i = 0; i < per; ++i)
             if (first + i < N) {
                 const uint32_t n = first + i;
-                const int c = __ldg(counts + n);
+                const int c = __ldcg(counts + n);
                 rays[(size_t)n * 3 + 0] = (int)n;
                 rays[(size_t)n * 3 + 1] = offset;
                 rays[(size_t)n * 3 + 2] = c;
@@ -607,6 +630,12 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(const int* __restrict_
         counter[0] = carry + s_warp[31];
         counter[1] += (int)N;
     }
+}
+
+__global__ void __launch_bounds__(1024) march_scan_kernel(const int* __restrict__ counts, uint32_t N, int* __restrict__ rays,
+                                                          int* __restrict__ counter) {
+    __shared__ int s_warp[32];
+    scan_ray_counts(counts, N, rays, counter, s_warp);
 }
 
 __global__ void __launch_bounds__(128) march_write_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
@@ -1343,8 +1372,8 @@ extern "C" int ngp_march_set_option(int option, int value) {
 }
 
 extern "C" uint64_t ngp_march_rays_train_workspace(uint32_t N, uint32_t max_steps) {
-    // per-ray counts + (warp-per-ray walk) a private slab of max_steps rows (xyz 12 B + deltas 8 B) per ray
-    return (((uint64_t)N * sizeof(int) + 255) / 256) * 256 + (uint64_t)N * max_steps * 20 + 256;
+    // election counter (256 B) + per-ray counts + (warp-per-ray walk) a private slab of max_steps rows (xyz 12 B + deltas 8 B)
+    return 256 + (((uint64_t)N * sizeof(int) + 255) / 256) * 256 + (uint64_t)N * max_steps * 20 + 256;
 }
 
 extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
@@ -1358,7 +1387,8 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
     if (!workspace || workspace_bytes < ngp_march_rays_train_workspace(N, max_steps)) return NGP_ERR_WORKSPACE;
     if (N == 0) return NGP_OK;
     cudaStream_t st = as_stream(stream);
-    int* counts = static_cast<int*>(workspace);
+    unsigned int* blocks_done = static_cast<unsigned int*>(workspace);
+    int* counts = reinterpret_cast<int*>(static_cast<uint8_t*>(workspace) + 256);
     if (march::g_thread_per_ray) {
         march::march_count_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears,
                                                                 fars, noises, counts);
@@ -1367,12 +1397,13 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
                                                                 nears, fars, noises, counts, rays, xyzs, dirs, deltas);
     } else {
         // warp per ray, single walk into per-ray slabs (scratch after the counts), scan, packed copy
-        float* slab_xyz = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + (((size_t)N * sizeof(int) + 255) / 256) * 256);
+        float* slab_xyz = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 256 + (((size_t)N * sizeof(int) + 255) / 256) * 256);
         float* slab_delta = slab_xyz + (size_t)N * max_steps * 3;
         const int blocks = cdiv((uint64_t)N * 32, 128);
+        // the election counter is cleared in-stream (a 4-byte memset node; the workspace may be uninitialised memory)
+        cudaMemsetAsync(blocks_done, 0, sizeof(unsigned int), st);
         march::march_slab_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
-                                                         noises, counts, slab_xyz, slab_delta);
-        march::march_scan_kernel<<<1, 1024, 0, st>>>(counts, N, rays, counter);
+                                                         noises, counts, slab_xyz, slab_delta, blocks_done, rays, counter);
         march::march_compact_kernel<<<cdiv((uint64_t)N * 32, 256), 256, 0, st>>>(rays_d, rays, slab_xyz, slab_delta, max_steps, N, M,
                                                                                  xyzs, dirs, deltas);
     }

@@ -66,6 +66,10 @@ class FusedAdamScaler:
         # at 2 ranks (52 vs 64 us) - the multimem instructions cost latency and only pay once the fan-out is large
         env = os.environ.get("NGP_DP_MULTICAST", "auto")
         self.use_multicast = (peer_memory is not None and peer_memory.world > 4) if env == "auto" else env != "0"
+        # "blocks": independent blocks, no grid barriers (default); "coop": the cooperative three-barrier kernel
+        self.dp_kernel = os.environ.get("NGP_DP_KERNEL", "blocks")
+        if os.environ.get("NGP_DP_BLOCKS"):
+            _cabi.check(_cabi.load().ngp_dp_set_option(1, int(os.environ["NGP_DP_BLOCKS"])), "ngp_dp_set_option")
         if os.environ.get("NGP_DP_TIMEOUT_MS"):
             _cabi.check(_cabi.load().ngp_dp_set_option(0, int(os.environ["NGP_DP_TIMEOUT_MS"])), "ngp_dp_set_option")
         if peer_memory is None:
@@ -165,7 +169,13 @@ class FusedAdamScaler:
             rank, world = self.peer.rank, self.peer.world
             pg, pp, ph, pf = self.peer_ptrs
             mc = self.multicast if self.use_multicast else None
-        _cabi.call("ngp_adam_step_fused", dev, _cabi.ptr(self.flat_params), _cabi.ptr(self.flat_grads), _cabi.ptr(self.exp_avg),
+        name = "ngp_adam_step_fused"
+        if world > 1 and self.dp_kernel == "blocks":
+            # barrier-free variant (csrc/dp_step.cu adam_dp_kernel): the inf / nan verdict comes from each rank's own bucket
+            # and rides on the first flag exchange - one small extra launch, no grid barriers, any grid size
+            _cabi.call("ngp_check_finite", dev, _cabi.ptr(self.flat_grads), self.numel, self.state[3:].data_ptr())
+            name = "ngp_adam_step_dp"
+        _cabi.call(name, dev, _cabi.ptr(self.flat_params), _cabi.ptr(self.flat_grads), _cabi.ptr(self.exp_avg),
                    _cabi.ptr(self.exp_avg_sq), _cabi.ptr(self.flat_half), self.numel, self.n_seg, self.seg_end, self.seg_lr,
                    float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,
                    self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
