@@ -140,7 +140,7 @@ def require_contiguous(*tensors):
 
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
-KERNELS_PER_CALL = {"ngp_march_rays_train": 2, "ngp_update_density_grid": 2, "ngp_compact_alive": 2}
+KERNELS_PER_CALL = {"ngp_march_rays_train": 3, "ngp_update_density_grid": 2, "ngp_compact_alive": 2}
 LAUNCHES = 0       # running count of our kernels launched through this module
 PROFILE = None     # optional {entry point name: [(start_event, end_event), ...]} filled while set (bench.py)
 

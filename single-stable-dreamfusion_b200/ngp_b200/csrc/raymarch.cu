@@ -1400,10 +1400,19 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
         float* slab_xyz = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 256 + (((size_t)N * sizeof(int) + 255) / 256) * 256);
         float* slab_delta = slab_xyz + (size_t)N * max_steps * 3;
         const int blocks = cdiv((uint64_t)N * 32, 128);
-        // the election counter is cleared in-stream (a 4-byte memset node; the workspace may be uninitialised memory)
-        cudaMemsetAsync(blocks_done, 0, sizeof(unsigned int), st);
-        march::march_slab_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
-                                                         noises, counts, slab_xyz, slab_delta, blocks_done, rays, counter);
+        if (N <= 8192) {
+            // few rays per launch (a data-parallel rank's chain): the LAST block of the walk scans the counts - one launch
+            // and one dependent-launch gap less.  The election counter is cleared in-stream (a 4-byte memset node; the
+            // workspace may be uninitialised memory)
+            cudaMemsetAsync(blocks_done, 0, sizeof(unsigned int), st);
+            march::march_slab_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                                             noises, counts, slab_xyz, slab_delta, blocks_done, rays, counter);
+        } else {
+            // many rays: a 1024-thread scan kernel beats 128 threads of the last walking block
+            march::march_slab_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
+                                                             noises, counts, slab_xyz, slab_delta, nullptr, rays, counter);
+            march::march_scan_kernel<<<1, 1024, 0, st>>>(counts, N, rays, counter);
+        }
         march::march_compact_kernel<<<cdiv((uint64_t)N * 32, 256), 256, 0, st>>>(rays_d, rays, slab_xyz, slab_delta, max_steps, N, M,
                                                                                  xyzs, dirs, deltas);
     }
