@@ -59,6 +59,8 @@ def parse():
                     "(rows: interleaved image rows, measured 9 %% faster at 8 GPUs than 8x8 blocks dealt along diagonals)")
     ap.add_argument("--pipeline", action="store_true", help="apply step k's optimizer update at the start of step k+1 "
                     "(beside the ray marching); measured: no gain, the marcher slows down by what the optimizer takes")
+    ap.add_argument("--no-overlap", action="store_true", help="run each step's ray marching inside the step instead of beside the "
+                    "previous step's field / backward / optimizer half (TrainStep(overlap=True), the default)")
     ap.add_argument("--chunks", type=int, default=0, help="ray chunks run as parallel chains (0 = the default, 2)")
     ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce instead of the fused peer-memory all-reduce + Adam")
     ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
@@ -251,7 +253,8 @@ def run_b200_arm(args):
     step_fn = TrainStep(model, Hl, W, lr=args.lr, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world,
                         manual=False if args.autograd else None, peer_allreduce=False if args.nccl else None,
                         pipelined=args.pipeline and not args.autograd, n_chunks=args.chunks or None,
-                        device_rays=(H, rank, world) if device_rays else None)
+                        device_rays=(H, rank, world) if device_rays else None,
+                        overlap=not (args.no_overlap or args.no_graph or args.autograd or args.pipeline))
     # one packed, pinned host buffer per batch: a step's inputs are ONE copy - [poses | intrinsics | G] (the rays of this
     # rank's interleaved image rows are generated by the step's prologue kernel), or [rays_o | rays_d | G] with --host-rays
     if device_rays:
@@ -348,8 +351,10 @@ def run_b200_arm(args):
     prof_samples = 0
     red_lane_ops = 0
     red_samples = 0
-    was_graph = step_fn.use_graph
-    step_fn.use_graph = False
+    was_graph, was_overlap = step_fn.use_graph, step_fn.overlap
+    step_fn.flush()
+    torch.cuda.synchronize()
+    step_fn.use_graph, step_fn.overlap = False, False
     saved_ws = (step_fn.n_chunks, step_fn._mws, step_fn._chain, getattr(model, "_train_ws", None), step_fn._side)
     if step_fn.manual:
         step_fn.n_chunks, step_fn._mws = 1, None
@@ -386,7 +391,7 @@ def run_b200_arm(args):
         lib.ngp_grid_red_count(ctypes.byref(n_red), 1)
         red_lane_ops = int(n_red.value)
         red_samples = int(sample_acc.item())
-    step_fn.use_graph = was_graph
+    step_fn.use_graph, step_fn.overlap = was_graph, was_overlap
     if step_fn.manual:
         step_fn.flush()
         torch.cuda.synchronize()
@@ -494,6 +499,7 @@ def run_b200_arm(args):
                 "sharding": ("8x8-pixel blocks of every view dealt along the block diagonals" if args.ray_order == "tiles"
                              else "image rows interleaved over ranks"),
                 "pipelined_optimizer": step_fn.pipelined,
+                "overlapped_steps": step_fn.overlap,
                 "step_inputs": ("camera poses + intrinsics + guidance gradient; rays generated on the device (nerf/utils.py:get_rays)"
                                 if device_rays else "pre-generated rays + guidance gradient"),
                 "ray_chunks": len(step_fn._mws["chunks"]) if step_fn._mws else 1,
@@ -506,7 +512,10 @@ def run_b200_arm(args):
                 "the 134+ MB/step of sample buffers exceed L2",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "result_read": ("every step copies its loss to pinned host memory; the host reads it two calls later, when that "
+                                    "step has completed (overlapped steps: no stall)" if step_fn.overlap else
+                                    "loss.item() after every step")},
             "gpu_launches": launches * world,
             "clocks": clk,
             "roofline": roofline,

@@ -32,7 +32,8 @@ def entropy_loss(weights_sum, lam=1e-4):
 class TrainStep:
     def __init__(self, model, H, W, lr=1e-3, max_steps=1024, lambda_entropy=1e-4, update_interval=16, graph=False,
                  world_size=1, fused_optimizer=True, lr_decay=None, manual=None, peer_allreduce=None, pipelined=False,
-                 n_chunks=None, device_rays=None, shading="albedo", ambient_ratio=None, lambda_orient=1e-2, lambda_smooth=0.0):
+                 n_chunks=None, device_rays=None, shading="albedo", ambient_ratio=None, lambda_orient=1e-2, lambda_smooth=0.0,
+                 overlap=False):
         """device_rays: None, or (H_full, row0, row_stride): the step's inputs are then camera POSES [B,4,4] and intrinsics
         [B,4] (fx, fy, cx, cy) instead of rays - the prologue kernel generates the rays of image rows row0, row0 + stride, ...
         (this TrainStep's H of them) of every view on the device (nerf/utils.py:43-106 get_rays; hand-scheduled step only).
@@ -55,12 +56,18 @@ class TrainStep:
             if manual:
                 raise RuntimeError("the hand-scheduled step implements albedo shading; use manual=False for shaded steps")
             manual = False
+        # overlap (hand-scheduled, graphed step only): the ray-marching half of step k+1 (prologue + march: it reads rays and
+        # the occupancy bitfield, no parameters) runs on its own stream WHILE the field / loss / backward / optimizer half of
+        # step k runs - two CUDA graphs per step and two alternating workspace sets, ordered by ordinary stream events.
+        # Arithmetic and update order are those of the sequential step; results arrive with a lag (see __call__).
+        self.overlap = bool(overlap)
         self.pipelined = bool(pipelined)
         self.device_rays = None if device_rays is None else tuple(int(v) for v in device_rays)
         self._pending = False
         self.n_chunks = n_chunks            # ray chunks run as parallel chains; None = 2 (measured: -6 % step time at 32768
         #                                     rays, -2.5 % at 4096; 3 chains are slower than 2)
         self._chain = []
+        self._chain_march = []
         self.max_steps, self.lam, self.update_interval = max_steps, lambda_entropy, update_interval
         self.world = world_size
         # Data parallel = the SAME step as one GPU rendering all rays: the guidance term is a per-pixel SUM (nerf/sd.py:115
@@ -121,6 +128,7 @@ class TrainStep:
         self._side_opt = torch.cuda.Stream(device=device, priority=-1) if (self.manual and self.pipelined) else None
         self.mirror_rng = False  # draw (and drop) the randn(3) run_cuda spends on light_d, to keep torch's RNG stream aligned
         self._mws = None
+        self._mws_sets = [None, None]      # overlap mode: the two alternating workspace sets
         self._ls_mirror = 0
         self._static_packed = None
         self._graph = None
@@ -185,11 +193,12 @@ class TrainStep:
         except AttributeError:
             return False
 
-    def _manual_workspace(self, N):
-        """Per-ray buffers of the whole step plus one sample workspace per ray chunk (render_train.TrainWorkspace)."""
+    def _manual_workspace(self, N, which=None):
+        """Per-ray buffers of the whole step plus one sample workspace per ray chunk (render_train.TrainWorkspace).
+        which: None = the step's single set; 0 / 1 = one of the two alternating sets of overlap mode."""
         from .render_train import TrainWorkspace
         dev = self.device
-        m = self._mws
+        m = self._mws if which is None else self._mws_sets[which]
         if m is not None and m["N"] == N:
             return m
         n_chunks = self.n_chunks if self.n_chunks else 2
@@ -206,8 +215,15 @@ class TrainStep:
             m["chunks"].append((base, n_c, ws))
             base += n_c
         self.model._train_ws = m["chunks"][0][2]  # (what run_cuda's own fused path would allocate; kept for introspection)
-        self._chain = [torch.cuda.Stream(device=dev) for _ in range(n_chunks - 1)]
-        self._mws = m
+        if len(self._chain) < n_chunks - 1:
+            # overlap mode: the compute phase is the critical path (high priority), the next step's marching fills its gaps
+            pr = -1 if self.overlap else 0
+            self._chain = [torch.cuda.Stream(device=dev, priority=pr) for _ in range(n_chunks - 1)]
+            self._chain_march = [torch.cuda.Stream(device=dev) for _ in range(n_chunks - 1)]
+        if which is None:
+            self._mws = m
+        else:
+            self._mws_sets[which] = m
         return m
 
     def _body_manual(self, rays_o, rays_d, G):
@@ -222,20 +238,47 @@ class TrainStep:
         chain's field kernels.
         Same arithmetic as _body (the autograd version of the reference's train_step, nerf/utils.py:337-403,708-713):
         every kernel is either the one autograd would call or a fusion of such kernels; gradients go straight into the
-        flat bucket (tests/test_gpu_train_step.py compares the two)."""
-        model, opt, dev = self.model, self.opt, self.device
-        B = rays_o.shape[0]
+        flat bucket (tests/test_gpu_train_step.py compares the two).
+        The step is two phases - _manual_march (reads rays + the occupancy bitfield, no parameters) and _manual_compute
+        (everything else) - run back to back here, and as separate graphs on separate streams in overlap mode."""
+        m = self._manual_march(rays_o, rays_d, G.shape[0], None, bg_early=True)
+        return self._manual_compute(m, G, bg_done=True)
+
+    def _manual_consts(self):
+        model, opt = self.model, self.opt
+        enc = model.encoder
+        l0, l1, l2 = model.sigma_net.net
+        field_params = (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)
+        c = dict(enc=enc, L=enc.offsets.shape[0] - 1, S=float(np.log2(enc.per_level_scale)),
+                 hw_field=[opt.half_view(t) for t in field_params], g_field=[opt.grad_view(t) for t in field_params],
+                 table_h=opt.half_view(enc.embeddings), g_table=opt.grad_view(enc.embeddings), has_bg=model.bg_radius > 0)
+        if c["has_bg"]:
+            b0, b1 = model.bg_net.net
+            bg_params = (b0.weight, b0.bias, b1.weight, b1.bias)
+            c["hw_bg"] = [opt.half_view(t) for t in bg_params]
+            c["g_bg"] = [opt.grad_view(t) for t in bg_params]
+        return c
+
+    def _bg_forward(self, m, c, after):
+        dev, P = self.device, _cabi.ptr
+        self._side.wait_stream(after)  # (the bg net reads the updated parameters / the generated ray directions)
+        with torch.cuda.stream(self._side):
+            _cabi.call("ngp_bg_forward", dev, P(m["rd_flat"]), m["N"], *[P(t) for t in c["hw_bg"]], 6, 64, P(m["bg"]))
+
+    def _manual_march(self, rays_o, rays_d, B, which, bg_early):
+        """Phase 1: prologue (rays from poses or given; near / far; counters; step_counter row) + per-chain ray marching."""
+        model, dev = self.model, self.device
         hw = self.H * self.W
         poses = intr = None
         if self.device_rays is not None:
             # (rays_o, rays_d) carry (poses [B,4,4], intrinsics [B,4]); the rays live in the step's workspace
             poses, intr = rays_o, rays_d
             N = B * hw
-            if poses.shape != (B, 4, 4) or intr.shape != (B, 4) or G.shape != (B, 3, self.H, self.W):
-                raise RuntimeError("poses [B, 4, 4], intrinsics [B, 4] and G [B, 3, H, W] expected")
-            if not (poses.is_contiguous() and intr.is_contiguous() and G.is_contiguous() and poses.dtype == intr.dtype == G.dtype == torch.float32):
-                raise RuntimeError("contiguous fp32 poses, intrinsics and G expected")
-            m = self._manual_workspace(N)
+            if poses.shape != (B, 4, 4) or intr.shape != (B, 4):
+                raise RuntimeError("poses [B, 4, 4] and intrinsics [B, 4] expected")
+            if not (poses.is_contiguous() and intr.is_contiguous() and poses.dtype == intr.dtype == torch.float32):
+                raise RuntimeError("contiguous fp32 poses and intrinsics expected")
+            m = self._manual_workspace(N, which)
             if "ro" not in m:
                 m["ro"], m["rd"] = torch.empty(N, 3, device=dev), torch.empty(N, 3, device=dev)
             ro, rd = m["ro"], m["rd"]
@@ -243,39 +286,22 @@ class TrainStep:
             ro = rays_o.reshape(-1, 3)
             rd = rays_d.reshape(-1, 3)
             N = ro.shape[0]
-            if N != B * hw or G.shape != (B, 3, self.H, self.W):
-                raise RuntimeError("rays [B, H*W, 3] and G [B, 3, H, W] expected")
-            if not (ro.is_contiguous() and rd.is_contiguous() and G.is_contiguous() and ro.dtype == rd.dtype == G.dtype == torch.float32):
-                raise RuntimeError("contiguous fp32 rays and G expected")
-            m = self._manual_workspace(N)
-        enc = model.encoder
-        L = enc.offsets.shape[0] - 1
-        S = float(np.log2(enc.per_level_scale))
-        l0, l1, l2 = model.sigma_net.net
-        field_params = (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)
-        hw_field = [opt.half_view(t) for t in field_params]
-        g_field = [opt.grad_view(t) for t in field_params]
-        table_h, g_table = opt.half_view(enc.embeddings), opt.grad_view(enc.embeddings)
+            if N != B * hw:
+                raise RuntimeError("rays [B, H*W, 3] expected")
+            if not (ro.is_contiguous() and rd.is_contiguous() and ro.dtype == rd.dtype == torch.float32):
+                raise RuntimeError("contiguous fp32 rays expected")
+            m = self._manual_workspace(N, which)
+        m["ro_flat"], m["rd_flat"] = ro, rd
+        c = self._manual_consts()
         P = _cabi.ptr
         main = torch.cuda.current_stream(dev)
-        has_bg = model.bg_radius > 0
-        if has_bg:
-            b0, b1 = model.bg_net.net
-            bg_params = (b0.weight, b0.bias, b1.weight, b1.bias)
-            hw_bg = [opt.half_view(t) for t in bg_params]
-            g_bg = [opt.grad_view(t) for t in bg_params]
         if self.pipelined:
             self._side_opt.wait_stream(main)
             with torch.cuda.stream(self._side_opt):
                 self._apply_update(deferred=True)  # the PREVIOUS step's update, beside this step's ray marching
-        def bg_forward():
-            self._side.wait_stream(self._side_opt if self.pipelined else main)  # (the bg net reads the updated parameters)
-            with torch.cuda.stream(self._side):
-                _cabi.call("ngp_bg_forward", dev, P(rd), N, *[P(t) for t in hw_bg], 6, 64, P(m["bg"]))
-
         if poses is None:
-            if has_bg:
-                bg_forward()
+            if c["has_bg"] and bg_early:
+                self._bg_forward(m, c, self._side_opt if self.pipelined else main)
             _cabi.call("ngp_train_prologue", dev, P(ro), P(rd), P(model.aabb_train), N, 0.2, P(m["nears"]), P(m["fars"]),
                        P(m["counters"]), m["counters"].numel(), P(m["loss"]), P(model.step_counter), P(self._local_step_dev),
                        P(m["cur_row"]))
@@ -284,8 +310,10 @@ class TrainStep:
             _cabi.call("ngp_train_prologue_rays", dev, P(poses), P(intr), 1, B, h_full, self.W, row0, row_stride, self.H, P(ro),
                        P(rd), P(model.aabb_train), 0.2, P(m["nears"]), P(m["fars"]), P(m["counters"]), m["counters"].numel(),
                        P(m["loss"]), P(model.step_counter), P(self._local_step_dev), P(m["cur_row"]))
-            if has_bg:
-                bg_forward()    # (reads the generated ray directions)
+            if c["has_bg"] and bg_early:
+                if self.pipelined:
+                    self._side.wait_stream(self._side_opt)
+                self._bg_forward(m, c, main)    # (reads the generated ray directions)
         if self.mirror_rng:
             torch.randn(3, device=dev)  # nerf/renderer.py:464 (light direction; unused by albedo shading)
         if self.fixed_noises is not None:
@@ -294,16 +322,45 @@ class TrainStep:
             m["noises"].uniform_()  # the torch.rand(N) of the reference's wrapper (raymarching.py:213-216)
 
         chunks = m["chunks"]
-        streams = [main] + self._chain[:len(chunks) - 1]
+        chain = self._chain if which is None else self._chain_march
+        streams = [main] + chain[:len(chunks) - 1]
         for st in streams[1:]:
             st.wait_stream(main)
+        for st, (base, n_c, ws) in zip(streams, chunks):
+            with torch.cuda.stream(st):
+                sl = slice(base, base + n_c)
+                _cabi.call("ngp_march_rays_train", dev, P(ro[sl]), P(rd[sl]), P(model.density_bitfield), float(model.bound), 0.0,
+                           int(self.max_steps), n_c, int(model.cascade), int(model.grid_size), ws.cap, P(m["nears"][sl]),
+                           P(m["fars"][sl]), P(ws.xyzs), None, P(ws.deltas), P(ws.rays), P(ws.counter), P(m["noises"][sl]),
+                           P(ws.march_ws), ws.march_ws.numel())
+        if which is not None:       # a phase of its own: join the chains (in the fused step they run on into phase 2)
+            for st in streams[1:]:
+                main.wait_stream(st)
+        return m
+
+    def _manual_compute(self, m, G, bg_done):
+        """Phase 2: background net, per chain field forward -> per-ray loss -> field backward -> grid scatter, optimizer."""
+        model, opt, dev = self.model, self.opt, self.device
+        N, hw = m["N"], self.H * self.W
+        B = N // hw
+        if G.shape != (B, 3, self.H, self.W) or not G.is_contiguous() or G.dtype != torch.float32:
+            raise RuntimeError("contiguous fp32 G [B, 3, H, W] expected")
+        c = self._manual_consts()
+        enc, L, S, has_bg = c["enc"], c["L"], c["S"], c["has_bg"]
+        hw_field, g_field, table_h, g_table = c["hw_field"], c["g_field"], c["table_h"], c["g_table"]
+        rd = m["rd_flat"]
+        P = _cabi.ptr
+        main = torch.cuda.current_stream(dev)
+        if has_bg and not bg_done:
+            self._bg_forward(m, c, main)
+        chunks = m["chunks"]
+        streams = [main] + self._chain[:len(chunks) - 1]
+        if not bg_done:             # a phase of its own: fork the chains here (in the fused step phase 1 already did)
+            for st in streams[1:]:
+                st.wait_stream(main)
 
         def forward_and_loss(base, n_c, ws):
             sl = slice(base, base + n_c)
-            _cabi.call("ngp_march_rays_train", dev, P(ro[sl]), P(rd[sl]), P(model.density_bitfield), float(model.bound), 0.0,
-                       int(self.max_steps), n_c, int(model.cascade), int(model.grid_size), ws.cap, P(m["nears"][sl]),
-                       P(m["fars"][sl]), P(ws.xyzs), None, P(ws.deltas), P(ws.rays), P(ws.counter), P(m["noises"][sl]),
-                       P(ws.march_ws), ws.march_ws.numel())
             if self.pipelined:
                 torch.cuda.current_stream(dev).wait_stream(self._side_opt)  # the field reads the updated parameters
             _cabi.call("ngp_field_forward", dev, P(ws.xyzs), ws.cap, P(ws.counter), P(table_h), P(enc.offsets), L, 2, S,
@@ -332,8 +389,8 @@ class TrainStep:
             for st in streams:
                 self._side.wait_stream(st)
             with torch.cuda.stream(self._side):
-                _cabi.call("ngp_bg_backward", dev, P(rd), P(m["d_bg"]), N, *[P(t) for t in hw_bg], 6, 64,
-                           *[P(t) for t in g_bg])
+                _cabi.call("ngp_bg_backward", dev, P(rd), P(m["d_bg"]), N, *[P(t) for t in c["hw_bg"]], 6, 64,
+                           *[P(t) for t in c["g_bg"]])
         for st, (base, n_c, ws) in zip(streams, chunks):
             with torch.cuda.stream(st):
                 backward(ws)
@@ -381,6 +438,10 @@ class TrainStep:
     def flush(self):
         """Pipelined mode: apply the update that is still pending (no-op otherwise).  After it the parameters are what
         the un-pipelined step would have left."""
+        if self.overlap and self._ov is not None and self._ov["pending"]:
+            self._overlap_compute(1 - self._ov["parity"])     # the marched, not yet computed batch
+            self._ov["pending"] = False
+            torch.cuda.current_stream(self.device).wait_stream(self._ov["S_c"])
         if self.manual and self.pipelined and self._pending:
             self._apply_update(deferred=True)
             self.opt.state[6:7].zero_()  # nothing pending: the next step's leading launch only re-arms
@@ -432,6 +493,8 @@ class TrainStep:
         """rays_o, rays_d [B, H*W, 3], G [B, 3, H, W] - or a single packed buffer from pack_inputs().
         device_rays mode: poses [B, 4, 4], intrinsics [B, 4], G - or a packed buffer from pack_pose_inputs()."""
         model = self.model
+        if self.overlap:
+            return self._call_overlap(rays_o, rays_d, G)
         packed = None
         if rays_d is None:
             packed = rays_o
@@ -492,6 +555,134 @@ class TrainStep:
         if not self.manual:
             self.samples.add_(model._train_ws.counter[0].long())
         return self.loss
+
+    # -- overlap mode: march(k+1) beside compute(k) ---------------------------------------------------------------------
+    _ov = None
+
+    def _overlap_compute(self, q):
+        ov = self._ov
+        with torch.cuda.stream(ov["S_c"]):
+            ov["S_c"].wait_event(ov["ev_march"][q])
+            ov["g_compute"][q].replay()
+            ov["ev_compute"][q].record(ov["S_c"])
+        _cabi.LAUNCHES += ov["launches"][1]
+
+    def _call_overlap(self, a, b=None, G=None):
+        """One call = launch the MARCH half of this batch (stream S_m) and the COMPUTE half of the previous batch (stream
+        S_c); the two run concurrently.  Returns the loss of the batch before the previous one as a 0-dim pinned CPU tensor
+        (its compute has completed - no device sync, no stall); flush() computes the batch still pending.  Parameter
+        updates happen in batch order exactly as in the sequential step; an occupancy refresh (every update_interval
+        steps) first drains the pending compute, so it sees the same parameters and is seen by the same marches."""
+        if not (self.manual and self.use_graph and self.fused_optimizer) or self.pipelined:
+            raise RuntimeError("overlap=True needs the hand-scheduled, graphed step with the fused optimizer (and not pipelined=True)")
+        model, dev = self.model, self.device
+        packed = a if b is None else (self.pack_pose_inputs(a, b, G) if self.device_rays is not None else self.pack_inputs(a, b, G))
+        B = self._batch_of(packed)
+        cur = torch.cuda.current_stream(dev)
+        if self._ov is None:
+            self._capture_overlap(packed, B)
+        ov = self._ov
+        p = ov["parity"]
+        S_m, S_c = ov["S_m"], ov["S_c"]
+        ov["ev_compute"][p].synchronize()       # set p is free: compute(k-2) has finished (host-side: bounds the run-ahead)
+        loss_out = ov["loss_ret"][p]
+        loss_out.copy_(ov["loss_host"][p])      # its loss, before this call's graphs may overwrite the host slot
+        S_m.wait_stream(cur)                    # the caller's input batch
+        with torch.cuda.stream(S_m):
+            ov["static"][p].copy_(packed, non_blocking=True)
+            if self.global_step % self.update_interval == 0:
+                if ov["pending"]:               # the refresh must see the parameters of the completed previous step
+                    self._overlap_compute(1 - p)
+                    ov["pending"] = False
+                S_m.wait_stream(S_c)
+                if self.world > 1 and self.opt.peer_ptrs is not None and self.global_step > 0 and self.opt.comm_error:
+                    raise RuntimeError("data-parallel step: a peer did not reach the gradient exchange in time (see "
+                                       "NGP_DP_TIMEOUT_MS); parameters were left untouched from that step on")
+                with torch.autocast("cuda", torch.float16):
+                    model.update_extra_state()
+                self.n_updates += 1
+            self.global_step += 1
+            self.opt.attach_grads()
+            self.opt.sync_shadow_if_changed()
+            if self._ls_mirror != model.local_step:
+                self._local_step_dev.fill_(model.local_step)
+                self._ls_mirror = model.local_step
+            ov["g_march"][p].replay()
+            ov["ev_march"][p].record(S_m)
+        _cabi.LAUNCHES += ov["launches"][0]
+        if ov["pending"]:
+            self._overlap_compute(1 - p)
+        ov["pending"] = True
+        ov["parity"] = 1 - p
+        model.local_step += 1
+        self._ls_mirror = model.local_step
+        self.loss = loss_out
+        return loss_out
+
+    def _capture_overlap(self, packed, B):
+        """Warm up (real steps, rolled back afterwards) and capture the four graphs: march / compute x two workspace sets."""
+        model, dev = self.model, self.device
+        per = packed.numel()
+        S_m, S_c = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev, priority=-1)
+        ov = dict(S_m=S_m, S_c=S_c, parity=0, pending=False, B=B,
+                  static=[torch.empty(per, dtype=torch.float32, device=dev) for _ in range(2)],
+                  ev_march=[torch.cuda.Event() for _ in range(2)], ev_compute=[torch.cuda.Event() for _ in range(2)],
+                  loss_host=[torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)],
+                  loss_ret=[torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)],
+                  g_march=[None, None], g_compute=[None, None], launches=[0, 0])
+        cur = torch.cuda.current_stream(dev)
+        saved_step = model.local_step
+        snap = self._snapshot_training_state()
+        rng = torch.cuda.get_rng_state(dev)
+        S_m.wait_stream(cur)
+        with torch.cuda.stream(S_m):
+            for p in (0, 1):
+                ov["static"][p].copy_(packed)
+        S_c.wait_stream(S_m)
+
+        def march(p):
+            ins = self._unpack(ov["static"][p], B)
+            return self._manual_march(ins[0], ins[1], B, p, bg_early=False)
+
+        def compute(p):
+            m = self._mws_sets[p]
+            loss = self._manual_compute(m, self._unpack(ov["static"][p], B)[2], bg_done=False)
+            ov["loss_host"][p].copy_(loss, non_blocking=True)
+
+        for p in (0, 1):
+            for _ in range(2):                   # warm-up: allocations, lazy initialisation, kernel attributes
+                with torch.cuda.stream(S_m):
+                    march(p)
+                S_c.wait_stream(S_m)
+                with torch.cuda.stream(S_c):
+                    compute(p)
+                S_m.wait_stream(S_c)
+        torch.cuda.synchronize(dev)
+        self._restore_training_state(snap)
+        model.local_step = saved_step
+        self._local_step_dev.fill_(saved_step)
+        self._ls_mirror = saved_step
+        torch.cuda.synchronize(dev)
+        for p in (0, 1):
+            l0 = _cabi.LAUNCHES
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=S_m, capture_error_mode="thread_local"):
+                march(p)
+            ov["g_march"][p] = g
+            l1 = _cabi.LAUNCHES
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=S_c, capture_error_mode="thread_local"):
+                compute(p)
+            ov["g_compute"][p] = g
+            ov["launches"] = [l1 - l0, _cabi.LAUNCHES - l1]
+            _cabi.LAUNCHES = l0
+        torch.cuda.set_rng_state(rng, dev)
+        model.local_step = saved_step
+        self._pending = False
+        cur.wait_stream(S_m)
+        cur.wait_stream(S_c)
+        self._mws = self._mws_sets[0]
+        self._ov = ov
 
     def _capture(self, rays_o, rays_d, G):
         model = self.model

@@ -449,3 +449,44 @@ def test_device_rays_step_equals_the_host_rays_step():
         assert abs(other[0] - got[0][0]) <= 1e-6 * abs(got[0][0])
         rel = ((other[1] - got[0][1]).norm() / got[0][1].norm()).item()
         assert rel < 1e-4, rel
+
+
+@pytest.mark.parametrize("device_rays", [False, True])
+def test_overlapped_steps_match_sequential_steps(device_rays):
+    """overlap=True runs the marching half of step k+1 beside the compute half of step k (two graphs per step, two
+    workspace sets); parameter updates, sample counts and run_cuda's bookkeeping must be those of the sequential graphed
+    step - across an occupancy refresh too (22 steps, update_interval 16)."""
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    n_steps, views = 22, 2
+    poses, intr = provider.make_training_poses(n_steps * views, 64, 64, seed=5)
+    poses, intr = poses.view(n_steps, views, 4, 4).to(DEV), intr.view(n_steps, views, 4).to(DEV)
+    G = torch.randn(n_steps, views, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2)) * 1e-2
+    noises = torch.rand(views * 4096, device=DEV, generator=torch.Generator(device=DEV).manual_seed(9))
+    out = []
+    for overlap in (False, True):
+        m = _bench_like_model()
+        step = TrainStep(m, 64, 64, lr=1e-4, graph=True, manual=True, overlap=overlap, device_rays=(64, 0, 1) if device_rays else None)
+        step.fixed_noises = noises
+        torch.manual_seed(3)       # the occupancy refresh draws its jitter from torch's generator
+        losses = []
+        for i in range(n_steps):
+            if device_rays:
+                batch = step.pack_pose_inputs(poses[i], intr[i], G[i])
+            else:
+                ro, rd = provider.get_rays_device(poses[i], intr[i], 64, 64)
+                batch = step.pack_inputs(ro, rd, G[i])
+            losses.append(float(step(batch).item()))
+        step.flush()
+        torch.cuda.synchronize()
+        assert step.opt.steps_taken == n_steps and step.n_updates == 2 and not step.opt.comm_error
+        out.append(dict(params={n: p.detach().clone() for n, p in m.named_parameters()}, samples=int(step.samples.item()),
+                        counter=m.step_counter.clone(), local_step=m.local_step, losses=losses, bits=m.density_bitfield.clone()))
+    a, b = out
+    assert a["samples"] == b["samples"] > 0 and a["local_step"] == b["local_step"]
+    assert torch.equal(a["counter"], b["counter"]) and torch.equal(a["bits"], b["bits"])
+    # the overlapped run reports losses two calls late: loss[k] of the sequential run == returned[k + 2]
+    np.testing.assert_allclose(b["losses"][2:], a["losses"][:-2], rtol=1e-4)
+    for n in a["params"]:
+        rel = ((a["params"][n] - b["params"][n]).norm() / a["params"][n].norm()).item()
+        assert rel < 1e-3, (n, rel)         # same updates in the same order; fp32 atomics order is the only difference
