@@ -8,11 +8,15 @@ VARIANTS=${@:-default pipeline coop}
 O=gpurun_out
 mkdir -p $O
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
+if [ -z "$SKIP_DP_CHECK" ]; then
 $RUN tests/dp_peer_check.py > $O/dp_check_${TAG}_n$N.json 2> $O/dp_check_${TAG}_n$N.err; echo "dp_check rc $?"; cat $O/dp_check_${TAG}_n$N.json
 NGP_DP_KERNEL=coop $RUN tests/dp_peer_check.py > $O/dp_check_${TAG}_coop_n$N.json 2> $O/dp_check_${TAG}_coop_n$N.err; echo "dp_check coop rc $?"; cat $O/dp_check_${TAG}_coop_n$N.json
+fi
 for v in $VARIANTS; do
   case $v in
     default) ENVV=""; ARGS="";;
+    no_overlap) ENVV=""; ARGS="--no-overlap";;
+    skip_check) ENVV=""; ARGS="";;
     pipeline) ENVV=""; ARGS="--pipeline";;
     coop) ENVV="NGP_DP_KERNEL=coop"; ARGS="";;
     coop_pipeline) ENVV="NGP_DP_KERNEL=coop"; ARGS="--pipeline";;
