@@ -58,9 +58,11 @@ def parse():
     ap.add_argument("--ray-order", default="rows", choices=["tiles", "rows"], help="sharding of a view's rays over the ranks "
                     "(rows: interleaved image rows, measured 9 %% faster at 8 GPUs than 8x8 blocks dealt along diagonals)")
     ap.add_argument("--pipeline", action="store_true", help="apply step k's optimizer update at the start of step k+1 "
-                    "(beside the ray marching); measured: no gain, the marcher slows down by what the optimizer takes")
-    ap.add_argument("--no-overlap", action="store_true", help="run each step's ray marching inside the step instead of beside the "
-                    "previous step's field / backward / optimizer half (TrainStep(overlap=True), the default)")
+                    "(beside the ray marching) also on ONE GPU; with more GPUs it is the default (measured at 8: -11 %% step time)")
+    ap.add_argument("--no-pipeline", action="store_true", help="multi-GPU: run the fused all-reduce + Adam at the end of its own step")
+    ap.add_argument("--overlap", action="store_true", help="run each step's ray marching beside the previous step's field / backward "
+                    "/ optimizer half (TrainStep(overlap=True)); measured: slower at 1 GPU (both halves are issue-bound: 2.19 vs 2.11 ms) "
+                    "and host-bound at 8 (0.58 vs 0.39 ms per step), kept as an option")
     ap.add_argument("--chunks", type=int, default=0, help="ray chunks run as parallel chains (0 = the default, 2)")
     ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce instead of the fused peer-memory all-reduce + Adam")
     ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
@@ -252,9 +254,10 @@ def run_b200_arm(args):
     # random-init occupancy so that every timed pass sees the same ~3.4 M samples per step
     step_fn = TrainStep(model, Hl, W, lr=args.lr, max_steps=MAX_STEPS, graph=not args.no_graph, world_size=world,
                         manual=False if args.autograd else None, peer_allreduce=False if args.nccl else None,
-                        pipelined=args.pipeline and not args.autograd, n_chunks=args.chunks or None,
+                        pipelined=(False if (args.no_pipeline or args.autograd or args.overlap) else (True if args.pipeline else None)),
+                        n_chunks=args.chunks or None,
                         device_rays=(H, rank, world) if device_rays else None,
-                        overlap=not (args.no_overlap or args.no_graph or args.autograd or args.pipeline))
+                        overlap=bool(args.overlap and not (args.no_graph or args.autograd)))
     # one packed, pinned host buffer per batch: a step's inputs are ONE copy - [poses | intrinsics | G] (the rays of this
     # rank's interleaved image rows are generated by the step's prologue kernel), or [rays_o | rays_d | G] with --host-rays
     if device_rays:

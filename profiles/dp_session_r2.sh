@@ -15,7 +15,8 @@ fi
 for v in $VARIANTS; do
   case $v in
     default) ENVV=""; ARGS="";;
-    no_overlap) ENVV=""; ARGS="--no-overlap";;
+    overlap) ENVV=""; ARGS="--overlap";;
+    no_pipeline) ENVV=""; ARGS="--no-pipeline";;
     skip_check) ENVV=""; ARGS="";;
     pipeline) ENVV=""; ARGS="--pipeline";;
     coop) ENVV="NGP_DP_KERNEL=coop"; ARGS="";;

@@ -63,8 +63,45 @@ def raw(src, dst):
                     f.write("| %s | %s | %s |\n" % (m, r[idx[m]], units[idx[m]]))
 
 
+def traffic(src, dst, samples_per_launch=None):
+    """profiles/ncu_traffic.json: measured DRAM bytes per launch of every kernel in a `ncu --set full` capture (mean over the
+    captured launches), keyed by the C-ABI entry point bench.py times.  bench.py puts the entry of its dominant kernel into
+    `roofline.traffic`."""
+    import json
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[0]
+    idx = {h: i for i, h in enumerate(hdr)}
+    entry_of = {"encode_backward_warpagg_kernel": "ngp_grid_scatter_samples", "field_forward_kernel": "ngp_field_forward",
+                "field_backward_kernel": "ngp_field_backward", "train_ray_loss_kernel": "ngp_train_ray_loss",
+                "march_slab_kernel": "ngp_march_rays_train", "adam_step_fused_kernel": "ngp_adam_step_fused"}
+    agg = collections.defaultdict(list)
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        for k, entry in entry_of.items():
+            if k in name:
+                rd = float(r[idx["dram__bytes_read.sum"]].replace(",", ""))
+                wr = float(r[idx["dram__bytes_write.sum"]].replace(",", ""))
+                ur, uw = rows[1][idx["dram__bytes_read.sum"]], rows[1][idx["dram__bytes_write.sum"]]
+                mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                agg[entry].append((rd * mult.get(ur, 1) + wr * mult.get(uw, 1), float(r[idx["gpu__time_duration.sum"]].replace(",", ""))))
+    res = {}
+    for entry, vals in agg.items():
+        # launches of very different sizes (e.g. the 2 M-point occupancy refresh) would blur the mean: keep the modal half
+        vals.sort()
+        mid = vals[len(vals) // 4: max(len(vals) // 4 + 1, 3 * len(vals) // 4)]
+        res[entry] = {"dram_bytes_per_launch": sum(v[0] for v in mid) / len(mid), "launches_in_capture": len(vals),
+                      "samples_per_launch": samples_per_launch, "capture": src.split("/")[-1],
+                      "how": "ncu --set full --clock-control none: dram__bytes_read.sum + dram__bytes_write.sum, mean of the "
+                             "middle half of the captured launches"}
+    with open(dst, "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], float(sys.argv[4]) if len(sys.argv) > 4 else None)
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
     else:
         raw(sys.argv[2], sys.argv[3])

@@ -26,10 +26,11 @@ def orbit_cameras(n_frames=100, H=800, W=800, radius=1.8, theta_deg=60.0, fovy_d
 def render_frame(model, pose, intrinsics, H, W, bg_color=None, perturb=False, max_steps=1024, dt_gamma=0, shading="albedo",
                  ambient_ratio=1.0, light_d=None):
     """test_step (nerf/utils.py:435-456) for one camera: pred_rgb [H, W, 3], pred_depth [H, W] (device tensors)."""
+    from . import _nvtx
     rays_o, rays_d = provider.get_rays_device(pose[None], intrinsics, H, W)
     if bg_color is None:
         bg_color = torch.ones(3, device=rays_o.device)
-    with torch.autocast("cuda", torch.float16):
+    with torch.autocast("cuda", torch.float16), _nvtx.range("ngp.orbit.frame"):
         out = model.render(rays_o, rays_d, staged=True, perturb=perturb, light_d=light_d, ambient_ratio=ambient_ratio,
                            shading=shading, force_all_rays=True, bg_color=bg_color, max_steps=max_steps, dt_gamma=dt_gamma)
     return out["image"].reshape(H, W, 3), out["depth"].reshape(H, W)

@@ -195,7 +195,9 @@ class NeRFRenderer(nn.Module):
             done = False
             if shading == 'albedo' and self.infer_loop == 'graph' and self._fused_training_path(rays_o):
                 # the whole loop as one CUDA-graph launch with a conditional WHILE node: no host sync per iteration
-                res = self._run_infer_loop(rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh)
+                from . import _nvtx
+                with _nvtx.range("ngp.infer.loop"):
+                    res = self._run_infer_loop(rays_o, rays_d, nears, fars, perturb, dt_gamma, max_steps, T_thresh)
                 if res is not None:
                     weights_sum, depth, image = res
                     done = True

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _cabi
+from . import _cabi, _nvtx
 from .optim import FusedAdamScaler
 from .parallel import FlatGradBucket, PeerMemory
 from .step_ops import entropy_loss as fused_entropy_loss
@@ -31,7 +31,7 @@ def entropy_loss(weights_sum, lam=1e-4):
 
 class TrainStep:
     def __init__(self, model, H, W, lr=1e-3, max_steps=1024, lambda_entropy=1e-4, update_interval=16, graph=False,
-                 world_size=1, fused_optimizer=True, lr_decay=None, manual=None, peer_allreduce=None, pipelined=False,
+                 world_size=1, fused_optimizer=True, lr_decay=None, manual=None, peer_allreduce=None, pipelined=None,
                  n_chunks=None, device_rays=None, shading="albedo", ambient_ratio=None, lambda_orient=1e-2, lambda_smooth=0.0,
                  overlap=False):
         """device_rays: None, or (H_full, row0, row_stride): the step's inputs are then camera POSES [B,4,4] and intrinsics
@@ -44,7 +44,9 @@ class TrainStep:
         pipelined (hand-scheduled step only): apply step k's optimizer update (and gradient all-reduce) at the START of
         step k+1, on the side stream, overlapped with that step's ray marching (which reads no parameters).  Same
         arithmetic in the same order; the parameters lag one update behind until flush() - called automatically before
-        every occupancy refresh, and by the user before reading the parameters."""
+        every occupancy refresh, and by the user before reading the parameters.  None = on for world_size > 1 with the fused
+        peer all-reduce (measured at 8 GPUs: 0.385 vs 0.432 ms per step - the cross-GPU exchange and its wait for the slowest
+        rank hide behind the marcher), off on one GPU (the update is 1.6 % of the step and the marcher is issue-bound)."""
         self.model, self.H, self.W = model, H, W
         # shading != 'albedo' (after albedo_iters the reference draws 'textureless' / 'lambertian' with ambient_ratio 0.1,
         # nerf/utils.py:345-356, and adds lambda_orient * loss_orient [+ lambda_smooth * loss_smooth], :396-402): runs
@@ -61,6 +63,7 @@ class TrainStep:
         # step k runs - two CUDA graphs per step and two alternating workspace sets, ordered by ordinary stream events.
         # Arithmetic and update order are those of the sequential step; results arrive with a lag (see __call__).
         self.overlap = bool(overlap)
+        self._pipelined_request = pipelined
         self.pipelined = bool(pipelined)
         self.device_rays = None if device_rays is None else tuple(int(v) for v in device_rays)
         self._pending = False
@@ -114,6 +117,9 @@ class TrainStep:
             self.scaler = torch.amp.GradScaler("cuda")
             self.bucket = FlatGradBucket(list(model.parameters()), device)
             self.flat_grads = self.bucket.flat
+        if self._pipelined_request is None:
+            self.pipelined = bool(self.manual and fused_optimizer and world_size > 1 and self.opt.peer_ptrs is not None
+                                  and not self.overlap)
         if world_size > 1 and dist.is_available() and dist.is_initialized() and not hasattr(model, "dp_shard"):
             model.dp_shard = (dist.get_rank(), world_size)  # occupancy refresh: 1/world of the cells per rank + all-gather
         self.global_step = 0
@@ -241,8 +247,10 @@ class TrainStep:
         flat bucket (tests/test_gpu_train_step.py compares the two).
         The step is two phases - _manual_march (reads rays + the occupancy bitfield, no parameters) and _manual_compute
         (everything else) - run back to back here, and as separate graphs on separate streams in overlap mode."""
-        m = self._manual_march(rays_o, rays_d, G.shape[0], None, bg_early=True)
-        return self._manual_compute(m, G, bg_done=True)
+        with _nvtx.range("ngp.step.march"):
+            m = self._manual_march(rays_o, rays_d, G.shape[0], None, bg_early=True)
+        with _nvtx.range("ngp.step.compute"):
+            return self._manual_compute(m, G, bg_done=True)
 
     def _manual_consts(self):
         model, opt = self.model, self.opt
@@ -408,9 +416,10 @@ class TrainStep:
         return m["loss"]
 
     def _apply_update(self, deferred):
-        if self.world > 1 and self.opt.peer_ptrs is None:
-            dist.all_reduce(self.opt.flat_grads, op=dist.ReduceOp.SUM)
-        self.opt.step_fused(deferred=deferred)
+        with _nvtx.range("ngp.step.optimizer"):
+            if self.world > 1 and self.opt.peer_ptrs is None:
+                dist.all_reduce(self.opt.flat_grads, op=dist.ReduceOp.SUM)
+            self.opt.step_fused(deferred=deferred)
 
     # -- checkpoints in the reference Trainer's layout (nerf/utils.py:847-968) -------------------------------------------
     def save_checkpoint(self, path, epoch=0, full=True):
@@ -510,7 +519,7 @@ class TrainStep:
             if self.use_graph and not self.fused_optimizer:
                 from . import field
                 field.invalidate_half_cache()  # graph replays update the parameters without bumping ._version
-            with torch.autocast("cuda", torch.float16):
+            with torch.autocast("cuda", torch.float16), _nvtx.range("ngp.occupancy_refresh"):
                 model.update_extra_state()
             self.n_updates += 1
         self.global_step += 1
