@@ -1067,6 +1067,30 @@ __global__ void __launch_bounds__(128) march_infer_kernel(uint32_t n_alive, uint
     }
 }
 
+// Warp-per-ray variant for ONE sample per ray (the first iterations of a frame, n_step == 1 while most rays are alive):
+// there every ray first crosses the empty space in front of the object - hundreds of lattice points - before it emits its
+// sample, and one thread per ray walks them serially.  walk_ray_warp classifies 32 lattice points per iteration and is
+// bit-identical to the serial loop (it is the training marcher's walk, checked against the reference there).
+__global__ void __launch_bounds__(128) march_infer_warp_kernel(uint32_t n_alive, uint32_t n_step, const int* __restrict__ rays_alive,
+                                                               const float* __restrict__ rays_t, const float* __restrict__ rays_o,
+                                                               const float* __restrict__ rays_d, float bound, float dt_gamma,
+                                                               uint32_t max_steps, uint32_t C, uint32_t H,
+                                                               const uint8_t* __restrict__ grid, const float* __restrict__ fars,
+                                                               float* __restrict__ xyzs, float* __restrict__ dirs,
+                                                               float* __restrict__ deltas, const float* __restrict__ noises) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    for (uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_alive; n += warps) {
+        const int id = rays_alive[n];
+        const Ray r = load_ray(rays_o, rays_d, (uint32_t)id);
+        float t = rays_t[id];
+        t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * (noises ? noises[n] : 0.f);
+        walk_ray_warp<true>(p, r, t, fars[id], n_step, lane, xyzs + (size_t)n * n_step * 3, dirs ? dirs + (size_t)n * n_step * 3 : nullptr,
+                            deltas + (size_t)n * n_step * 2);
+    }
+}
+
 __global__ void __launch_bounds__(128) composite_infer_kernel(uint32_t n_alive, uint32_t n_step, float T_thresh, int* rays_alive,
                                                               float* rays_t, const float* __restrict__ sigmas,
                                                               const float* __restrict__ rgbs, const float* __restrict__ deltas,
@@ -1195,6 +1219,24 @@ __global__ void __launch_bounds__(128) infer_march_kernel(const InferState* __re
     const int* __restrict__ rays_alive = alive_buf + (size_t)st->cur * N;
     const bool first = st->step == 0;
     const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    if (n_step == 1) {
+        // one sample per ray (most rays still alive, crossing the empty space in front of the object): one WARP per ray,
+        // 32 lattice points classified per iteration (see march_infer_warp_kernel)
+        const int lane = threadIdx.x & 31;
+        const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+        for (uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_alive; n += warps) {
+            const int id = rays_alive[n];
+            const Ray r = load_ray(rays_o, rays_d, (uint32_t)id);
+            float t = rays_t[id];
+            t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * ((first && noises) ? noises[n] : 0.f);
+            const uint32_t got = walk_ray_warp<true>(p, r, t, fars[id], 1u, lane, xyzs + (size_t)n * 3, nullptr, deltas + (size_t)n * 2);
+            if (got == 0 && lane == 0) {
+                xyzs[(size_t)n * 3] = 0.f; xyzs[(size_t)n * 3 + 1] = 0.f; xyzs[(size_t)n * 3 + 2] = 0.f;
+                deltas[(size_t)n * 2] = 0.f; deltas[(size_t)n * 2 + 1] = 0.f;
+            }
+        }
+        return;
+    }
     for (uint32_t n = blockIdx.x * blockDim.x + threadIdx.x; n < n_alive; n += gridDim.x * blockDim.x) {
         const int id = rays_alive[n];
         const Ray r = load_ray(rays_o, rays_d, (uint32_t)id);
@@ -1524,6 +1566,14 @@ extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
         return NGP_ERR_BAD_ARG;
     if (C == 0 || H == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
     if (n_alive == 0 || n_step == 0) return NGP_OK;
+    if (n_step == 1 && !march::g_thread_per_ray) {
+        // (the caller's buffers are zero-filled, raymarching.py:334-336: rays that emit nothing leave their slot untouched)
+        const int blocks = min(cdiv((uint64_t)n_alive * 32, 128), num_sms() * 16);
+        march::march_infer_warp_kernel<<<blocks, 128, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound,
+                                                                               dt_gamma, max_steps, C, H, grid, fars, xyzs, dirs, deltas,
+                                                                               noises);
+        return launch_status();
+    }
     march::march_infer_kernel<<<cdiv(n_alive, 128), 128, 0, as_stream(stream)>>>(
         n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs,
         deltas, noises);
@@ -1686,7 +1736,8 @@ extern "C" int ngp_render_infer_loop(const float* rays_o, const float* rays_d, c
             if ((e = cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) break;
             const int persistent = num_sms() * 8;
             const int g128 = min(cdiv(N, 128), persistent);
-            march::infer_march_kernel<<<g128, 128, 0, cs>>>(st, N, alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
+            const int g_march = min(cdiv((uint64_t)N * 32, 128), num_sms() * 16);   // warp-per-ray passes need the wide grid
+            march::infer_march_kernel<<<g_march, 128, 0, cs>>>(st, N, alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
                                                             fars, xyzs, deltas, noises);
             rc = ngp_field_forward(xyzs, (uint32_t)(align_up((uint64_t)N, 128)), &st->rows, table, offsets, L, Cfeat, S, Hres, gridtype,
                                    align_corners, bound, w1, b1, w2, b2, w3, b3, hidden, out_dim, sigma, rgb, nullptr, nullptr, nullptr,
