@@ -21,6 +21,7 @@ namespace march {
 
 // test / profiling switch (ngp_march_set_option 0): 1 = the reference's decomposition, one thread per ray
 bool g_thread_per_ray = false;
+bool g_infer_warp_march = false;  // ngp_march_set_option 1: warp-per-ray walk for one-sample inference calls
 
 NGP_DEVINL float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }  // raymarching.cu:34
 
@@ -1219,9 +1220,12 @@ __global__ void __launch_bounds__(128) infer_march_kernel(const InferState* __re
     const int* __restrict__ rays_alive = alive_buf + (size_t)st->cur * N;
     const bool first = st->step == 0;
     const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
-    if (n_step == 1) {
-        // one sample per ray (most rays still alive, crossing the empty space in front of the object): one WARP per ray,
-        // 32 lattice points classified per iteration (see march_infer_warp_kernel)
+    if (first && n_step == 1 && n_alive <= 16384u) {
+        // first iteration of a SMALL frame: every ray starts at its near plane and crosses the empty space in front of the
+        // object (hundreds of lattice points) before its first sample, and there are too few rays to fill the machine with
+        // one thread each - one WARP per ray, 32 lattice points classified per iteration (see march_infer_warp_kernel).
+        // The warp walk spends ~10x the lane-time of the serial walk, so with many rays (800x800: 640 000) a thread per ray
+        // wins (measured: 13.5 vs 9.35 ms per frame), as it does on later iterations that start next to the last sample.
         const int lane = threadIdx.x & 31;
         const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
         for (uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_alive; n += warps) {
@@ -1410,6 +1414,7 @@ extern "C" int ngp_packbits(const float* grid, uint32_t N, float density_thresh,
 
 extern "C" int ngp_march_set_option(int option, int value) {
     if (option == 0) { march::g_thread_per_ray = (value != 0); return NGP_OK; }
+    if (option == 1) { march::g_infer_warp_march = (value != 0); return NGP_OK; }
     return NGP_ERR_BAD_ARG;
 }
 
@@ -1566,7 +1571,9 @@ extern "C" int ngp_march_rays(uint32_t n_alive, uint32_t n_step, const int* rays
         return NGP_ERR_BAD_ARG;
     if (C == 0 || H == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
     if (n_alive == 0 || n_step == 0) return NGP_OK;
-    if (n_step == 1 && !march::g_thread_per_ray) {
+    if (n_step == 1 && march::g_infer_warp_march) {   // opt-in (ngp_march_set_option 1): pays only when the rays start far from
+        //                                                  the object, i.e. on a frame's FIRST call; the device-driven loop
+        //                                                  (ngp_render_infer_loop) selects it there by itself
         // (the caller's buffers are zero-filled, raymarching.py:334-336: rays that emit nothing leave their slot untouched)
         const int blocks = min(cdiv((uint64_t)n_alive * 32, 128), num_sms() * 16);
         march::march_infer_warp_kernel<<<blocks, 128, 0, as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound,
@@ -1736,7 +1743,7 @@ extern "C" int ngp_render_infer_loop(const float* rays_o, const float* rays_d, c
             if ((e = cudaStreamBeginCaptureToGraph(cs, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal)) != cudaSuccess) break;
             const int persistent = num_sms() * 8;
             const int g128 = min(cdiv(N, 128), persistent);
-            const int g_march = min(cdiv((uint64_t)N * 32, 128), num_sms() * 16);   // warp-per-ray passes need the wide grid
+            const int g_march = N <= 16384u ? min(cdiv((uint64_t)N * 32, 128), num_sms() * 16) : g128;   // (warp-per-ray first pass)
             march::infer_march_kernel<<<g_march, 128, 0, cs>>>(st, N, alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
                                                             fars, xyzs, deltas, noises);
             rc = ngp_field_forward(xyzs, (uint32_t)(align_up((uint64_t)N, 128)), &st->rows, table, offsets, L, Cfeat, S, Hres, gridtype,
