@@ -141,6 +141,8 @@ def require_contiguous(*tensors):
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); everything else launches one
 KERNELS_PER_CALL = {"ngp_march_rays_train": 3, "ngp_update_density_grid": 2, "ngp_compact_alive": 2}
+DEBUG_SYNC = os.environ.get("NGP_DEBUG_SYNC", "0") not in ("", "0")   # synchronise + check for a CUDA fault after EVERY entry point
+#                    (the reference never checks: faults surface at the next sync; this pins them to the call)
 LAUNCHES = 0       # running count of our kernels launched through this module
 PROFILE = None     # optional {entry point name: [(start_event, end_event), ...]} filled while set (bench.py)
 
@@ -162,6 +164,11 @@ def call(name, device, *args):
             rc = getattr(lib, name)(*args, stream())
     LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     check(rc, name)
+    if DEBUG_SYNC and not torch.cuda.is_current_stream_capturing():
+        try:
+            torch.cuda.synchronize(device)
+        except RuntimeError as e:
+            raise RuntimeError("%s: asynchronous CUDA fault: %s" % (name, e)) from e
 
 
 def call_rc(name, device, *args, launches=1):
