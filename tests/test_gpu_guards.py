@@ -31,7 +31,7 @@ class Guards:
         raw = self.orig["empty"](n_al + 2 * PAD, dtype=torch.uint8, device=device)
         raw.fill_(SENTINEL)
         self.records.append((raw, n))
-        return raw[PAD:PAD + n].view(dtype).view(*shape)
+        return raw[PAD:PAD + n].view(dtype).view(tuple(shape))
 
     @staticmethod
     def _shape(args):
