@@ -394,3 +394,66 @@ def test_train_ray_loss_restatement_is_consistent():
         assert abs(fd - out["grad_rgbs"][idx, 1]) < 2e-3 * max(1.0, abs(fd))
     assert abs(out["loss"] - lam * np.mean([-a * np.log2(a) - (1 - a) * np.log2(1 - a) for a in np.clip(out["weights_sum"], 1e-5, 1 - 1e-5).astype(np.float64)])) < 1e-6
     np.testing.assert_allclose(out["grad_bg"], (1 - out["weights_sum"])[:, None] * g_ray, rtol=1e-6)
+
+
+def test_field_and_bg_oracle_gradients_match_finite_differences():
+    """oracle.field_backward / bg_backward (the fp64 checkers of the tcgen05 field kernels and of the fused step) against
+    central differences of oracle.field_forward / bg_forward (un-rounded mode), on the cfg3 table layout."""
+    rng = np.random.default_rng(0)
+    offs, S = util.make_offsets(log2_hashmap_size=16)
+    table = rng.uniform(-0.5, 0.5, (offs[-1], 2)).astype(np.float16).astype(np.float32)
+    W = [(rng.standard_normal(s) * sc).astype(np.float16).astype(np.float32) for s, sc in (((64, 32), 0.05), ((64, 64), 0.15), ((4, 64), 0.15))]
+    b = [(rng.standard_normal(n) * 0.1).astype(np.float16).astype(np.float32) for n in (64, 64, 4)]
+    x = rng.uniform(-0.9, 0.9, (500, 3)).astype(np.float32)
+    ds, da = rng.standard_normal(500) * 0.1, rng.standard_normal((500, 3))
+    S = np.float32(S)
+    f = O.field_forward(x, table, offs, S, 16, W, b, round_hidden=False)
+    g = O.field_backward(f, ds, da, offs, offs[-1], S, 16)
+
+    def loss(W_, b_, t_):
+        ff = O.field_forward(x, t_, offs, S, 16, W_, b_, round_hidden=False)
+        return float((ff["sigma"] * ds).sum() + (ff["albedo"] * da).sum())
+
+    eps = 2.0 ** -8          # representable in fp16 next to the quantised weights
+    for li, key, idx, e_w, tol in ((1, "w2", (3, 5), eps, 2e-3), (2, "w3", (1, 7), eps, 2e-3), (0, "w1", (10, 4), 2.0 ** -11, 1e-2)):
+        Wp, Wm = [w.copy() for w in W], [w.copy() for w in W]          # (a step on W1 crosses ReLU kinks of 500 x 64 units:
+        Wp[li][idx] += e_w; Wm[li][idx] -= e_w                          #  smaller step, looser bound)
+        fd = (loss(Wp, b, table) - loss(Wm, b, table)) / (2 * e_w)
+        assert abs(fd - g[key][idx]) <= tol * abs(g[key][idx]) + 1e-6, (key, fd, g[key][idx])
+    bp, bm = [v.copy() for v in b], [v.copy() for v in b]
+    bp[2][0] += eps; bm[2][0] -= eps
+    fd = (loss(W, bp, table) - loss(W, bm, table)) / (2 * eps)
+    assert abs(fd - g["b3"][0]) <= 2e-3 * abs(g["b3"][0])
+    r = int(np.argmax(np.abs(g["table"][:, 0])))       # the encoder is linear in the table: a large step is exact up to the MLP
+    tp, tm = table.copy(), table.copy()
+    tp[r, 0] += 2.0 ** -6; tm[r, 0] -= 2.0 ** -6
+    fd = (loss(W, b, tp) - loss(W, b, tm)) / (2 * 2.0 ** -6)
+    assert abs(fd - g["table"][r, 0]) <= 5e-2 * abs(g["table"][r, 0]), (fd, g["table"][r, 0])
+    # the rounded ("spec") forward stays within fp16 noise of the exact one
+    fr = O.field_forward(x, table, offs, S, 16, W, b, round_hidden=True)
+    assert np.abs(fr["albedo"] - f["albedo"]).max() < 2e-3
+
+    # background net
+    d = rng.standard_normal((300, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    Wb = [(rng.standard_normal(s) * 0.2).astype(np.float16).astype(np.float32) for s in ((64, 39), (3, 64))]
+    bb = [(rng.standard_normal(n) * 0.1).astype(np.float16).astype(np.float32) for n in (64, 3)]
+    up = rng.standard_normal((300, 3))
+    fb = O.bg_forward(d, Wb, bb)
+    gb = O.bg_backward(fb, up)
+    assert fb["rgb"].shape == (300, 3) and (fb["rgb"] > 0).all() and (fb["rgb"] < 1).all()
+    # bg_forward rounds to fp16 at every Linear (finite differences would see the staircase): check the chain rule on an
+    # un-rounded re-evaluation of the same graph instead
+    e, Wq = fb["e"], fb["W"]
+
+    def bg_loss(W1, b2):
+        h = np.maximum(e @ W1.T + np.asarray(bb[0], np.float64), 0.0)
+        out = h @ Wq[1].T + b2
+        return float(((1.0 / (1.0 + np.exp(-out))) * up).sum())
+    W1 = Wq[0].copy()
+    b2 = np.asarray(bb[1], np.float64).copy()
+    W1p, W1m = W1.copy(), W1.copy()
+    W1p[5, 7] += 1e-5; W1m[5, 7] -= 1e-5
+    fd = (bg_loss(W1p, b2) - bg_loss(W1m, b2)) / 2e-5
+    # (gb is evaluated at the fp16-rounded activations; the un-rounded graph agrees to fp16 noise)
+    assert abs(fd - gb["w1"][5, 7]) <= 2e-2 * abs(gb["w1"][5, 7]) + 1e-4, (fd, gb["w1"][5, 7])
