@@ -43,9 +43,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="train", choices=["train", "infer"], help="train: the -O train step (the headline "
+    ap.add_argument("--config", default="train", choices=["train", "infer", "encoder"], help="train: the -O train step (the headline "
                     "metric, BASELINE configs[2]/[3]); infer: BASELINE configs[4], the 100-frame 800x800 test orbit through "
-                    "the inference branch of run_cuda (1 GPU; a secondary line with its own metric)")
+                    "the inference branch of run_cuda; encoder: BASELINE configs[1], the standalone GridEncoder on 2^22 points "
+                    "(1 GPU; secondary lines with their own metrics)")
     ap.add_argument("--frames", type=int, default=100, help="--config infer: frames of the orbit")
     ap.add_argument("--res", type=int, default=800, help="--config infer: image side")
     ap.add_argument("--views", type=int, default=VIEWS_PER_STEP, help="camera views per step, whole job")
@@ -779,6 +780,105 @@ def run_infer_config(args):
     sys.stdout.flush()
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs[1]: GridEncoder standalone, 16 levels x 2 features, hash 2^19, base 16 -> 2048, 2^22 points, fp16 fwd+bwd
+# ---------------------------------------------------------------------------------------------------
+def run_encoder_config(args):
+    import numpy as np
+    import torch
+    from ngp_b200 import _cabi
+    from gridencoder import GridEncoder
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(device)
+    _cabi.load()
+    torch.manual_seed(0)
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19,
+                      desired_resolution=2048, gridtype="hash").to(device)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-1, 1)
+    B = 1 << 22
+    n_pool = 4                        # 4 x 50 MB of inputs and 4 x 134 MB of upstream gradients: more than fits beside the table in L2
+    xs = [torch.rand(B, 3, device=device, generator=torch.Generator(device=device).manual_seed(1 + k)) * 2 - 1 for k in range(n_pool)]
+    with torch.autocast("cuda", torch.float16):
+        out = enc(xs[0], bound=1)
+    gs = [torch.randn(out.shape, device=device, dtype=out.dtype, generator=torch.Generator(device=device).manual_seed(20 + k))
+          for k in range(n_pool)]
+    x_host = xs[0].cpu().pin_memory()
+
+    def fwd(i):
+        with torch.no_grad(), torch.autocast("cuda", torch.float16):
+            return enc(xs[i % n_pool], bound=1)
+
+    def fwd_bwd(i, x=None):
+        enc.embeddings.grad = None
+        with torch.autocast("cuda", torch.float16):
+            o = enc(xs[i % n_pool] if x is None else x, bound=1)
+        o.backward(gs[i % n_pool])
+
+    def timed(fn, iters, warm):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(warm + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    clocks = ClockSampler(device.index)
+    clocks.start()
+    time.sleep(1.0)
+    steps, warm = max(args.steps // 4, 8), max(args.warmup, 3)
+    launches0 = _cabi.LAUNCHES
+    t_f = timed(fwd, steps, warm)
+    t_fb = timed(fwd_bwd, steps, warm)
+    launches = _cabi.LAUNCHES - launches0
+
+    def e2e(i):
+        fwd_bwd(i, x_host.to(device, non_blocking=True))
+        enc.embeddings.grad.view(-1)[:1].cpu()          # a read of the step's result
+    t_e2e = timed(e2e, steps, warm)
+    clk = clocks.stop()
+    gathers_s, reds_s = measure_l2_peaks(device)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    ach = 512.0 * B / (t_f * 1e-3) / 1e9
+    line = {"metric": "GridEncoder points/s (16x2 hash 2^19, 2^22 points, fp16 fwd+bwd)", "value": B / (t_fb * 1e-3), "unit": "points/s",
+            "n_gpus": 1, "steps": steps, "warmup": warm, "ms_per_step": t_fb, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: GridEncoder standalone, 16 levels x 2 feats, log2_hashmap 19, base res 16, desired "
+                                   "res 2048, 2^22 uniformly random points, fp16 autocast, forward + backward (fp32-accumulated table gradient)",
+                       "fwd_ms": t_f, "fwd_points_per_s": B / (t_f * 1e-3), "bwd_ms": t_fb - t_f,
+                       "timing": "4 rotating input / gradient sets (736 MB) so no step finds its streams in L2; the 24.5 MB fp16 table is "
+                                 "L2-resident by design"},
+            "e2e": {"value": B / (t_e2e * 1e-3), "unit": "points/s", "h2d_bytes_per_step": B * 12, "d2h_bytes_per_step": 4, "ms_per_step": t_e2e},
+            "gpu_launches": launches, "clocks": clk,
+            "roofline": {"kernel": "ngp_grid_encode_forward", "bound": "l2-gather", "unit": "GB/s", "achieved": ach,
+                         "peak": gathers_s * 4 / 1e9, "frac": ach / (gathers_s * 4 / 1e9), "traffic": None,
+                         "peak_source": "measured in this run: ngp_bench_gather4, random 4-byte gathers over a 32 MB L2-resident table",
+                         "backward": {"bound": "l2-atomic", "red_lane_ops_per_s": 128.0 * B / ((t_fb - t_f) * 1e-3), "peak_lane_ops_per_s": reds_s,
+                                      "frac": 128.0 * B / ((t_fb - t_f) * 1e-3) / reds_s,
+                                      "note": "random points share no cells: all 128 reds per point are issued (x-neighbour pairs merged "
+                                              "into 16-byte reds where aligned, so the issued count is somewhat lower)"},
+                         "hbm": {"algorithmic_bytes_per_point": 76, "achieved_gbs": 76.0 * B / (t_f * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs")}}}
+    if not args.no_ref_cuda:
+        try:
+            env = dict(os.environ)
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(k, None)
+            out = subprocess.run([sys.executable, "-m", "oracle.ref_pipeline", "encoder"], cwd=ROOT, env=env, capture_output=True,
+                                 text=True, timeout=600)
+            tag = [l for l in out.stdout.splitlines() if l.startswith("REF_PIPELINE_JSON ")]
+            line["ref_cuda_ext"] = json.loads(tag[-1][len("REF_PIPELINE_JSON "):]) if tag else {"unavailable": (out.stderr or out.stdout)[-300:]}
+            if "fwd_bwd_ms" in line["ref_cuda_ext"]:
+                line["ref_cuda_ext"]["speedup_fwd_bwd"] = line["ref_cuda_ext"]["fwd_bwd_ms"] / t_fb
+        except Exception as e:  # noqa: BLE001
+            line["ref_cuda_ext"] = {"unavailable": repr(e)[:200]}
+    emit(line)
+    sys.stdout.flush()
+
+
 _REAL_STDOUT = None
 
 
@@ -803,6 +903,9 @@ def main():
     elif args.config == "infer":
         if int(os.environ.get("RANK", "0")) == 0:
             run_infer_config(args)
+    elif args.config == "encoder":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_encoder_config(args)
     else:
         run_b200_arm(args)
 

@@ -426,11 +426,63 @@ def time_reference_inference(device, frames=20, res=800, max_steps=1024):
             "what": "reference CUDA extensions + the reference's host inference loop and per-frame host conversion, %dx%d" % (res, res)}
 
 
+def time_reference_encoder(device, points=1 << 22, iters=8):
+    """The reference's GridEncoder path (its extension + its wrapper's casts / permutes / zero-fills, grid.py:19-84) on BASELINE
+    configs[1]: hash 2^19, 16 x 2, base 16 -> 2048, fp16 autocast, forward and forward + backward."""
+    ns = ref_ext.load()
+    if ns is None:
+        return {"unavailable": "oracle/_ref not built"}
+    L, C, base, log2, desired = 16, 2, 16, 19, 2048
+    pls = np.exp2(np.log2(desired / base) / (L - 1))
+    offs, off = [], 0
+    for i in range(L):
+        res = int(np.ceil(base * pls ** i))
+        offs.append(off)
+        off += int(np.ceil(min(2 ** log2, (res + 1) ** 3) / 8) * 8)
+    offs.append(off)
+    offsets = torch.from_numpy(np.array(offs, np.int32)).to(device)
+    torch.manual_seed(0)
+    emb = nn.Parameter(torch.empty(off, C, device=device).uniform_(-1, 1))
+    xs = [torch.rand(points, 3, device=device, generator=torch.Generator(device=device).manual_seed(1 + k)) for k in range(4)]
+    S = float(np.log2(pls))
+    with torch.autocast("cuda", torch.float16):
+        out = _RefGridEncode.apply(xs[0], emb, offsets, S, base, 0, ns)
+    gs = [torch.randn(out.shape, device=device, dtype=out.dtype, generator=torch.Generator(device=device).manual_seed(20 + k)) for k in range(4)]
+
+    def fwd(i):
+        with torch.no_grad(), torch.autocast("cuda", torch.float16):
+            _RefGridEncode.apply(xs[i % 4], emb, offsets, S, base, 0, ns)
+
+    def fwd_bwd(i):
+        emb.grad = None
+        with torch.autocast("cuda", torch.float16):
+            o = _RefGridEncode.apply(xs[i % 4], emb, offsets, S, base, 0, ns)
+        o.backward(gs[i % 4])
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(3 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    t_f, t_fb = timed(fwd), timed(fwd_bwd)
+    return {"fwd_ms": t_f, "fwd_bwd_ms": t_fb, "points": points, "fwd_bwd_points_per_s": points / (t_fb * 1e-3),
+            "what": "reference gridencoder extension + its Python wrapper (table cast, [L,B,C] permute copies, fp16 atomics)"}
+
+
 if __name__ == "__main__":
     # run in a fresh process (own CUDA context / caching allocator): the reference empties the allocator cache every
     # step (raymarching.py:231), which must not be charged for another workload's cached blocks
     import json
     import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "encoder":
+        print("REF_PIPELINE_JSON " + json.dumps(time_reference_encoder(torch.device("cuda", 0))), flush=True)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "infer":
         res = time_reference_inference(torch.device("cuda", 0), frames=int(sys.argv[2]) if len(sys.argv) > 2 else 20,
                                        res=int(sys.argv[3]) if len(sys.argv) > 3 else 800)

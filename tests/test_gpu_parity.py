@@ -571,3 +571,51 @@ def test_march_thread_per_ray_variant_is_bit_identical(case):
         assert np.array_equal(N_(xyzs[:total]), ox[:total]) and np.array_equal(N_(deltas[:total]), ol[:total])
         assert np.array_equal(N_(dirs[:total]), od[:total])
         assert not xyzs[total:].any()
+
+
+def test_cfg2_full_size_encoder_vs_reference_extension(ref_ext):
+    """BASELINE configs[1] at its REAL size: hash grid 2^19 rows/level, 16 x 2, base 16 -> 2048, 2^22 points, fp16.
+    Forward bit-equal to the reference extension; backward (fp32-accumulated here, fp16 atomics there) agrees with it to the
+    reference's own rounding, conserves the gradient mass exactly (corner weights of a level sum to 1: the size-independent
+    property) and a 2^16-point slice matches the exact fp64 sum of the C oracle."""
+    from gridencoder import GridEncoder
+    from oracle import oracle as O
+    from oracle import ref_ext as R
+    torch.manual_seed(0)
+    enc = GridEncoder(input_dim=3, num_levels=16, level_dim=2, base_resolution=16, log2_hashmap_size=19, desired_resolution=2048,
+                      gridtype="hash").to(DEV)
+    with torch.no_grad():
+        enc.embeddings.uniform_(-1, 1)
+    B = 1 << 22
+    x = torch.rand(B, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 2 - 1
+    with torch.autocast("cuda", torch.float16):
+        out = enc(x, bound=1)
+    assert out.dtype == torch.half and out.shape == (B, 32)
+    emb_h = enc.embeddings.detach().half()
+    x01 = ((x + 1) / 2).contiguous()
+    S = float(np.log2(enc.per_level_scale))
+    ref_out, _, _ = R.grid_encode_forward(ref_ext, x01, emb_h, enc.offsets, S, 16, False, 0, False)
+    assert torch.equal(out, ref_out.to(out.dtype))
+    g = torch.randn(out.shape, device=DEV, dtype=out.dtype, generator=torch.Generator(device=DEV).manual_seed(2))
+    out.backward(g)
+    mine = enc.embeddings.grad
+    assert mine.dtype == torch.float32
+    theirs = R.grid_encode_backward(ref_ext, g.contiguous(), x01, emb_h, enc.offsets, S, 16, None, 0, False)[0].float()
+    rel = ((mine - theirs).norm() / mine.norm()).item()
+    assert rel < 5e-3, rel                                   # the reference accumulates in fp16
+    # mass conservation per level and channel, all 4 M points (fp64 sums on the device)
+    offs = enc.offsets.cpu().numpy()
+    gl = g.double().view(B, 16, 2).sum(0)
+    for l in range(16):
+        got = mine[offs[l]:offs[l + 1]].double().sum(0)
+        assert torch.allclose(got, gl[l], rtol=1e-5, atol=1e-3), (l, got, gl[l])
+    # exact sum on a slice the C oracle finishes in seconds
+    n = 1 << 16
+    sc, _ = device_scales(16, np.float32(S), 16)
+    enc.embeddings.grad = None
+    with torch.autocast("cuda", torch.float16):
+        o2 = enc(x[:n].contiguous(), bound=1)
+    o2.backward(g[:n].contiguous())
+    truth = O.grid_encode_backward(N_(g[:n]), N_(x01[:n]), offs, enc.embeddings.shape[0], 2, np.float32(S), 16, gridtype=0,
+                                   scale_override=sc)
+    assert util.rel_l2(N_(enc.embeddings.grad), truth) < 1e-6
