@@ -18,7 +18,7 @@
 namespace ngp {
 namespace field {
 
-int g_fwd_ctas_per_sm = 4;   // ngp_field_set_option(0, n): 46.5 KB of shared memory per CTA -> at most 4 resident
+int g_fwd_ctas_per_sm = 5;   // ngp_field_set_option(0, n): 38.5 KB of shared memory per CTA -> at most 5 resident
 int g_fwd_carveout = -1;     // ngp_field_set_option(1, percent); -1 = driver default
 
 constexpr uint32_t kTile = 128;   // samples per CTA tile == threads per CTA == TMEM lanes
@@ -89,11 +89,12 @@ NGP_DEVINL uint32_t encode_level(const float (&x01)[3], const uint32_t* __restri
     return *reinterpret_cast<uint32_t*>(&acc);
 }
 
-// shared-memory carve-up of the forward kernel.  Two activation buffers used alternately: phase k of a tile writes
-// one while the bulk store + MMAs of phase k-1 may still be reading the other (see the hazard notes in the kernel).
+// shared-memory carve-up of the forward kernel: one tile for the encodings and ONE for the hidden activations - h2
+// overwrites h1 in place once the layer-2 MMAs have read it (see the hazard notes in the kernel).  38.5 KB instead of the
+// 46.5 KB of two alternating [128 x 64] buffers: a fifth CTA fits on the SM (the kernel is bound by gather latency).
 struct FwdSmem {
-    static constexpr uint32_t buf0 = 0;                     // [128 x 64] (or the [128 x 32] encodings in its first 8 KB)
-    static constexpr uint32_t buf1 = buf0 + kHidTileBytes;
+    static constexpr uint32_t buf0 = 0;                     // [128 x 32] encodings
+    static constexpr uint32_t buf1 = buf0 + kEncTileBytes;  // [128 x 64] h1, then h2
     static constexpr uint32_t w1 = buf1 + kHidTileBytes;    // [64 x 32]
     static constexpr uint32_t w2 = w1 + 4 * kCs64;          // [64 x 64]
     static constexpr uint32_t w3 = w2 + 8 * kCs64;          // [16 x 64] (rows 4.. zero)
@@ -134,12 +135,15 @@ NGP_DEVINL void hidden_epilogue(const uint32_t (&acc)[NCOLS], const float* bias,
 
 // Forward.  Per tile three phases, each: all threads write one operand tile -> fence + barrier -> thread 0 issues the
 // bulk (TMA) store of that tile to the save buffer and the layer's MMAs -> everyone waits for the MMAs on an mbarrier
-// and reads its accumulator row from TMEM.  Shared-memory hazards:
-//   * a tile buffer is rewritten two phases after it was last read (buffers alternate), and thread 0 waits for the
-//     READ side of its outstanding bulk stores right before every barrier - so the barrier that precedes a write to
-//     buffer X also publishes "the store that read X has finished reading";
-//   * MMAs that read a buffer were awaited by every thread (mbarrier) before the phase that wrote the other buffer.
-__global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a) {
+// and reads its accumulator row from TMEM.  Shared-memory hazards (E = encodings tile, Hd = hidden tile):
+//   * E is rewritten by the NEXT tile's encode: its readers - the layer-1 MMAs (awaited by every thread) and the bulk
+//     store of the encodings - are long done; thread 0 still waits for the store's READ side before the barrier that
+//     ends the tile, which orders it before any thread's next write;
+//   * Hd holds h1, then h2 in place: the layer-2 epilogue overwrites h1 only after every thread has seen the layer-2 MMAs
+//     complete AND thread 0 has waited for the READ side of the h1 bulk store and a block barrier has published that -
+//     the store was issued before the MMAs, so by then it has normally finished reading (no stall in practice);
+//     symmetrically the next tile's layer-1 epilogue overwrites h2 after the layer-3 MMAs and the h2 store have read it.
+__global__ void __launch_bounds__(kTile, 5) field_forward_kernel(const FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ grid::FastLevel<3> s_levels[kLevels];
     __shared__ uint64_t bar;
@@ -173,12 +177,12 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
     const bool save = a.enc != nullptr;
     const uint32_t* table_u32 = reinterpret_cast<const uint32_t*>(a.gd.table);
     const bool align = a.gd.align_corners != 0;
-    uint32_t phase = 0, par = 0;
+    uint32_t phase = 0;
+    uint8_t* bufA = smem + FwdSmem::buf0;  // encodings
+    uint8_t* bufB = smem + FwdSmem::buf1;  // h1, then h2
+    const uint32_t sA = tc::smem_u32(bufA), sB = tc::smem_u32(bufB);
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, par ^= 1) {
-        uint8_t* bufA = smem + (par ? FwdSmem::buf1 : FwdSmem::buf0);  // encodings, then h2
-        uint8_t* bufB = smem + (par ? FwdSmem::buf0 : FwdSmem::buf1);  // h1
-        const uint32_t sA = tc::smem_u32(bufA), sB = tc::smem_u32(bufB);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t m = tile * kTile + r;
         const bool active = m < M;
         float x[3] = {0.f, 0.f, 0.f};
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
         }
         tc::mbar_wait(&bar, phase); phase ^= 1;
         tc::tc_fence_after_sync();
+        // (Hd is free: the previous tile ended with "h2 store has read Hd" + a block barrier, see the end of the loop body)
 #pragma unroll
         for (uint32_t half = 0; half < 2; ++half) {
             uint32_t acc[32];
@@ -218,7 +223,6 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
             tc::tmem_ld_wait();
             hidden_epilogue<32>(acc, s_bias, half * 32, r, bufB);
         }
-        if (save && r == 0) tc::bulk_store_wait_read();
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
@@ -234,14 +238,16 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
         }
         tc::mbar_wait(&bar, phase); phase ^= 1;
         tc::tc_fence_after_sync();
-#pragma unroll
-        for (uint32_t half = 0; half < 2; ++half) {
-            uint32_t acc[32];
-            tc::tmem_ld_x32(tmem_row + half * 32, acc);
-            tc::tmem_ld_wait();
-            hidden_epilogue<32>(acc, s_bias + 64, half * 32, r, bufA);
+        uint32_t acc_lo[32], acc_hi[32];     // the whole accumulator row leaves TMEM before h1 is overwritten in place
+        tc::tmem_ld_x32(tmem_row, acc_lo);
+        tc::tmem_ld_x32(tmem_row + 32, acc_hi);
+        tc::tmem_ld_wait();
+        if (save) {                          // h1's bulk store must have finished READING Hd before anybody rewrites it
+            if (r == 0) tc::bulk_store_wait_read();
+            __syncthreads();
         }
-        if (save && r == 0) tc::bulk_store_wait_read();
+        hidden_epilogue<32>(acc_lo, s_bias + 64, 0, r, bufB);
+        hidden_epilogue<32>(acc_hi, s_bias + 64, 32, r, bufB);
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
@@ -249,10 +255,10 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
         // ---- layer 3: [128 x 64] x W3^T (4 outputs padded to 16) ----
         if (r == 0) {
             tc::tc_fence_after_sync();
-            if (save) tc::bulk_store(a.h2 + (size_t)tile * (kTile * kHid), bufA, kHidTileBytes);
+            if (save) tc::bulk_store(a.h2 + (size_t)tile * (kTile * kHid), bufB, kHidTileBytes);
 #pragma unroll
             for (uint32_t k = 0; k < kHid / 16; ++k)
-                tc::umma_f16(tmem, tc::desc_k_major(sA, kCs128, k), tc::desc_k_major(sw3, kCs16, k), idesc_o, k > 0);
+                tc::umma_f16(tmem, tc::desc_k_major(sB, kCs128, k), tc::desc_k_major(sw3, kCs16, k), idesc_o, k > 0);
             tc::umma_commit(&bar);
         }
         tc::mbar_wait(&bar, phase); phase ^= 1;
@@ -275,6 +281,10 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const FwdArgs a
             }
         }
         tc::tc_fence_before_sync();  // the next tile's first MMA overwrites these TMEM columns
+        if (save) {                  // the encodings / h2 stores have read E / Hd: both may be rewritten by the next tile
+            if (r == 0) tc::bulk_store_wait_read();
+            __syncthreads();
+        }
     }
     if (save && r == 0) tc::bulk_store_wait_all();
     __syncthreads();
