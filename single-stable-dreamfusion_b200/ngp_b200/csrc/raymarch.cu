@@ -62,6 +62,10 @@ NGP_DEVINL int level_from_dt(float dt, float H, float n_cascades) {
 struct MarchParams {
     const uint8_t* __restrict__ grid;
     float bound, dt_gamma, dt_min, dt_max, rH, H3, Hf, Cf, Hm1;
+    // one cascade (bound <= 1, the -O default): the level is 0 for every position and every step size, so the cascade
+    // selection (two frexpf, a scalbnf, a division) collapses to these two per-launch constants - same values, hoisted
+    bool single;
+    float mip_bound0, mip_rbound0;
 };
 
 NGP_DEVINL MarchParams make_params(const uint8_t* grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
@@ -77,6 +81,9 @@ NGP_DEVINL MarchParams make_params(const uint8_t* grid, float bound, float dt_ga
     p.Hf = (float)H;
     p.Cf = (float)C;
     p.Hm1 = (float)(H - 1);
+    p.single = (C == 1);
+    p.mip_bound0 = fminf(scalbnf(1.0f, 0), bound);
+    p.mip_rbound0 = 1 / p.mip_bound0;
     return p;
 }
 
@@ -104,9 +111,14 @@ NGP_DEVINL Cell classify(const MarchParams& p, const Ray& r, float t) {
     c.z = clampf(r.oz + t * r.dz, -p.bound, p.bound);
     c.dt = clampf(t * p.dt_gamma, p.dt_min, p.dt_max);
 
-    const int level = max(level_from_pos(c.x, c.y, c.z, p.Cf), level_from_dt(c.dt, p.Hf, p.Cf));
-    c.mip_bound = fminf(scalbnf(1.0f, level), p.bound);
-    const float mip_rbound = 1 / c.mip_bound;
+    int level = 0;
+    float mip_rbound = p.mip_rbound0;
+    c.mip_bound = p.mip_bound0;
+    if (!p.single) {   // (warp-uniform)
+        level = max(level_from_pos(c.x, c.y, c.z, p.Cf), level_from_dt(c.dt, p.Hf, p.Cf));
+        c.mip_bound = fminf(scalbnf(1.0f, level), p.bound);
+        mip_rbound = 1 / c.mip_bound;
+    }
 
     // `0.5 * (x*rb + 1) * H` is evaluated in double by the reference; both factors are exactly
     // representable so the float product below rounds to the same value (DESIGN.md "marcher").
