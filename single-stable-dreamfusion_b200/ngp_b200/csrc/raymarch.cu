@@ -66,6 +66,9 @@ struct MarchParams {
     // selection (two frexpf, a scalbnf, a division) collapses to these two per-launch constants - same values, hoisted
     bool single;
     float mip_bound0, mip_rbound0;
+    // optional shared-memory table spread3(i), i < H (the warp-per-ray marcher: its LSU is idle, its issue slots are not -
+    // three LDS replace 24 multiply / mask instructions of the bit interleave)
+    const uint32_t* lut;
 };
 
 NGP_DEVINL MarchParams make_params(const uint8_t* grid, float bound, float dt_gamma, uint32_t max_steps, uint32_t C,
@@ -81,6 +84,7 @@ NGP_DEVINL MarchParams make_params(const uint8_t* grid, float bound, float dt_ga
     p.Hf = (float)H;
     p.Cf = (float)C;
     p.Hm1 = (float)(H - 1);
+    p.lut = nullptr;
     p.single = (C == 1);
     p.mip_bound0 = fminf(scalbnf(1.0f, 0), bound);
     p.mip_rbound0 = 1 / p.mip_bound0;
@@ -126,7 +130,8 @@ NGP_DEVINL Cell classify(const MarchParams& p, const Ray& r, float t) {
     c.ny = (int)clampf(__fmul_rn(0.5f * (c.y * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
     c.nz = (int)clampf(__fmul_rn(0.5f * (c.z * mip_rbound + 1), p.Hf), 0.0f, p.Hm1);
 
-    const uint32_t index = level * p.H3 + morton_encode(c.nx, c.ny, c.nz);  // float arithmetic, as in :378
+    const uint32_t morton = p.lut ? (p.lut[c.nx] | (p.lut[c.ny] << 1) | (p.lut[c.nz] << 2)) : morton_encode(c.nx, c.ny, c.nz);
+    const uint32_t index = level * p.H3 + morton;  // float arithmetic, as in :378
     c.occ = p.grid[index / 8] & (1 << (index % 8));
     return c;
 }
@@ -535,10 +540,17 @@ __global__ void __launch_bounds__(128) march_slab_kernel(const float* __restrict
                                                          int* __restrict__ counter) {
     __shared__ int s_warp[32];
     __shared__ bool s_last;
+    __shared__ uint32_t s_lut[1024];
+    const bool use_lut = H <= 1024u;
+    if (use_lut) {
+        for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) s_lut[i] = spread3(i);
+        __syncthreads();
+    }
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (n < N) {
-        const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+        MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+        if (use_lut) p.lut = s_lut;
         const Ray r = load_ray(rays_o, rays_d, n);
         const float t0 = perturbed_start(p, nears[n], noises[n]);
         const uint32_t steps = walk_ray_warp<true>(p, r, t0, fars[n], max_steps, lane, slab_xyz + (size_t)n * max_steps * 3, nullptr,
