@@ -651,21 +651,28 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
             }
             valid = !out_of_unit_cube<D>(x);  // gridencoder.cu:253-258
         }
-        // half2 gradient rows are fetched four levels (one 16-byte load) at a time: a sample's [L*C] row is 2 sectors,
-        // and 16 separate 4-byte loads spread over the whole level loop kept missing L1
+        // half2 gradient rows: a sample's [L*C] row is 2 sectors; for the 16-level field all four 16-byte quarters are
+        // fetched up front (four loads in flight instead of one per level group).  Samples behind their ray's
+        // early-termination point carry an all-zero row; a warp whose 32 rows are all zero has nothing to add and
+        // skips the whole level loop (adding exact zeros is the identity, so the result is unchanged).
         uint32_t graw[4] = {0u, 0u, 0u, 0u};
-        for (uint32_t level0 = 0; level0 < L; level0 += 4) {
-            if constexpr (kPacked) {
-                if ((L % 4) == 0) {
-                    uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                    if (valid) q = __ldg(reinterpret_cast<const uint4*>(grad + ((size_t)b * L + level0) * C));
-                    graw[0] = q.x; graw[1] = q.y; graw[2] = q.z; graw[3] = q.w;
-                } else {
+        uint4 gq[4];
+        constexpr bool kRow16 = kPacked;
+        const bool row16 = kRow16 && L == 16;
+        if constexpr (kPacked) {
+            if (row16) {
+                uint32_t any = 0u;
 #pragma unroll
-                    for (uint32_t j = 0; j < 4; ++j)
-                        graw[j] = (valid && level0 + j < L) ? __ldg(reinterpret_cast<const uint32_t*>(grad + ((size_t)b * L + level0 + j) * C)) : 0u;
+                for (uint32_t q = 0; q < 4; ++q) {
+                    gq[q] = make_uint4(0u, 0u, 0u, 0u);
+                    if (valid) gq[q] = __ldg(reinterpret_cast<const uint4*>(grad + (size_t)b * 32) + q);
+                    any |= (gq[q].x | gq[q].y | gq[q].z | gq[q].w) & 0x7fff7fffu;     // (-0 is zero too)
                 }
+                if (!__any_sync(0xffffffffu, any != 0u)) continue;
             }
+        }
+        // one group of (up to) four levels, gradients in graw[0..3]
+        auto process_group = [&](uint32_t level0, const uint32_t (&gr)[4]) {
 #pragma unroll
             for (uint32_t lj = 0; lj < 4; ++lj) {
                 const uint32_t level = level0 + lj;
@@ -675,7 +682,7 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
 #pragma unroll
                 for (uint32_t c = 0; c < C; ++c) g[c] = 0.f;
                 if constexpr (kPacked) {
-                    const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&graw[lj]));
+                    const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&gr[lj]));
                     g[0] = gf.x; g[1] = gf.y;
                 } else {
                     if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
@@ -685,6 +692,28 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
                 else if (lp.used == 3)  warpagg_level<3, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
                 else if (lp.used == 2)  warpagg_level<2, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
                 else                    warpagg_level<1, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
+            }
+        };
+        if (row16) {
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+                const uint32_t gr[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
+                process_group(q * 4, gr);
+            }
+        } else {
+            for (uint32_t level0 = 0; level0 < L; level0 += 4) {
+                if constexpr (kPacked) {
+                    if ((L % 4) == 0) {
+                        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                        if (valid) q = __ldg(reinterpret_cast<const uint4*>(grad + ((size_t)b * L + level0) * C));
+                        graw[0] = q.x; graw[1] = q.y; graw[2] = q.z; graw[3] = q.w;
+                    } else {
+#pragma unroll
+                        for (uint32_t j = 0; j < 4; ++j)
+                            graw[j] = (valid && level0 + j < L) ? __ldg(reinterpret_cast<const uint32_t*>(grad + ((size_t)b * L + level0 + j) * C)) : 0u;
+                    }
+                }
+                process_group(level0, graw);
             }
         }
     }
