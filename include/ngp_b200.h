@@ -218,6 +218,19 @@ int ngp_grid_scatter_samples(const void* d_enc, const float* xyzs, float bound, 
                              const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
                              int align_corners, float* grad_table, void* stream);
 
+/* The same scatter with the table gradient split over two fp32 buffers (no reference counterpart; it replaces the
+ * per-corner atomicAdd of gridencoder.cu:298-310 like the call above).  The SM issues vector reds at a fixed rate per
+ * lane whatever their width, so the two x-neighbours of a corner pair go out as ONE 16-byte red - which needs the pair
+ * 16-byte aligned.  Pairs starting on an even table row are aligned in grad_table; pairs starting on an odd row are
+ * aligned in grad_table_odd, a buffer indexed exactly like grad_table whose address is 8 bytes off a 16-byte boundary.
+ * gradient = grad_table + grad_table_odd: fold with ngp_grid_fold_odd before anything reads it. */
+int ngp_grid_scatter_samples_split(const void* d_enc, const float* xyzs, float bound, const int* count_ptr, uint32_t M_cap,
+                                   const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
+                                   int align_corners, float* grad_table, float* grad_table_odd, void* stream);
+
+/* grad_table[i] += grad_table_odd[i]; grad_table_odd[i] = 0 for i < n (n even; both buffers 8-byte aligned). */
+int ngp_grid_fold_odd(float* grad_table, float* grad_table_odd, uint64_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * The steps either side of the render inside one train step.  The reference runs these as
  * chains of eager PyTorch kernels; each entry point below is one launch.

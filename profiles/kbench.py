@@ -57,6 +57,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     p = _cabi.ptr
     grad_table = torch.zeros_like(enc.embeddings)
+    grad_odd = torch.zeros(grad_table.numel() + 4, device=dev)[2:2 + grad_table.numel()]
     gflat = torch.zeros(64 * 32 + 64 + 64 * 64 + 64 + 256 + 4, device=dev)
     sizes = [64 * 32, 64, 64 * 64, 64, 4 * 64, 4]
     gw = torch.split(gflat, sizes)
@@ -82,6 +83,14 @@ def main():
             "ngp_grid_scatter_samples", dev, p(ws.d_enc), p(ws.xyzs), float(model.bound), p(ws.counter), ws.cap,
             p(enc.offsets), L, 2, S, int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)),
             p(grad_table)),
+        "ngp_grid_scatter_samples_split": lambda: _cabi.call(
+            "ngp_grid_scatter_samples_split", dev, p(ws.d_enc), p(ws.xyzs), float(model.bound), p(ws.counter), ws.cap,
+            p(enc.offsets), L, 2, S, int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)),
+            p(grad_table), p(grad_odd)),
+        "ngp_grid_fold_odd": lambda: _cabi.call("ngp_grid_fold_odd", dev, p(grad_table), p(grad_odd), grad_table.numel()),
+        "ngp_train_ray_loss": lambda: _cabi.call(
+            "ngp_train_ray_loss", dev, p(ws.sigma), p(ws.rgb), p(ws.deltas), p(ws.rays), ws.cap, N, 1e-4, None, 1.0, p(g_img), 0,
+            0, N, 1e-4, None, p(wsum), p(depth), p(image), None, p(ws.d_sigma), p(ws.d_rgb), None, None, None, None, None),
         "ngp_composite_rays_train_forward": lambda: _cabi.call(
             "ngp_composite_rays_train_forward", dev, p(ws.sigma), p(ws.rgb), p(ws.deltas), p(ws.rays), ws.cap, N, 1e-4,
             p(wsum), p(depth), p(image)),
@@ -142,10 +151,12 @@ def main():
                 print(json.dumps({"microbench": "red", "floats_per_op": width, "active_lanes": 32 // lane_stride,
                                   "Gops_per_s": round(ops / best / 1e6, 1), "GB_per_s": round(ops * width * 4 / best / 1e6, 1)}), flush=True)
     if args.sweep:
-        for ctas in (2, 3, 4):
+        for groups, ctas in ((1, 7), (1, 5), (2, 4), (2, 3), (4, 2)):
             for carve in (-1, 100):
-                assert lib.ngp_field_set_option(0, ctas) == 0 and lib.ngp_field_set_option(1, carve) == 0
-                report("ngp_field_forward", {"ctas_per_sm": ctas, "carveout": carve})
+                assert lib.ngp_field_set_option(2, groups) == 0 and lib.ngp_field_set_option(0, ctas) == 0
+                assert lib.ngp_field_set_option(1, carve) == 0
+                report("ngp_field_forward", {"groups": groups, "ctas_per_sm": ctas, "carveout": carve})
+        assert lib.ngp_field_set_option(2, 2) == 0 and lib.ngp_field_set_option(0, 0) == 0 and lib.ngp_field_set_option(1, -1) == 0
 
 
 if __name__ == "__main__":

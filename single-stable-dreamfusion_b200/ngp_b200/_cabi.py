@@ -53,6 +53,8 @@ SIGNATURES = {
     "ngp_field_backward": (_i32, [_u32, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp]),
     "ngp_grid_scatter_samples": (_i32, [_vp, _vp, _f32, _vp, _u32, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _vp, _vp]),
+    "ngp_grid_scatter_samples_split": (_i32, [_vp, _vp, _f32, _vp, _u32, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _vp, _vp, _vp]),
+    "ngp_grid_fold_odd": (_i32, [_vp, _vp, _u64, _vp]),
     "ngp_tc_selftest": (_i32, [_i32, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
     "ngp_field_set_option": (_i32, [_i32, _i32]),
     "ngp_bg_forward": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),

@@ -18,8 +18,9 @@
 namespace ngp {
 namespace field {
 
-int g_fwd_ctas_per_sm = 5;   // ngp_field_set_option(0, n): 38.5 KB of shared memory per CTA -> at most 5 resident
+int g_fwd_ctas_per_sm = 0;   // ngp_field_set_option(0, n): resident CTAs per SM the grid is sized for (0 = 8 / groups)
 int g_fwd_carveout = -1;     // ngp_field_set_option(1, percent); -1 = driver default
+int g_fwd_groups = 2;        // ngp_field_set_option(2, g): 128-thread groups per CTA (1, 2 or 4)
 
 constexpr uint32_t kTile = 128;   // samples per CTA tile == threads per CTA == TMEM lanes
 constexpr uint32_t kLevels = 16;  // grid levels (x 2 features = 32 MLP inputs)
@@ -89,17 +90,18 @@ NGP_DEVINL uint32_t encode_level(const float (&x01)[3], const uint32_t* __restri
     return *reinterpret_cast<uint32_t*>(&acc);
 }
 
-// shared-memory carve-up of the forward kernel: one tile for the encodings and ONE for the hidden activations - h2
-// overwrites h1 in place once the layer-2 MMAs have read it (see the hazard notes in the kernel).  38.5 KB instead of the
-// 46.5 KB of two alternating [128 x 64] buffers: a fifth CTA fits on the SM (the kernel is bound by gather latency).
+// shared-memory carve-up of the forward kernel.  A CTA holds G independent GROUPS of 128 threads; the weights, biases and
+// level descriptors are shared by the groups (they were 14.5 of the 38.5 KB of the one-group CTA, replicated five times per
+// SM), and each group owns ONE [128 x 64] operand tile: the encodings occupy its first four chunks, h1 overwrites them once
+// the layer-1 MMAs have read them, h2 overwrites h1 once the layer-2 MMAs have.  G = 2: 46.5 KB per 8 warps -> 4 CTAs = 32
+// warps per SM (the register file's limit at 64 registers per thread) instead of 20.
 struct FwdSmem {
-    static constexpr uint32_t buf0 = 0;                     // [128 x 32] encodings
-    static constexpr uint32_t buf1 = buf0 + kEncTileBytes;  // [128 x 64] h1, then h2
-    static constexpr uint32_t w1 = buf1 + kHidTileBytes;    // [64 x 32]
+    static constexpr uint32_t w1 = 0;                       // [64 x 32]
     static constexpr uint32_t w2 = w1 + 4 * kCs64;          // [64 x 64]
     static constexpr uint32_t w3 = w2 + 8 * kCs64;          // [16 x 64] (rows 4.. zero)
     static constexpr uint32_t bias = w3 + 8 * kCs16;        // b1[64] b2[64] b3[4] as float
-    static constexpr uint32_t total = bias + (64 + 64 + 4) * 4;
+    static constexpr uint32_t tiles = (bias + (64 + 64 + 4) * 4 + 127) / 128 * 128;   // G x [128 x 64]
+    static constexpr uint32_t total(uint32_t G) { return tiles + G * kHidTileBytes; }
 };
 
 struct FwdArgs {
@@ -115,12 +117,18 @@ struct FwdArgs {
     __half* h2;
 };
 
-// bias + fp16 rounding + ReLU of one accumulator row segment, written as 16-byte chunks of the next operand tile.
+// barrier among the 128 threads of one group (ids 1.. : 0 is __syncthreads)
+NGP_DEVINL void group_sync(uint32_t grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+// bias + fp16 rounding + ReLU of one accumulator row segment, written as 16-byte chunks of the next operand tile and - for
+// the backward - to the same offsets of the tile's image in global memory (a warp's 32 rows of one chunk are 512
+// contiguous bytes either way).
 // The reference's Linear under autocast returns half(acc + bias) and applies ReLU to the half value: two fp32 adds, ONE
 // packed conversion (cvt.rn.f16x2.f32) and one packed max per column pair - same bits as converting, widening, comparing
 // and re-packing each value (the earlier form, ~2x the instructions of this epilogue).
 template <uint32_t NCOLS>
-NGP_DEVINL void hidden_epilogue(const uint32_t (&acc)[NCOLS], const float* bias, uint32_t col0, uint32_t r, uint8_t* tile) {
+NGP_DEVINL void hidden_epilogue(const uint32_t (&acc)[NCOLS], const float* bias, uint32_t col0, uint32_t r, uint8_t* tile,
+                                uint8_t* gsave) {
     const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
     for (uint32_t q = 0; q < NCOLS / 8; ++q) {
@@ -135,41 +143,44 @@ NGP_DEVINL void hidden_epilogue(const uint32_t (&acc)[NCOLS], const float* bias,
             h = __hmax2(h, zero);
             w[j] = *reinterpret_cast<uint32_t*>(&h);
         }
-        *reinterpret_cast<uint4*>(tile + tc::tile_chunk_off(r, col0 / 8 + q, kCs128)) = make_uint4(w[0], w[1], w[2], w[3]);
+        const uint32_t off = tc::tile_chunk_off(r, col0 / 8 + q, kCs128);
+        const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(tile + off) = v;
+        if (gsave) __stcs(reinterpret_cast<uint4*>(gsave + off), v);
     }
 }
 
-// Forward.  Per tile three phases, each: all threads write one operand tile -> fence + barrier -> thread 0 issues the
-// bulk (TMA) store of that tile to the save buffer and the layer's MMAs -> everyone waits for the MMAs on an mbarrier
-// and reads its accumulator row from TMEM.  Shared-memory hazards (E = encodings tile, Hd = hidden tile):
-//   * E is rewritten by the NEXT tile's encode: its readers - the layer-1 MMAs (awaited by every thread) and the bulk
-//     store of the encodings - are long done; thread 0 still waits for the store's READ side before the barrier that
-//     ends the tile, which orders it before any thread's next write;
-//   * Hd holds h1, then h2 in place: the layer-2 epilogue overwrites h1 only after every thread has seen the layer-2 MMAs
-//     complete AND thread 0 has waited for the READ side of the h1 bulk store and a block barrier has published that -
-//     the store was issued before the MMAs, so by then it has normally finished reading (no stall in practice);
-//     symmetrically the next tile's layer-1 epilogue overwrites h2 after the layer-3 MMAs and the h2 store have read it.
-__global__ void __launch_bounds__(kTile, 5) field_forward_kernel(const FwdArgs a) {
+// Forward.  Per tile and group three phases, each: the group's threads write the operand tile -> fence + group barrier ->
+// the group's thread 0 issues the layer's MMAs -> everyone waits for them on the group's mbarrier and reads its accumulator
+// row from TMEM (the group's 64 columns).  Hazards on the one operand tile: every overwrite (h1 over the encodings, h2 over
+// h1, the next tile's encodings over h2) happens after ALL threads of the group have observed the completion of the MMAs
+// that read the old contents; the saves for the backward go from registers straight to global memory, so nothing else
+// ever reads the tile.  TMEM: the next tile's first MMA is issued behind a group barrier that every thread reaches after
+// its last tcgen05.ld has completed.
+template <uint32_t G>
+__global__ void __launch_bounds__(kTile * G, 8 / G) field_forward_kernel(const FwdArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ grid::FastLevel<3> s_levels[kLevels];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[G];
     __shared__ uint32_t tmem_base_s;
-    const uint32_t r = threadIdx.x, warp = r >> 5;
+    const uint32_t grp = threadIdx.x >> 7, r = threadIdx.x & 127u, warp = r >> 5;
 
-    if (r < kLevels) s_levels[r] = grid::make_fast_level<3>(a.gd.offsets, r, a.gd.S, a.gd.H, a.gd.gridtype, a.gd.align_corners != 0);
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
-    if (r == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+    if (threadIdx.x < kLevels)
+        s_levels[threadIdx.x] = grid::make_fast_level<3>(a.gd.offsets, threadIdx.x, a.gd.S, a.gd.H, a.gd.gridtype, a.gd.align_corners != 0);
+    if (threadIdx.x < 32) tc::tmem_alloc(&tmem_base_s, 64 * G);
+    if (r == 0) { tc::mbar_init(&bars[grp], 1); tc::fence_mbar_init(); }
     load_weight_tile(a.w.w1, kHid, kHid, kIn, smem + FwdSmem::w1);
     load_weight_tile(a.w.w2, kHid, kHid, kHid, smem + FwdSmem::w2);
     load_weight_tile(a.w.w3, kOut, kOutPad, kHid, smem + FwdSmem::w3);
     float* s_bias = reinterpret_cast<float*>(smem + FwdSmem::bias);
-    if (r < 64) { s_bias[r] = __half2float(a.w.b1[r]); s_bias[64 + r] = __half2float(a.w.b2[r]); }
-    if (r < 4) s_bias[128 + r] = __half2float(a.w.b3[r]);
+    if (threadIdx.x < 64) { s_bias[threadIdx.x] = __half2float(a.w.b1[threadIdx.x]); s_bias[64 + threadIdx.x] = __half2float(a.w.b2[threadIdx.x]); }
+    if (threadIdx.x < 4) s_bias[128 + threadIdx.x] = __half2float(a.w.b3[threadIdx.x]);
     tc::fence_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
-    const uint32_t tmem = tmem_base_s;
+    uint64_t* bar = &bars[grp];
+    const uint32_t tmem = tmem_base_s + grp * 64;                      // this group's accumulator columns
     const uint32_t tmem_row = tc::tmem_addr(tmem, warp * 32, 0);
 
     const uint32_t sw1 = tc::smem_u32(smem + FwdSmem::w1), sw2 = tc::smem_u32(smem + FwdSmem::w2);
@@ -184,11 +195,10 @@ __global__ void __launch_bounds__(kTile, 5) field_forward_kernel(const FwdArgs a
     const uint32_t* table_u32 = reinterpret_cast<const uint32_t*>(a.gd.table);
     const bool align = a.gd.align_corners != 0;
     uint32_t phase = 0;
-    uint8_t* bufA = smem + FwdSmem::buf0;  // encodings
-    uint8_t* bufB = smem + FwdSmem::buf1;  // h1, then h2
-    const uint32_t sA = tc::smem_u32(bufA), sB = tc::smem_u32(bufB);
+    uint8_t* buf = smem + FwdSmem::tiles + grp * kHidTileBytes;   // encodings (chunks 0..3), then h1, then h2
+    const uint32_t sT = tc::smem_u32(buf);
 
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (uint32_t tile = blockIdx.x * G + grp; tile < n_tiles; tile += gridDim.x * G) {
         const uint32_t m = tile * kTile + r;
         const bool active = m < M;
         float x[3] = {0.f, 0.f, 0.f};
@@ -197,77 +207,79 @@ __global__ void __launch_bounds__(kTile, 5) field_forward_kernel(const FwdArgs a
         const float x01[3] = {__fmul_rn(__fadd_rn(x[0], a.gd.bound), inv_2b), __fmul_rn(__fadd_rn(x[1], a.gd.bound), inv_2b),
                               __fmul_rn(__fadd_rn(x[2], a.gd.bound), inv_2b)};
         const bool oob = grid::out_of_unit_cube<3>(x01);
+        uint8_t* g_enc = save ? reinterpret_cast<uint8_t*>(a.enc) + (size_t)tile * kEncTileBytes : nullptr;
         for (uint32_t cc = 0; cc < 4; ++cc) {  // 4 levels = one 16-byte chunk of the operand row
             uint32_t e[4] = {0u, 0u, 0u, 0u};  // out-of-cube samples encode to zeros (gridencoder.cu:106-122)
             if (!oob) {
 #pragma unroll
                 for (uint32_t j = 0; j < 4; ++j) e[j] = encode_level(x01, table_u32, align, s_levels[cc * 4 + j]);
             }
-            *reinterpret_cast<uint4*>(bufA + tc::tile_chunk_off(r, cc, kCs128)) = make_uint4(e[0], e[1], e[2], e[3]);
+            const uint32_t off = tc::tile_chunk_off(r, cc, kCs128);
+            const uint4 v = make_uint4(e[0], e[1], e[2], e[3]);
+            *reinterpret_cast<uint4*>(buf + off) = v;
+            if (save) __stcs(reinterpret_cast<uint4*>(g_enc + off), v);
         }
-        if (save && r == 0) tc::bulk_store_wait_read();
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
-        __syncthreads();
+        group_sync(grp);
 
         // ---- layer 1: [128 x 32] x W1^T -> TMEM [128 x 64] ----
         if (r == 0) {
             tc::tc_fence_after_sync();
-            if (save) tc::bulk_store(a.enc + (size_t)tile * (kTile * kIn), bufA, kEncTileBytes);
 #pragma unroll
             for (uint32_t k = 0; k < kIn / 16; ++k)
-                tc::umma_f16(tmem, tc::desc_k_major(sA, kCs128, k), tc::desc_k_major(sw1, kCs64, k), idesc_h, k > 0);
-            tc::umma_commit(&bar);
+                tc::umma_f16(tmem, tc::desc_k_major(sT, kCs128, k), tc::desc_k_major(sw1, kCs64, k), idesc_h, k > 0);
+            tc::umma_commit(bar);
         }
-        tc::mbar_wait(&bar, phase); phase ^= 1;
+        tc::mbar_wait(bar, phase); phase ^= 1;
         tc::tc_fence_after_sync();
-        // (Hd is free: the previous tile ended with "h2 store has read Hd" + a block barrier, see the end of the loop body)
+        {
+            uint8_t* g_h1 = save ? reinterpret_cast<uint8_t*>(a.h1) + (size_t)tile * kHidTileBytes : nullptr;
 #pragma unroll
-        for (uint32_t half = 0; half < 2; ++half) {
-            uint32_t acc[32];
-            tc::tmem_ld_x32(tmem_row + half * 32, acc);
-            tc::tmem_ld_wait();
-            hidden_epilogue<32>(acc, s_bias, half * 32, r, bufB);
+            for (uint32_t half = 0; half < 2; ++half) {
+                uint32_t acc[32];
+                tc::tmem_ld_x32(tmem_row + half * 32, acc);
+                tc::tmem_ld_wait();
+                hidden_epilogue<32>(acc, s_bias, half * 32, r, buf, g_h1);
+            }
         }
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
-        __syncthreads();
+        group_sync(grp);
 
         // ---- layer 2: [128 x 64] x W2^T ----
         if (r == 0) {
             tc::tc_fence_after_sync();
-            if (save) tc::bulk_store(a.h1 + (size_t)tile * (kTile * kHid), bufB, kHidTileBytes);
 #pragma unroll
             for (uint32_t k = 0; k < kHid / 16; ++k)
-                tc::umma_f16(tmem, tc::desc_k_major(sB, kCs128, k), tc::desc_k_major(sw2, kCs64, k), idesc_h, k > 0);
-            tc::umma_commit(&bar);
+                tc::umma_f16(tmem, tc::desc_k_major(sT, kCs128, k), tc::desc_k_major(sw2, kCs64, k), idesc_h, k > 0);
+            tc::umma_commit(bar);
         }
-        tc::mbar_wait(&bar, phase); phase ^= 1;
+        tc::mbar_wait(bar, phase); phase ^= 1;
         tc::tc_fence_after_sync();
-        uint32_t acc_lo[32], acc_hi[32];     // the whole accumulator row leaves TMEM before h1 is overwritten in place
-        tc::tmem_ld_x32(tmem_row, acc_lo);
-        tc::tmem_ld_x32(tmem_row + 32, acc_hi);
-        tc::tmem_ld_wait();
-        if (save) {                          // h1's bulk store must have finished READING Hd before anybody rewrites it
-            if (r == 0) tc::bulk_store_wait_read();
-            __syncthreads();
+        {
+            uint8_t* g_h2 = save ? reinterpret_cast<uint8_t*>(a.h2) + (size_t)tile * kHidTileBytes : nullptr;
+#pragma unroll
+            for (uint32_t half = 0; half < 2; ++half) {
+                uint32_t acc[32];
+                tc::tmem_ld_x32(tmem_row + half * 32, acc);
+                tc::tmem_ld_wait();
+                hidden_epilogue<32>(acc, s_bias + 64, half * 32, r, buf, g_h2);
+            }
         }
-        hidden_epilogue<32>(acc_lo, s_bias + 64, 0, r, bufB);
-        hidden_epilogue<32>(acc_hi, s_bias + 64, 32, r, bufB);
         tc::fence_async_smem();
         tc::tc_fence_before_sync();
-        __syncthreads();
+        group_sync(grp);
 
         // ---- layer 3: [128 x 64] x W3^T (4 outputs padded to 16) ----
         if (r == 0) {
             tc::tc_fence_after_sync();
-            if (save) tc::bulk_store(a.h2 + (size_t)tile * (kTile * kHid), bufB, kHidTileBytes);
 #pragma unroll
             for (uint32_t k = 0; k < kHid / 16; ++k)
-                tc::umma_f16(tmem, tc::desc_k_major(sB, kCs128, k), tc::desc_k_major(sw3, kCs16, k), idesc_o, k > 0);
-            tc::umma_commit(&bar);
+                tc::umma_f16(tmem, tc::desc_k_major(sT, kCs128, k), tc::desc_k_major(sw3, kCs16, k), idesc_o, k > 0);
+            tc::umma_commit(bar);
         }
-        tc::mbar_wait(&bar, phase); phase ^= 1;
+        tc::mbar_wait(bar, phase); phase ^= 1;
         tc::tc_fence_after_sync();
         {
             uint32_t acc[16];
@@ -286,15 +298,10 @@ __global__ void __launch_bounds__(kTile, 5) field_forward_kernel(const FwdArgs a
                 for (int j = 0; j < 3; ++j) a.rgb[(size_t)m * 3 + j] = __half2float(__float2half_rn(1.0f / (1.0f + expf(-h[j + 1]))));
             }
         }
-        tc::tc_fence_before_sync();  // the next tile's first MMA overwrites these TMEM columns
-        if (save) {                  // the encodings / h2 stores have read E / Hd: both may be rewritten by the next tile
-            if (r == 0) tc::bulk_store_wait_read();
-            __syncthreads();
-        }
+        tc::tc_fence_before_sync();  // the next tile's first MMA (behind the next group barrier) overwrites these TMEM columns
     }
-    if (save && r == 0) tc::bulk_store_wait_all();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 64);
+    if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 64 * G);
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -621,20 +628,28 @@ extern "C" int ngp_field_forward(const float* xyzs, uint32_t M, const int* count
            static_cast<const __half*>(b2), static_cast<const __half*>(w3), static_cast<const __half*>(b3)};
     a.sigma = sigma; a.rgb = rgb;
     a.enc = static_cast<__half*>(enc_save); a.h1 = static_cast<__half*>(h1_save); a.h2 = static_cast<__half*>(h2_save);
-    static PerDeviceAttr attr;
-    rc = set_kernel_smem(&attr, reinterpret_cast<const void*>(field::field_forward_kernel), (int)field::FwdSmem::total,
-                         field::g_fwd_carveout);
+    static PerDeviceAttr attr[3];
+    const int G = field::g_fwd_groups, slot = G == 1 ? 0 : (G == 2 ? 1 : 2);
+    const void* fn = G == 1 ? reinterpret_cast<const void*>(field::field_forward_kernel<1>)
+                   : G == 2 ? reinterpret_cast<const void*>(field::field_forward_kernel<2>)
+                            : reinterpret_cast<const void*>(field::field_forward_kernel<4>);
+    const int smem = (int)field::FwdSmem::total(G);
+    rc = set_kernel_smem(&attr[slot], fn, smem, field::g_fwd_carveout);
     if (rc != NGP_OK) return rc;
     const int tiles = cdiv(M, field::kTile);
-    const int grid = min(tiles, num_sms() * field::g_fwd_ctas_per_sm);
-    field::field_forward_kernel<<<grid, field::kTile, field::FwdSmem::total, as_stream(stream)>>>(a);
+    const int per_sm = field::g_fwd_ctas_per_sm > 0 ? field::g_fwd_ctas_per_sm : (G == 1 ? 7 : 8 / G);
+    const int grid = min(cdiv(tiles, G), num_sms() * per_sm);
+    if (G == 1) field::field_forward_kernel<1><<<grid, field::kTile, smem, as_stream(stream)>>>(a);
+    else if (G == 2) field::field_forward_kernel<2><<<grid, field::kTile * 2, smem, as_stream(stream)>>>(a);
+    else field::field_forward_kernel<4><<<grid, field::kTile * 4, smem, as_stream(stream)>>>(a);
     return launch_status();
 }
 
-// tuning switches (profiles/kbench.py): 0 = forward CTAs per SM (grid size), 1 = forward smem carveout percent
-// (-1 = driver default).  More resident CTAs mean more gathers in flight but a smaller L1 for the table.
+// tuning switches (profiles/kbench.py): 0 = forward CTAs per SM (grid size; 0 = as many as fit), 1 = forward smem carveout
+// percent (-1 = driver default), 2 = 128-thread groups per forward CTA (1, 2, 4).  More resident CTAs mean more gathers in flight but a smaller L1 for the table.
 extern "C" int ngp_field_set_option(int option, int value) {
-    if (option == 0 && value >= 1 && value <= 4) { field::g_fwd_ctas_per_sm = value; return NGP_OK; }
+    if (option == 0 && value >= 0 && value <= 8) { field::g_fwd_ctas_per_sm = value; return NGP_OK; }
+    if (option == 2 && (value == 1 || value == 2 || value == 4)) { field::g_fwd_groups = value; return NGP_OK; }
     if (option == 1 && value >= -1 && value <= 100) { field::g_fwd_carveout = value; return NGP_OK; }
     return NGP_ERR_BAD_ARG;
 }

@@ -82,11 +82,15 @@ extern "C" int ngp_grid_level_params(uint32_t L, float S, uint32_t H, float* sca
 }
 
 // Sync-free training path: scatter the MLP's encoding gradients of the first *count_ptr samples.
-extern "C" int ngp_grid_scatter_samples(const void* d_enc, const float* xyzs, float bound, const int* count_ptr, uint32_t M_cap,
-                                        const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
-                                        int align_corners, float* grad_table, void* stream) {
+// grad_table_odd (optional): the odd-frame twin of the gradient table (see warpagg_level) - an fp32 buffer indexed like
+// grad_table whose ADDRESS is 8 bytes off a 16-byte boundary; the table gradient is then grad_table + grad_table_odd.
+static int scatter_samples(const void* d_enc, const float* xyzs, float bound, const int* count_ptr, uint32_t M_cap,
+                           const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                           float* grad_table, float* grad_table_odd, void* stream) {
     if (!d_enc || !xyzs || !offsets || !grad_table) return NGP_ERR_BAD_ARG;
     if (L == 0 || L > grid::kMaxLevels || gridtype > 1 || C != 2) return NGP_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(grad_table) & 15) != 0) return NGP_ERR_BAD_ARG;
+    if (grad_table_odd && (reinterpret_cast<uintptr_t>(grad_table_odd) & 15) != 8) return NGP_ERR_BAD_ARG;
     if (M_cap == 0) return NGP_OK;
     const int blocks = min(cdiv(M_cap, 256), num_sms() * 16);
     if (grid::g_count_reds) {   // measurement only (bench.py's roofline pass): same kernel, plus one counter per lane
@@ -94,10 +98,54 @@ extern "C" int ngp_grid_scatter_samples(const void* d_enc, const float* xyzs, fl
         if (cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), grid::g_red_lane_ops) != cudaSuccess) return launch_status();
         grid::encode_backward_warpagg_kernel<__half, 2, true><<<blocks, 256, 0, as_stream(stream)>>>(
             static_cast<const __half*>(d_enc), xyzs, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners != 0, count_ptr,
-            bound, ctr);
+            bound, ctr, grad_table_odd);
         return launch_status();
     }
     grid::encode_backward_warpagg_kernel<__half, 2><<<blocks, 256, 0, as_stream(stream)>>>(
-        static_cast<const __half*>(d_enc), xyzs, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners != 0, count_ptr, bound);
+        static_cast<const __half*>(d_enc), xyzs, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners != 0, count_ptr, bound,
+        nullptr, grad_table_odd);
+    return launch_status();
+}
+
+extern "C" int ngp_grid_scatter_samples(const void* d_enc, const float* xyzs, float bound, const int* count_ptr, uint32_t M_cap,
+                                        const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
+                                        int align_corners, float* grad_table, void* stream) {
+    return scatter_samples(d_enc, xyzs, bound, count_ptr, M_cap, offsets, L, C, S, H, gridtype, align_corners, grad_table, nullptr,
+                           stream);
+}
+
+extern "C" int ngp_grid_scatter_samples_split(const void* d_enc, const float* xyzs, float bound, const int* count_ptr,
+                                              uint32_t M_cap, const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H,
+                                              uint32_t gridtype, int align_corners, float* grad_table, float* grad_table_odd,
+                                              void* stream) {
+    if (!grad_table_odd) return NGP_ERR_BAD_ARG;
+    return scatter_samples(d_enc, xyzs, bound, count_ptr, M_cap, offsets, L, C, S, H, gridtype, align_corners, grad_table,
+                           grad_table_odd, stream);
+}
+
+namespace ngp { namespace grid {
+// grad_table += grad_table_odd; grad_table_odd = 0   (n floats, n even; float2 granularity: the twin is 8-byte aligned)
+__global__ void __launch_bounds__(256) fold_odd_kernel(float2* __restrict__ dst, float2* __restrict__ odd, uint64_t n2) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float2 o = odd[i];
+        if (o.x != 0.f || o.y != 0.f) {
+            float2 d = dst[i];
+            d.x += o.x; d.y += o.y;
+            dst[i] = d;
+            odd[i] = make_float2(0.f, 0.f);
+        }
+    }
+}
+} }
+
+extern "C" int ngp_grid_fold_odd(float* grad_table, float* grad_table_odd, uint64_t n, void* stream) {
+    if (!grad_table || !grad_table_odd || (n & 1)) return NGP_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(grad_table) & 7) != 0 || (reinterpret_cast<uintptr_t>(grad_table_odd) & 7) != 0) return NGP_ERR_BAD_ARG;
+    if (n == 0) return NGP_OK;
+    const uint64_t n2 = n / 2;
+    const uint64_t want = (n2 + 255) / 256, most = (uint64_t)num_sms() * 8;
+    const int blocks = (int)(want < most ? want : most);
+    grid::fold_odd_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(grad_table),
+                                                               reinterpret_cast<float2*>(grad_table_odd), n2);
     return launch_status();
 }

@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
 // post-aggregation atomic lane-ops that bench.py's roofline divides by the measured red issue ceiling.
 template <uint32_t USED, bool HASHED, uint32_t C, bool COUNT = false>
 NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool align_corners, bool valid, const float (&g)[C],
-                              uint32_t lane, float* __restrict__ grad_table, uint32_t* reds = nullptr) {
+                              uint32_t lane, float* __restrict__ grad_table, float* __restrict__ grad_odd, uint32_t* reds = nullptr) {
     constexpr uint32_t NC = 1u << USED;  // distinct rows per cell
     float frac[USED];
     uint32_t base[USED];
@@ -592,13 +592,18 @@ NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool 
     if constexpr (C == 2 && !HASHED && USED >= 1) {
         // The SM issues reds at a fixed rate per LANE-op whatever their width (profiles/: ~217 G ops/s for 4-, 8- and
         // 16-byte reds alike), so the two x-neighbours of a corner pair - adjacent rows of a linear level - go out
-        // as ONE 16-byte red whenever the pair is 16-byte aligned.
+        // as ONE 16-byte red whenever the pair is 16-byte aligned.  Pairs that start on an odd row are not - unless the
+        // caller supplies the ODD-FRAME TWIN of the table (`grad_odd`: same indexing, but the buffer starts 8 bytes off a
+        // 16-byte boundary, so exactly the odd-row pairs are aligned there).  The sum of the two buffers is the gradient
+        // (ngp_grid_fold_odd, or the optimizer's finite-check pass); every pair then costs one lane-op instead of 1.5.
+        float* tbl_odd = grad_odd ? grad_odd + (size_t)lp.offset * C : nullptr;
 #pragma unroll
         for (uint32_t corner = 0; corner < NC; corner += 2) {
             const uint32_t lo = rows[corner], hi = rows[corner + 1];
             float* dst = tbl + (size_t)lo * 2;
-            if (hi == lo + 1 && (((lp.offset + lo) & 1u) == 0)) {
-                red_add_f32x4(dst, v[corner][0], v[corner][1], v[corner + 1][0], v[corner + 1][1]);
+            const bool even = ((lp.offset + lo) & 1u) == 0;
+            if (hi == lo + 1 && (even || tbl_odd)) {
+                red_add_f32x4(even ? dst : tbl_odd + (size_t)lo * 2, v[corner][0], v[corner][1], v[corner + 1][0], v[corner + 1][1]);
                 if constexpr (COUNT) *reds += 1u;
             } else {
                 red_add_f32x2(dst, v[corner][0], v[corner][1]);
@@ -626,7 +631,8 @@ template <typename T, uint32_t C, bool COUNT = false>
 __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
     const T* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
     float* __restrict__ grad_table, uint32_t B_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype,
-    bool align_corners, const int* __restrict__ count_ptr, float bound, unsigned long long* red_lane_ops = nullptr) {
+    bool align_corners, const int* __restrict__ count_ptr, float bound, unsigned long long* red_lane_ops = nullptr,
+    float* __restrict__ grad_odd = nullptr) {
     constexpr uint32_t D = 3;
     __shared__ FastLevel<D> s_levels[kMaxLevels];
     for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_fast_level<D>(offsets, l, S, H, gridtype, align_corners);
@@ -669,6 +675,9 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
                     any |= (gq[q].x | gq[q].y | gq[q].z | gq[q].w) & 0x7fff7fffu;     // (-0 is zero too)
                 }
                 if (!__any_sync(0xffffffffu, any != 0u)) continue;
+                // ... and a LANE whose row is all zero issues no reds of its own: it drops out of the run detection like an
+                // out-of-cube sample (its neighbours' runs simply end / start around it)
+                valid = valid && (any != 0u);
             }
         }
         // one group of (up to) four levels, gradients in graw[0..3]
@@ -688,10 +697,10 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
                     if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
                 }
                 // warp-uniform dispatch on the level's addressing class
-                if (lp.hashed)          warpagg_level<3, true, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
-                else if (lp.used == 3)  warpagg_level<3, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
-                else if (lp.used == 2)  warpagg_level<2, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
-                else                    warpagg_level<1, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, &reds);
+                if (lp.hashed)          warpagg_level<3, true, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds);
+                else if (lp.used == 3)  warpagg_level<3, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds);
+                else if (lp.used == 2)  warpagg_level<2, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds);
+                else                    warpagg_level<1, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds);
             }
         };
         if (row16) {

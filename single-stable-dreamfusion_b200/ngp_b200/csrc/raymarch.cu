@@ -905,8 +905,36 @@ NGP_DEVINL RaySample load_ray_sample(const RayLossArgs& a, const RaySpan& s, uin
     return v;
 }
 
+// The same prefix as serial_prefix() - same operations in the same order, so the same bits - with the 32 per-lane values
+// exchanged through shared memory: 2 STS + 16 broadcast LDS.128 instead of 64 SHFL (the kernel was bound by the shuffle
+// pipe: one warp-wide shuffle per cycle per SM).  s_om / s_d1: this warp's 32-float rows.
+NGP_DEVINL void serial_prefix_smem(float om, float d1, int lane, float T_in, float t_in, float* s_om, float* s_d1,
+                                   float& T_before, float& t_incl) {
+    s_om[lane] = om;
+    s_d1[lane] = d1;
+    __syncwarp();
+    float T = T_in, tt = t_in;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 o4 = reinterpret_cast<const float4*>(s_om)[q];
+        const float4 d4 = reinterpret_cast<const float4*>(s_d1)[q];
+        const float oj[4] = {o4.x, o4.y, o4.z, o4.w}, dj[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = q * 4 + k;
+            if (j < lane) T *= oj[k];
+            if (j <= lane) tt += dj[k];
+        }
+    }
+    __syncwarp();   // everyone has read the rows before the next chunk overwrites them
+    T_before = T;
+    t_incl = tt;
+}
+
 __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a) {
     __shared__ float s_loss[8];
+    __shared__ __align__(16) float s_om[8][32];
+    __shared__ __align__(16) float s_d1[8][32];
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float entropy = 0.f;
@@ -921,6 +949,8 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
     if (n < a.N) {
         const RaySpan s = load_span(a.rays, n, a.M);
         // ---- pass 1: composite forward ------------------------------------------------------------------------
+        // The transmittance BEFORE each sample is parked in grad_sigmas[m] (the row pass 2 overwrites with the gradient):
+        // pass 2 re-reads it - written by this very thread - instead of rebuilding the serial product.
         float r = 0, g = 0, b = 0, ws = 0, d = 0;
         if (s.live) {
             float T_carry = 1.0f, t_carry = 0.f;
@@ -939,7 +969,8 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
                     cr = cur.r; cg = cur.g; cb = cur.b;
                 }
                 float T_before, t_incl;
-                serial_prefix(om, d1, lane, T_carry, t_carry, T_before, t_incl);
+                serial_prefix_smem(om, d1, lane, T_carry, t_carry, s_om[warp], s_d1[warp], T_before, t_incl);
+                if (valid) a.grad_sigmas[(size_t)s.offset + base + lane] = T_before;
                 const float T_after = T_before * om;
                 const unsigned stop_mask = __ballot_sync(0xffffffffu, valid && (T_after < a.T_thresh));
                 const int stop_lane = stop_mask ? (__ffs(stop_mask) - 1) : 31;
@@ -994,9 +1025,10 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
         // ---- pass 2: composite backward --------------------------------------------------------------------------
         if (s.live) {
             const float r_final = r, g_final = g, b_final = b, ws_final = ws;
-            float T_carry = 1.0f, r_carry = 0.f, g_carry = 0.f, b_carry = 0.f;
+            float r_carry = 0.f, g_carry = 0.f, b_carry = 0.f;
             bool stopped = false;
             RaySample nxt = load_ray_sample(a, s, lane);
+            float T_nxt = (uint32_t)lane < s.count ? a.grad_sigmas[(size_t)s.offset + lane] : 1.0f;   // parked by pass 1
             for (uint32_t base = 0; base < s.count; base += 32) {
                 const uint32_t i = base + lane;
                 const bool valid = i < s.count;
@@ -1009,7 +1041,12 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
                     continue;
                 }
                 const RaySample cur = nxt;
-                if (base + 32 < s.count) nxt = load_ray_sample(a, s, base + 32 + lane);
+                const float T_before = T_nxt;
+                if (base + 32 < s.count) {
+                    nxt = load_ray_sample(a, s, base + 32 + lane);
+                    // (rows behind the stop chunk were never parked: whatever is read there is discarded with `stopped`)
+                    T_nxt = (base + 32 + lane < s.count) ? a.grad_sigmas[m + 32] : 1.0f;
+                }
                 float om = 1.0f, alpha = 0.f, d0 = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
                 if (valid) {
                     d0 = cur.d0;
@@ -1017,8 +1054,6 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
                     om = 1.0f - alpha;
                     cr = cur.r; cg = cur.g; cb = cur.b;
                 }
-                float T_before, unused_t;
-                serial_prefix(om, 0.f, lane, T_carry, 0.f, T_before, unused_t);
                 const float T_after = T_before * om;
                 const unsigned stop_mask = __ballot_sync(0xffffffffu, valid && (T_after < a.T_thresh));
                 const int stop_lane = stop_mask ? (__ffs(stop_mask) - 1) : 31;
@@ -1036,7 +1071,6 @@ __global__ void __launch_bounds__(256) train_ray_loss_kernel(const RayLossArgs a
                     a.grad_rgbs[m * 3] = 0.f; a.grad_rgbs[m * 3 + 1] = 0.f; a.grad_rgbs[m * 3 + 2] = 0.f;
                 }
                 if (stop_mask) { stopped = true; continue; }
-                T_carry = __shfl_sync(0xffffffffu, T_after, 31);
                 r_carry = __shfl_sync(0xffffffffu, r_run, 31);
                 g_carry = __shfl_sync(0xffffffffu, g_run, 31);
                 b_carry = __shfl_sync(0xffffffffu, b_run, 31);

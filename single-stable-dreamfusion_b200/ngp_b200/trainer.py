@@ -12,6 +12,7 @@ one ``cudaGraphLaunch``: the training render has static shapes and no host sync 
 optimizer is torch's fused capturable Adam driven by the scaler's device-side found_inf, and NCCL
 all-reduce is graph-capturable.  The occupancy refresh stays outside the graph (it runs every 16th step).
 """
+import os
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -78,6 +79,9 @@ class TrainStep:
         # entropy term is a MEAN over all rays of the job, so each rank's local mean is weighted 1 / world.
         self.lam_local = float(lambda_entropy) / float(world_size)
         self.fixed_noises = None  # tests: per-ray perturbation noise [N] used instead of a fresh torch.rand draw
+        # table-gradient scatter into two buffers (even / odd row pairs both as 16-byte reds); NGP_SPLIT_SCATTER=0: one buffer
+        self.split_scatter = os.environ.get("NGP_SPLIT_SCATTER", "1") not in ("", "0")
+        self._g_table_odd = None
         self.keep_grads = False   # tests: copy the gradient bucket to self.grad_snapshot right before the optimizer
         self.grad_snapshot = None  # (a device-to-device copy inside the step, so it also works in a graph replay)
         self.use_graph = graph
@@ -260,6 +264,15 @@ class TrainStep:
         c = dict(enc=enc, L=enc.offsets.shape[0] - 1, S=float(np.log2(enc.per_level_scale)),
                  hw_field=[opt.half_view(t) for t in field_params], g_field=[opt.grad_view(t) for t in field_params],
                  table_h=opt.half_view(enc.embeddings), g_table=opt.grad_view(enc.embeddings), has_bg=model.bg_radius > 0)
+        # odd-frame twin of the table gradient (ngp_grid_scatter_samples_split): indexed like g_table, 8 bytes off a 16-byte
+        # boundary; folded into g_table once per step, right before the optimizer / the gradient snapshot
+        c["g_table_odd"] = None
+        if self.split_scatter and c["g_table"].data_ptr() % 16 == 0 and c["g_table"].numel() % 2 == 0:
+            if self._g_table_odd is None or self._g_table_odd.numel() != c["g_table"].numel():
+                raw = torch.zeros(c["g_table"].numel() + 4, device=self.device, dtype=torch.float32)
+                self._g_table_odd = raw[2:2 + c["g_table"].numel()]
+                assert self._g_table_odd.data_ptr() % 16 == 8
+            c["g_table_odd"] = self._g_table_odd
         if c["has_bg"]:
             b0, b1 = model.bg_net.net
             bg_params = (b0.weight, b0.bias, b1.weight, b1.bias)
@@ -356,6 +369,7 @@ class TrainStep:
         c = self._manual_consts()
         enc, L, S, has_bg = c["enc"], c["L"], c["S"], c["has_bg"]
         hw_field, g_field, table_h, g_table = c["hw_field"], c["g_field"], c["table_h"], c["g_table"]
+        g_odd = c["g_table_odd"]
         rd = m["rd_flat"]
         P = _cabi.ptr
         main = torch.cuda.current_stream(dev)
@@ -386,9 +400,14 @@ class TrainStep:
             _cabi.call("ngp_field_backward", dev, ws.cap, P(ws.counter), P(hw_field[0]), P(hw_field[2]), P(hw_field[4]), 64, 4,
                        P(ws.d_sigma), P(ws.d_rgb), P(ws.sigma), P(ws.rgb), P(ws.enc), P(ws.h1), P(ws.h2), P(ws.d_enc),
                        *[P(t) for t in g_field])
-            _cabi.call("ngp_grid_scatter_samples", dev, P(ws.d_enc), P(ws.xyzs), float(model.bound), P(ws.counter), ws.cap,
-                       P(enc.offsets), L, 2, S, int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)),
-                       P(g_table))
+            if g_odd is None:
+                _cabi.call("ngp_grid_scatter_samples", dev, P(ws.d_enc), P(ws.xyzs), float(model.bound), P(ws.counter), ws.cap,
+                           P(enc.offsets), L, 2, S, int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)),
+                           P(g_table))
+            else:
+                _cabi.call("ngp_grid_scatter_samples_split", dev, P(ws.d_enc), P(ws.xyzs), float(model.bound), P(ws.counter),
+                           ws.cap, P(enc.offsets), L, 2, S, int(enc.base_resolution), int(enc.gridtype_id),
+                           int(bool(enc.align_corners)), P(g_table), P(g_odd))
 
         for st, (base, n_c, ws) in zip(streams, chunks):
             with torch.cuda.stream(st):
@@ -406,6 +425,8 @@ class TrainStep:
             main.wait_stream(st)
         if has_bg:
             main.wait_stream(self._side)
+        if g_odd is not None:
+            _cabi.call("ngp_grid_fold_odd", dev, P(g_table), P(g_odd), g_table.numel())
         if self.keep_grads:
             if self.grad_snapshot is None:
                 self.grad_snapshot = torch.empty_like(opt.flat_grads)

@@ -550,6 +550,59 @@ def test_grid_backward_warp_aggregated_on_ray_ordered_samples():
     assert util.rel_l2(N_(ge), truth) < 1e-6
 
 
+@pytest.mark.parametrize("gridtype,log2_T", [(1, 16), (0, 19)])
+def test_sample_scatter_single_and_split_buffers_vs_exact_sum(gridtype, log2_T):
+    """ngp_grid_scatter_samples (one gradient buffer) and ngp_grid_scatter_samples_split + ngp_grid_fold_odd (even / odd
+    row pairs as 16-byte reds into two buffers) against the oracle's exact sum, on ray-ordered marched samples in world
+    coordinates, with whole runs of all-zero gradient rows (samples behind a ray's early-termination point: their lanes
+    issue nothing) and a device-side row count smaller than the buffers."""
+    c = cabi()
+    case = MARCH_CASES[0]
+    rays_o, rays_d, bits, nears, fars, noises = _march_setup(case, seed=11)
+    ox, _, _, orays, ocounter = O.march_rays_train(rays_o, rays_d, 1.0, bits, 1, 128, nears, fars, noises, 0.0, 1024)
+    total = int(ocounter[0])
+    xyz = ox[:total].astype(np.float32).copy()
+    xyz[9] = [1.5, 0.0, 0.0]                         # outside [-bound, bound]
+    rng = np.random.default_rng(3)
+    g = (rng.standard_normal((total, 32)) * 1e-2).astype(np.float16)
+    for n in range(0, orays.shape[0], 3):            # every third ray: the last 60 % of its samples carry no gradient
+        o, k = int(orays[n, 1]), int(orays[n, 2])
+        g[o + int(0.4 * k):o + k] = 0
+    g[100:164] = 0                                   # two entirely dead warps
+    g[200] = -0.0
+    n_rows = total - 37
+    offs, S = util.make_offsets(log2_hashmap_size=log2_T)
+    dev_sc, _ = device_scales(16, np.float32(S), 16)
+    x01 = ((xyz + np.float32(1.0)) * np.float32(0.5)).astype(np.float32)
+    truth = O.grid_encode_backward(g[:n_rows], x01[:n_rows], offs, offs[-1], 2, np.float32(S), 16, gridtype=gridtype,
+                                   scale_override=dev_sc)
+    n_par = int(offs[-1]) * 2
+    g_t, x_t, offs_t = T(g), T(xyz), T(offs)
+    count = torch.tensor([n_rows, 0], dtype=torch.int32, device=DEV)
+    single = torch.zeros(n_par, device=DEV)
+    c.call("ngp_grid_scatter_samples", single.device, c.ptr(g_t), c.ptr(x_t), 1.0, c.ptr(count), total, c.ptr(offs_t), 16, 2,
+           float(S), 16, gridtype, 0, c.ptr(single))
+    even = torch.zeros(n_par, device=DEV)
+    odd = torch.zeros(n_par + 4, device=DEV)[2:2 + n_par]
+    assert even.data_ptr() % 16 == 0 and odd.data_ptr() % 16 == 8
+    c.call("ngp_grid_scatter_samples_split", even.device, c.ptr(g_t), c.ptr(x_t), 1.0, c.ptr(count), total, c.ptr(offs_t), 16, 2,
+           float(S), 16, gridtype, 0, c.ptr(even), c.ptr(odd))
+    torch.cuda.synchronize()
+    odd_share = odd.abs().sum().item() / (even.abs().sum().item() + odd.abs().sum().item())
+    c.call("ngp_grid_fold_odd", even.device, c.ptr(even), c.ptr(odd), n_par)
+    torch.cuda.synchronize()
+    assert odd.abs().sum().item() == 0
+    assert util.rel_l2(N_(single).reshape(-1, 2), truth) < 1e-6
+    assert util.rel_l2(N_(even).reshape(-1, 2), truth) < 1e-6
+    if gridtype == 1:
+        assert 0.2 < odd_share < 0.8                 # tiled levels: about half of the pairs start on an odd row
+    # a misaligned twin is refused, not silently mis-added
+    bad = torch.zeros(n_par + 4, device=DEV)
+    rc = c.load().ngp_grid_scatter_samples_split(c.ptr(g_t), c.ptr(x_t), 1.0, c.ptr(count), total, c.ptr(offs_t), 16, 2, float(S),
+                                                  16, gridtype, 0, c.ptr(even), c.ptr(bad), None)
+    assert rc != 0
+
+
 @pytest.mark.parametrize("case", MARCH_CASES)
 def test_march_thread_per_ray_variant_is_bit_identical(case):
     """The C ABI keeps the reference's one-thread-per-ray decomposition behind an option; both must agree bit for bit

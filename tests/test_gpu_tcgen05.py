@@ -121,3 +121,41 @@ def test_fused_field_matches_fp64_reference_better_than_tolerance():
         a_ref = torch.sigmoid(o[:, 1:])
     assert ((s1.double() - s_ref).abs() / s_ref).max().item() < 4e-3
     assert (a1.double() - a_ref).abs().max().item() < 1.5e-3
+
+
+@pytest.mark.parametrize("groups", [1, 2, 4])
+def test_fused_field_forward_groups_agree_bitwise(groups):
+    """The forward kernel with 1, 2 or 4 independent 128-thread groups per CTA (ngp_field_set_option 2) is the same
+    arithmetic per sample: outputs and the three saved activation tiles are bit-equal across the variants, at a size
+    with ragged tail tiles and fewer tiles than groups x CTAs as well."""
+    from ngp_b200 import _cabi
+    from ngp_b200.field import cached_half
+    lib = _cabi.load()
+    m = _field_models()
+    enc = m.encoder
+    table = cached_half(enc.embeddings)
+    l0, l1, l2 = m.sigma_net.net
+    hw = [cached_half(t) for t in (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)]
+    P = _cabi.ptr
+    S = float(np.log2(enc.per_level_scale))
+    outs = {}
+    for M in (300, 70001):
+        x = ((torch.rand(M, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(M)) * 2 - 1) * 0.95).contiguous()
+        tiles = (M + 127) // 128
+        for g in (1, groups):
+            assert lib.ngp_field_set_option(2, g) == 0
+            try:
+                sigma = torch.empty(M, device=DEV); rgb = torch.empty(M, 3, device=DEV)
+                e = torch.zeros(tiles * 128 * 32, dtype=torch.half, device=DEV)
+                h1 = torch.zeros(tiles * 128 * 64, dtype=torch.half, device=DEV)
+                h2 = torch.zeros(tiles * 128 * 64, dtype=torch.half, device=DEV)
+                _cabi.call("ngp_field_forward", torch.device(DEV), P(x), M, None, P(table), P(enc.offsets), 16, 2, S,
+                           int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), 1.0,
+                           *[P(t) for t in hw], 64, 4, P(sigma), P(rgb), P(e), P(h1), P(h2))
+                torch.cuda.synchronize()
+                outs[g] = (sigma, rgb, e, h1, h2)
+            finally:
+                assert lib.ngp_field_set_option(2, 2) == 0
+        for a, b in zip(outs[1], outs[groups]):
+            assert torch.equal(a, b)
+        assert torch.isfinite(outs[groups][0]).all() and outs[groups][3].abs().sum().item() > 0
