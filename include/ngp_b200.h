@@ -70,7 +70,9 @@ int ngp_grid_encode_backward(const void* grad, const float* inputs, const void* 
 
 /* Tuning / test switches.  option 0: value != 0 disables the warp-aggregated scatter of the backward (every
  * sample then issues its own atomics, like the reference).  option 1: value != 0 makes ngp_grid_scatter_samples run
- * its counting build (measurement only): every red instruction a lane issues AFTER warp aggregation is counted. */
+ * its counting build (measurement only): every red instruction a lane issues AFTER warp aggregation is counted.
+ * option 2: longest run of neighbouring lanes ngp_grid_scatter_samples[_split] sums before issuing the reds (4, 8, 16 or
+ * 32 = a whole warp): shorter runs mean fewer shuffle steps and a few more reds at the coarse levels. */
 int ngp_grid_set_option(int option, int value);
 /* Reads (and optionally resets) that counter into *lane_ops (HOST pointer); synchronises the device. */
 int ngp_grid_red_count(uint64_t* lane_ops, int reset);
@@ -112,8 +114,10 @@ int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t
                          uint64_t workspace_bytes, void* stream);
 /* (dirs may be NULL: the albedo-shaded training path never reads the per-sample directions.) */
 uint64_t ngp_march_rays_train_workspace(uint32_t N, uint32_t max_steps);
-/* option 0: value != 0 selects the one-thread-per-ray kernels (the reference's decomposition) instead of the
- * default warp-per-ray walk; results are bit-identical. */
+/* option 0: value != 0 selects the one-thread-per-ray count / write kernels (the reference's decomposition) instead of
+ * the default walks; option 1: warp-per-ray walk for one-sample inference calls; option 2: ngp_march_rays_train launches of
+ * at least `value` rays with dt_gamma == 0 use the thread-per-ray walk with closed-form lattice jumps, smaller ones the
+ * warp-per-ray walk (0 = never; default 16384).  Results are bit-identical in every mode. */
 int ngp_march_set_option(int option, int value);
 
 /* raymarching.cu:580 */

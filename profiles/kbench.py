@@ -132,7 +132,14 @@ def main():
 
     for name in calls:
         report(name)
-    report("ngp_march_rays_train")
+    for cap in (4, 8, 16, 32):
+        assert lib.ngp_grid_set_option(2, cap) == 0
+        report("ngp_grid_scatter_samples_split", {"max_run": cap})
+    assert lib.ngp_grid_set_option(2, 8) == 0
+    for min_rays in (0, 1):
+        assert lib.ngp_march_set_option(2, min_rays) == 0
+        report("ngp_march_rays_train", {"walk": "thread per ray, closed-form jumps" if min_rays else "warp per ray"})
+    assert lib.ngp_march_set_option(2, 16384) == 0
     if args.red:
         words = 1 << 23
         ftable = torch.zeros(words, dtype=torch.float32, device=dev)

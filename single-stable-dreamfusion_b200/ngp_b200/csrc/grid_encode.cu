@@ -5,6 +5,7 @@ using namespace ngp;
 
 namespace ngp { namespace grid {
 bool g_disable_warpagg = false;
+int g_scatter_max_run = 8;                          // ngp_grid_set_option(2, x): longest run of lanes summed before the reds
 bool g_count_reds = false;                          // ngp_grid_set_option(1, x): the counting build of the scatter
 __device__ unsigned long long g_red_lane_ops = 0;   // post-aggregation red instructions x active lanes, ngp_grid_red_count
 } }
@@ -12,6 +13,7 @@ __device__ unsigned long long g_red_lane_ops = 0;   // post-aggregation red inst
 extern "C" int ngp_grid_set_option(int option, int value) {
     if (option == 0) { grid::g_disable_warpagg = (value != 0); return NGP_OK; }
     if (option == 1) { grid::g_count_reds = (value != 0); return NGP_OK; }
+    if (option == 2 && (value == 4 || value == 8 || value == 16 || value == 32)) { grid::g_scatter_max_run = value; return NGP_OK; }
     return NGP_ERR_BAD_ARG;
 }
 
@@ -98,12 +100,12 @@ static int scatter_samples(const void* d_enc, const float* xyzs, float bound, co
         if (cudaGetSymbolAddress(reinterpret_cast<void**>(&ctr), grid::g_red_lane_ops) != cudaSuccess) return launch_status();
         grid::encode_backward_warpagg_kernel<__half, 2, true><<<blocks, 256, 0, as_stream(stream)>>>(
             static_cast<const __half*>(d_enc), xyzs, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners != 0, count_ptr,
-            bound, ctr, grad_table_odd);
+            bound, ctr, grad_table_odd, (uint32_t)grid::g_scatter_max_run);
         return launch_status();
     }
     grid::encode_backward_warpagg_kernel<__half, 2><<<blocks, 256, 0, as_stream(stream)>>>(
         static_cast<const __half*>(d_enc), xyzs, offsets, grad_table, M_cap, L, S, H, gridtype, align_corners != 0, count_ptr, bound,
-        nullptr, grad_table_odd);
+        nullptr, grad_table_odd, (uint32_t)grid::g_scatter_max_run);
     return launch_status();
 }
 

@@ -505,61 +505,11 @@ __global__ void __launch_bounds__(256) encode_backward_kernel(
 // active LANE, so fewer active lanes is a direct speed-up; levels whose cells are finer than the sample
 // spacing have runs of length 1 and pay only two shuffles and a ballot.
 // -------------------------------------------------------------------------------------------------
-// One level of the warp-aggregated scatter, specialised at compile time on how the level addresses its rows:
-// USED = axes that enter the row index (a 'tiled' level whose table is smaller than (res+1)^2 drops z: 4 distinct
-// rows per cell, and since the weights of the two z corners sum to 1 only the (x, y) bilinear weights are needed),
-// HASHED = spatial hash of all three axes.
-// COUNT (measurement builds of the kernel only): `reds` accumulates the red instructions THIS lane issued, i.e. the
-// post-aggregation atomic lane-ops that bench.py's roofline divides by the measured red issue ceiling.
-template <uint32_t USED, bool HASHED, uint32_t C, bool COUNT = false>
-NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool align_corners, bool valid, const float (&g)[C],
-                              uint32_t lane, float* __restrict__ grad_table, float* __restrict__ grad_odd, uint32_t* reds = nullptr) {
-    constexpr uint32_t NC = 1u << USED;  // distinct rows per cell
-    float frac[USED];
-    uint32_t base[USED];
-    {
-        float xs[USED];
-#pragma unroll
-        for (uint32_t d = 0; d < USED; ++d) xs[d] = x[d];
-        locate<USED>(xs, lp.scale, align_corners, frac, base);
-    }
-    // run detection: same cell (over the axes the level uses) as the previous lane, both valid
-    uint32_t kxy = base[0], kz = 0u;
-    if constexpr (USED >= 2) kxy |= base[1] << 16;
-    if constexpr (USED >= 3) kz = base[2];
-    if (!valid) { kxy = 0xffffffffu; kz = 0x80000000u | lane; }
-    const uint32_t pxy = __shfl_up_sync(0xffffffffu, kxy, 1);
-    uint32_t pz = kz;
-    if constexpr (USED >= 3) pz = __shfl_up_sync(0xffffffffu, kz, 1);  // every lane shuffles (no short-circuit around it)
-    const bool head = (lane == 0) || !valid || (pxy != kxy) || (pz != kz);
-    const uint32_t heads = __ballot_sync(0xffffffffu, head);
-    // last lane of my run = (next head above me) - 1
-    const uint32_t above = (lane == 31) ? 0u : (heads >> (lane + 1));
-    const uint32_t run_end = above ? (lane + (uint32_t)__ffs(above) - 1u) : 31u;
-    // longest run in the warp bounds the number of reduction steps (warp-uniform)
-    const uint32_t my_len = head ? (run_end - lane + 1u) : 0u;
-    const uint32_t max_len = __reduce_max_sync(0xffffffffu, my_len);
-
-    float wts[NC];
-    corner_weights<USED>(frac, wts);
-    float v[NC][C];
-#pragma unroll
-    for (uint32_t corner = 0; corner < NC; ++corner) {
-#pragma unroll
-        for (uint32_t c = 0; c < C; ++c) v[corner][c] = wts[corner] * g[c];
-    }
-    for (uint32_t off = 1; off < max_len; off <<= 1) {
-        const bool take = (lane + off) <= run_end;
-#pragma unroll
-        for (uint32_t corner = 0; corner < NC; ++corner) {
-#pragma unroll
-            for (uint32_t c = 0; c < C; ++c) {
-                const float o = __shfl_down_sync(0xffffffffu, v[corner][c], off);
-                if (take) v[corner][c] += o;
-            }
-        }
-    }
-    if (head && valid) {
+// The reds of ONE cell of one level: v[corner][c] = the summed contributions to the cell's 2^USED distinct rows.
+template <uint32_t USED, bool HASHED, uint32_t C, bool COUNT>
+NGP_DEVINL void issue_cell_reds(const FastLevel<3>& lp, const uint32_t (&base)[USED], const float (&v)[1u << USED][C],
+                                float* __restrict__ grad_table, float* __restrict__ grad_odd, uint32_t* reds) {
+    constexpr uint32_t NC = 1u << USED;
     uint32_t rows[NC];
     if constexpr (HASHED) {
         constexpr uint32_t kPrimes[3] = {1u, 2654435761u, 805459861u};
@@ -624,7 +574,66 @@ NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool 
             if constexpr (COUNT) *reds += (C <= 2 ? 1u : C / 4);
         }
     }
-    }  // head && valid
+}
+
+// One level of the warp-aggregated scatter, specialised at compile time on how the level addresses its rows:
+// USED = axes that enter the row index (a 'tiled' level whose table is smaller than (res+1)^2 drops z: 4 distinct
+// rows per cell, and since the weights of the two z corners sum to 1 only the (x, y) bilinear weights are needed),
+// HASHED = spatial hash of all three axes.
+// COUNT (measurement builds of the kernel only): `reds` accumulates the red instructions THIS lane issued, i.e. the
+// post-aggregation atomic lane-ops that bench.py's roofline divides by the measured red issue ceiling.
+template <uint32_t USED, bool HASHED, uint32_t C, bool COUNT = false>
+NGP_DEVINL void warpagg_level(const FastLevel<3>& lp, const float (&x)[3], bool align_corners, bool valid, const float (&g)[C],
+                              uint32_t lane, float* __restrict__ grad_table, float* __restrict__ grad_odd, uint32_t* reds = nullptr,
+                              uint32_t run_cap = 32u) {
+    constexpr uint32_t NC = 1u << USED;  // distinct rows per cell
+    float frac[USED];
+    uint32_t base[USED];
+    {
+        float xs[USED];
+#pragma unroll
+        for (uint32_t d = 0; d < USED; ++d) xs[d] = x[d];
+        locate<USED>(xs, lp.scale, align_corners, frac, base);
+    }
+    // run detection: same cell (over the axes the level uses) as the previous lane, both valid
+    uint32_t kxy = base[0], kz = 0u;
+    if constexpr (USED >= 2) kxy |= base[1] << 16;
+    if constexpr (USED >= 3) kz = base[2];
+    if (!valid) { kxy = 0xffffffffu; kz = 0x80000000u | lane; }
+    const uint32_t pxy = __shfl_up_sync(0xffffffffu, kxy, 1);
+    uint32_t pz = kz;
+    if constexpr (USED >= 3) pz = __shfl_up_sync(0xffffffffu, kz, 1);  // every lane shuffles (no short-circuit around it)
+    // run_cap (a power of two <= 32) additionally starts a run every run_cap lanes: fewer reduction steps below (they
+    // are ~1/3 of this kernel's instructions, which is what bounds it) for a few more reds at the coarse levels
+    const bool head = ((lane & (run_cap - 1u)) == 0) || !valid || (pxy != kxy) || (pz != kz);
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    // last lane of my run = (next head above me) - 1
+    const uint32_t above = (lane == 31) ? 0u : (heads >> (lane + 1));
+    const uint32_t run_end = above ? (lane + (uint32_t)__ffs(above) - 1u) : 31u;
+    // longest run in the warp bounds the number of reduction steps (warp-uniform)
+    const uint32_t my_len = head ? (run_end - lane + 1u) : 0u;
+    const uint32_t max_len = __reduce_max_sync(0xffffffffu, my_len);
+
+    float wts[NC];
+    corner_weights<USED>(frac, wts);
+    float v[NC][C];
+#pragma unroll
+    for (uint32_t corner = 0; corner < NC; ++corner) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) v[corner][c] = wts[corner] * g[c];
+    }
+    for (uint32_t off = 1; off < max_len; off <<= 1) {
+        const bool take = (lane + off) <= run_end;
+#pragma unroll
+        for (uint32_t corner = 0; corner < NC; ++corner) {
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) {
+                const float o = __shfl_down_sync(0xffffffffu, v[corner][c], off);
+                if (take) v[corner][c] += o;
+            }
+        }
+    }
+    if (head && valid) issue_cell_reds<USED, HASHED, C, COUNT>(lp, base, v, grad_table, grad_odd, reds);
 }
 
 template <typename T, uint32_t C, bool COUNT = false>
@@ -632,7 +641,7 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
     const T* __restrict__ grad, const float* __restrict__ inputs, const int* __restrict__ offsets,
     float* __restrict__ grad_table, uint32_t B_cap, uint32_t L, float S, uint32_t H, uint32_t gridtype,
     bool align_corners, const int* __restrict__ count_ptr, float bound, unsigned long long* red_lane_ops = nullptr,
-    float* __restrict__ grad_odd = nullptr) {
+    float* __restrict__ grad_odd = nullptr, uint32_t run_cap = 32u) {
     constexpr uint32_t D = 3;
     __shared__ FastLevel<D> s_levels[kMaxLevels];
     for (uint32_t l = threadIdx.x; l < L; l += blockDim.x) s_levels[l] = make_fast_level<D>(offsets, l, S, H, gridtype, align_corners);
@@ -680,36 +689,36 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
                 valid = valid && (any != 0u);
             }
         }
-        // one group of (up to) four levels, gradients in graw[0..3]
-        auto process_group = [&](uint32_t level0, const uint32_t (&gr)[4]) {
+        // One level.  The loops over the levels below are deliberately ROLLED: with the 16 levels unrolled the kernel held
+        // 64 copies of warpagg_level (27.7 k instructions, 440 KB of code) and every 32 samples walked 16 different copies
+        // through the instruction cache; rolled it is one copy per addressing class.
+        auto process_level = [&](uint32_t level, uint32_t g_packed) {
+            const FastLevel<D>& lp = s_levels[level];
+            float g[C];
 #pragma unroll
-            for (uint32_t lj = 0; lj < 4; ++lj) {
-                const uint32_t level = level0 + lj;
-                if (level >= L) break;
-                const FastLevel<D>& lp = s_levels[level];
-                float g[C];
-#pragma unroll
-                for (uint32_t c = 0; c < C; ++c) g[c] = 0.f;
-                if constexpr (kPacked) {
-                    const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&gr[lj]));
-                    g[0] = gf.x; g[1] = gf.y;
-                } else {
-                    if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
-                }
-                // warp-uniform dispatch on the level's addressing class
-                if (lp.hashed)          warpagg_level<3, true, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds);
-                else if (lp.used == 3)  warpagg_level<3, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds);
-                else if (lp.used == 2)  warpagg_level<2, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds);
-                else                    warpagg_level<1, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds);
+            for (uint32_t c = 0; c < C; ++c) g[c] = 0.f;
+            if constexpr (kPacked) {
+                const float2 gf = __half22float2(*reinterpret_cast<const __half2*>(&g_packed));
+                g[0] = gf.x; g[1] = gf.y;
+            } else {
+                if (valid) load_row<T, C>(grad + ((size_t)b * L + level) * C, g);
             }
+            // warp-uniform dispatch on the level's addressing class
+            if (lp.hashed)          warpagg_level<3, true, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds, run_cap);
+            else if (lp.used == 3)  warpagg_level<3, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds, run_cap);
+            else if (lp.used == 2)  warpagg_level<2, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds, run_cap);
+            else                    warpagg_level<1, false, C, COUNT>(lp, x, align_corners, valid, g, lane, grad_table, grad_odd, &reds, run_cap);
         };
+        auto pick = [](const uint4& v, uint32_t j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); };
         if (row16) {
-#pragma unroll
-            for (uint32_t q = 0; q < 4; ++q) {
-                const uint32_t gr[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w};
-                process_group(q * 4, gr);
+#pragma unroll 1
+            for (uint32_t level = 0; level < 16; ++level) {
+                const uint32_t q = level >> 2;
+                const uint4 cur = q == 0 ? gq[0] : (q == 1 ? gq[1] : (q == 2 ? gq[2] : gq[3]));
+                process_level(level, pick(cur, level & 3u));
             }
         } else {
+#pragma unroll 1
             for (uint32_t level0 = 0; level0 < L; level0 += 4) {
                 if constexpr (kPacked) {
                     if ((L % 4) == 0) {
@@ -722,7 +731,9 @@ __global__ void __launch_bounds__(256) encode_backward_warpagg_kernel(
                             graw[j] = (valid && level0 + j < L) ? __ldg(reinterpret_cast<const uint32_t*>(grad + ((size_t)b * L + level0 + j) * C)) : 0u;
                     }
                 }
-                process_group(level0, graw);
+                const uint4 cur = make_uint4(graw[0], graw[1], graw[2], graw[3]);
+#pragma unroll 1
+                for (uint32_t lj = 0; lj < 4 && level0 + lj < L; ++lj) process_level(level0 + lj, pick(cur, lj));
             }
         }
     }

@@ -22,6 +22,9 @@ namespace march {
 // test / profiling switch (ngp_march_set_option 0): 1 = the reference's decomposition, one thread per ray
 bool g_thread_per_ray = false;
 bool g_infer_warp_march = false;  // ngp_march_set_option 1: warp-per-ray walk for one-sample inference calls
+// ngp_march_set_option 2: launches of at least this many rays with dt_gamma == 0 use the thread-per-ray walk with closed-form
+// lattice jumps (fewer instructions, but a ray is one serial chain); smaller ones keep the warp-per-ray walk.  0 = never.
+uint32_t g_thread_march_min_rays = 16384;
 
 NGP_DEVINL float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }  // raymarching.cu:34
 
@@ -570,6 +573,118 @@ __global__ void __launch_bounds__(128) march_slab_kernel(const float* __restrict
     __threadfence();
     scan_ray_counts(counts, N, rays, counter, s_warp);
     if (threadIdx.x == 0) *blocks_done = 0u;     // ready for the next launch on this workspace
+}
+
+// -------------------------------------------------------------------------------------------------
+// Thread-per-ray walk with CLOSED-FORM lattice jumps (constant step, dt_gamma == 0: the -O configuration).
+// The warp-per-ray walk above classifies all 32 lattice points of a window although, in empty space, only the first point
+// of each cell is visited (a 128^3 cell is ~4.6 steps long): ~8 k warp instructions per ray.  Here one thread follows the
+// reference's own serial chain - classify, then either emit + one real `t += dt`, or jump out of the empty cell - but the
+// reference's inner `do t += dt; while (t < tt)` (raymarching.cu:396-398) is collapsed: inside a binade every float is a
+// multiple of u = 2^(e-23) and fl(t + dt) = t + m u with m = rn(dt / u) for every t of the binade (unless dt / u is an exact
+// tie), so n steps add n * m to the bit pattern.  The jump takes the n = ceil((tt - t) / (m u)) >= 1 steps the loop would,
+// as long as they stay inside the binade; a binade crossing (at most four per ray) or a tie is one REAL float addition.
+// Same lattice, same visited points, same bits - at ~1/15 of the instructions; the price is latency (a ray is one serial
+// chain), so small launches keep the warp-per-ray walk.
+// -------------------------------------------------------------------------------------------------
+NGP_DEVINL float lattice_jump(float t, float tt, float dtc) {
+    const int tti = __float_as_int(tt);          // tt >= t > 0 or +inf: the bit patterns order like the values
+    do {
+        const int tb = __float_as_int(t);
+        const int e = ((tb >> 23) & 0xff) - 127;
+        if (tb > 0 && e > -100 && e < 100) {
+            const float rr = scalbnf(dtc, 23 - e);              // dt / u, exact
+            const float fl = floorf(rr);
+            if (rr < 4194304.f && (rr - fl) != 0.5f && rr >= 0.5f) {
+                const uint32_t m = (uint32_t)__float2int_rn(rr);                       // >= 1
+                const uint32_t room = (0x7fffffu - ((uint32_t)tb & 0x7fffffu)) / m;      // steps that stay inside the binade
+                uint32_t need = 1u;
+                if (tti > tb) need = ((uint32_t)(tti - tb) + m - 1u) / m;                // first lattice point >= tt
+                if (need <= room) return __int_as_float(tb + (int)(need * m));
+                t = __int_as_float(tb + (int)(room * m));   // `room` steps; still < tt, since need > room
+            }
+        }
+        t += dtc;        // the crossing (or tie / denormal) step, in float arithmetic as the reference
+    } while (t < tt);
+    return t;
+}
+
+// slab row = (x, y, z, t after the sample's step): ONE 16-byte store per sample; dt is the constant step and
+// deltas[1] = t_after - previous t_after (raymarching.cu:461) are rebuilt by march_compact4_kernel.
+__global__ void __launch_bounds__(128) march_slab_thread_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                                const uint8_t* __restrict__ grid, float bound, uint32_t max_steps,
+                                                                uint32_t N, uint32_t C, uint32_t H, const float* __restrict__ nears,
+                                                                const float* __restrict__ fars, const float* __restrict__ noises,
+                                                                int* __restrict__ counts, float4* __restrict__ slab,
+                                                                unsigned int* __restrict__ blocks_done, int* __restrict__ rays,
+                                                                int* __restrict__ counter) {
+    __shared__ int s_warp[32];
+    __shared__ bool s_last;
+    __shared__ uint32_t s_lut[1024];
+    const bool use_lut = H <= 1024u;
+    if (use_lut) {
+        for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) s_lut[i] = spread3(i);
+        __syncthreads();
+    }
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < N) {
+        MarchParams p = make_params(grid, bound, 0.f, max_steps, C, H);
+        if (use_lut) p.lut = s_lut;
+        const Ray r = load_ray(rays_o, rays_d, n);
+        const float far = fars[n];
+        const float dtc = clampf(0.f, p.dt_min, p.dt_max);
+        float t = perturbed_start(p, nears[n], noises[n]);
+        float4* row = slab + (size_t)n * max_steps;
+        uint32_t steps = 0;
+        while (t < far && steps < max_steps) {
+            const Cell c = classify(p, r, t);
+            if (c.occ) {
+                t += c.dt;                                   // (c.dt == dtc; raymarching.cu:425)
+                row[steps++] = make_float4(c.x, c.y, c.z, t);
+            } else {
+                t = lattice_jump(t, cell_exit(p, r, c, t), dtc);
+            }
+        }
+        counts[n] = (int)steps;
+    }
+    if (!blocks_done) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(blocks_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    scan_ray_counts(counts, N, rays, counter, s_warp);
+    if (threadIdx.x == 0) *blocks_done = 0u;
+}
+
+__global__ void __launch_bounds__(256) march_compact4_kernel(const float* __restrict__ rays_d, const int* __restrict__ rays,
+                                                             const float4* __restrict__ slab, const float* __restrict__ nears,
+                                                             const float* __restrict__ noises, uint32_t max_steps, uint32_t N,
+                                                             uint32_t M, uint32_t C, uint32_t H, float* __restrict__ xyzs,
+                                                             float* __restrict__ dirs, float* __restrict__ deltas) {
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (n >= N) return;
+    const uint32_t offset = (uint32_t)rays[(size_t)n * 3 + 1], count = (uint32_t)rays[(size_t)n * 3 + 2];
+    if (count == 0 || offset + count > M) return;  // raymarching.cu:415-416
+    const MarchParams p = make_params(nullptr, 1.f, 0.f, max_steps, C, H);
+    const float dtc = clampf(0.f, p.dt_min, p.dt_max);
+    const float t0 = perturbed_start(p, nears[n], noises[n]);     // last_t before the first sample (raymarching.cu:351,425)
+    const float4* src = slab + (size_t)n * max_steps;
+    float* ox = xyzs + (size_t)offset * 3;
+    float2* od = reinterpret_cast<float2*>(deltas) + offset;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    if (dirs) { d0 = rays_d[n * 3]; d1 = rays_d[n * 3 + 1]; d2 = rays_d[n * 3 + 2]; }
+    for (uint32_t i = lane; i < count; i += 32) {
+        const float4 v = src[i];
+        const float prev = i ? src[i - 1].w : t0;
+        ox[i * 3] = v.x; ox[i * 3 + 1] = v.y; ox[i * 3 + 2] = v.z;
+        od[i] = make_float2(dtc, v.w - prev);
+        if (dirs) { float* pd = dirs + ((size_t)offset + i) * 3; pd[0] = d0; pd[1] = d1; pd[2] = d2; }
+    }
 }
 
 __global__ void __launch_bounds__(256) march_compact_kernel(const float* __restrict__ rays_d, const int* __restrict__ rays,
@@ -1473,6 +1588,7 @@ extern "C" int ngp_packbits(const float* grid, uint32_t N, float density_thresh,
 extern "C" int ngp_march_set_option(int option, int value) {
     if (option == 0) { march::g_thread_per_ray = (value != 0); return NGP_OK; }
     if (option == 1) { march::g_infer_warp_march = (value != 0); return NGP_OK; }
+    if (option == 2 && value >= 0) { march::g_thread_march_min_rays = (uint32_t)value; return NGP_OK; }
     return NGP_ERR_BAD_ARG;
 }
 
@@ -1505,6 +1621,15 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
         float* slab_xyz = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + 256 + (((size_t)N * sizeof(int) + 255) / 256) * 256);
         float* slab_delta = slab_xyz + (size_t)N * max_steps * 3;
         const int blocks = cdiv((uint64_t)N * 32, 128);
+        if (dt_gamma == 0.f && march::g_thread_march_min_rays && N >= march::g_thread_march_min_rays) {
+            float4* slab4 = reinterpret_cast<float4*>(slab_xyz);   // (256-byte aligned; 16 of the 20 bytes per row are used)
+            march::march_slab_thread_kernel<<<cdiv(N, 128), 128, 0, st>>>(rays_o, rays_d, grid, bound, max_steps, N, C, H, nears, fars,
+                                                                         noises, counts, slab4, nullptr, rays, counter);
+            march::march_scan_kernel<<<1, 1024, 0, st>>>(counts, N, rays, counter);
+            march::march_compact4_kernel<<<cdiv((uint64_t)N * 32, 256), 256, 0, st>>>(rays_d, rays, slab4, nears, noises, max_steps, N, M,
+                                                                                     C, H, xyzs, dirs, deltas);
+            return launch_status();
+        }
         if (N <= 8192) {
             // few rays per launch (a data-parallel rank's chain): the LAST block of the walk scans the counts - one launch
             // and one dependent-launch gap less.  The election counter is cleared in-stream (a 4-byte memset node; the

@@ -550,9 +550,11 @@ def test_grid_backward_warp_aggregated_on_ray_ordered_samples():
     assert util.rel_l2(N_(ge), truth) < 1e-6
 
 
+@pytest.mark.parametrize("max_run", [32, 8, 4])
 @pytest.mark.parametrize("gridtype,log2_T", [(1, 16), (0, 19)])
-def test_sample_scatter_single_and_split_buffers_vs_exact_sum(gridtype, log2_T):
-    """ngp_grid_scatter_samples (one gradient buffer) and ngp_grid_scatter_samples_split + ngp_grid_fold_odd (even / odd
+def test_sample_scatter_single_and_split_buffers_vs_exact_sum(gridtype, log2_T, max_run, request):
+    """(max_run: the longest run of lanes the kernel sums before its reds, ngp_grid_set_option 2.)
+    ngp_grid_scatter_samples (one gradient buffer) and ngp_grid_scatter_samples_split + ngp_grid_fold_odd (even / odd
     row pairs as 16-byte reds into two buffers) against the oracle's exact sum, on ray-ordered marched samples in world
     coordinates, with whole runs of all-zero gradient rows (samples behind a ray's early-termination point: their lanes
     issue nothing) and a device-side row count smaller than the buffers."""
@@ -580,6 +582,9 @@ def test_sample_scatter_single_and_split_buffers_vs_exact_sum(gridtype, log2_T):
     g_t, x_t, offs_t = T(g), T(xyz), T(offs)
     count = torch.tensor([n_rows, 0], dtype=torch.int32, device=DEV)
     single = torch.zeros(n_par, device=DEV)
+    default_run = 8
+    assert c.load().ngp_grid_set_option(2, max_run) == 0
+    request.addfinalizer(lambda: c.load().ngp_grid_set_option(2, default_run))
     c.call("ngp_grid_scatter_samples", single.device, c.ptr(g_t), c.ptr(x_t), 1.0, c.ptr(count), total, c.ptr(offs_t), 16, 2,
            float(S), 16, gridtype, 0, c.ptr(single))
     even = torch.zeros(n_par, device=DEV)
@@ -672,3 +677,40 @@ def test_cfg2_full_size_encoder_vs_reference_extension(ref_ext):
     truth = O.grid_encode_backward(N_(g[:n]), N_(x01[:n]), offs, enc.embeddings.shape[0], 2, np.float32(S), 16, gridtype=0,
                                    scale_override=sc)
     assert util.rel_l2(N_(enc.embeddings.grad), truth) < 1e-6
+
+
+THREAD_MARCH_CASES = [
+    MARCH_CASES[0],
+    MARCH_CASES[1],
+    dict(side=48, cascade=2, bound=2.0, dt_gamma=0.0, max_steps=512),     # two cascades, constant step
+    dict(side=40, cascade=3, bound=4.0, dt_gamma=0.0, max_steps=1024),    # t spans five binades (0.2 .. 12)
+    dict(side=32, cascade=1, bound=1.0, dt_gamma=0.0, max_steps=4096),    # step 2^-10 * sqrt(3) / 2: other m per binade
+]
+
+
+@pytest.mark.parametrize("case", THREAD_MARCH_CASES)
+@pytest.mark.parametrize("seed", [2, 7])
+def test_march_thread_walk_with_closed_form_jumps_is_bit_identical(case, seed):
+    """ngp_march_set_option(2, n): launches of >= n rays with dt_gamma == 0 run one THREAD per ray and collapse the
+    reference's inner `do t += dt; while (t < tt)` into integer arithmetic on the bit pattern of t (exact inside a binade;
+    binade crossings and ties take a real float step).  Counts, offsets, positions and both deltas must equal the oracle's
+    serial float loop bit for bit - including rays that hit the max_steps cap, several cascades and t ranges over many
+    binades - and the warp-per-ray walk's output."""
+    c = cabi()
+    rays_o, rays_d, bits, nears, fars, noises = _march_setup(case, seed=seed)
+    ox, od, ol, orays, ocounter = O.march_rays_train(rays_o, rays_d, case["bound"], bits, case["cascade"], 128, nears, fars,
+                                                     noises, case["dt_gamma"], case["max_steps"])
+    total = int(ocounter[0])
+    assert total > 0
+    outs = []
+    for min_rays in (1, 0):
+        assert c.load().ngp_march_set_option(2, min_rays) == 0
+        try:
+            outs.append(_my_march(case, rays_o, rays_d, bits, nears, fars, noises))
+        finally:
+            assert c.load().ngp_march_set_option(2, 16384) == 0
+    for xyzs, dirs, deltas, rays, counter in outs:
+        assert np.array_equal(N_(rays), orays) and np.array_equal(N_(counter), ocounter)
+        assert np.array_equal(N_(xyzs[:total]), ox[:total]) and np.array_equal(N_(deltas[:total]), ol[:total])
+        assert np.array_equal(N_(dirs[:total]), od[:total])
+        assert not xyzs[total:].any()
