@@ -117,7 +117,7 @@ uint64_t ngp_march_rays_train_workspace(uint32_t N, uint32_t max_steps);
 /* option 0: value != 0 selects the one-thread-per-ray count / write kernels (the reference's decomposition) instead of
  * the default walks; option 1: warp-per-ray walk for one-sample inference calls; option 2: ngp_march_rays_train launches of
  * at least `value` rays with dt_gamma == 0 use the thread-per-ray walk with closed-form lattice jumps, smaller ones the
- * warp-per-ray walk (0 = never; default 16384).  Results are bit-identical in every mode. */
+ * warp-per-ray walk (0 = never, the default: it is not faster).  Results are bit-identical in every mode. */
 int ngp_march_set_option(int option, int value);
 
 /* raymarching.cu:580 */

@@ -139,7 +139,7 @@ def main():
     for min_rays in (0, 1):
         assert lib.ngp_march_set_option(2, min_rays) == 0
         report("ngp_march_rays_train", {"walk": "thread per ray, closed-form jumps" if min_rays else "warp per ray"})
-    assert lib.ngp_march_set_option(2, 16384) == 0
+    assert lib.ngp_march_set_option(2, 0) == 0
     if args.red:
         words = 1 << 23
         ftable = torch.zeros(words, dtype=torch.float32, device=dev)

@@ -23,8 +23,9 @@ namespace march {
 bool g_thread_per_ray = false;
 bool g_infer_warp_march = false;  // ngp_march_set_option 1: warp-per-ray walk for one-sample inference calls
 // ngp_march_set_option 2: launches of at least this many rays with dt_gamma == 0 use the thread-per-ray walk with closed-form
-// lattice jumps (fewer instructions, but a ray is one serial chain); smaller ones keep the warp-per-ray walk.  0 = never.
-uint32_t g_thread_march_min_rays = 16384;
+// lattice jumps (fewer instructions, but a ray is one serial ~0.2 ms chain); smaller ones keep the warp-per-ray walk.
+// 0 = never (the default: measured 0.314 vs 0.310 ms at 32768 rays, 0.232 vs 0.066 ms at 4096).
+uint32_t g_thread_march_min_rays = 0;
 
 NGP_DEVINL float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }  // raymarching.cu:34
 
@@ -91,6 +92,9 @@ NGP_DEVINL MarchParams make_params(const uint8_t* grid, float bound, float dt_ga
     p.single = (C == 1);
     p.mip_bound0 = fminf(scalbnf(1.0f, 0), bound);
     p.mip_rbound0 = 1 / p.mip_bound0;
+    // (opaque to the optimiser: otherwise it merges this division with classify()'s per-point `1 / mip_bound` of the
+    //  multi-cascade path and re-evaluates the reciprocal for every lattice point of single-cascade scenes too)
+    asm volatile("" : "+f"(p.mip_rbound0));
     return p;
 }
 
@@ -111,7 +115,7 @@ struct Cell {
     int nx, ny, nz;
     bool occ;
 };
-NGP_DEVINL Cell classify(const MarchParams& p, const Ray& r, float t) {
+NGP_DEVINL Cell classify(const MarchParams& p, const Ray& r, float t, uint32_t* cached_index = nullptr, bool* cached_occ = nullptr) {
     Cell c;
     c.x = clampf(r.ox + t * r.dx, -p.bound, p.bound);
     c.y = clampf(r.oy + t * r.dy, -p.bound, p.bound);
@@ -135,6 +139,11 @@ NGP_DEVINL Cell classify(const MarchParams& p, const Ray& r, float t) {
 
     const uint32_t morton = p.lut ? (p.lut[c.nx] | (p.lut[c.ny] << 1) | (p.lut[c.nz] << 2)) : morton_encode(c.nx, c.ny, c.nz);
     const uint32_t index = level * p.H3 + morton;  // float arithmetic, as in :378
+    if (cached_index) {       // (serial walks: the previous point's cell is usually this point's cell)
+        if (index != *cached_index) { *cached_index = index; *cached_occ = p.grid[index / 8] & (1 << (index % 8)); }
+        c.occ = *cached_occ;
+        return c;
+    }
     c.occ = p.grid[index / 8] & (1 << (index % 8));
     return c;
 }
@@ -159,6 +168,40 @@ NGP_DEVINL bool probe(const MarchParams& p, const Ray& r, float& t, float& x, fl
     return false;
 }
 
+// Per-binade constants of the jump, recomputed only when t enters another binade (at most five times per ray)
+struct Binade {
+    int key;        // sign + exponent bits of the t they were derived for (-1: none yet)
+    uint32_t m;     // lattice step in units of the binade's ulp
+    float inv_m;
+    bool ok;        // closed form applies (no tie, m >= 1, sane exponent)
+};
+NGP_DEVINL void binade_setup(int tb, float dtc, Binade& b) {
+    b.key = tb >> 23;
+    b.ok = false; b.m = 1u; b.inv_m = 1.f;
+    const int e = ((tb >> 23) & 0xff) - 127;
+    if (tb > 0 && e > -100 && e < 100) {
+        const float rr = scalbnf(dtc, 23 - e);              // dt / u, exact
+        const float fl = floorf(rr);
+        if (rr < 4194304.f && (rr - fl) != 0.5f && rr >= 0.5f) {
+            b.m = (uint32_t)__float2int_rn(rr);
+            b.inv_m = __frcp_rn((float)b.m);
+            b.ok = true;
+        }
+    }
+}
+// floor(a / m) and ceil(a / m) for a < 2^23 through one float multiply and exact integer fix-ups (the estimate is within
+// one of the quotient): the 32-bit integer division they replace is ~20 dependent instructions on the ray's serial chain
+NGP_DEVINL uint32_t floor_div(uint32_t a, uint32_t m, float inv_m) {
+    uint32_t q = (uint32_t)(__uint2float_rz(a) * inv_m);
+    if (q * m > a) --q;
+    if (q * m > a) --q;
+    if ((q + 1u) * m <= a) ++q;
+    return q;
+}
+NGP_DEVINL uint32_t ceil_div(uint32_t a, uint32_t m, float inv_m) {
+    const uint32_t f = floor_div(a, m, inv_m);
+    return f * m == a ? f : f + 1u;
+}
 // -------------------------------------------------------------------------------------------------
 // Warp-per-ray walk.  The candidate parameters of a ray form a FIXED lattice T_0 = t0,
 // T_{k+1} = T_k + clamp(T_k * dt_gamma, dt_min, dt_max): both branches of the reference loop advance t by exactly
@@ -177,29 +220,24 @@ NGP_DEVINL uint32_t walk_ray_warp(const MarchParams& p, const Ray& r, float t0, 
     float pending = -FLT_MAX;    // the next visited point is the first with T >= pending
     float last_t = t0;           // t after the previously emitted sample (raymarching.cu:425,462)
     uint32_t emitted = 0;
+    Binade bn;
+    bn.key = -1; bn.m = 1u; bn.inv_m = 1.f; bn.ok = false;
     while (Tb < far && emitted < limit) {
         // lane i holds lattice point i of the window: T = Tb advanced i times
         float T, T_next;
         bool closed_form = false;
+        int tb = 0;
         if (p.dt_gamma == 0.f) {
             // Constant step dtc.  Inside one binade [2^e, 2^(e+1)) every float is a multiple of u = 2^(e-23), so the
             // rounded sum fl(T + dtc) equals T + m*u with m = rn(dtc / u) for EVERY T of the binade (no tie) - the
             // serial additions collapse to integer arithmetic on the bit pattern.  Ties and binade crossings (a
-            // handful of windows per ray) fall back to the serial loop below.
-            const float dtc = clampf(0.f, p.dt_min, p.dt_max);
-            const int tb = __float_as_int(Tb);
-            const int e = ((tb >> 23) & 0xff) - 127;
-            if (tb > 0 && e > -100 && e < 100) {
-                const float rr = scalbnf(dtc, 23 - e);              // dtc / u, exact
-                const float fl = floorf(rr);
-                if (rr < 4194304.f && (rr - fl) != 0.5f) {
-                    const int m = __float2int_rn(rr);
-                    if ((tb & 0x7fffff) + 32 * m <= 0x7fffff) {     // all 33 values stay inside the binade
-                        T = __int_as_float(tb + lane * m);
-                        T_next = __int_as_float(tb + (lane + 1) * m);
-                        closed_form = true;
-                    }
-                }
+            // handful of windows per ray) fall back to the serial loop below.  (m is cached per binade.)
+            tb = __float_as_int(Tb);
+            if ((tb >> 23) != bn.key) binade_setup(tb, clampf(0.f, p.dt_min, p.dt_max), bn);
+            if (bn.ok && ((uint32_t)tb & 0x7fffffu) + 32u * bn.m <= 0x7fffffu) {   // all 33 values stay inside the binade
+                T = __int_as_float(tb + lane * (int)bn.m);
+                T_next = __int_as_float(tb + (lane + 1) * (int)bn.m);
+                closed_form = true;
             }
         }
         if (!closed_form) {
@@ -228,12 +266,23 @@ NGP_DEVINL uint32_t walk_ray_warp(const MarchParams& p, const Ray& r, float t0, 
         }
         // next pointer: lower_bound over the lanes above me of T >= tt (the do-while always advances once)
         uint32_t lo = lane + 1, hi = 32;
+        if (closed_form) {
+            // the window's lattice is tb + j * m in bit patterns (positive floats order like their bits): the first j with
+            // T_j >= tt is ceil((bits(tt) - tb) / m), exact through one float multiply and integer fix-ups
+            const int tti = __float_as_int(tt);
+            if (tti > tb) {
+                const uint32_t diff = (uint32_t)(tti - tb);
+                const uint32_t j = diff >= 32u * bn.m ? 32u : ceil_div(diff, bn.m, bn.inv_m);
+                lo = max(lo, j);
+            }
+        } else {
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
-            const uint32_t mid = (lo + hi) >> 1;
-            const float Tm = __shfl_sync(FULL, T, mid & 31);
-            if (lo < hi) {
-                if (Tm >= tt) hi = mid; else lo = mid + 1;
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const float Tm = __shfl_sync(FULL, T, mid & 31);
+                if (lo < hi) {
+                    if (Tm >= tt) hi = mid; else lo = mid + 1;
+                }
             }
         }
         // (lo == hi now, except for the degenerate single-candidate case handled by the loop above)
@@ -242,40 +291,43 @@ NGP_DEVINL uint32_t walk_ray_warp(const MarchParams& p, const Ray& r, float t0, 
         unsigned vis = 1u << (__ffs(start_mask) - 1);
         uint32_t hop = nxt;
 #pragma unroll
-        for (int it = 0; it < 5; ++it) {
+        for (int it = 0; it < 5; ++it) {   // (leaving the loop as soon as a round adds nothing was measured SLOWER: 0.323 vs 0.310 ms)
             const unsigned contrib = (((vis >> lane) & 1u) && hop < 32u) ? (1u << hop) : 0u;
             vis |= __reduce_or_sync(FULL, contrib);
             const uint32_t h2 = __shfl_sync(FULL, hop, hop & 31);
             hop = hop < 32u ? h2 : 32u;
         }
         vis &= valid;
-        unsigned emit_mask = vis & __ballot_sync(FULL, c.occ);
-        const uint32_t room = limit - emitted;
-        if ((uint32_t)__popc(emit_mask) > room) {   // keep the first `room` samples only (max_steps cap)
-            const uint32_t last = __fns(emit_mask, 0, (int)room);
-            emit_mask &= (last >= 31u) ? FULL : ((2u << last) - 1u);
-        }
-        if (WRITE) {
-            const unsigned below = emit_mask & lt_mask;
-            const int prev = below ? (31 - __clz(below)) : 0;
-            const float prev_after = __shfl_sync(FULL, T_next, prev);
-            if ((emit_mask >> lane) & 1u) {
-                const size_t row = emitted + __popc(below);
-                xyzs[row * 3 + 0] = c.x; xyzs[row * 3 + 1] = c.y; xyzs[row * 3 + 2] = c.z;
-                if (dirs) { dirs[row * 3 + 0] = r.dx; dirs[row * 3 + 1] = r.dy; dirs[row * 3 + 2] = r.dz; }
-                deltas[row * 2 + 0] = c.dt;
-                deltas[row * 2 + 1] = T_next - (below ? prev_after : last_t);  // t - last_t (:461)
+        const unsigned occ_mask = __ballot_sync(FULL, c.occ);
+        unsigned emit_mask = vis & occ_mask;
+        if (emit_mask) {            // (warp-uniform: most windows of a ray cross empty space and emit nothing)
+            const uint32_t room = limit - emitted;
+            if ((uint32_t)__popc(emit_mask) > room) {   // keep the first `room` samples only (max_steps cap)
+                const uint32_t last = __fns(emit_mask, 0, (int)room);
+                emit_mask &= (last >= 31u) ? FULL : ((2u << last) - 1u);
             }
-        }
-        if (emit_mask) {
-            last_t = __shfl_sync(FULL, T_next, 31 - __clz(emit_mask));
-            emitted += __popc(emit_mask);
+            if (WRITE) {
+                const unsigned below = emit_mask & lt_mask;
+                const int prev = below ? (31 - __clz(below)) : 0;
+                const float prev_after = __shfl_sync(FULL, T_next, prev);
+                if ((emit_mask >> lane) & 1u) {
+                    const size_t row = emitted + __popc(below);
+                    xyzs[row * 3 + 0] = c.x; xyzs[row * 3 + 1] = c.y; xyzs[row * 3 + 2] = c.z;
+                    if (dirs) { dirs[row * 3 + 0] = r.dx; dirs[row * 3 + 1] = r.dy; dirs[row * 3 + 2] = r.dz; }
+                    deltas[row * 2 + 0] = c.dt;
+                    deltas[row * 2 + 1] = T_next - (below ? prev_after : last_t);  // t - last_t (:461)
+                }
+            }
+            if (emit_mask) {
+                last_t = __shfl_sync(FULL, T_next, 31 - __clz(emit_mask));
+                emitted += __popc(emit_mask);
+            }
         }
         if (valid != FULL || vis == 0u) break;   // the lattice passed `far` inside this window
         // carry: the last visited lane points past the window; if it was empty its exit parameter is pending
         const int last_vis = 31 - __clz(vis);
         const float tt_last = __shfl_sync(FULL, tt, last_vis);
-        const bool occ_last = (__ballot_sync(FULL, c.occ) >> last_vis) & 1u;
+        const bool occ_last = (occ_mask >> last_vis) & 1u;
         pending = occ_last ? -FLT_MAX : tt_last;
         Tb = __shfl_sync(FULL, T_next, 31);
     }
@@ -587,22 +639,22 @@ __global__ void __launch_bounds__(128) march_slab_kernel(const float* __restrict
 // Same lattice, same visited points, same bits - at ~1/15 of the instructions; the price is latency (a ray is one serial
 // chain), so small launches keep the warp-per-ray walk.
 // -------------------------------------------------------------------------------------------------
-NGP_DEVINL float lattice_jump(float t, float tt, float dtc) {
+NGP_DEVINL float lattice_jump(float t, float tt, float dtc, Binade& b) {
     const int tti = __float_as_int(tt);          // tt >= t > 0 or +inf: the bit patterns order like the values
     do {
         const int tb = __float_as_int(t);
-        const int e = ((tb >> 23) & 0xff) - 127;
-        if (tb > 0 && e > -100 && e < 100) {
-            const float rr = scalbnf(dtc, 23 - e);              // dt / u, exact
-            const float fl = floorf(rr);
-            if (rr < 4194304.f && (rr - fl) != 0.5f && rr >= 0.5f) {
-                const uint32_t m = (uint32_t)__float2int_rn(rr);                       // >= 1
-                const uint32_t room = (0x7fffffu - ((uint32_t)tb & 0x7fffffu)) / m;      // steps that stay inside the binade
-                uint32_t need = 1u;
-                if (tti > tb) need = ((uint32_t)(tti - tb) + m - 1u) / m;                // first lattice point >= tt
-                if (need <= room) return __int_as_float(tb + (int)(need * m));
-                t = __int_as_float(tb + (int)(room * m));   // `room` steps; still < tt, since need > room
+        if ((tb >> 23) != b.key) binade_setup(tb, dtc, b);
+        if (b.ok) {
+            const uint32_t avail = 0x7fffffu - ((uint32_t)tb & 0x7fffffu);            // ulps left in the binade
+            uint32_t need_ulps = b.m;                                                 // the do-while always steps once
+            bool inside = true;
+            if (tti > tb) {
+                const uint32_t diff = (uint32_t)(tti - tb);
+                inside = diff <= avail;                                               // (otherwise tt lies beyond the binade)
+                if (inside) need_ulps = max(ceil_div(diff, b.m, b.inv_m), 1u) * b.m;   // first lattice point >= tt
             }
+            if (inside && need_ulps <= avail) return __int_as_float(tb + (int)need_ulps);
+            t = __int_as_float(tb + (int)(floor_div(avail, b.m, b.inv_m) * b.m));     // the last point of the binade: still < tt
         }
         t += dtc;        // the crossing (or tie / denormal) step, in float arithmetic as the reference
     } while (t < tt);
@@ -636,13 +688,17 @@ __global__ void __launch_bounds__(128) march_slab_thread_kernel(const float* __r
         float t = perturbed_start(p, nears[n], noises[n]);
         float4* row = slab + (size_t)n * max_steps;
         uint32_t steps = 0;
+        Binade bn;
+        bn.key = -1; bn.m = 1u; bn.inv_m = 1.f; bn.ok = false;
+        uint32_t last_index = 0xffffffffu;   // consecutive samples stay ~4 steps in a cell: its bit is fetched once
+        bool last_occ = false;
         while (t < far && steps < max_steps) {
-            const Cell c = classify(p, r, t);
+            const Cell c = classify(p, r, t, &last_index, &last_occ);
             if (c.occ) {
                 t += c.dt;                                   // (c.dt == dtc; raymarching.cu:425)
                 row[steps++] = make_float4(c.x, c.y, c.z, t);
             } else {
-                t = lattice_jump(t, cell_exit(p, r, c, t), dtc);
+                t = lattice_jump(t, cell_exit(p, r, c, t), dtc, bn);
             }
         }
         counts[n] = (int)steps;

@@ -425,7 +425,8 @@ class TrainStep:
             main.wait_stream(st)
         if has_bg:
             main.wait_stream(self._side)
-        if g_odd is not None:
+        if g_odd is not None and (self.keep_grads or not self.pipelined):
+            # (pipelined: folded by _apply_update on the optimizer's side stream, beside the next step's ray marching)
             _cabi.call("ngp_grid_fold_odd", dev, P(g_table), P(g_odd), g_table.numel())
         if self.keep_grads:
             if self.grad_snapshot is None:
@@ -438,6 +439,9 @@ class TrainStep:
 
     def _apply_update(self, deferred):
         with _nvtx.range("ngp.step.optimizer"):
+            if deferred and self._g_table_odd is not None and not self.keep_grads:
+                g_table = self.opt.grad_view(self.model.encoder.embeddings)
+                _cabi.call("ngp_grid_fold_odd", self.device, _cabi.ptr(g_table), _cabi.ptr(self._g_table_odd), g_table.numel())
             if self.world > 1 and self.opt.peer_ptrs is None:
                 dist.all_reduce(self.opt.flat_grads, op=dist.ReduceOp.SUM)
             self.opt.step_fused(deferred=deferred)

@@ -703,12 +703,12 @@ def test_march_thread_walk_with_closed_form_jumps_is_bit_identical(case, seed):
     total = int(ocounter[0])
     assert total > 0
     outs = []
-    for min_rays in (1, 0):
+    for min_rays in (1, 0):                       # thread-per-ray walk, then the default warp-per-ray walk
         assert c.load().ngp_march_set_option(2, min_rays) == 0
         try:
             outs.append(_my_march(case, rays_o, rays_d, bits, nears, fars, noises))
         finally:
-            assert c.load().ngp_march_set_option(2, 16384) == 0
+            assert c.load().ngp_march_set_option(2, 0) == 0
     for xyzs, dirs, deltas, rays, counter in outs:
         assert np.array_equal(N_(rays), orays) and np.array_equal(N_(counter), ocounter)
         assert np.array_equal(N_(xyzs[:total]), ox[:total]) and np.array_equal(N_(deltas[:total]), ol[:total])
