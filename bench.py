@@ -70,6 +70,8 @@ def parse():
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
     ap.add_argument("--host-rays", action="store_true", help="feed pre-generated rays (1.18 MB / step) instead of camera poses; "
                     "default: the step's input is 8 poses + intrinsics + the guidance gradient, rays are generated on the device")
+    ap.add_argument("--sync-loss", action="store_true", help="e2e leg: read every step's loss with loss.item() (a device sync per "
+                    "step, as the reference loop does) instead of the asynchronous pinned-memory read")
     ap.add_argument("--no-shading", action="store_true", help="skip the secondary lambertian-vs-albedo step timing")
     ap.add_argument("--ref-steps", type=int, default=200, help="timed steps of the reference CUDA-extension pipeline")
     ap.add_argument("--ref-warmup", type=int, default=50)
@@ -293,7 +295,12 @@ def run_b200_arm(args):
             # graph mode copies the packed batch straight into the step's static input buffer (H2D when it is a host batch)
             loss = step_fn(host_batch(i) if e2e else dev_pool[i % n_pool])
             if e2e:
-                loss.item()  # device -> host read of the step's result
+                # device -> host read of the step's result, every step: the loss is copied to pinned host memory right
+                # behind the step and consumed two calls later (TrainStep.read_loss_async), --sync-loss: loss.item()
+                if args.sync_loss:
+                    loss.item()
+                else:
+                    step_fn.read_loss_async(lag=2)
 
     # ---- warm-up ------------------------------------------------------------------------------------
     # the clock sampler (an nvidia-smi child process) is started BEFORE the warm-up: its start-up takes driver locks that
@@ -518,9 +525,9 @@ def run_b200_arm(args):
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * world,
                     "ms_per_step": ms_e2e / args.steps,
-                    "result_read": ("every step copies its loss to pinned host memory; the host reads it two calls later, when that "
-                                    "step has completed (overlapped steps: no stall)" if step_fn.overlap else
-                                    "loss.item() after every step")},
+                    "result_read": ("loss.item() after every step" if (args.sync_loss and not step_fn.overlap) else
+                                    "every step copies its loss (4 bytes) to pinned host memory behind the step; the host reads "
+                                    "the value two calls later, when that copy has landed (no per-step device sync)")},
             "gpu_launches": launches * world,
             "clocks": clk,
             "roofline": roofline,

@@ -82,6 +82,9 @@ class TrainStep:
         # table-gradient scatter into two buffers (even / odd row pairs both as 16-byte reds); NGP_SPLIT_SCATTER=0: one buffer
         self.split_scatter = os.environ.get("NGP_SPLIT_SCATTER", "1") not in ("", "0")
         self._g_table_odd = None
+        # overlap mode: ONE graph per call (march(k) || compute(k-1), forked and joined inside the graph) instead of two
+        # graphs on two streams tied by events; NGP_OVERLAP_FUSED=0 keeps the two-graph form
+        self.overlap_fused = os.environ.get("NGP_OVERLAP_FUSED", "1") not in ("", "0")
         self.keep_grads = False   # tests: copy the gradient bucket to self.grad_snapshot right before the optimizer
         self.grad_snapshot = None  # (a device-to-device copy inside the step, so it also works in a graph replay)
         self.use_graph = graph
@@ -219,8 +222,14 @@ class TrainStep:
                  counters=torch.zeros(n_chunks, 2, dtype=torch.int32, device=dev),
                  cur_row=torch.zeros(1, dtype=torch.int32, device=dev), chunks=[])
         base = 0
+        sizes = [N // n_chunks + (1 if c < N % n_chunks else 0) for c in range(n_chunks)]
+        fr = os.environ.get("NGP_CHUNK_FRACTIONS")    # e.g. "0.4,0.6": unequal chains (their kernel phases then interleave)
+        if fr and len(fr.split(",")) == n_chunks and N >= 256 * n_chunks:
+            f = [float(v) for v in fr.split(",")]
+            sizes = [max(128, int(N * v / sum(f)) // 128 * 128) for v in f]
+            sizes[-1] = N - sum(sizes[:-1])
         for c in range(n_chunks):
-            n_c = N // n_chunks + (1 if c < N % n_chunks else 0)
+            n_c = sizes[c]
             ws = TrainWorkspace(n_c, self.max_steps, dev, counter=m["counters"][c])
             m["chunks"].append((base, n_c, ws))
             base += n_c
@@ -469,13 +478,45 @@ class TrainStep:
             self.opt.sync_shadow_if_changed()
         return info
 
+    def read_loss_async(self, lag=2):
+        """The reference loop reads `loss.item()` after every step (nerf/utils.py:712), a device sync per step.  This is the
+        same read without the stall: every call copies the latest step's loss (device scalar) into a slot of a small pinned
+        ring and returns, as a Python float, the loss of `lag` calls ago - whose copy has certainly landed (its event is
+        awaited, normally already complete).  None for the first `lag` calls; overlap mode already returns pinned, lagged
+        losses and is passed through."""
+        if self.loss is None:
+            return None
+        if not self.loss.is_cuda:
+            return float(self.loss)
+        ring = getattr(self, "_loss_ring", None)
+        if ring is None or ring["lag"] != lag:
+            n = lag + 2
+            ring = dict(lag=lag, n=n, i=0, host=[torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(n)],
+                        ev=[torch.cuda.Event() for _ in range(n)])
+            self._loss_ring = ring
+        k = ring["i"]
+        ring["host"][k % ring["n"]].copy_(self.loss, non_blocking=True)
+        ring["ev"][k % ring["n"]].record()
+        ring["i"] = k + 1
+        if k < lag:
+            return None
+        j = (k - lag) % ring["n"]
+        ring["ev"][j].synchronize()
+        return float(ring["host"][j])
+
     def flush(self):
         """Pipelined mode: apply the update that is still pending (no-op otherwise).  After it the parameters are what
         the un-pipelined step would have left."""
         if self.overlap and self._ov is not None and self._ov["pending"]:
-            self._overlap_compute(1 - self._ov["parity"])     # the marched, not yet computed batch
+            if self._ov["g_fused"] is not None:
+                with torch.cuda.stream(self._ov["S_f"]):
+                    self._ov["g_compute"][1 - self._ov["parity"]].replay()
+                _cabi.LAUNCHES += self._ov["launches"][1]
+                torch.cuda.current_stream(self.device).wait_stream(self._ov["S_f"])
+            else:
+                self._overlap_compute(1 - self._ov["parity"])     # the marched, not yet computed batch
+                torch.cuda.current_stream(self.device).wait_stream(self._ov["S_c"])
             self._ov["pending"] = False
-            torch.cuda.current_stream(self.device).wait_stream(self._ov["S_c"])
         if self.manual and self.pipelined and self._pending:
             self._apply_update(deferred=True)
             self.opt.state[6:7].zero_()  # nothing pending: the next step's leading launch only re-arms
@@ -617,6 +658,8 @@ class TrainStep:
             self._capture_overlap(packed, B)
         ov = self._ov
         p = ov["parity"]
+        if ov["g_fused"] is not None:
+            return self._call_overlap_fused(packed, cur)
         S_m, S_c = ov["S_m"], ov["S_c"]
         ov["ev_compute"][p].synchronize()       # set p is free: compute(k-2) has finished (host-side: bounds the run-ahead)
         loss_out = ov["loss_ret"][p]
@@ -646,6 +689,56 @@ class TrainStep:
         _cabi.LAUNCHES += ov["launches"][0]
         if ov["pending"]:
             self._overlap_compute(1 - p)
+        ov["pending"] = True
+        ov["parity"] = 1 - p
+        model.local_step += 1
+        self._ls_mirror = model.local_step
+        self.loss = loss_out
+        return loss_out
+
+    def _call_overlap_fused(self, packed, cur):
+        """Overlap mode, one graph per call.  Call k (parity p = k % 2) puts batch k into input set p and replays, on ONE
+        stream, the graph { march(set p) || compute(set 1 - p) }: batch k is marched while batch k - 1 - marched by the
+        previous call - goes through field / loss / backward / scatter / optimizer.  Calls follow each other in stream order,
+        so no events tie them; the host only waits for the graph of call k - 2 (the one of call k - 1 keeps the device busy
+        meanwhile) and returns the loss that graph produced: the loss of batch k - 3, as a pinned CPU scalar.
+        The first call, and every call that refreshes the occupancy grid (which must see the previous step's parameters and be
+        seen by this step's march), run the halves as separate graphs: pending compute, refresh, march."""
+        model, ov = self.model, self._ov
+        p = ov["parity"]
+        S_f = ov["S_f"]
+        ov["ev_graph"][p].synchronize()
+        loss_out = ov["loss_ret"][p]
+        loss_out.copy_(ov["loss_host"][1 - p])
+        S_f.wait_stream(cur)                    # the caller's input batch
+        with torch.cuda.stream(S_f):
+            ov["static"][p].copy_(packed, non_blocking=True)
+            refresh = self.global_step % self.update_interval == 0
+            split = refresh or not ov["pending"]
+            if split and ov["pending"]:
+                ov["g_compute"][1 - p].replay()
+                _cabi.LAUNCHES += ov["launches"][1]
+                ov["pending"] = False
+            if refresh:
+                if self.world > 1 and self.opt.peer_ptrs is not None and self.global_step > 0 and self.opt.comm_error:
+                    raise RuntimeError("data-parallel step: a peer did not reach the gradient exchange in time (see "
+                                       "NGP_DP_TIMEOUT_MS); parameters were left untouched from that step on")
+                with torch.autocast("cuda", torch.float16):
+                    model.update_extra_state()
+                self.n_updates += 1
+            self.global_step += 1
+            self.opt.attach_grads()
+            self.opt.sync_shadow_if_changed()
+            if self._ls_mirror != model.local_step:
+                self._local_step_dev.fill_(model.local_step)
+                self._ls_mirror = model.local_step
+            if split:
+                ov["g_march"][p].replay()
+                _cabi.LAUNCHES += ov["launches"][0]
+            else:
+                ov["g_fused"][p].replay()
+                _cabi.LAUNCHES += ov["launches"][0] + ov["launches"][1]
+            ov["ev_graph"][p].record(S_f)
         ov["pending"] = True
         ov["parity"] = 1 - p
         model.local_step += 1
@@ -710,6 +803,28 @@ class TrainStep:
             ov["g_compute"][p] = g
             ov["launches"] = [l1 - l0, _cabi.LAUNCHES - l1]
             _cabi.LAUNCHES = l0
+        ov["g_fused"] = None
+        if self.overlap_fused:
+            # the same two halves once more, as the two branches of ONE graph: set p marches while set 1 - p computes
+            S_f = torch.cuda.Stream(device=dev)
+            S_f.wait_stream(S_m)
+            S_f.wait_stream(S_c)
+            ov["S_f"], ov["ev_graph"], ov["g_fused"] = S_f, [torch.cuda.Event() for _ in range(2)], [None, None]
+            for p in (0, 1):
+                l0 = _cabi.LAUNCHES
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=S_f, capture_error_mode="thread_local"):
+                    S_m.wait_stream(S_f)
+                    S_c.wait_stream(S_f)
+                    with torch.cuda.stream(S_c):
+                        compute(1 - p)
+                    with torch.cuda.stream(S_m):
+                        march(p)
+                    S_f.wait_stream(S_m)
+                    S_f.wait_stream(S_c)
+                ov["g_fused"][p] = g
+                _cabi.LAUNCHES = l0
+            cur.wait_stream(S_f)
         torch.cuda.set_rng_state(rng, dev)
         model.local_step = saved_step
         self._pending = False

@@ -451,11 +451,14 @@ def test_device_rays_step_equals_the_host_rays_step():
         assert rel < 1e-4, rel
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("device_rays", [False, True])
-def test_overlapped_steps_match_sequential_steps(device_rays):
-    """overlap=True runs the marching half of step k+1 beside the compute half of step k (two graphs per step, two
-    workspace sets); parameter updates, sample counts and run_cuda's bookkeeping must be those of the sequential graphed
-    step - across an occupancy refresh too (22 steps, update_interval 16)."""
+def test_overlapped_steps_match_sequential_steps(device_rays, fused, monkeypatch):
+    """overlap=True runs the marching half of step k+1 beside the compute half of step k - as the two branches of ONE graph
+    per call (fused, the default) or as two graphs on two streams tied by events; two workspace sets either way.  Parameter
+    updates, sample counts and run_cuda's bookkeeping must be those of the sequential graphed step - across an occupancy
+    refresh too (22 steps, update_interval 16)."""
+    monkeypatch.setenv("NGP_OVERLAP_FUSED", "1" if fused else "0")
     from ngp_b200 import provider
     from ngp_b200.trainer import TrainStep
     n_steps, views = 22, 2
@@ -485,8 +488,30 @@ def test_overlapped_steps_match_sequential_steps(device_rays):
     a, b = out
     assert a["samples"] == b["samples"] > 0 and a["local_step"] == b["local_step"]
     assert torch.equal(a["counter"], b["counter"]) and torch.equal(a["bits"], b["bits"])
-    # the overlapped run reports losses two calls late: loss[k] of the sequential run == returned[k + 2]
-    np.testing.assert_allclose(b["losses"][2:], a["losses"][:-2], rtol=1e-4)
+    # the overlapped run reports losses late: loss[k] of the sequential run == returned[k + lag]
+    lag = 3 if fused else 2
+    np.testing.assert_allclose(b["losses"][lag:], a["losses"][:-lag], rtol=1e-4)
     for n in a["params"]:
         rel = ((a["params"][n] - b["params"][n]).norm() / a["params"][n].norm()).item()
         assert rel < 1e-3, (n, rel)         # same updates in the same order; fp32 atomics order is the only difference
+
+
+def test_read_loss_async_returns_the_lagged_loss_without_a_sync():
+    """TrainStep.read_loss_async: every call copies the step's loss to a pinned ring and hands back the loss of `lag`
+    calls ago - the values loss.item() would have returned, two calls later."""
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    views, n_steps = 1, 7
+    poses, intr = provider.make_training_poses(n_steps * views, 64, 64, seed=8)
+    poses, intr = poses.view(n_steps, views, 4, 4).to(DEV), intr.view(n_steps, views, 4).to(DEV)
+    G = torch.randn(n_steps, views, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(4)) * 1e-2
+    m = _bench_like_model()
+    step = TrainStep(m, 64, 64, lr=1e-3, graph=True, manual=True, device_rays=(64, 0, 1))
+    sync, lagged = [], []
+    for i in range(n_steps):
+        loss = step(step.pack_pose_inputs(poses[i], intr[i], G[i]))
+        lagged.append(step.read_loss_async(lag=2))
+        sync.append(float(loss.item()))
+    assert lagged[:2] == [None, None]
+    np.testing.assert_allclose(lagged[2:], sync[:-2], rtol=0, atol=0)
+    assert len(set(sync)) > 1 and all(np.isfinite(sync))
