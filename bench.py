@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--chunks", type=int, default=0, help="ray chunks run as parallel chains (0 = the default, 2)")
     ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce instead of the fused peer-memory all-reduce + Adam")
     ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
+    ap.add_argument("--timeline", default=None, help="write the kernel timeline (CUPTI: name, stream, start, duration) of 3 "
+                    "graphed steps to this JSON file - where the step's time goes between the kernels")
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
     ap.add_argument("--host-rays", action="store_true", help="feed pre-generated rays (1.18 MB / step) instead of camera poses; "
                     "default: the step's input is 8 poses + intrinsics + the guidance gradient, rays are generated on the device")
@@ -319,7 +321,9 @@ def run_b200_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    host_t0 = time.perf_counter()
     run_steps(args.steps, False, 1000, record=True)
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host time to ENQUEUE a step (the loop does not sync)
     step_fn.flush()  # pipelined optimizer: the last step's update belongs to the timed work
     e1.record()
     barrier()
@@ -354,6 +358,24 @@ def run_b200_arm(args):
             f.write("# torch.profiler (CUPTI) kernel times over 5 steps of the graphed train step; divide by 5 for per step\n")
             f.write(prof_t.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
 
+    if args.timeline and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof_t:
+            run_steps(4, False, 2600)
+            step_fn.flush()
+            torch.cuda.synchronize()
+        with tempfile.NamedTemporaryFile(suffix=".json") as tf:
+            prof_t.export_chrome_trace(tf.name)
+            tr = json.load(open(tf.name))
+        ev = [e for e in tr.get("traceEvents", []) if e.get("ph") == "X" and e.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset")]
+        ev.sort(key=lambda e: e["ts"])
+        t0 = ev[0]["ts"] if ev else 0.0
+        rows = [dict(t_us=round(e["ts"] - t0, 2), dur_us=round(e["dur"], 2), stream=e.get("args", {}).get("stream"),
+                     name=e["name"][:70], grid=e.get("args", {}).get("grid"), block=e.get("args", {}).get("block")) for e in ev]
+        with open(args.timeline, "w") as f:
+            json.dump(rows, f, indent=0)
+
     # ---- per-kernel durations for the roofline: a few EAGER steps with CUDA events around our entry points ----
     # (events cannot be recorded inside a graph replay; same kernels, same data shapes).  ONE serial chain on ONE stream:
     # concurrent chains inflate each other's event-to-event times, and a side-stream kernel's events would include its
@@ -371,7 +393,7 @@ def run_b200_arm(args):
         step_fn.n_chunks, step_fn._mws = 1, None
         step_fn._side = torch.cuda.current_stream(device)
     names = ["ngp_grid_scatter_samples", "ngp_grid_encode_backward", "ngp_field_forward", "ngp_field_backward",
-             "ngp_march_rays_train", "ngp_composite_rays_train_forward", "ngp_composite_rays_train_backward",
+             "ngp_march_rays_train", "ngp_march_rays_train_packed", "ngp_composite_rays_train_forward", "ngp_composite_rays_train_backward",
              "ngp_grid_encode_forward", "ngp_train_prologue", "ngp_train_prologue_rays", "ngp_train_ray_loss", "ngp_bg_forward", "ngp_bg_backward",
              "ngp_adam_step_fused", "ngp_grid_scatter_samples_split", "ngp_grid_fold_odd"]
     step_fn.global_step = 1  # keep the occupancy refresh out of the profiled steps
@@ -529,6 +551,7 @@ def run_b200_arm(args):
                                     "every step copies its loss (4 bytes) to pinned host memory behind the step; the host reads "
                                     "the value two calls later, when that copy has landed (no per-step device sync)")},
             "gpu_launches": launches * world,
+            "host_enqueue_ms_per_step": host_ms,
             "clocks": clk,
             "roofline": roofline,
         }

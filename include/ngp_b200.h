@@ -106,7 +106,8 @@ int ngp_packbits(const float* grid, uint32_t N, float density_thresh, uint8_t* b
  * rays[n] describes ray n and offsets are an exclusive prefix sum - one of the orders the
  * reference itself can produce.  A ray whose offset+count > M is recorded in `rays` but writes no
  * samples (raymarching.cu:416).  workspace: device scratch of >=
- * ngp_march_rays_train_workspace(N, max_steps) bytes (per-ray counts + one max_steps-row slab per ray). */
+ * ngp_march_rays_train_workspace(N, max_steps) bytes (per-ray counts + one max_steps-row slab per ray).  The first 256
+ * bytes of a NEW workspace must be zero-filled once by the caller (block-election word); every call leaves them zero. */
 int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
                          const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
@@ -114,6 +115,15 @@ int ngp_march_rays_train(const float* rays_o, const float* rays_d, const uint8_t
                          uint64_t workspace_bytes, void* stream);
 /* (dirs may be NULL: the albedo-shaded training path never reads the per-sample directions.) */
 uint64_t ngp_march_rays_train_workspace(uint32_t N, uint32_t max_steps);
+/* The same marcher as ONE launch without scratch: each ray is walked once (its samples' lattice parameters parked in shared
+ * memory), claims its rows with one atomicAdd on counter[0] - the reference's slot allocation, raymarching.cu:405-406 - and
+ * writes them in place.  Same samples per ray, bit for bit; rays[n] = (n, offset, count) still describes ray n, but offsets
+ * follow completion order instead of ray order (as in the reference).  max_steps <= 2048 (else NGP_ERR_UNSUPPORTED: use
+ * ngp_march_rays_train).  The hand-scheduled train step uses this one. */
+int ngp_march_rays_train_packed(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                int* rays, int* counter, const float* noises, void* stream);
 /* option 0: value != 0 selects the one-thread-per-ray count / write kernels (the reference's decomposition) instead of
  * the default walks; option 1: warp-per-ray walk for one-sample inference calls; option 2: ngp_march_rays_train launches of
  * at least `value` rays with dt_gamma == 0 use the thread-per-ray walk with closed-form lattice jumps, smaller ones the
@@ -320,6 +330,9 @@ int ngp_enable_peer_access(int peer_device);
  * ngp_train_prologue: near_far_from_aabb (raymarching.cu:92-156) for N rays + the step's device-side bookkeeping: zero-fill
  * of counters i32[n_counters] and loss f32[1]; opens the step's row of run_cuda's 16-step window (nerf/renderer.py:466-467):
  * *cur_row = *local_step % 16, step_counter[*cur_row] = (0, 0), ++*local_step.  Each pointer group may be NULL.
+ * noises (optional, f32[N]) + rng (u64[3]: seed, step counter, scratch - zero the scratch once): the per-ray march jitter the
+ * reference draws with torch.rand(N) (raymarching.py:213-216), from a counter-based generator keyed by (seed, counter, ray);
+ * the launch advances the counter by one, so consecutive steps draw fresh, reproducible noise without a generator launch.
  * ngp_train_ray_loss: per ray, in one launch: composite_rays_train forward (raymarching.cu:501-588), the background blend
  * (nerf/renderer.py:541-545), the gradients of the two losses of Trainer.train_step at the ray - grad_pred (the guidance
  * gradient wrt the blended image, [B,3,pixels_per_view] NCHW as nerf/sd.py:115 passes it, or [N,3] if pixels_per_view is
@@ -331,7 +344,7 @@ int ngp_enable_peer_access(int peer_device);
  * *samples_total += counter[0]; step_counter[*cur_row] += counter. */
 int ngp_train_prologue(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near, float* nears,
                        float* fars, int* counters, uint32_t n_counters, float* loss, int* step_counter, int* local_step,
-                       int* cur_row, void* stream);
+                       int* cur_row, float* noises, uint64_t* rng, void* stream);
 int ngp_train_ray_loss(const float* sigmas, const float* rgbs, const float* deltas, const int* rays, uint32_t M, uint32_t N,
                        float T_thresh, const void* bg_half, float bg_const, const float* grad_pred, uint32_t pixels_per_view,
                        uint32_t ray_base, uint32_t n_rays_total, float lambda_entropy, const float* scale, float* weights_sum,
@@ -383,7 +396,8 @@ int ngp_get_rays(const float* poses, const float* intrinsics, int intrinsics_per
 int ngp_train_prologue_rays(const float* poses, const float* intrinsics, int intrinsics_per_view, uint32_t B, uint32_t H,
                             uint32_t W, uint32_t row0, uint32_t row_stride, uint32_t n_rows, float* rays_o, float* rays_d,
                             const float* aabb, float min_near, float* nears, float* fars, int* counters, uint32_t n_counters,
-                            float* loss, int* step_counter, int* local_step, int* cur_row, void* stream);
+                            float* loss, int* step_counter, int* local_step, int* cur_row, float* noises, uint64_t* rng,
+                            void* stream);
 
 /* End of run_cuda (nerf/renderer.py:535-557): image_out = image + (1 - weights_sum) * bg, depth_out =
  * clamp(depth - nears, 0) / (fars - nears) (NaN where the ray misses the box, as the reference), mask = nears < fars.
@@ -419,6 +433,15 @@ int ngp_bench_red8(float* table, uint32_t table_words, uint32_t n_threads, uint3
  * issues (1 = all 32 lanes).  Separates the per-lane issue cost from the L2 cost of the scatter. */
 int ngp_bench_red_width(float* table, uint32_t table_words, uint32_t n_threads, uint32_t iters, uint32_t seed,
                         uint32_t width, uint32_t lane_stride, void* stream);
+
+/* cudaGraphLaunch of an instantiated graph (cudaGraphExec_t) on `stream`.  The host framework's own replay call also
+ * enqueues two fill kernels per replay for its random generators; a captured hand-scheduled step draws its noise on the
+ * device (ngp_train_prologue), so it is launched bare. */
+int ngp_graph_launch(void* graph_exec, void* stream);
+
+/* Timeline support: writes the device's nanosecond clock (%globaltimer) to *slot when `stream` reaches this launch.
+ * Capturable; NGP_TRACE-style tools bracket every entry point of a graphed step with two stamps (profiles/tools/timeline.py). */
+int ngp_stamp(uint64_t* slot, void* stream);
 
 /* Hardware self-test of the hand-written tcgen05 path (one CTA, one small fp16 GEMM with fp32 accumulate):
  * mode 0: D[128,N] = A[128,K] B[N,K]^T ; mode 1: D[M,N] = A[128,M]^T B[128,N] (M in {64,128}) ;

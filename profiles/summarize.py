@@ -74,7 +74,7 @@ def traffic(src, dst, samples_per_launch=None):
     idx = {h: i for i, h in enumerate(hdr)}
     entry_of = {"encode_backward_warpagg_kernel": "ngp_grid_scatter_samples", "field_forward_kernel": "ngp_field_forward",
                 "field_backward_kernel": "ngp_field_backward", "train_ray_loss_kernel": "ngp_train_ray_loss",
-                "march_slab_kernel": "ngp_march_rays_train", "adam_step_fused_kernel": "ngp_adam_step_fused"}
+                "march_slab_kernel": "ngp_march_rays_train", "march_packed_kernel": "ngp_march_rays_train_packed", "adam_step_fused_kernel": "ngp_adam_step_fused"}
     agg = collections.defaultdict(list)
     for r in rows[2:]:
         name = r[idx["Kernel Name"]]

@@ -32,6 +32,7 @@ SIGNATURES = {
     "ngp_morton3D_invert": (_i32, [_vp, _u32, _vp, _vp]),
     "ngp_packbits": (_i32, [_vp, _u32, _f32, _vp, _vp]),
     "ngp_march_rays_train": (_i32, [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "ngp_march_rays_train_packed": (_i32, [_vp, _vp, _vp, _f32, _f32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ngp_march_set_option": (_i32, [_i32, _i32]),
     "ngp_march_rays_train_workspace": (_u64, [_u32, _u32]),
     "ngp_composite_rays_train_forward": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _vp, _vp, _vp]),
@@ -55,6 +56,8 @@ SIGNATURES = {
     "ngp_grid_scatter_samples": (_i32, [_vp, _vp, _f32, _vp, _u32, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _vp, _vp]),
     "ngp_grid_scatter_samples_split": (_i32, [_vp, _vp, _f32, _vp, _u32, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _vp, _vp, _vp]),
     "ngp_grid_fold_odd": (_i32, [_vp, _vp, _u64, _vp]),
+    "ngp_stamp": (_i32, [_vp, _vp]),
+    "ngp_graph_launch": (_i32, [_vp, _vp]),
     "ngp_tc_selftest": (_i32, [_i32, _vp, _vp, _vp, _u32, _u32, _u32, _vp]),
     "ngp_field_set_option": (_i32, [_i32, _i32]),
     "ngp_bg_forward": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
@@ -71,7 +74,7 @@ SIGNATURES = {
     "ngp_dp_flags_bytes": (_u64, []),
     "ngp_dp_set_option": (_i32, [_i32, _i32]),
     "ngp_enable_peer_access": (_i32, [_i32]),
-    "ngp_train_prologue": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_train_prologue": (_i32, [_vp, _vp, _vp, _u32, _f32, _vp, _vp, _vp, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ngp_stencil_points": (_i32, [_vp, _u32, _f32, _f32, _i32, _vp, _vp]),
     "ngp_shade_forward": (_i32, [_vp, _vp, _u32, _u32, _vp, _f32, _i32, _vp, _vp, _vp]),
     "ngp_shade_backward": (_i32, [_vp, _vp, _u32, _u32, _vp, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -81,7 +84,7 @@ SIGNATURES = {
     "ngp_render_infer_state": (_i32, [_vp, C.POINTER(_i32), _vp]),
     "ngp_get_rays": (_i32, [_vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "ngp_train_prologue_rays": (_i32, [_vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _u32,
-                                       _vp, _vp, _vp, _vp, _vp]),
+                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ngp_train_ray_loss": (_i32, [_vp, _vp, _vp, _vp, _u32, _u32, _f32, _vp, _f32, _vp, _u32, _u32, _u32, _f32, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ngp_blend_background_forward": (_i32, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _u32, _vp, _vp, _vp, _vp]),
@@ -147,6 +150,9 @@ DEBUG_SYNC = os.environ.get("NGP_DEBUG_SYNC", "0") not in ("", "0")   # synchron
 #                    (the reference never checks: faults surface at the next sync; this pins them to the call)
 LAUNCHES = 0       # running count of our kernels launched through this module
 PROFILE = None     # optional {entry point name: [(start_event, end_event), ...]} filled while set (bench.py)
+TRACE = None       # optional dict(buf=int64 device tensor, rows=[(name, stream id)]): every entry point called while it is
+#                    set is bracketed by two ngp_stamp launches (%globaltimer) on its stream - capturable, so a graphed step
+#                    replays its own timeline into `buf` (profiles/tools/timeline.py)
 
 
 def call(name, device, *args):
@@ -162,6 +168,14 @@ def call(name, device, *args):
             rc = getattr(lib, name)(*args, stream())
             e1.record()
             prof.append((e0, e1))
+        elif TRACE is not None and 2 * len(TRACE["rows"]) + 2 <= TRACE["buf"].numel():
+            st = stream()
+            i = len(TRACE["rows"])
+            TRACE["rows"].append((name, st))
+            base = TRACE["buf"].data_ptr()
+            lib.ngp_stamp(base + 16 * i, st)
+            rc = getattr(lib, name)(*args, st)
+            lib.ngp_stamp(base + 16 * i + 8, st)
         else:
             rc = getattr(lib, name)(*args, stream())
     LAUNCHES += KERNELS_PER_CALL.get(name, 1)

@@ -67,3 +67,9 @@ extern "C" int ngp_device_info(char* name, int name_len, int* sm_count, int* cc_
     if (cc_minor) *cc_minor = prop.minor;
     return NGP_OK;
 }
+
+extern "C" int ngp_graph_launch(void* graph_exec, void* stream) {
+    if (!graph_exec) return NGP_ERR_BAD_ARG;
+    const cudaError_t e = cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), ngp::as_stream(stream));
+    return e == cudaSuccess ? NGP_OK : (int)e;
+}

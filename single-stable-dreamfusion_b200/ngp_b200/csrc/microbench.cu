@@ -60,6 +60,13 @@ __global__ void __launch_bounds__(256) red_width_kernel(float* table, uint32_t m
     }
 }
 
+// one thread, one store: the device's nanosecond clock (%globaltimer) at the moment the stream reaches this node
+__global__ void stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    *slot = t;
+}
+
 }  // namespace ubench
 }  // namespace ngp
 
@@ -92,5 +99,11 @@ extern "C" int ngp_bench_red_width(float* table, uint32_t table_words, uint32_t 
     else if (width == 2) ubench::red_width_kernel<2><<<grid, block, 0, st>>>(table, table_words / 2 - 1, n_threads, iters, seed, lane_stride);
     else if (width == 4) ubench::red_width_kernel<4><<<grid, block, 0, st>>>(table, table_words / 4 - 1, n_threads, iters, seed, lane_stride);
     else return NGP_ERR_UNSUPPORTED;
+    return launch_status();
+}
+
+extern "C" int ngp_stamp(uint64_t* slot, void* stream) {
+    if (!slot) return NGP_ERR_BAD_ARG;
+    ubench::stamp_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
     return launch_status();
 }

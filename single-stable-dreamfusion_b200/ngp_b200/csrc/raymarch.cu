@@ -209,9 +209,11 @@ NGP_DEVINL uint32_t ceil_div(uint32_t a, uint32_t m, float inv_m) {
 // its exit parameter).  So 32 lanes evaluate 32 consecutive lattice points (each lane re-doing the serial additions
 // from the window base, which keeps every T bit-identical), classify their cells in parallel, turn "where do I go
 // next" into a pointer per lane and resolve the visited chain with 5 rounds of pointer doubling.
-// Returns the number of emitted samples (<= limit); WRITE stores them at rows [0, n) of the given pointers.
+// Returns the number of emitted samples (<= limit); WRITE == 1 stores them at rows [0, n) of the given pointers,
+// WRITE == 2 only records their lattice parameters T in `xyzs` (a shared-memory buffer of `limit` floats: position, step
+// and delta of a sample are functions of T and of the previous sample's T, see march_packed_kernel).
 // -------------------------------------------------------------------------------------------------
-template <bool WRITE>
+template <int WRITE>
 NGP_DEVINL uint32_t walk_ray_warp(const MarchParams& p, const Ray& r, float t0, float far, uint32_t limit, int lane,
                                   float* __restrict__ xyzs, float* __restrict__ dirs, float* __restrict__ deltas) {
     constexpr unsigned FULL = 0xffffffffu;
@@ -306,7 +308,9 @@ NGP_DEVINL uint32_t walk_ray_warp(const MarchParams& p, const Ray& r, float t0, 
                 const uint32_t last = __fns(emit_mask, 0, (int)room);
                 emit_mask &= (last >= 31u) ? FULL : ((2u << last) - 1u);
             }
-            if (WRITE) {
+            if (WRITE == 2) {
+                if ((emit_mask >> lane) & 1u) xyzs[emitted + __popc(emit_mask & lt_mask)] = T;
+            } else if (WRITE == 1) {
                 const unsigned below = emit_mask & lt_mask;
                 const int prev = below ? (31 - __clz(below)) : 0;
                 const float prev_after = __shfl_sync(FULL, T_next, prev);
@@ -376,11 +380,41 @@ __global__ void near_far_kernel(const float* __restrict__ rays_o, const float* _
 // bookkeeping, so no separate fill launches are needed: zero the sample-counter pairs and the loss accumulator; open the
 // step's row of run_cuda's 16-step counter window (nerf/renderer.py:466-467): *cur_row = *local_step % 16,
 // step_counter[*cur_row] = 0, ++*local_step.
+// Per-ray march jitter on the device (the reference draws torch.rand(N) per call, raymarching.py:213-216): a counter-based
+// generator keyed by (seed, step counter, ray) - three rounds of a 32-bit avalanche mix, top 24 bits -> [0, 1) like
+// torch.rand.  Drawing it here removes the uniform_ launch from the step and, in graph mode, the two seed / offset fill
+// kernels torch enqueues before every replay of a graph that contains one of its generators.
+// rng = u64[3]: seed, step counter, (low word) block-election counter.  Thread 0 of every block reads the counter before it
+// signs off; the LAST block to sign off advances it, so every ray of a step sees the same counter and steps never repeat.
+NGP_DEVINL uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+NGP_DEVINL float ray_noise(unsigned long long seed, unsigned long long ctr, uint32_t n) {
+    uint32_t x = mix32(n ^ (uint32_t)seed);
+    x = mix32(x + (uint32_t)ctr * 0x9E3779B9u + (uint32_t)(ctr >> 32));
+    x = mix32(x ^ (uint32_t)(seed >> 32));
+    return (float)(x >> 8) * (1.0f / 16777216.0f);
+}
+NGP_DEVINL void rng_step_done(unsigned long long* rng, unsigned long long ctr) {   // thread 0 of every block, after its reads
+    __threadfence();
+    unsigned int* done = reinterpret_cast<unsigned int*>(rng + 2);
+    if (atomicAdd(done, 1u) == gridDim.x - 1) {
+        rng[1] = ctr + 1ull;
+        *done = 0u;
+    }
+}
+
 __global__ void train_prologue_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                       const float* __restrict__ aabb, uint32_t N, float min_near, float* nears,
                                       float* fars, int* counters, uint32_t n_counters, float* loss, int* step_counter,
-                                      int* local_step, int* cur_row) {
+                                      int* local_step, int* cur_row, float* noises, unsigned long long* rng) {
+    __shared__ unsigned long long s_rng[2];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (noises) {
+        if (threadIdx.x == 0) { s_rng[0] = rng[0]; s_rng[1] = rng[1]; }
+        __syncthreads();
+    }
     if (n == 0) {
         for (uint32_t i = 0; counters && i < n_counters; ++i) counters[i] = 0;
         if (loss) *loss = 0.f;
@@ -392,12 +426,15 @@ __global__ void train_prologue_kernel(const float* __restrict__ rays_o, const fl
             *local_step += 1;
         }
     }
-    if (n >= N) return;
-    const Ray r = load_ray(rays_o, rays_d, n);
-    float lo, hi;
-    near_far_of(r, aabb, min_near, lo, hi);
-    nears[n] = lo;
-    fars[n] = hi;
+    if (n < N) {
+        const Ray r = load_ray(rays_o, rays_d, n);
+        float lo, hi;
+        near_far_of(r, aabb, min_near, lo, hi);
+        nears[n] = lo;
+        fars[n] = hi;
+        if (noises) noises[n] = ray_noise(s_rng[0], s_rng[1], n);
+    }
+    if (noises && threadIdx.x == 0) rng_step_done(rng, s_rng[1]);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -445,8 +482,13 @@ __global__ void get_rays_kernel(const RayGen g, float* __restrict__ rays_o, floa
 __global__ void train_prologue_rays_kernel(const RayGen g, float* __restrict__ rays_o, float* __restrict__ rays_d,
                                            const float* __restrict__ aabb, float min_near, float* nears, float* fars,
                                            int* counters, uint32_t n_counters, float* loss, int* step_counter, int* local_step,
-                                           int* cur_row) {
+                                           int* cur_row, float* noises, unsigned long long* rng) {
+    __shared__ unsigned long long s_rng[2];
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (noises) {
+        if (threadIdx.x == 0) { s_rng[0] = rng[0]; s_rng[1] = rng[1]; }
+        __syncthreads();
+    }
     if (n == 0) {
         for (uint32_t i = 0; counters && i < n_counters; ++i) counters[i] = 0;
         if (loss) *loss = 0.f;
@@ -458,14 +500,17 @@ __global__ void train_prologue_rays_kernel(const RayGen g, float* __restrict__ r
             *local_step += 1;
         }
     }
-    if (n >= g.B * g.n_rows * g.W) return;
-    const Ray r = generate_ray(g, n);
-    rays_o[n * 3] = r.ox; rays_o[n * 3 + 1] = r.oy; rays_o[n * 3 + 2] = r.oz;
-    rays_d[n * 3] = r.dx; rays_d[n * 3 + 1] = r.dy; rays_d[n * 3 + 2] = r.dz;
-    float lo, hi;
-    near_far_of(r, aabb, min_near, lo, hi);
-    nears[n] = lo;
-    fars[n] = hi;
+    if (n < g.B * g.n_rows * g.W) {
+        const Ray r = generate_ray(g, n);
+        rays_o[n * 3] = r.ox; rays_o[n * 3 + 1] = r.oy; rays_o[n * 3 + 2] = r.oz;
+        rays_d[n * 3] = r.dx; rays_d[n * 3 + 1] = r.dy; rays_d[n * 3 + 2] = r.dz;
+        float lo, hi;
+        near_far_of(r, aabb, min_near, lo, hi);
+        nears[n] = lo;
+        fars[n] = hi;
+        if (noises) noises[n] = ray_noise(s_rng[0], s_rng[1], n);
+    }
+    if (noises && threadIdx.x == 0) rng_step_done(rng, s_rng[1]);
 }
 
 __global__ void sph_from_ray_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, float radius,
@@ -555,7 +600,7 @@ __global__ void __launch_bounds__(128) march_count_warp_kernel(const float* __re
     const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
     const Ray r = load_ray(rays_o, rays_d, n);
     const float t0 = perturbed_start(p, nears[n], noises[n]);
-    const uint32_t steps = walk_ray_warp<false>(p, r, t0, fars[n], max_steps, lane, nullptr, nullptr, nullptr);
+    const uint32_t steps = walk_ray_warp<0>(p, r, t0, fars[n], max_steps, lane, nullptr, nullptr, nullptr);
     if (lane == 0) counts[n] = (int)steps;
 }
 
@@ -576,7 +621,7 @@ __global__ void __launch_bounds__(128) march_write_warp_kernel(const float* __re
     const MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
     const Ray r = load_ray(rays_o, rays_d, n);
     const float t0 = perturbed_start(p, nears[n], noises[n]);
-    walk_ray_warp<true>(p, r, t0, fars[n], num_steps, lane, xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr,
+    walk_ray_warp<1>(p, r, t0, fars[n], num_steps, lane, xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr,
                         deltas + (size_t)offset * 2);
 }
 
@@ -608,7 +653,7 @@ __global__ void __launch_bounds__(128) march_slab_kernel(const float* __restrict
         if (use_lut) p.lut = s_lut;
         const Ray r = load_ray(rays_o, rays_d, n);
         const float t0 = perturbed_start(p, nears[n], noises[n]);
-        const uint32_t steps = walk_ray_warp<true>(p, r, t0, fars[n], max_steps, lane, slab_xyz + (size_t)n * max_steps * 3, nullptr,
+        const uint32_t steps = walk_ray_warp<1>(p, r, t0, fars[n], max_steps, lane, slab_xyz + (size_t)n * max_steps * 3, nullptr,
                                                    slab_delta + (size_t)n * max_steps * 2);
         if (lane == 0) counts[n] = (int)steps;
     }
@@ -625,6 +670,62 @@ __global__ void __launch_bounds__(128) march_slab_kernel(const float* __restrict
     __threadfence();
     scan_ray_counts(counts, N, rays, counter, s_warp);
     if (threadIdx.x == 0) *blocks_done = 0u;     // ready for the next launch on this workspace
+}
+
+// Single-pass, slab-free variant ("packed"): the warp walks its ray ONCE, parking the lattice parameter T of every emitted
+// sample in shared memory (4 bytes per sample: the clamped position is o + T d, the step clamp(T dt_gamma), and
+// deltas[1] = (T + step) - (previous sample's T + step), raymarching.cu:425,461), then claims its rows with ONE
+// atomicAdd on the sample counter - the reference's own slot allocation (raymarching.cu:405-406) - and writes them straight
+// to their final place.  No per-ray slab (N x max_steps rows of scratch), no scan launch, no compaction copy; the price is
+// the reference's row order: rays land in completion order (each ray's samples stay contiguous, rays[n] still describes
+// ray n), which every consumer of `rays` accepts.
+__global__ void __launch_bounds__(128) march_packed_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                           const uint8_t* __restrict__ grid, float bound, float dt_gamma,
+                                                           uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                                           const float* __restrict__ nears, const float* __restrict__ fars,
+                                                           const float* __restrict__ noises, float* __restrict__ xyzs,
+                                                           float* __restrict__ dirs, float* __restrict__ deltas,
+                                                           int* __restrict__ rays, int* __restrict__ counter) {
+    extern __shared__ float s_T[];          // [4 warps][max_steps]
+    __shared__ uint32_t s_lut[1024];
+    const bool use_lut = H <= 1024u;
+    if (use_lut) {
+        for (uint32_t i = threadIdx.x; i < H; i += blockDim.x) s_lut[i] = spread3(i);
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(counter + 1, (int)N);   // rays seen (raymarching.cu:406)
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    MarchParams p = make_params(grid, bound, dt_gamma, max_steps, C, H);
+    if (use_lut) p.lut = s_lut;
+    const Ray r = load_ray(rays_o, rays_d, n);
+    const float t0 = perturbed_start(p, nears[n], noises[n]);
+    float* sT = s_T + (threadIdx.x >> 5) * max_steps;
+    const uint32_t steps = walk_ray_warp<2>(p, r, t0, fars[n], max_steps, lane, sT, nullptr, nullptr);
+    __syncwarp();
+    uint32_t offset = 0;
+    if (lane == 0) {
+        if (steps) offset = (uint32_t)atomicAdd(counter, (int)steps);
+        rays[(size_t)n * 3 + 0] = (int)n;
+        rays[(size_t)n * 3 + 1] = (int)offset;
+        rays[(size_t)n * 3 + 2] = (int)steps;
+    }
+    offset = __shfl_sync(0xffffffffu, offset, 0);
+    if (steps == 0 || offset + steps > M) return;     // raymarching.cu:415-416
+    float* ox = xyzs + (size_t)offset * 3;
+    float2* od = reinterpret_cast<float2*>(deltas) + offset;
+    for (uint32_t i = lane; i < steps; i += 32) {
+        const float T = sT[i];
+        const float dt = clampf(T * p.dt_gamma, p.dt_min, p.dt_max);
+        float prev_after = t0;                               // t after the previous sample's step (t0 before the first)
+        if (i) { const float Tp = sT[i - 1]; prev_after = Tp + clampf(Tp * p.dt_gamma, p.dt_min, p.dt_max); }
+        ox[i * 3 + 0] = clampf(__fmaf_rn(T, r.dx, r.ox), -p.bound, p.bound);   // = classify()'s position
+        ox[i * 3 + 1] = clampf(__fmaf_rn(T, r.dy, r.oy), -p.bound, p.bound);
+        ox[i * 3 + 2] = clampf(__fmaf_rn(T, r.dz, r.oz), -p.bound, p.bound);
+        od[i] = make_float2(dt, (T + dt) - prev_after);
+        if (dirs) { float* pd = dirs + ((size_t)offset + i) * 3; pd[0] = r.dx; pd[1] = r.dy; pd[2] = r.dz; }
+    }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -1316,7 +1417,7 @@ __global__ void __launch_bounds__(128) march_infer_warp_kernel(uint32_t n_alive,
         const Ray r = load_ray(rays_o, rays_d, (uint32_t)id);
         float t = rays_t[id];
         t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * (noises ? noises[n] : 0.f);
-        walk_ray_warp<true>(p, r, t, fars[id], n_step, lane, xyzs + (size_t)n * n_step * 3, dirs ? dirs + (size_t)n * n_step * 3 : nullptr,
+        walk_ray_warp<1>(p, r, t, fars[id], n_step, lane, xyzs + (size_t)n * n_step * 3, dirs ? dirs + (size_t)n * n_step * 3 : nullptr,
                             deltas + (size_t)n * n_step * 2);
     }
 }
@@ -1462,7 +1563,7 @@ __global__ void __launch_bounds__(128) infer_march_kernel(const InferState* __re
             const Ray r = load_ray(rays_o, rays_d, (uint32_t)id);
             float t = rays_t[id];
             t += clampf(t * p.dt_gamma, p.dt_min, p.dt_max) * ((first && noises) ? noises[n] : 0.f);
-            const uint32_t got = walk_ray_warp<true>(p, r, t, fars[id], 1u, lane, xyzs + (size_t)n * 3, nullptr, deltas + (size_t)n * 2);
+            const uint32_t got = walk_ray_warp<1>(p, r, t, fars[id], 1u, lane, xyzs + (size_t)n * 3, nullptr, deltas + (size_t)n * 2);
             if (got == 0 && lane == 0) {
                 xyzs[(size_t)n * 3] = 0.f; xyzs[(size_t)n * 3 + 1] = 0.f; xyzs[(size_t)n * 3 + 2] = 0.f;
                 deltas[(size_t)n * 2] = 0.f; deltas[(size_t)n * 2 + 1] = 0.f;
@@ -1688,9 +1789,9 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
         }
         if (N <= 8192) {
             // few rays per launch (a data-parallel rank's chain): the LAST block of the walk scans the counts - one launch
-            // and one dependent-launch gap less.  The election counter is cleared in-stream (a 4-byte memset node; the
-            // workspace may be uninitialised memory)
-            cudaMemsetAsync(blocks_done, 0, sizeof(unsigned int), st);
+            // and one dependent-launch gap less.  The election counter (first word of the workspace) must be zero on entry:
+            // the caller zero-fills the head of a NEW workspace once, the electing block leaves it zero again (a memset
+            // node per call cost 2-4 us on the step's critical path)
             march::march_slab_kernel<<<blocks, 128, 0, st>>>(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, nears, fars,
                                                              noises, counts, slab_xyz, slab_delta, blocks_done, rays, counter);
         } else {
@@ -1702,6 +1803,20 @@ extern "C" int ngp_march_rays_train(const float* rays_o, const float* rays_d, co
         march::march_compact_kernel<<<cdiv((uint64_t)N * 32, 256), 256, 0, st>>>(rays_d, rays, slab_xyz, slab_delta, max_steps, N, M,
                                                                                  xyzs, dirs, deltas);
     }
+    return launch_status();
+}
+
+extern "C" int ngp_march_rays_train_packed(const float* rays_o, const float* rays_d, const uint8_t* grid, float bound,
+                                           float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H, uint32_t M,
+                                           const float* nears, const float* fars, float* xyzs, float* dirs, float* deltas,
+                                           int* rays, int* counter, const float* noises, void* stream) {
+    if (!rays_o || !rays_d || !grid || !nears || !fars || !xyzs || !deltas || !rays || !counter || !noises)
+        return NGP_ERR_BAD_ARG;
+    if (C == 0 || H == 0 || max_steps == 0) return NGP_ERR_BAD_ARG;
+    if (max_steps > 2048 || (reinterpret_cast<uintptr_t>(deltas) & 7)) return NGP_ERR_UNSUPPORTED;   // 4 x max_steps floats of smem
+    if (N == 0) return NGP_OK;
+    march::march_packed_kernel<<<cdiv((uint64_t)N * 32, 128), 128, 4 * max_steps * sizeof(float), as_stream(stream)>>>(
+        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, noises, xyzs, dirs, deltas, rays, counter);
     return launch_status();
 }
 
@@ -1732,10 +1847,12 @@ extern "C" int ngp_composite_rays_train_backward(const float* grad_weights_sum, 
 
 extern "C" int ngp_train_prologue(const float* rays_o, const float* rays_d, const float* aabb, uint32_t N, float min_near,
                                   float* nears, float* fars, int* counters, uint32_t n_counters, float* loss,
-                                  int* step_counter, int* local_step, int* cur_row, void* stream) {
-    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NGP_ERR_BAD_ARG;
+                                  int* step_counter, int* local_step, int* cur_row, float* noises, uint64_t* rng,
+                                  void* stream) {
+    if (!rays_o || !rays_d || !aabb || !nears || !fars || (noises && !rng)) return NGP_ERR_BAD_ARG;
     march::train_prologue_kernel<<<N ? cdiv(N, 128) : 1, 128, 0, as_stream(stream)>>>(
-        rays_o, rays_d, aabb, N, min_near, nears, fars, counters, n_counters, loss, step_counter, local_step, cur_row);
+        rays_o, rays_d, aabb, N, min_near, nears, fars, counters, n_counters, loss, step_counter, local_step, cur_row, noises,
+        reinterpret_cast<unsigned long long*>(rng));
     return launch_status();
 }
 
@@ -1767,14 +1884,15 @@ extern "C" int ngp_train_prologue_rays(const float* poses, const float* intrinsi
                                        uint32_t H, uint32_t W, uint32_t row0, uint32_t row_stride, uint32_t n_rows,
                                        float* rays_o, float* rays_d, const float* aabb, float min_near, float* nears,
                                        float* fars, int* counters, uint32_t n_counters, float* loss, int* step_counter,
-                                       int* local_step, int* cur_row, void* stream) {
-    if (!rays_o || !rays_d || !aabb || !nears || !fars) return NGP_ERR_BAD_ARG;
+                                       int* local_step, int* cur_row, float* noises, uint64_t* rng, void* stream) {
+    if (!rays_o || !rays_d || !aabb || !nears || !fars || (noises && !rng)) return NGP_ERR_BAD_ARG;
     march::RayGen g;
     const int rc = make_raygen(g, poses, intrinsics, B, H, W, row0, row_stride, n_rows, intrinsics_per_view);
     if (rc != NGP_OK) return rc;
     const uint32_t N = g.B * g.n_rows * g.W;
     march::train_prologue_rays_kernel<<<cdiv(N, 128), 128, 0, as_stream(stream)>>>(
-        g, rays_o, rays_d, aabb, min_near, nears, fars, counters, n_counters, loss, step_counter, local_step, cur_row);
+        g, rays_o, rays_d, aabb, min_near, nears, fars, counters, n_counters, loss, step_counter, local_step, cur_row, noises,
+        reinterpret_cast<unsigned long long*>(rng));
     return launch_status();
 }
 

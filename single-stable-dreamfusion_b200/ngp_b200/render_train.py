@@ -34,9 +34,20 @@ class TrainWorkspace:
         self.enc, self.h1, self.h2 = e(cap, 32, dtype=f16), e(cap, 64, dtype=f16), e(cap, 64, dtype=f16)
         self.d_sigma, self.d_rgb, self.d_enc = e(cap), e(cap, 3), e(cap, 32, dtype=f16)
         self.rays = torch.empty(n_rays, 3, device=device, dtype=torch.int32)
-        lib = _cabi.load()
-        self.march_ws = torch.empty(int(lib.ngp_march_rays_train_workspace(n_rays, int(max_steps))), device=device, dtype=torch.uint8)
+        self._device = device
+        self._march_ws = None
         self.counter = torch.zeros(2, device=device, dtype=torch.int32) if counter is None else counter
+
+    @property
+    def march_ws(self):
+        """Scratch of the ray-ordered marcher (per-ray slabs, 20 bytes x n_rays x max_steps): allocated on first use - the
+        packed marcher of the hand-scheduled step (ngp_march_rays_train_packed) needs none."""
+        if self._march_ws is None:
+            lib = _cabi.load()
+            self._march_ws = torch.empty(int(lib.ngp_march_rays_train_workspace(self.n_rays, int(self.max_steps))),
+                                         device=self._device, dtype=torch.uint8)
+            self._march_ws[:256].zero_()   # block-election word: zero once, every call leaves it zero (include/ngp_b200.h)
+        return self._march_ws
 
     @property
     def nbytes(self):

@@ -140,11 +140,24 @@ class TrainStep:
         # thousands of ray-marching CTAs it runs beside (otherwise it only starts when the marcher's last wave does)
         self._side_opt = torch.cuda.Stream(device=device, priority=-1) if (self.manual and self.pipelined) else None
         self.mirror_rng = False  # draw (and drop) the randn(3) run_cuda spends on light_d, to keep torch's RNG stream aligned
+        # Per-ray march jitter of the hand-scheduled step: drawn by the prologue kernel from a counter-based generator
+        # (csrc/raymarch.cu ray_noise; [seed, step counter, scratch]) instead of a torch.rand launch - in graph mode torch
+        # also enqueues two seed / offset fill kernels before every replay of a graph that holds one of its generators.
+        # The seed follows torch.manual_seed (+ the rank, so ranks jitter differently); mirror_rng / fixed_noises /
+        # NGP_DEVICE_NOISE=0 keep torch.rand.
+        # ray marching of the hand-scheduled step as ONE launch without scratch (ngp_march_rays_train_packed: rays land in
+        # completion order, like the reference's); NGP_PACKED_MARCH=0: ray-ordered walk -> scan -> packed copy
+        self.packed_march = os.environ.get("NGP_PACKED_MARCH", "1") not in ("", "0")
+        self.device_noise = bool(self.manual) and os.environ.get("NGP_DEVICE_NOISE", "1") not in ("", "0")
+        rank = dist.get_rank() if (world_size > 1 and dist.is_available() and dist.is_initialized()) else 0
+        seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFFFFFF
+        self._rng = torch.tensor([seed, 0, 0], dtype=torch.int64, device=device)
         self._mws = None
         self._mws_sets = [None, None]      # overlap mode: the two alternating workspace sets
         self._ls_mirror = 0
         self._static_packed = None
         self._graph = None
+        self._graph_exec = 0
         self._graph_launches = 0
         self._static = None
         self.loss = None
@@ -329,17 +342,19 @@ class TrainStep:
             self._side_opt.wait_stream(main)
             with torch.cuda.stream(self._side_opt):
                 self._apply_update(deferred=True)  # the PREVIOUS step's update, beside this step's ray marching
+        dev_noise = self.device_noise and not self.mirror_rng and self.fixed_noises is None
+        noise_args = (P(m["noises"]), P(self._rng)) if dev_noise else (None, None)
         if poses is None:
             if c["has_bg"] and bg_early:
                 self._bg_forward(m, c, self._side_opt if self.pipelined else main)
             _cabi.call("ngp_train_prologue", dev, P(ro), P(rd), P(model.aabb_train), N, 0.2, P(m["nears"]), P(m["fars"]),
                        P(m["counters"]), m["counters"].numel(), P(m["loss"]), P(model.step_counter), P(self._local_step_dev),
-                       P(m["cur_row"]))
+                       P(m["cur_row"]), *noise_args)
         else:
             h_full, row0, row_stride = self.device_rays
             _cabi.call("ngp_train_prologue_rays", dev, P(poses), P(intr), 1, B, h_full, self.W, row0, row_stride, self.H, P(ro),
                        P(rd), P(model.aabb_train), 0.2, P(m["nears"]), P(m["fars"]), P(m["counters"]), m["counters"].numel(),
-                       P(m["loss"]), P(model.step_counter), P(self._local_step_dev), P(m["cur_row"]))
+                       P(m["loss"]), P(model.step_counter), P(self._local_step_dev), P(m["cur_row"]), *noise_args)
             if c["has_bg"] and bg_early:
                 if self.pipelined:
                     self._side.wait_stream(self._side_opt)
@@ -348,7 +363,7 @@ class TrainStep:
             torch.randn(3, device=dev)  # nerf/renderer.py:464 (light direction; unused by albedo shading)
         if self.fixed_noises is not None:
             m["noises"].copy_(self.fixed_noises)
-        else:
+        elif not dev_noise:
             m["noises"].uniform_()  # the torch.rand(N) of the reference's wrapper (raymarching.py:213-216)
 
         chunks = m["chunks"]
@@ -359,10 +374,17 @@ class TrainStep:
         for st, (base, n_c, ws) in zip(streams, chunks):
             with torch.cuda.stream(st):
                 sl = slice(base, base + n_c)
-                _cabi.call("ngp_march_rays_train", dev, P(ro[sl]), P(rd[sl]), P(model.density_bitfield), float(model.bound), 0.0,
-                           int(self.max_steps), n_c, int(model.cascade), int(model.grid_size), ws.cap, P(m["nears"][sl]),
-                           P(m["fars"][sl]), P(ws.xyzs), None, P(ws.deltas), P(ws.rays), P(ws.counter), P(m["noises"][sl]),
-                           P(ws.march_ws), ws.march_ws.numel())
+                if self.packed_march and self.max_steps <= 2048:
+                    # one launch, no scratch: rows claimed with the reference's atomicAdd, rays land in completion order
+                    _cabi.call("ngp_march_rays_train_packed", dev, P(ro[sl]), P(rd[sl]), P(model.density_bitfield),
+                               float(model.bound), 0.0, int(self.max_steps), n_c, int(model.cascade), int(model.grid_size),
+                               ws.cap, P(m["nears"][sl]), P(m["fars"][sl]), P(ws.xyzs), None, P(ws.deltas), P(ws.rays),
+                               P(ws.counter), P(m["noises"][sl]))
+                else:
+                    _cabi.call("ngp_march_rays_train", dev, P(ro[sl]), P(rd[sl]), P(model.density_bitfield), float(model.bound),
+                               0.0, int(self.max_steps), n_c, int(model.cascade), int(model.grid_size), ws.cap,
+                               P(m["nears"][sl]), P(m["fars"][sl]), P(ws.xyzs), None, P(ws.deltas), P(ws.rays), P(ws.counter),
+                               P(m["noises"][sl]), P(ws.march_ws), ws.march_ws.numel())
         if which is not None:       # a phase of its own: join the chains (in the fused step they run on into phase 2)
             for st in streams[1:]:
                 main.wait_stream(st)
@@ -623,7 +645,13 @@ class TrainStep:
             rd_s.copy_(rays_d, non_blocking=True)
             g_s.copy_(G, non_blocking=True)
         before = model.local_step
-        self._graph.replay()
+        if self._graph_exec:
+            # bare cudaGraphLaunch: torch's replay() first enqueues two fill kernels (seed / offset of its generators),
+            # ~7 us of serial device time per step; this graph holds no torch generator (device-side noise)
+            with torch.cuda.device(self.device):
+                _cabi.check(_cabi.load().ngp_graph_launch(self._graph_exec, _cabi.stream()), "ngp_graph_launch")
+        else:
+            self._graph.replay()
         self._pending = True
         _cabi.LAUNCHES += self._graph_launches  # our kernels inside the replayed graph
         self._bookkeeping_after(before)
@@ -870,10 +898,19 @@ class TrainStep:
         _cabi.LAUNCHES = launches0  # capture launches nothing
         model.local_step = saved_step
         self._pending = snap["pending"]
+        # a graph without torch generators (hand-scheduled step, device-side noise) is launched bare (see __call__)
+        self._graph_exec = 0
+        no_torch_rng = self.manual and self.device_noise and not self.mirror_rng and self.fixed_noises is None
+        if no_torch_rng and os.environ.get("NGP_RAW_GRAPH_LAUNCH", "1") not in ("", "0") and hasattr(self._graph, "raw_cuda_graph_exec"):
+            try:
+                self._graph_exec = int(self._graph.raw_cuda_graph_exec())
+            except Exception:  # noqa: BLE001 - older torch: keep replay()
+                self._graph_exec = 0
 
     def _snapshot_training_state(self):
         """Everything a train step mutates besides its own scratch (see _capture)."""
-        snap = dict(step_counter=self.model.step_counter.clone(), samples=self.samples.clone(), pending=self._pending)
+        snap = dict(step_counter=self.model.step_counter.clone(), samples=self.samples.clone(), pending=self._pending,
+                    rng=self._rng.clone())
         if self.fused_optimizer:
             o = self.opt
             snap["opt"] = [t.clone() for t in (o.flat_params, o.flat_half, o.exp_avg, o.exp_avg_sq, o.state)]
@@ -889,6 +926,7 @@ class TrainStep:
         with torch.no_grad():
             self.model.step_counter.copy_(snap["step_counter"])
             self.samples.copy_(snap["samples"])
+            self._rng.copy_(snap["rng"])
             if self.fused_optimizer:
                 o = self.opt
                 err = o.state[5].clone()   # a cross-GPU timeout during the warm-up must stay visible

@@ -15,7 +15,9 @@ _bwd = torch.amp.custom_bwd(device_type='cuda')
 
 
 def _workspace(nbytes, device):
-    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+    ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+    ws[:256].zero_()   # ngp_march_rays_train: the head of a new workspace (block-election word) must be zero
+    return ws
 
 
 # ----------------------------------------

@@ -141,6 +141,7 @@ def test_cuda_march_composite_vs_reference_golden(name, kw):
     counter = torch.zeros(2, dtype=torch.int32, device=ro.device)
     nz = T(c["noises"])
     ws_ = torch.empty(int(cb.load().ngp_march_rays_train_workspace(N, c["max_steps"])), dtype=torch.uint8, device=ro.device)
+    ws_[:256].zero_()   # a new workspace's head must be zero (include/ngp_b200.h)
     cb.call("ngp_march_rays_train", ro.device, cb.ptr(ro), cb.ptr(rd), cb.ptr(bits), float(c["bound"]), float(c["dt_gamma"]),
             c["max_steps"], N, c["cascade"], 128, M, cb.ptr(nears), cb.ptr(fars), cb.ptr(xyzs), cb.ptr(dirs), cb.ptr(deltas),
             cb.ptr(rays), cb.ptr(counter), cb.ptr(nz), cb.ptr(ws_), ws_.numel())

@@ -287,6 +287,7 @@ def _my_march(case, rays_o, rays_d, bits, nears, fars, noises, M=None):
     rays = torch.empty(N, 3, dtype=torch.int32, device=DEV)
     counter = torch.zeros(2, dtype=torch.int32, device=DEV)
     ws = torch.empty(int(lib.ngp_march_rays_train_workspace(N, int(case["max_steps"]))), dtype=torch.uint8, device=DEV)
+    ws[:256].zero_()   # a new workspace's head must be zero (include/ngp_b200.h)
     # keep every input tensor alive in a local: c.ptr() only returns an integer address
     ro, rd, bf, ne, fa, nz = T(rays_o), T(rays_d), T(bits), T(nears), T(fars), T(noises)
     c.call("ngp_march_rays_train", xyzs.device, c.ptr(ro), c.ptr(rd), c.ptr(bf), float(case["bound"]),
@@ -318,6 +319,65 @@ def test_march_rays_train_bit_exact_vs_oracle_and_reference(case, ref_ext):
     counts, (cx, cdirs, cl) = R.canonical_rays(rrays, rx, rd, rl)
     assert torch.equal(counts.int(), rays[:, 2])
     assert torch.equal(cx, xyzs[:total]) and torch.equal(cl, deltas[:total]) and torch.equal(cdirs, dirs[:total])
+
+
+def _my_march_packed(case, rays_o, rays_d, bits, nears, fars, noises, M=None, start=0):
+    c = cabi()
+    N = rays_o.shape[0]
+    M = N * case["max_steps"] if M is None else M
+    xyzs = torch.zeros(M, 3, device=DEV); dirs = torch.zeros(M, 3, device=DEV); deltas = torch.zeros(M, 2, device=DEV)
+    rays = torch.empty(N, 3, dtype=torch.int32, device=DEV)
+    counter = torch.tensor([start, 0], dtype=torch.int32, device=DEV)
+    ro, rd, bf, ne, fa, nz = T(rays_o), T(rays_d), T(bits), T(nears), T(fars), T(noises)
+    c.call("ngp_march_rays_train_packed", xyzs.device, c.ptr(ro), c.ptr(rd), c.ptr(bf), float(case["bound"]),
+           float(case["dt_gamma"]), case["max_steps"], N, case["cascade"], 128, M, c.ptr(ne), c.ptr(fa),
+           c.ptr(xyzs), c.ptr(dirs), c.ptr(deltas), c.ptr(rays), c.ptr(counter), c.ptr(nz))
+    torch.cuda.synchronize()
+    return xyzs, dirs, deltas, rays, counter
+
+
+@pytest.mark.parametrize("case", MARCH_CASES)
+def test_march_rays_train_packed_same_samples_per_ray(case):
+    """The one-launch marcher of the hand-scheduled step (rows claimed with the reference's atomicAdd, raymarching.cu:405-406):
+    same counts and, per ray, bit-identical samples as the oracle; the row blocks tile [start, start + total) exactly."""
+    rays_o, rays_d, bits, nears, fars, noises = _march_setup(case, seed=1)
+    ox, od, ol, orays, ocounter = O.march_rays_train(rays_o, rays_d, case["bound"], bits, case["cascade"], 128, nears, fars,
+                                                     noises, case["dt_gamma"], case["max_steps"])
+    total, N = int(ocounter[0]), rays_o.shape[0]
+    start = 384
+    xyzs, dirs, deltas, rays, counter = _my_march_packed(case, rays_o, rays_d, bits, nears, fars, noises,
+                                                         M=N * case["max_steps"] + start, start=start)
+    r = N_(rays)
+    assert counter[0].item() == start + total and counter[1].item() == N
+    assert np.array_equal(r[:, 0], np.arange(N)) and np.array_equal(r[:, 2], orays[:, 2])
+    live = r[:, 2] > 0
+    order = np.argsort(r[live, 1], kind="stable")
+    offs, cnts = r[live, 1][order], r[live, 2][order]
+    assert offs[0] == start and np.array_equal(offs[1:], offs[:-1] + cnts[:-1]) and offs[-1] + cnts[-1] == start + total
+    # gather every ray's block into ray order and compare bit for bit with the oracle's ray-ordered rows
+    idx = np.concatenate([np.arange(o, o + c) for o, c in zip(r[live, 1], r[live, 2])])
+    gx, gl, gd = N_(xyzs)[idx], N_(deltas)[idx], N_(dirs)[idx]
+    assert np.array_equal(gx.view(np.uint32), ox[:total].view(np.uint32))
+    assert np.array_equal(gl.view(np.uint32), ol[:total].view(np.uint32))
+    assert np.array_equal(gd, od[:total])
+    assert not xyzs[:start].any() and not xyzs[start + total:].any()   # nothing written outside the claimed rows
+
+
+def test_march_rays_train_packed_overflow_drops_whole_rays():
+    """Rays whose claimed block does not fit in M rows are recorded but write nothing (raymarching.cu:415-416)."""
+    case = MARCH_CASES[0]
+    rays_o, rays_d, bits, nears, fars, noises = _march_setup(case, seed=2)
+    full = O.march_rays_train(rays_o, rays_d, 1.0, bits, 1, 128, nears, fars, noises, 0.0, 1024)
+    total = int(full[4][0])
+    M = total // 3
+    xyzs, dirs, deltas, rays, counter = _my_march_packed(case, rays_o, rays_d, bits, nears, fars, noises, M=M)
+    r = N_(rays)
+    assert counter[0].item() == total and np.array_equal(r[:, 2], full[3][:, 2])
+    fits = (r[:, 2] > 0) & (r[:, 1] + r[:, 2] <= M)
+    written = np.zeros(M, bool)
+    for o, c in r[fits][:, 1:]:
+        written[o:o + c] = True
+    assert fits.any() and np.array_equal(N_(xyzs).any(axis=1) | written, written)
 
 
 def test_march_rays_train_overflow_and_python_wrapper():

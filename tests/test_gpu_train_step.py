@@ -515,3 +515,73 @@ def test_read_loss_async_returns_the_lagged_loss_without_a_sync():
     assert lagged[:2] == [None, None]
     np.testing.assert_allclose(lagged[2:], sync[:-2], rtol=0, atol=0)
     assert len(set(sync)) > 1 and all(np.isfinite(sync))
+
+
+def _mix32(x):
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16); x = (x * np.uint32(0x7feb352d)).astype(np.uint32)
+    x ^= x >> np.uint32(15); x = (x * np.uint32(0x846ca68b)).astype(np.uint32)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def _ray_noise_np(seed, ctr, n):
+    """numpy restatement of csrc/raymarch.cu ray_noise (counter-based per-ray jitter of the hand-scheduled step)."""
+    n = np.arange(n, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        x = _mix32(n ^ np.uint32(seed & 0xffffffff))
+        x = _mix32((x + np.uint32((ctr * 0x9E3779B9) & 0xffffffff) + np.uint32((ctr >> 32) & 0xffffffff)).astype(np.uint32))
+        x = _mix32(x ^ np.uint32((seed >> 32) & 0xffffffff))
+    return (x >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+
+
+def test_device_side_ray_noise():
+    """The prologue kernel draws the per-ray march jitter itself (the reference: torch.rand(N), raymarching.py:213-216):
+    values in [0, 1), reproducible from (seed, step counter, ray), a fresh draw every launch, counter advanced by exactly one."""
+    from ngp_b200 import _cabi
+    N = 5000
+    g = torch.Generator(device=DEV).manual_seed(0)
+    ro = torch.randn(N, 3, device=DEV, generator=g) * 0.1 + torch.tensor([0.0, 0.0, 3.0], device=DEV)
+    rd = torch.nn.functional.normalize(torch.randn(N, 3, device=DEV, generator=g) * 0.2 - torch.tensor([0.0, 0.0, 1.0], device=DEV), dim=-1)
+    aabb = torch.tensor([-1.0, -1, -1, 1, 1, 1], device=DEV)
+    nears, fars, noises = (torch.empty(N, device=DEV) for _ in range(3))
+    seed = 0x123456789ABCDEF
+    rng = torch.tensor([seed, 7, 0], dtype=torch.int64, device=DEV)
+    P = _cabi.ptr
+    draws = []
+    for k in range(3):
+        _cabi.call("ngp_train_prologue", torch.device(DEV), P(ro), P(rd), P(aabb), N, 0.2, P(nears), P(fars), None, 0, None, None,
+                   None, None, P(noises), P(rng))
+        torch.cuda.synchronize()
+        assert rng.tolist() == [seed, 8 + k, 0]
+        draws.append(noises.cpu().numpy().copy())
+        assert np.array_equal(draws[-1], _ray_noise_np(seed, 7 + k, N))
+    u = np.concatenate(draws)
+    assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005
+    assert not np.array_equal(draws[0], draws[1])
+    assert abs(np.corrcoef(draws[0], draws[1])[0, 1]) < 0.05 and abs(np.corrcoef(draws[0][:-1], draws[0][1:])[0, 1]) < 0.05
+    # without a noise buffer the launch leaves the generator alone
+    _cabi.call("ngp_train_prologue", torch.device(DEV), P(ro), P(rd), P(aabb), N, 0.2, P(nears), P(fars), None, 0, None, None,
+               None, None, None, None)
+    torch.cuda.synchronize()
+    assert rng.tolist() == [seed, 10, 0]
+
+
+def test_graphed_step_draws_fresh_noise_every_replay():
+    """Graph replays of the hand-scheduled step advance the device-side generator (no torch generator inside the graph)."""
+    from ngp_b200 import provider
+    from ngp_b200.trainer import TrainStep
+    ro, rd = provider.make_training_views(1, 64, 64, seed=4, pin=False)
+    ro, rd = ro.to(DEV), rd.to(DEV)
+    G = torch.randn(1, 3, 64, 64, device=DEV, generator=torch.Generator(device=DEV).manual_seed(2)) * 1e-2
+    m = _bench_like_model()
+    step = TrainStep(m, 64, 64, lr=1e-5, graph=True, manual=True)
+    assert step.device_noise
+    seen = []
+    for k in range(3):
+        step(ro, rd, G)
+        torch.cuda.synchronize()
+        assert step._rng[1].item() == k + 1 and step._rng[2].item() == 0
+        seen.append(step._mws["noises"].clone())
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    assert np.array_equal(seen[2].cpu().numpy(), _ray_noise_np(int(step._rng[0].item()), 2, 4096))
