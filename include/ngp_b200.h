@@ -211,6 +211,18 @@ int ngp_field_forward(const float* xyzs, uint32_t M, const int* count_ptr, const
                       const void* w1, const void* b1, const void* w2, const void* b2, const void* w3, const void* b3,
                       uint32_t hidden, uint32_t out_dim, float* sigma, float* rgb, void* enc_save, void* h1_save,
                       void* h2_save, void* stream);
+/* The same forward reading the table through a QUAD table: quads u32[rows,4] (16-byte aligned), row r of a linear / tiled
+ * level = the fp16x2 features of rows r, r+1, r+stride_y, r+stride_y+1 of that level (wrapped as gridencoder.cu:54-72 wraps
+ * them) = the four corners of one z slice of the cell whose base corner is row r, so a level costs one or two 16-byte
+ * gathers per sample instead of four to eight 4-byte ones.  Same values in the same order: bit-equal outputs.  Built from
+ * the fp16 table by ngp_grid_quad_table (rows = offsets[L]; 16 bytes per row) - rebuild after every parameter update. */
+int ngp_grid_quad_table(const void* table, const int* offsets, uint32_t L, uint32_t total_rows, float S, uint32_t H,
+                        uint32_t gridtype, int align_corners, void* quads, void* stream);
+int ngp_field_forward_quads(const float* xyzs, uint32_t M, const int* count_ptr, const void* table, const void* quads,
+                            const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
+                            int align_corners, float bound, const void* w1, const void* b1, const void* w2, const void* b2,
+                            const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* sigma, float* rgb,
+                            void* enc_save, void* h1_save, void* h2_save, void* stream);
 
 /* Backward of the MLP part: from d_sigma f32[M], d_rgb f32[M,3] (+ the forward outputs and saves) to
  * d_enc f16[M,32] (gradient wrt the grid encoding - feed it to ngp_grid_encode_backward) and the fp32 weight /
@@ -254,6 +266,11 @@ int ngp_grid_fold_odd(float* grad_table, float* grad_table_odd, uint64_t n, void
 /* GradScaler's inf/nan check (torch.amp.GradScaler.unscale_, called from nerf/utils.py:709 scaler.step):
  * sets *found_inf = 1.0f (device f32, never cleared here) if any of grads f32[n] is not finite.  grads 16-byte aligned. */
 int ngp_check_finite(const float* grads, uint64_t n, float* found_inf, void* stream);
+/* The same verdict with the odd-frame twin of the table gradient (ngp_grid_scatter_samples_split) folded into the bucket on
+ * the way: grad_table (a sub-range of grads, table_n floats) += grad_table_odd, grad_table_odd = 0 - what ngp_grid_fold_odd
+ * followed by ngp_check_finite do, in one pass. */
+int ngp_check_finite_fold(float* grads, uint64_t n, float* grad_table, float* grad_table_odd, uint64_t table_n,
+                          float* found_inf, void* stream);
 
 /* scaler.step(optimizer) + scaler.update() for Adam over ONE flat parameter buffer (main.py:128 Adam betas
  * (0.9,0.99) eps 1e-15; network_grid.py:170-181 lr groups; main.py:131 LambdaLR 0.1^(iter/iters);

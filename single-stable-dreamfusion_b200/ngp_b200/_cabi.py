@@ -51,6 +51,9 @@ SIGNATURES = {
     "ngp_bench_red_width": (_i32, [_vp, _u32, _u32, _u32, _u32, _u32, _u32, _vp]),
     "ngp_field_forward": (_i32, [_vp, _u32, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_field_forward_quads": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _f32, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ngp_grid_quad_table": (_i32, [_vp, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _vp, _vp]),
     "ngp_field_backward": (_i32, [_u32, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp]),
     "ngp_grid_scatter_samples": (_i32, [_vp, _vp, _f32, _vp, _u32, _vp, _u32, _u32, _f32, _u32, _u32, _i32, _vp, _vp]),
@@ -63,6 +66,7 @@ SIGNATURES = {
     "ngp_bg_forward": (_i32, [_vp, _u32, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp]),
     "ngp_bg_backward": (_i32, [_vp, _vp, _u32, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _vp]),
     "ngp_check_finite": (_i32, [_vp, _u64, _vp, _vp]),
+    "ngp_check_finite_fold": (_i32, [_vp, _u64, _vp, _vp, _u64, _vp, _vp]),
     "ngp_adam_step": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64), C.POINTER(_f32), _f32, _f32, _f32, _f32,
                              _f32, _f32, _f32, _f32, _u32, _i32, _vp, _vp, _vp]),
     "ngp_adam_step_fused": (_i32, [_vp, _vp, _vp, _vp, _vp, _u64, _u32, C.POINTER(_u64), C.POINTER(_f32), _f32, _f32, _f32, _f32,

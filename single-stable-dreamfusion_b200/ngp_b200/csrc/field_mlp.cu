@@ -38,6 +38,7 @@ struct Weights {
 
 struct GridDesc {
     const __half* table;
+    const uint4* quads;   // optional quad table (ngp_grid_quad_table): row r of a linear level = the four (x, y) corners at r
     const int* offsets;
     float S;
     uint32_t H, gridtype;
@@ -82,6 +83,34 @@ NGP_DEVINL uint32_t encode_level(const float (&x01)[3], const uint32_t* __restri
 #pragma unroll
         for (uint32_t c = 0; c < 8; ++c) raw[c] = __ldg(tbl + ridx[c]);  // (used == 1 reloads equal rows: same values)
     }
+    float wts[8];
+    grid::corner_weights<3>(frac, wts);
+    __half2 acc = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+    for (uint32_t c = 0; c < 8; ++c) acc = grid::half2_axpy(acc, wts[c], raw[c]);
+    return *reinterpret_cast<uint32_t*>(&acc);
+}
+
+// The same level from the QUAD table (linear / tiled levels only): row r holds the features of rows r, r + 1, r + stride_y
+// and r + stride_y + 1 (each wrapped like corner_rows wraps them), i.e. the cell's four corners of one z slice in corner
+// order - ONE 16-byte gather per slice instead of four 4-byte gathers and their address arithmetic.  Same feature values,
+// same accumulation order: bit-equal to encode_level.
+NGP_DEVINL uint32_t wrap_row(const grid::FastLevel<3>& lp, uint32_t row) {
+    if (lp.wrap == grid::kWrapMask) return row & lp.mask;
+    if (lp.wrap == grid::kWrapMod) return row % lp.size;
+    return row;
+}
+NGP_DEVINL uint32_t encode_level_quads(const float (&x01)[3], const uint4* __restrict__ quads, bool align_corners,
+                                       const grid::FastLevel<3>& lp) {
+    float frac[3];
+    uint32_t base[3];
+    grid::locate<3>(x01, lp.scale, align_corners, frac, base);
+    const uint32_t lin = base[0] * lp.stride[0] + base[1] * lp.stride[1] + base[2] * lp.stride[2];
+    const uint4* __restrict__ q = quads + lp.offset;
+    const uint4 lo = __ldg(q + wrap_row(lp, lin));
+    uint4 hi = lo;                                   // levels that ignore z: both slices are the same rows
+    if (lp.used == 3) hi = __ldg(q + wrap_row(lp, lin + lp.stride[2]));
+    const uint32_t raw[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     float wts[8];
     grid::corner_weights<3>(frac, wts);
     __half2 acc = __floats2half2_rn(0.f, 0.f);
@@ -193,6 +222,7 @@ __global__ void __launch_bounds__(kTile * G, 8 / G) field_forward_kernel(const F
     const float inv_2b = __fdiv_rn(1.0f, 2 * a.gd.bound);
     const bool save = a.enc != nullptr;
     const uint32_t* table_u32 = reinterpret_cast<const uint32_t*>(a.gd.table);
+    const uint4* quads = a.gd.quads;
     const bool align = a.gd.align_corners != 0;
     uint32_t phase = 0;
     uint8_t* buf = smem + FwdSmem::tiles + grp * kHidTileBytes;   // encodings (chunks 0..3), then h1, then h2
@@ -212,7 +242,10 @@ __global__ void __launch_bounds__(kTile * G, 8 / G) field_forward_kernel(const F
             uint32_t e[4] = {0u, 0u, 0u, 0u};  // out-of-cube samples encode to zeros (gridencoder.cu:106-122)
             if (!oob) {
 #pragma unroll
-                for (uint32_t j = 0; j < 4; ++j) e[j] = encode_level(x01, table_u32, align, s_levels[cc * 4 + j]);
+                for (uint32_t j = 0; j < 4; ++j) {
+                    const grid::FastLevel<3>& lp = s_levels[cc * 4 + j];
+                    e[j] = (quads && !lp.hashed) ? encode_level_quads(x01, quads, align, lp) : encode_level(x01, table_u32, align, lp);
+                }
             }
             const uint32_t off = tc::tile_chunk_off(r, cc, kCs128);
             const uint4 v = make_uint4(e[0], e[1], e[2], e[3]);
@@ -602,28 +635,66 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const BwdArgs 
     if (warp == 0) tc::tmem_dealloc(tmem, kTmemColsBwd);
 }
 
+// quads[g] for every row g of the table (see encode_level_quads); rows of hashed levels are copied plainly (never read)
+__global__ void __launch_bounds__(256) quad_table_kernel(const uint32_t* __restrict__ table, const int* __restrict__ offsets,
+                                                         uint32_t L, float S, uint32_t H, uint32_t gridtype, bool align_corners,
+                                                         uint4* __restrict__ quads) {
+    __shared__ grid::FastLevel<3> s_levels[grid::kMaxLevels];
+    if (threadIdx.x < L) s_levels[threadIdx.x] = grid::make_fast_level<3>(offsets, threadIdx.x, S, H, gridtype, align_corners);
+    __syncthreads();
+    const uint32_t rows = s_levels[L - 1].offset + s_levels[L - 1].size;
+    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < rows; g += gridDim.x * blockDim.x) {
+        uint32_t l = 0;
+        while (l + 1 < L && g >= s_levels[l + 1].offset) ++l;
+        const grid::FastLevel<3>& lp = s_levels[l];
+        const uint32_t r = g - lp.offset;
+        const uint32_t* __restrict__ t = table + lp.offset;
+        uint32_t n[3] = {r + 1u, r + lp.stride[1], r + lp.stride[1] + 1u};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            n[k] = wrap_row(lp, n[k]);
+            if (n[k] >= lp.size) n[k] -= lp.size;   // (unwrapped levels: rows past the end are nobody's neighbours)
+            if (lp.hashed) n[k] = r;
+        }
+        quads[g] = make_uint4(__ldg(t + r), __ldg(t + n[0]), __ldg(t + n[1]), __ldg(t + n[2]));
+    }
+}
+
 }  // namespace field
 }  // namespace ngp
 
 using namespace ngp;
+
+extern "C" int ngp_grid_quad_table(const void* table, const int* offsets, uint32_t L, uint32_t total_rows, float S, uint32_t H,
+                                   uint32_t gridtype, int align_corners, void* quads, void* stream) {
+    if (!table || !offsets || !quads) return NGP_ERR_BAD_ARG;
+    if (L == 0 || L > grid::kMaxLevels || gridtype > 1) return NGP_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(quads) & 15) != 0 || (reinterpret_cast<uintptr_t>(table) & 3) != 0) return NGP_ERR_BAD_ARG;
+    if (total_rows == 0) return NGP_OK;
+    const int blocks = min(cdiv(total_rows, 256 * 4), num_sms() * 8);
+    field::quad_table_kernel<<<blocks, 256, 0, as_stream(stream)>>>(static_cast<const uint32_t*>(table), offsets, L, S, H, gridtype,
+                                                                   align_corners != 0, static_cast<uint4*>(quads));
+    return launch_status();
+}
 
 static int check_field_dims(uint32_t L, uint32_t C, uint32_t D, uint32_t hidden, uint32_t out) {
     if (L != field::kLevels || C != 2 || D != 3 || hidden != field::kHid || out != field::kOut) return NGP_ERR_UNSUPPORTED;
     return NGP_OK;
 }
 
-extern "C" int ngp_field_forward(const float* xyzs, uint32_t M, const int* count_ptr, const void* table, const int* offsets,
-                                 uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, int align_corners,
-                                 float bound, const void* w1, const void* b1, const void* w2, const void* b2,
-                                 const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* sigma,
-                                 float* rgb, void* enc_save, void* h1_save, void* h2_save, void* stream) {
+static int field_forward_impl(const float* xyzs, uint32_t M, const int* count_ptr, const void* table, const void* quads,
+                              const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                              float bound, const void* w1, const void* b1, const void* w2, const void* b2,
+                              const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* sigma,
+                              float* rgb, void* enc_save, void* h1_save, void* h2_save, void* stream) {
     if (!xyzs || !table || !offsets || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 || !sigma || !rgb) return NGP_ERR_BAD_ARG;
     int rc = check_field_dims(L, C, 3, hidden, out_dim);
     if (rc != NGP_OK) return rc;
     if (M == 0) return NGP_OK;
     field::FwdArgs a;
     a.xyzs = xyzs; a.M = M; a.count_ptr = count_ptr;
-    a.gd = {static_cast<const __half*>(table), offsets, S, H, gridtype, align_corners, bound};
+    if (quads && (reinterpret_cast<uintptr_t>(quads) & 15) != 0) return NGP_ERR_BAD_ARG;
+    a.gd = {static_cast<const __half*>(table), static_cast<const uint4*>(quads), offsets, S, H, gridtype, align_corners, bound};
     a.w = {static_cast<const __half*>(w1), static_cast<const __half*>(b1), static_cast<const __half*>(w2),
            static_cast<const __half*>(b2), static_cast<const __half*>(w3), static_cast<const __half*>(b3)};
     a.sigma = sigma; a.rgb = rgb;
@@ -643,6 +714,25 @@ extern "C" int ngp_field_forward(const float* xyzs, uint32_t M, const int* count
     else if (G == 2) field::field_forward_kernel<2><<<grid, field::kTile * 2, smem, as_stream(stream)>>>(a);
     else field::field_forward_kernel<4><<<grid, field::kTile * 4, smem, as_stream(stream)>>>(a);
     return launch_status();
+}
+
+extern "C" int ngp_field_forward(const float* xyzs, uint32_t M, const int* count_ptr, const void* table, const int* offsets,
+                                 uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                 float bound, const void* w1, const void* b1, const void* w2, const void* b2,
+                                 const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* sigma,
+                                 float* rgb, void* enc_save, void* h1_save, void* h2_save, void* stream) {
+    return field_forward_impl(xyzs, M, count_ptr, table, nullptr, offsets, L, C, S, H, gridtype, align_corners, bound, w1, b1, w2, b2,
+                              w3, b3, hidden, out_dim, sigma, rgb, enc_save, h1_save, h2_save, stream);
+}
+
+extern "C" int ngp_field_forward_quads(const float* xyzs, uint32_t M, const int* count_ptr, const void* table, const void* quads,
+                                       const int* offsets, uint32_t L, uint32_t C, float S, uint32_t H, uint32_t gridtype,
+                                       int align_corners, float bound, const void* w1, const void* b1, const void* w2,
+                                       const void* b2, const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim,
+                                       float* sigma, float* rgb, void* enc_save, void* h1_save, void* h2_save, void* stream) {
+    if (!quads) return NGP_ERR_BAD_ARG;
+    return field_forward_impl(xyzs, M, count_ptr, table, quads, offsets, L, C, S, H, gridtype, align_corners, bound, w1, b1, w2, b2,
+                              w3, b3, hidden, out_dim, sigma, rgb, enc_save, h1_save, h2_save, stream);
 }
 
 // tuning switches (profiles/kbench.py): 0 = forward CTAs per SM (grid size; 0 = as many as fit), 1 = forward smem carveout

@@ -34,6 +34,27 @@ __global__ void __launch_bounds__(256) check_finite_kernel(const float4* __restr
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.0f;
 }
 
+// found_inf of the bucket with the odd-frame twin of the table gradient (ngp_grid_scatter_samples_split) folded in on the
+// way: g[t_lo2 .. t_hi2) += odd, odd = 0 (float2 units; the twin is 8-byte aligned) - one pass over the bucket instead of a
+// fold launch followed by a check launch on the critical path of the data-parallel step
+__global__ void __launch_bounds__(256) check_finite_fold_kernel(float2* __restrict__ g2, uint64_t n2, uint64_t t_lo2, uint64_t t_hi2,
+                                                                float2* __restrict__ odd2, float* __restrict__ found_inf) {
+    bool bad = false;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
+        float2 v = g2[i];
+        if (i >= t_lo2 && i < t_hi2) {
+            const float2 o = odd2[i - t_lo2];
+            if (o.x != 0.f || o.y != 0.f) {
+                v.x += o.x; v.y += o.y;
+                g2[i] = v;
+                odd2[i - t_lo2] = make_float2(0.f, 0.f);
+            }
+        }
+        bad = bad || (((v.x - v.x) + (v.y - v.y)) != 0.f);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *found_inf = 1.0f;
+}
+
 // ---- Adam + GradScaler -------------------------------------------------------------------------------------------
 // state layout (fp32, device): [0] loss scale, [1] growth tracker, [2] optimizer step count, [3] found_inf,
 // [4] steps skipped so far.  `blocks_done` is a zero-initialised uint32 used to elect the last block, which applies
@@ -247,6 +268,21 @@ extern "C" int ngp_check_finite(const float* grads, uint64_t n, float* found_inf
     const uint64_t want = (n / 4 + 255) / 256 + 1, cap = (uint64_t)num_sms() * 8;
     const int blocks = (int)(want < cap ? want : cap);
     step::check_finite_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(grads), grads, n, found_inf);
+    return launch_status();
+}
+
+extern "C" int ngp_check_finite_fold(float* grads, uint64_t n, float* grad_table, float* grad_table_odd, uint64_t table_n,
+                                     float* found_inf, void* stream) {
+    if (!grads || !found_inf || !grad_table || !grad_table_odd) return NGP_ERR_BAD_ARG;
+    if ((n & 1) || (table_n & 1) || grad_table < grads || grad_table + table_n > grads + n) return NGP_ERR_BAD_ARG;
+    if (((reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(grad_table) | reinterpret_cast<uintptr_t>(grad_table_odd)) & 7) != 0)
+        return NGP_ERR_BAD_ARG;
+    if (n == 0) return NGP_OK;
+    const uint64_t n2 = n / 2, t_lo2 = (uint64_t)(grad_table - grads) / 2, t_hi2 = t_lo2 + table_n / 2;
+    const uint64_t want = (n2 + 255) / 256, cap = (uint64_t)num_sms() * 8;
+    const int blocks = (int)(want < cap ? want : cap);
+    step::check_finite_fold_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<float2*>(grads), n2, t_lo2, t_hi2,
+                                                                         reinterpret_cast<float2*>(grad_table_odd), found_inf);
     return launch_status();
 }
 

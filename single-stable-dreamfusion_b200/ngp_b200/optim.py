@@ -157,11 +157,13 @@ class FusedAdamScaler:
                    self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
                    int(bool(zero_grads)), _cabi.ptr(self.state), _cabi.ptr(self._blocks_done))
 
-    def step_fused(self, deferred=False):
+    def step_fused(self, deferred=False, fold=None):
         """The same step as ONE cooperative launch (finite check -> grid barrier -> Adam ...), and - with peer
         memory - the data-parallel gradient all-reduce fused in: reduce-scatter by P2P loads, Adam on this rank's
         slice, new parameters written to every replica (csrc/dp_step.cu).  Always zero-fills the gradients.
-        deferred: the launch only arms (state[6] = 1) when nothing is pending yet - see TrainStep(pipelined=True)."""
+        deferred: the launch only arms (state[6] = 1) when nothing is pending yet - see TrainStep(pipelined=True).
+        fold: optional (grad_table view, odd-frame twin) of the split table scatter: the twin is added into the bucket
+        before the update (inside the finite check of the barrier-free data-parallel variant, a launch of its own otherwise)."""
         dev = self.device
         if self.peer_ptrs is None:
             rank, world, pg, pp, ph, pf, mc = 0, 1, None, None, None, None, None
@@ -173,8 +175,15 @@ class FusedAdamScaler:
         if world > 1 and self.dp_kernel == "blocks":
             # barrier-free variant (csrc/dp_step.cu adam_dp_kernel): the inf / nan verdict comes from each rank's own bucket
             # and rides on the first flag exchange - one small extra launch, no grid barriers, any grid size
-            _cabi.call("ngp_check_finite", dev, _cabi.ptr(self.flat_grads), self.numel, self.state[3:].data_ptr())
+            if fold is not None:
+                _cabi.call("ngp_check_finite_fold", dev, _cabi.ptr(self.flat_grads), self.numel, _cabi.ptr(fold[0]),
+                           _cabi.ptr(fold[1]), fold[0].numel(), self.state[3:].data_ptr())
+                fold = None
+            else:
+                _cabi.call("ngp_check_finite", dev, _cabi.ptr(self.flat_grads), self.numel, self.state[3:].data_ptr())
             name = "ngp_adam_step_dp"
+        if fold is not None:
+            _cabi.call("ngp_grid_fold_odd", dev, _cabi.ptr(fold[0]), _cabi.ptr(fold[1]), fold[0].numel())
         _cabi.call(name, dev, _cabi.ptr(self.flat_params), _cabi.ptr(self.flat_grads), _cabi.ptr(self.exp_avg),
                    _cabi.ptr(self.exp_avg_sq), _cabi.ptr(self.flat_half), self.numel, self.n_seg, self.seg_end, self.seg_lr,
                    float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,

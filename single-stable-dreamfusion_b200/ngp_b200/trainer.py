@@ -136,6 +136,10 @@ class TrainStep:
         # background-net branch of the step (default priority: it fills the gaps of the main chain, measured faster than
         # a high-priority branch that takes SM slots away from the field kernels)
         self._side = torch.cuda.Stream(device=device) if self.manual else None
+        # the background net's FORWARD is tiny (one CTA per 128 rays) and the per-ray loss kernels wait for it: on a
+        # default-priority stream it queued behind the field forward's 592 CTAs whenever both became runnable together
+        # (pipelined optimizer: both wait for the update) and delayed the loss kernels by ~25 us - high priority
+        self._side_fwd = torch.cuda.Stream(device=device, priority=-1) if self.manual else None
         # pipelined optimizer launch: its own HIGH-priority stream, so that its 148 cooperative CTAs are placed ahead of the
         # thousands of ray-marching CTAs it runs beside (otherwise it only starts when the marcher's last wave does)
         self._side_opt = torch.cuda.Stream(device=device, priority=-1) if (self.manual and self.pipelined) else None
@@ -148,6 +152,13 @@ class TrainStep:
         # ray marching of the hand-scheduled step as ONE launch without scratch (ngp_march_rays_train_packed: rays land in
         # completion order, like the reference's); NGP_PACKED_MARCH=0: ray-ordered walk -> scan -> packed copy
         self.packed_march = os.environ.get("NGP_PACKED_MARCH", "1") not in ("", "0")
+        # field forward through a quad table of the fp16 embeddings (csrc/field_mlp.cu encode_level_quads: one or two 16-byte
+        # gathers per level instead of four to eight 4-byte ones), rebuilt every step beside the ray marching.  On by
+        # default on one GPU; a data-parallel rank's few samples do not repay the rebuild, which there sits between the
+        # optimizer and the forward (NGP_QUAD_TABLE=1 / 0 forces it)
+        qt = os.environ.get("NGP_QUAD_TABLE", "auto")
+        self.quad_table = (world_size == 1) if qt == "auto" else qt not in ("", "0")
+        self._quads = None
         self.device_noise = bool(self.manual) and os.environ.get("NGP_DEVICE_NOISE", "1") not in ("", "0")
         rank = dist.get_rank() if (world_size > 1 and dist.is_available() and dist.is_initialized()) else 0
         seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFFFFFF
@@ -295,6 +306,12 @@ class TrainStep:
                 self._g_table_odd = raw[2:2 + c["g_table"].numel()]
                 assert self._g_table_odd.data_ptr() % 16 == 8
             c["g_table_odd"] = self._g_table_odd
+        c["quads"] = None
+        if self.quad_table:
+            rows = c["table_h"].shape[0]
+            if self._quads is None or self._quads.shape[0] != rows:
+                self._quads = torch.zeros(rows, 4, dtype=torch.int32, device=self.device)
+            c["quads"] = self._quads
         if c["has_bg"]:
             b0, b1 = model.bg_net.net
             bg_params = (b0.weight, b0.bias, b1.weight, b1.bias)
@@ -304,8 +321,15 @@ class TrainStep:
 
     def _bg_forward(self, m, c, after):
         dev, P = self.device, _cabi.ptr
-        self._side.wait_stream(after)  # (the bg net reads the updated parameters / the generated ray directions)
-        with torch.cuda.stream(self._side):
+        self._side_fwd.wait_stream(after)  # (the bg net reads the updated parameters / the generated ray directions)
+        if c["quads"] is not None:      # the step's quad table, from the parameters this step's forward will read
+            enc = c["enc"]
+            with torch.cuda.stream(self._side_fwd):
+                _cabi.call("ngp_grid_quad_table", dev, P(c["table_h"]), P(enc.offsets), c["L"], c["table_h"].shape[0], c["S"],
+                           int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), P(c["quads"]))
+        if not c["has_bg"]:
+            return
+        with torch.cuda.stream(self._side_fwd):
             _cabi.call("ngp_bg_forward", dev, P(m["rd_flat"]), m["N"], *[P(t) for t in c["hw_bg"]], 6, 64, P(m["bg"]))
 
     def _manual_march(self, rays_o, rays_d, B, which, bg_early):
@@ -345,7 +369,7 @@ class TrainStep:
         dev_noise = self.device_noise and not self.mirror_rng and self.fixed_noises is None
         noise_args = (P(m["noises"]), P(self._rng)) if dev_noise else (None, None)
         if poses is None:
-            if c["has_bg"] and bg_early:
+            if (c["has_bg"] or c["quads"] is not None) and bg_early:
                 self._bg_forward(m, c, self._side_opt if self.pipelined else main)
             _cabi.call("ngp_train_prologue", dev, P(ro), P(rd), P(model.aabb_train), N, 0.2, P(m["nears"]), P(m["fars"]),
                        P(m["counters"]), m["counters"].numel(), P(m["loss"]), P(model.step_counter), P(self._local_step_dev),
@@ -355,9 +379,9 @@ class TrainStep:
             _cabi.call("ngp_train_prologue_rays", dev, P(poses), P(intr), 1, B, h_full, self.W, row0, row_stride, self.H, P(ro),
                        P(rd), P(model.aabb_train), 0.2, P(m["nears"]), P(m["fars"]), P(m["counters"]), m["counters"].numel(),
                        P(m["loss"]), P(model.step_counter), P(self._local_step_dev), P(m["cur_row"]), *noise_args)
-            if c["has_bg"] and bg_early:
+            if (c["has_bg"] or c["quads"] is not None) and bg_early:
                 if self.pipelined:
-                    self._side.wait_stream(self._side_opt)
+                    self._side_fwd.wait_stream(self._side_opt)
                 self._bg_forward(m, c, main)    # (reads the generated ray directions)
         if self.mirror_rng:
             torch.randn(3, device=dev)  # nerf/renderer.py:464 (light direction; unused by albedo shading)
@@ -404,7 +428,7 @@ class TrainStep:
         rd = m["rd_flat"]
         P = _cabi.ptr
         main = torch.cuda.current_stream(dev)
-        if has_bg and not bg_done:
+        if (has_bg or c["quads"] is not None) and not bg_done:
             self._bg_forward(m, c, main)
         chunks = m["chunks"]
         streams = [main] + self._chain[:len(chunks) - 1]
@@ -416,11 +440,18 @@ class TrainStep:
             sl = slice(base, base + n_c)
             if self.pipelined:
                 torch.cuda.current_stream(dev).wait_stream(self._side_opt)  # the field reads the updated parameters
-            _cabi.call("ngp_field_forward", dev, P(ws.xyzs), ws.cap, P(ws.counter), P(table_h), P(enc.offsets), L, 2, S,
-                       int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), float(model.bound),
-                       *[P(t) for t in hw_field], 64, 4, P(ws.sigma), P(ws.rgb), P(ws.enc), P(ws.h1), P(ws.h2))
+            if c["quads"] is not None:
+                torch.cuda.current_stream(dev).wait_stream(self._side_fwd)   # the step's quad table
+                _cabi.call("ngp_field_forward_quads", dev, P(ws.xyzs), ws.cap, P(ws.counter), P(table_h), P(c["quads"]),
+                           P(enc.offsets), L, 2, S, int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)),
+                           float(model.bound), *[P(t) for t in hw_field], 64, 4, P(ws.sigma), P(ws.rgb), P(ws.enc), P(ws.h1),
+                           P(ws.h2))
+            else:
+                _cabi.call("ngp_field_forward", dev, P(ws.xyzs), ws.cap, P(ws.counter), P(table_h), P(enc.offsets), L, 2, S,
+                           int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), float(model.bound),
+                           *[P(t) for t in hw_field], 64, 4, P(ws.sigma), P(ws.rgb), P(ws.enc), P(ws.h1), P(ws.h2))
             if has_bg:
-                torch.cuda.current_stream(dev).wait_stream(self._side)
+                torch.cuda.current_stream(dev).wait_stream(self._side_fwd)
             _cabi.call("ngp_train_ray_loss", dev, P(ws.sigma), P(ws.rgb), P(ws.deltas), P(ws.rays), ws.cap, n_c, 1e-4,
                        P(m["bg"][sl]) if has_bg else None, 1.0, P(G), hw, base, N, float(self.lam_local), opt.state.data_ptr(),
                        P(m["weights_sum"][sl]), P(m["depth"][sl]), P(m["image"][sl]), P(m["d_bg"][sl]) if has_bg else None,
@@ -456,8 +487,8 @@ class TrainStep:
             main.wait_stream(st)
         if has_bg:
             main.wait_stream(self._side)
-        if g_odd is not None and (self.keep_grads or not self.pipelined):
-            # (pipelined: folded by _apply_update on the optimizer's side stream, beside the next step's ray marching)
+        if g_odd is not None and self.keep_grads:
+            # (otherwise folded by _apply_update, inside or right before the optimizer launch)
             _cabi.call("ngp_grid_fold_odd", dev, P(g_table), P(g_odd), g_table.numel())
         if self.keep_grads:
             if self.grad_snapshot is None:
@@ -470,12 +501,15 @@ class TrainStep:
 
     def _apply_update(self, deferred):
         with _nvtx.range("ngp.step.optimizer"):
-            if deferred and self._g_table_odd is not None and not self.keep_grads:
-                g_table = self.opt.grad_view(self.model.encoder.embeddings)
-                _cabi.call("ngp_grid_fold_odd", self.device, _cabi.ptr(g_table), _cabi.ptr(self._g_table_odd), g_table.numel())
+            fold = None
+            if self._g_table_odd is not None and not self.keep_grads:
+                fold = (self.opt.grad_view(self.model.encoder.embeddings), self._g_table_odd)
             if self.world > 1 and self.opt.peer_ptrs is None:
+                if fold is not None:   # NCCL all-reduce of the bucket: fold first
+                    _cabi.call("ngp_grid_fold_odd", self.device, _cabi.ptr(fold[0]), _cabi.ptr(fold[1]), fold[0].numel())
+                    fold = None
                 dist.all_reduce(self.opt.flat_grads, op=dist.ReduceOp.SUM)
-            self.opt.step_fused(deferred=deferred)
+            self.opt.step_fused(deferred=deferred, fold=fold)
 
     # -- checkpoints in the reference Trainer's layout (nerf/utils.py:847-968) -------------------------------------------
     def save_checkpoint(self, path, epoch=0, full=True):
@@ -544,6 +578,23 @@ class TrainStep:
             self.opt.state[6:7].zero_()  # nothing pending: the next step's leading launch only re-arms
             self._pending = False
 
+    def _comm_error_lagged(self):
+        """The fused data-parallel optimizer's sticky time-out flag WITHOUT a device sync: every call copies the flag to
+        pinned host memory behind the work enqueued so far and evaluates the copy of the PREVIOUS call (one refresh interval
+        earlier, long landed).  `opt.comm_error` (a blocking read) drained the launch queue at every occupancy refresh."""
+        st = getattr(self, "_comm_flag", None)
+        if st is None:
+            st = dict(host=torch.zeros(1, dtype=torch.float32).pin_memory(), ev=torch.cuda.Event(), armed=False)
+            self._comm_flag = st
+        bad = False
+        if st["armed"]:
+            st["ev"].synchronize()        # recorded a whole refresh interval ago
+            bad = bool(st["host"][0] != 0)
+        st["host"].copy_(self.opt.state[5:6], non_blocking=True)
+        st["ev"].record()
+        st["armed"] = True
+        return bad
+
     def _bookkeeping_after(self, local_step_before):
         """Python-side effects of run_cuda that a graph replay does not re-execute."""
         model = self.model
@@ -599,7 +650,7 @@ class TrainStep:
         if self.global_step % self.update_interval == 0:
             self.flush()  # (pipelined mode) the refresh must see the parameters of the completed previous step
             if self.fused_optimizer and self.world > 1 and self.opt.peer_ptrs is not None and self.global_step > 0 \
-                    and self.opt.comm_error:
+                    and self._comm_error_lagged():
                 # a cross-GPU wait inside the fused all-reduce + Adam kernel timed out: from that launch on the kernel
                 # applies nothing on any rank that saw the flag (csrc/dp_step.cu) - stop instead of training on
                 raise RuntimeError("data-parallel step: a peer did not reach the gradient exchange in time (see "

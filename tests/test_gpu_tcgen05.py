@@ -159,3 +159,58 @@ def test_fused_field_forward_groups_agree_bitwise(groups):
         for a, b in zip(outs[1], outs[groups]):
             assert torch.equal(a, b)
         assert torch.isfinite(outs[groups][0]).all() and outs[groups][3].abs().sum().item() > 0
+
+
+def test_fused_field_forward_through_the_quad_table_is_bit_equal():
+    """ngp_field_forward_quads reads the same feature rows as ngp_field_forward, four corners per 16-byte gather from the
+    quad table (ngp_grid_quad_table): outputs and saved activation tiles must be bit-equal, points on the faces of the box
+    and in the cells where the tiled levels wrap included; the quad rows themselves are checked against the table."""
+    from ngp_b200 import _cabi
+    from ngp_b200.field import cached_half
+    m = _field_models()
+    enc = m.encoder
+    table = cached_half(enc.embeddings)
+    l0, l1, l2 = m.sigma_net.net
+    hw = [cached_half(t) for t in (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)]
+    P = _cabi.ptr
+    S = float(np.log2(enc.per_level_scale))
+    rows = table.shape[0]
+    quads = torch.zeros(rows, 4, dtype=torch.int32, device=DEV)
+    dev = torch.device(DEV)
+    _cabi.call("ngp_grid_quad_table", dev, P(table), P(enc.offsets), 16, rows, S, int(enc.base_resolution), int(enc.gridtype_id),
+               int(bool(enc.align_corners)), P(quads))
+    torch.cuda.synchronize()
+    # quad rows vs the table: column 0 is the row itself, column 1 its x neighbour (the next row of the level, wrapped)
+    t32 = table.contiguous().view(torch.int32).view(-1)
+    assert torch.equal(quads[:, 0], t32)
+    offs = enc.offsets.cpu().tolist()
+    for lv in (0, 5, 15):
+        lo, hi = offs[lv], offs[lv + 1]
+        assert torch.equal(quads[lo:hi - 1, 1], t32[lo + 1:hi]) and quads[hi - 1, 1].item() == t32[lo].item()
+    for M in (300, 70001):
+        g = torch.Generator(device=DEV).manual_seed(M)
+        x = (torch.rand(M, 3, device=DEV, generator=g) * 2 - 1)
+        x[:50] = torch.where(torch.rand(50, 3, device=DEV, generator=g) < 0.3, torch.sign(x[:50]), x[:50])   # on the faces
+        x[50:60] = 1.0
+        x[60:70] = -1.0
+        x = x.contiguous()
+        tiles = (M + 127) // 128
+        outs = []
+        for use_quads in (False, True):
+            sigma = torch.empty(M, device=DEV); rgb = torch.empty(M, 3, device=DEV)
+            e = torch.zeros(tiles * 128 * 32, dtype=torch.half, device=DEV)
+            h1 = torch.zeros(tiles * 128 * 64, dtype=torch.half, device=DEV)
+            h2 = torch.zeros(tiles * 128 * 64, dtype=torch.half, device=DEV)
+            if use_quads:
+                _cabi.call("ngp_field_forward_quads", dev, P(x), M, None, P(table), P(quads), P(enc.offsets), 16, 2, S,
+                           int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), 1.0,
+                           *[P(t) for t in hw], 64, 4, P(sigma), P(rgb), P(e), P(h1), P(h2))
+            else:
+                _cabi.call("ngp_field_forward", dev, P(x), M, None, P(table), P(enc.offsets), 16, 2, S,
+                           int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), 1.0,
+                           *[P(t) for t in hw], 64, 4, P(sigma), P(rgb), P(e), P(h1), P(h2))
+            torch.cuda.synchronize()
+            outs.append((sigma, rgb, e, h1, h2))
+        for a, b in zip(*outs):
+            assert torch.equal(a, b)
+        assert outs[1][2].abs().sum().item() > 0
