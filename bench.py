@@ -388,11 +388,13 @@ def run_b200_arm(args):
     step_fn.flush()
     torch.cuda.synchronize()
     step_fn.use_graph, step_fn.overlap = False, False
-    saved_ws = (step_fn.n_chunks, step_fn._mws, step_fn._chain, getattr(model, "_train_ws", None), step_fn._side)
+    saved_ws = (step_fn.n_chunks, step_fn._mws, step_fn._chain, getattr(model, "_train_ws", None), step_fn._side,
+                step_fn._side_fwd)
     if step_fn.manual:
         step_fn.n_chunks, step_fn._mws = 1, None
-        step_fn._side = torch.cuda.current_stream(device)
-    names = ["ngp_grid_scatter_samples", "ngp_grid_encode_backward", "ngp_field_forward", "ngp_field_backward",
+        step_fn._side = step_fn._side_fwd = torch.cuda.current_stream(device)
+    names = ["ngp_grid_scatter_samples", "ngp_grid_encode_backward", "ngp_field_forward", "ngp_field_forward_quads",
+             "ngp_grid_quad_table", "ngp_field_backward",
              "ngp_march_rays_train", "ngp_march_rays_train_packed", "ngp_composite_rays_train_forward", "ngp_composite_rays_train_backward",
              "ngp_grid_encode_forward", "ngp_train_prologue", "ngp_train_prologue_rays", "ngp_train_ray_loss", "ngp_bg_forward", "ngp_bg_backward",
              "ngp_adam_step_fused", "ngp_grid_scatter_samples_split", "ngp_grid_fold_odd"]
@@ -409,7 +411,9 @@ def run_b200_arm(args):
     for name, evs in prof.items():
         if evs:
             # (the two-buffer scatter is the same kernel as ngp_grid_scatter_samples: reported under that name)
-            kern[name.replace("_samples_split", "_samples")] = (sum(a.elapsed_time(b) for a, b in evs), len(evs))
+            # (and the quad-table forward is the same kernel as ngp_field_forward)
+            kern[name.replace("_samples_split", "_samples").replace("_forward_quads", "_forward")] = (
+                sum(a.elapsed_time(b) for a, b in evs), len(evs))
     # post-aggregation atomic traffic of the grid scatter: the counting build of the same kernel over the same steps
     # (untimed; one counter add per lane) - the roofline divides these lane-ops by the measured red issue ceiling
     if step_fn.manual:
@@ -429,7 +433,7 @@ def run_b200_arm(args):
     if step_fn.manual:
         step_fn.flush()
         torch.cuda.synchronize()
-        step_fn.n_chunks, step_fn._mws, step_fn._chain, model._train_ws, step_fn._side = saved_ws
+        step_fn.n_chunks, step_fn._mws, step_fn._chain, model._train_ws, step_fn._side, step_fn._side_fwd = saved_ws
     if world > 1:
         dist.barrier()
 

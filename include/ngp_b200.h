@@ -282,7 +282,10 @@ int ngp_check_finite_fold(float* grads, uint64_t n, float* grad_table, float* gr
  *   lr * exp(lr_decay_ln * min(steps, lr_decay_steps)), and the scale grows by growth_factor every
  *   growth_interval clean steps.  half_shadow (optional f16[n]) receives the fp16 cast of the new parameters (what
  *   autocast re-derives every forward, gridencoder/grid.py:38-39); zero_grads != 0 zero-fills grads on the way out
- *   (optimizer.zero_grad, nerf/utils.py:700).  blocks_done: zero-initialised device u32 scratch (left zero). */
+ *   (optimizer.zero_grad, nerf/utils.py:700).  blocks_done: zero-initialised device u32 scratch (left zero).
+ *   zero_grads is a bit set: bit 0 = zero-fill the gradients; bit 1 = deferred (state must then have 7 entries): a launch
+ *   that finds state[6] == 0 applies nothing and only sets state[6] = 1 - the update of step k launched at the start of
+ *   step k + 1, where the very first launch has nothing to apply (TrainStep(pipelined=True)). */
 int ngp_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, void* half_shadow, uint64_t n,
                   uint32_t n_segments, const uint64_t* seg_end, const float* seg_lr, float beta1, float beta2, float eps,
                   float grad_div, float lr_decay_ln, float lr_decay_steps, float growth_factor, float backoff_factor,

@@ -71,7 +71,17 @@ def main():
     nears, fars = raymarching.near_far_from_aabb(ro_f, rd_f, model.aabb_train)
     noises = torch.rand(N, device=dev)
 
+    quads = torch.zeros(table.shape[0], 4, dtype=torch.int32, device=dev)
+    _cabi.call("ngp_grid_quad_table", dev, p(table), p(enc.offsets), L, table.shape[0], S, int(enc.base_resolution),
+               int(enc.gridtype_id), int(bool(enc.align_corners)), p(quads))
     calls = {
+        "ngp_field_forward_quads": lambda: _cabi.call(
+            "ngp_field_forward_quads", dev, p(ws.xyzs), ws.cap, p(ws.counter), p(table), p(quads), p(enc.offsets), L, 2, S,
+            int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), float(model.bound),
+            *[p(t) for t in hw], 64, 4, p(ws.sigma), p(ws.rgb), p(ws.enc), p(ws.h1), p(ws.h2)),
+        "ngp_grid_quad_table": lambda: _cabi.call(
+            "ngp_grid_quad_table", dev, p(table), p(enc.offsets), L, table.shape[0], S, int(enc.base_resolution),
+            int(enc.gridtype_id), int(bool(enc.align_corners)), p(quads)),
         "ngp_field_forward": lambda: _cabi.call(
             "ngp_field_forward", dev, p(ws.xyzs), ws.cap, p(ws.counter), p(table), p(enc.offsets), L, 2, S,
             int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), float(model.bound),
@@ -104,6 +114,13 @@ def main():
         _cabi.call("ngp_march_rays_train", dev, p(ro_f), p(rd_f), p(model.density_bitfield), float(model.bound), 0.0, 1024, N,
                    int(model.cascade), int(model.grid_size), ws.cap, p(nears), p(fars), p(ws.xyzs), None, p(ws.deltas),
                    p(ws.rays), p(ws.counter), p(noises), p(ws.march_ws), ws.march_ws.numel())
+
+    def march_packed():
+        ws.counter.zero_()
+        _cabi.call("ngp_march_rays_train_packed", dev, p(ro_f), p(rd_f), p(model.density_bitfield), float(model.bound), 0.0, 1024,
+                   N, int(model.cascade), int(model.grid_size), ws.cap, p(nears), p(fars), p(ws.xyzs), None, p(ws.deltas),
+                   p(ws.rays), p(ws.counter), p(noises))
+    calls["ngp_march_rays_train_packed"] = march_packed
 
     def time_call(fn, iters):
         for _ in range(3):

@@ -76,11 +76,23 @@ struct AdamArgs {
     float growth, backoff;
     uint32_t growth_interval;
     int zero_grads;
+    int deferred;      // 1: a launch that finds state[6] == 0 applies nothing and only raises state[6] (pipelined step, see dp_step.cu)
     float* state;
     uint32_t* blocks_done;
 };
 
 __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
+    if (a.deferred && *(volatile float*)(a.state + 6) == 0.f) {
+        // deferred mode, nothing pending yet: every block reads the flag before it signs off, the last one raises it
+        __shared__ bool s_arm_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_arm_last = atomicAdd(a.blocks_done, 1u) == gridDim.x - 1;
+            if (s_arm_last) { a.state[3] = 0.f; a.state[6] = 1.f; *a.blocks_done = 0u; }
+        }
+        return;
+    }
     const float scale = a.state[0];
     const float step0 = a.state[2];
     const bool skip = a.state[3] != 0.f;
@@ -307,7 +319,7 @@ extern "C" int ngp_adam_step(float* params, float* grads, float* exp_avg, float*
     a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_div = grad_div > 0.f ? grad_div : 1.f;
     a.lr_decay_ln = lr_decay_ln; a.lr_decay_steps = lr_decay_steps;
     a.growth = growth_factor; a.backoff = backoff_factor; a.growth_interval = growth_interval;
-    a.zero_grads = zero_grads; a.state = state; a.blocks_done = blocks_done;
+    a.zero_grads = zero_grads & 1; a.deferred = (zero_grads >> 1) & 1; a.state = state; a.blocks_done = blocks_done;
     const uint64_t want = (n / 4 + 255) / 256 + 1, cap = (uint64_t)num_sms() * 8;
     const int blocks = (int)(want < cap ? want : cap);
     step::adam_step_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a);

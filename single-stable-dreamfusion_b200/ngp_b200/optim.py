@@ -147,15 +147,22 @@ class FusedAdamScaler:
     def zero_grad(self):
         self.flat_grads.zero_()
 
-    def step(self, zero_grads=True):
-        """scaler.step(optimizer) + scaler.update() (+ optimizer.zero_grad()): two launches, no host sync."""
+    def step(self, zero_grads=True, deferred=False, fold=None):
+        """scaler.step(optimizer) + scaler.update() (+ optimizer.zero_grad()): two plain launches, no host sync.
+        deferred: the launch only arms (state[6] = 1) when nothing is pending yet - see TrainStep(pipelined=True).
+        fold: optional (grad_table view, odd-frame twin) of the split table scatter, added into the bucket inside the
+        finite check."""
         dev = self.device
-        _cabi.call("ngp_check_finite", dev, _cabi.ptr(self.flat_grads), self.numel, self.state[3:].data_ptr())
+        if fold is not None:
+            _cabi.call("ngp_check_finite_fold", dev, _cabi.ptr(self.flat_grads), self.numel, _cabi.ptr(fold[0]),
+                       _cabi.ptr(fold[1]), fold[0].numel(), self.state[3:].data_ptr())
+        else:
+            _cabi.call("ngp_check_finite", dev, _cabi.ptr(self.flat_grads), self.numel, self.state[3:].data_ptr())
         _cabi.call("ngp_adam_step", dev, _cabi.ptr(self.flat_params), _cabi.ptr(self.flat_grads), _cabi.ptr(self.exp_avg),
                    _cabi.ptr(self.exp_avg_sq), _cabi.ptr(self.flat_half), self.numel, self.n_seg, self.seg_end, self.seg_lr,
                    float(self.betas[0]), float(self.betas[1]), float(self.eps), self.grad_div, self.lr_decay_ln,
                    self.lr_decay_steps, float(self.growth_factor), float(self.backoff_factor), int(self.growth_interval),
-                   int(bool(zero_grads)), _cabi.ptr(self.state), _cabi.ptr(self._blocks_done))
+                   int(bool(zero_grads)) | (2 if deferred else 0), _cabi.ptr(self.state), _cabi.ptr(self._blocks_done))
 
     def step_fused(self, deferred=False, fold=None):
         """The same step as ONE cooperative launch (finite check -> grid barrier -> Adam ...), and - with peer

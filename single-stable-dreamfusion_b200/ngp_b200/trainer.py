@@ -156,6 +156,9 @@ class TrainStep:
         # gathers per level instead of four to eight 4-byte ones), rebuilt every step beside the ray marching.  On by
         # default on one GPU; a data-parallel rank's few samples do not repay the rebuild, which there sits between the
         # optimizer and the forward (NGP_QUAD_TABLE=1 / 0 forces it)
+        # one GPU: finite check (+ fold) and Adam as two plain launches instead of the one cooperative launch with its two
+        # grid barriers (NGP_ADAM_KERNEL=coop keeps that one)
+        self.adam_two_launch = os.environ.get("NGP_ADAM_KERNEL", "plain") != "coop"
         qt = os.environ.get("NGP_QUAD_TABLE", "auto")
         self.quad_table = (world_size == 1) if qt == "auto" else qt not in ("", "0")
         self._quads = None
@@ -504,12 +507,26 @@ class TrainStep:
             fold = None
             if self._g_table_odd is not None and not self.keep_grads:
                 fold = (self.opt.grad_view(self.model.encoder.embeddings), self._g_table_odd)
+            two_launch = self.world == 1 and self.adam_two_launch
+            in_check = two_launch or (self.world > 1 and self.opt.peer_ptrs is not None and self.opt.dp_kernel == "blocks")
+            if fold is not None and not in_check:
+                # cooperative kernel / NCCL all-reduce of the bucket: a fold launch of its own, first
+                _cabi.call("ngp_grid_fold_odd", self.device, _cabi.ptr(fold[0]), _cabi.ptr(fold[1]), fold[0].numel())
+                fold = None
             if self.world > 1 and self.opt.peer_ptrs is None:
-                if fold is not None:   # NCCL all-reduce of the bucket: fold first
-                    _cabi.call("ngp_grid_fold_odd", self.device, _cabi.ptr(fold[0]), _cabi.ptr(fold[1]), fold[0].numel())
-                    fold = None
                 dist.all_reduce(self.opt.flat_grads, op=dist.ReduceOp.SUM)
-            self.opt.step_fused(deferred=deferred, fold=fold)
+            kw = {} if fold is None else {"fold": fold}     # (folded inside the finite check)
+            if two_launch:
+                self.opt.step(deferred=deferred, **kw)      # finite check (+ fold) . Adam: two plain launches
+            else:
+                self.opt.step_fused(deferred=deferred, **kw)
+
+    def fold_table_grads(self):
+        """Add the odd-frame twin of the table gradient (split scatter) into the bucket now (tests that look at the bucket
+        before the optimizer; the step itself folds inside the optimizer's finite check)."""
+        if self._g_table_odd is not None:
+            g_table = self.opt.grad_view(self.model.encoder.embeddings)
+            _cabi.call("ngp_grid_fold_odd", self.device, _cabi.ptr(g_table), _cabi.ptr(self._g_table_odd), g_table.numel())
 
     # -- checkpoints in the reference Trainer's layout (nerf/utils.py:847-968) -------------------------------------------
     def save_checkpoint(self, path, epoch=0, full=True):

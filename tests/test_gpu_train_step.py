@@ -198,6 +198,8 @@ def test_hand_scheduled_step_matches_autograd_step(views, n_chunks):
         grads = []
 
         def capture(*a, _s=step, _g=grads, **k):
+            if _s.manual:
+                _s.fold_table_grads()     # (the step folds the split scatter's twin inside the optimizer's finite check)
             _g.append(_s.opt.flat_grads.clone())
             _s.opt.flat_grads.zero_()
         step.opt.step = capture
@@ -294,7 +296,8 @@ def test_pixel_sharded_ranks_sum_to_the_one_gpu_step():
         sel = lambda t: t.view(views, Hh, Ww, 3)[:, idx].reshape(views, Hl * Ww, 3).contiguous()  # noqa: E731
         step.fixed_noises = noises.view(views, Hh, Ww)[:, idx].reshape(-1).contiguous()
         grads = []
-        step._apply_update = lambda deferred=False, _s=step, _g=grads: (_g.append(_s.opt.flat_grads.clone()), _s.opt.flat_grads.zero_())
+        step._apply_update = lambda deferred=False, _s=step, _g=grads: (_s.fold_table_grads(), _g.append(_s.opt.flat_grads.clone()),
+                                                                        _s.opt.flat_grads.zero_())
         loss = step(sel(ro), sel(rd), G[:, :, idx].contiguous())
         torch.cuda.synchronize()
         return grads[0], loss.item(), step.opt.get_scale(), int(step.samples.item())
