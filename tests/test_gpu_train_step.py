@@ -449,7 +449,7 @@ def test_device_rays_step_equals_the_host_rays_step():
         got.append((loss.item(), step.grad_snapshot.clone(), int(step.samples.item()), m.step_counter[0].clone()))
     for other in got[1:]:
         assert other[2] == got[0][2] > 0 and torch.equal(other[3], got[0][3])
-        assert abs(other[0] - got[0][0]) <= 1e-6 * abs(got[0][0])
+        assert abs(other[0] - got[0][0]) <= 1e-5 * abs(got[0][0])   # (fp32 atomic sum over the rays: the order varies)
         rel = ((other[1] - got[0][1]).norm() / got[0][1].norm()).item()
         assert rel < 1e-4, rel
 
