@@ -67,6 +67,9 @@ def parse():
     ap.add_argument("--chunks", type=int, default=0, help="ray chunks run as parallel chains (0 = the default, 2)")
     ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce instead of the fused peer-memory all-reduce + Adam")
     ap.add_argument("--kernel-table", default=None, help="write a torch.profiler per-kernel table of 5 steps to this file")
+    ap.add_argument("--dp-sweep", action="store_true", help="multi-GPU: after the timed regions, re-time 100 steps under a few "
+                    "settings of the data-parallel step (optimizer grid size, quad table, chains, optimizer placement) in the "
+                    "same process group; results in the line's `dp_sweep`")
     ap.add_argument("--timeline", default=None, help="write the kernel timeline (CUPTI: name, stream, start, duration) of 3 "
                     "graphed steps to this JSON file - where the step's time goes between the kernels")
     ap.add_argument("--profile-steps", type=int, default=8, help="eager steps timed per kernel for the roofline")
@@ -358,6 +361,52 @@ def run_b200_arm(args):
             f.write("# torch.profiler (CUPTI) kernel times over 5 steps of the graphed train step; divide by 5 for per step\n")
             f.write(prof_t.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=90))
 
+    dp_sweep = None
+    if args.dp_sweep and world > 1 and step_fn.manual and step_fn.use_graph:
+        lib = _cabi.load()
+        dp_sweep = []
+
+        def variant(tag, setup, n=100):
+            step_fn.flush()
+            barrier()
+            setup()
+            step_fn._graph = None          # re-capture under the new setting
+            run_steps(20, False, 4000)
+            step_fn.flush()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            run_steps(n, False, 5000)
+            step_fn.flush()
+            b.record()
+            barrier()
+            t = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dp_sweep.append({"setting": tag, "ms_per_step": round(t.item(), 5)})
+
+        def set_blocks(v):
+            return lambda: _cabi.check(lib.ngp_dp_set_option(1, v), "ngp_dp_set_option")
+
+        def set_attr(**kw):
+            def f():
+                for k, v in kw.items():
+                    setattr(step_fn, k, v)
+                if "n_chunks" in kw:
+                    step_fn._mws = None
+            return f
+
+        variant("default", lambda: None)
+        for v in (14, 56, 112, 148):
+            variant("optimizer grid %d blocks" % v, set_blocks(v))
+        variant("default again", set_blocks(0))
+        variant("quad table on", set_attr(quad_table=True))
+        variant("quad table off, 1 chain", set_attr(quad_table=False, n_chunks=1))
+        variant("3 chains", set_attr(n_chunks=3))
+        variant("2 chains, optimizer at the end of its own step", set_attr(n_chunks=2, pipelined=False))
+        variant("default restored", set_attr(pipelined=True))
+        if rank == 0:
+            print("DP_SWEEP " + json.dumps(dp_sweep), file=sys.stderr, flush=True)
+
     if args.timeline and rank == 0:
         from torch.profiler import profile, ProfilerActivity
         torch.cuda.synchronize()
@@ -561,6 +610,8 @@ def run_b200_arm(args):
         }
         if dp_result is not None:
             line["dp_check"] = dp_result
+        if dp_sweep is not None:
+            line["dp_sweep"] = dp_sweep
         if not args.no_cpu_baseline:
             try:
                 v, cms, cores, desc = cpu_reference_run(args.cpu_sample_steps, 1)
