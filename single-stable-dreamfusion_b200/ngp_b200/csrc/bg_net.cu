@@ -42,14 +42,39 @@ struct SmemW {
     static constexpr uint32_t w1 = 0, b1 = w1 + kHid * 40, w2 = b1 + kHid, b2 = w2 + kOut * kHid, total = b2 + 4;
 };
 
+// (128 threads; fixed trip counts and loads gathered into registers before the stores, so the ~23 global loads of a thread are
+//  in flight together - as a plain strided loop they were 20 dependent round trips, ~10 us at the head of both kernels)
 NGP_DEVINL void load_weights(const Weights& w, float* s) {
-    for (uint32_t i = threadIdx.x; i < kHid * 40; i += blockDim.x) {
+    constexpr uint32_t kT = kRays;                       // threads per CTA
+    constexpr uint32_t kIt1 = (kHid * 40 + kT - 1) / kT; // 20
+    __half v1[kIt1];
+#pragma unroll
+    for (uint32_t it = 0; it < kIt1; ++it) {
+        const uint32_t i = it * kT + threadIdx.x;
         const uint32_t j = i / 40, k = i % 40;
-        s[SmemW::w1 + i] = k < kEnc ? __half2float(w.w1[j * kEnc + k]) : 0.f;
+        v1[it] = (i < kHid * 40 && k < kEnc) ? w.w1[j * kEnc + k] : __float2half(0.f);
     }
-    for (uint32_t i = threadIdx.x; i < kHid; i += blockDim.x) s[SmemW::b1 + i] = __half2float(w.b1[i]);
-    for (uint32_t i = threadIdx.x; i < kOut * kHid; i += blockDim.x) s[SmemW::w2 + i] = __half2float(w.w2[i]);
-    if (threadIdx.x < kOut) s[SmemW::b2 + threadIdx.x] = __half2float(w.b2[threadIdx.x]);
+    constexpr uint32_t kIt2 = (kOut * kHid + kT - 1) / kT;   // 2
+    __half v2[kIt2];
+#pragma unroll
+    for (uint32_t it = 0; it < kIt2; ++it) {
+        const uint32_t i = it * kT + threadIdx.x;
+        v2[it] = i < kOut * kHid ? w.w2[i] : __float2half(0.f);
+    }
+    const __half vb1 = threadIdx.x < kHid ? w.b1[threadIdx.x] : __float2half(0.f);
+    const __half vb2 = threadIdx.x < kOut ? w.b2[threadIdx.x] : __float2half(0.f);
+#pragma unroll
+    for (uint32_t it = 0; it < kIt1; ++it) {
+        const uint32_t i = it * kT + threadIdx.x;
+        if (i < kHid * 40) s[SmemW::w1 + i] = __half2float(v1[it]);
+    }
+#pragma unroll
+    for (uint32_t it = 0; it < kIt2; ++it) {
+        const uint32_t i = it * kT + threadIdx.x;
+        if (i < kOut * kHid) s[SmemW::w2 + i] = __half2float(v2[it]);
+    }
+    if (threadIdx.x < kHid) s[SmemW::b1 + threadIdx.x] = __half2float(vb1);
+    if (threadIdx.x < kOut) s[SmemW::b2 + threadIdx.x] = __half2float(vb2);
 }
 
 // hidden pre-activation j of one ray: half(enc_h . W1[j] + b1[j])
@@ -108,7 +133,7 @@ struct SmemB {
     static constexpr uint32_t total = gz2 + kTileB * 4 * 4;
 };
 
-__global__ void __launch_bounds__(kRays, 4) bg_backward_kernel(const float* __restrict__ dirs, const float* __restrict__ grad_out,
+__global__ void __launch_bounds__(kRays, 3) bg_backward_kernel(const float* __restrict__ dirs, const float* __restrict__ grad_out,
                                                             uint32_t N, const Weights w, float* __restrict__ gw1,
                                                             float* __restrict__ gb1, float* __restrict__ gw2,
                                                             float* __restrict__ gb2) {

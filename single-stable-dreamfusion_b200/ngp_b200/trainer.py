@@ -153,14 +153,10 @@ class TrainStep:
         # completion order, like the reference's); NGP_PACKED_MARCH=0: ray-ordered walk -> scan -> packed copy
         self.packed_march = os.environ.get("NGP_PACKED_MARCH", "1") not in ("", "0")
         # field forward through a quad table of the fp16 embeddings (csrc/field_mlp.cu encode_level_quads: one or two 16-byte
-        # gathers per level instead of four to eight 4-byte ones), rebuilt every step beside the ray marching.  On by
-        # default on one GPU; a data-parallel rank's few samples do not repay the rebuild, which there sits between the
-        # optimizer and the forward (NGP_QUAD_TABLE=1 / 0 forces it)
-        # one GPU: finite check (+ fold) and Adam as two plain launches instead of the one cooperative launch with its two
-        # grid barriers (NGP_ADAM_KERNEL=coop keeps that one)
-        self.adam_two_launch = os.environ.get("NGP_ADAM_KERNEL", "plain") != "coop"
-        qt = os.environ.get("NGP_QUAD_TABLE", "auto")
-        self.quad_table = (world_size == 1) if qt == "auto" else qt not in ("", "0")
+        # gathers per level instead of four to eight 4-byte ones), rebuilt every step beside the ray marching (13 us on a
+        # side stream).  Measured: forward 0.488 -> 0.417 ms at 3.3 M samples; 1-2 % of the step at 4096 rays per GPU too
+        # (2 and 8 GPUs, bench.py --dp-sweep).  NGP_QUAD_TABLE=0 turns it off.
+        self.quad_table = os.environ.get("NGP_QUAD_TABLE", "1") not in ("", "0")
         self._quads = None
         self.device_noise = bool(self.manual) and os.environ.get("NGP_DEVICE_NOISE", "1") not in ("", "0")
         rank = dist.get_rank() if (world_size > 1 and dist.is_available() and dist.is_initialized()) else 0
@@ -605,7 +601,8 @@ class TrainStep:
             self._comm_flag = st
         bad = False
         if st["armed"]:
-            st["ev"].synchronize()        # recorded a whole refresh interval ago
+            if not st["ev"].query():      # the host is more than a refresh interval ahead of the device: look next time
+                return False
             bad = bool(st["host"][0] != 0)
         st["host"].copy_(self.opt.state[5:6], non_blocking=True)
         st["ev"].record()
