@@ -157,6 +157,9 @@ class TrainStep:
         # side stream).  Measured: forward 0.488 -> 0.417 ms at 3.3 M samples; 1-2 % of the step at 4096 rays per GPU too
         # (2 and 8 GPUs, bench.py --dp-sweep).  NGP_QUAD_TABLE=0 turns it off.
         self.quad_table = os.environ.get("NGP_QUAD_TABLE", "1") not in ("", "0")
+        # one GPU: finite check (+ odd-frame fold) and Adam as two plain launches instead of the one cooperative launch with
+        # its two grid barriers (NGP_ADAM_KERNEL=coop keeps that one)
+        self.adam_two_launch = os.environ.get("NGP_ADAM_KERNEL", "plain") != "coop"
         self._quads = None
         self.device_noise = bool(self.manual) and os.environ.get("NGP_DEVICE_NOISE", "1") not in ("", "0")
         rank = dist.get_rank() if (world_size > 1 and dist.is_available() and dist.is_initialized()) else 0
