@@ -107,10 +107,20 @@ NGP_DEVINL uint32_t* flag_slot(uint32_t* pad, uint32_t barrier, uint32_t block, 
 // OR-ed over the ranks and returned to every thread of the block.  A timed-out wait sets the sticky error flag state[5]
 // and reports payload bit 1 (kPayloadError).
 constexpr uint32_t kPayloadInf = 1u, kPayloadError = 2u;
-NGP_DEVINL uint32_t xrank_barrier(const Args& a, uint32_t barrier, uint32_t block, uint32_t epoch, uint32_t payload) {
+// coef (optional, shared float[3]): while the first `world` threads exchange flags, the block's last thread evaluates the
+// step's Adam bias corrections and learning-rate factor into it (double-precision pow: microseconds on one thread, hidden
+// behind the wait for the peers)
+NGP_DEVINL uint32_t xrank_barrier(const Args& a, uint32_t barrier, uint32_t block, uint32_t epoch, uint32_t payload,
+                                  float* coef = nullptr, float step0 = 0.f) {
     __shared__ uint32_t s_or;
     if (threadIdx.x == 0) s_or = 0u;
     __syncthreads();
+    if (coef && threadIdx.x == blockDim.x - 1) {
+        const float t = step0 + 1.f;
+        coef[0] = (float)(1.0 - pow((double)a.beta1, (double)t));
+        coef[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)t));
+        coef[2] = a.lr_decay_ln != 0.f ? expf(a.lr_decay_ln * fminf(step0, a.lr_decay_steps)) : 1.f;
+    }
     if (threadIdx.x < a.world) {
         const uint32_t q = threadIdx.x;
         uint32_t got = 0;
@@ -336,19 +346,12 @@ __global__ void __launch_bounds__(512) adam_dp_kernel(const Args a) {
         const uint64_t b_hi = b_lo + chunk < hi ? b_lo + chunk : hi;
 
         const uint32_t mine = (*(volatile float*)(a.state + 3) != 0.f ? kPayloadInf : 0u);
-        const uint32_t any = xrank_barrier(a, 0, blockIdx.x, epoch, mine);      // B0
+        __shared__ float s_coef[3];
+        const uint32_t any = xrank_barrier(a, 0, blockIdx.x, epoch, mine, s_coef, step0);      // B0 (+ the step's coefficients)
         broken = (any & kPayloadError) != 0u;
         skip = (any & kPayloadInf) != 0u;
         if (!broken) {
             if (!skip) {
-                const float t = step0 + 1.f;
-                __shared__ float s_coef[3];
-                if (threadIdx.x == 0) {
-                    s_coef[0] = (float)(1.0 - pow((double)a.beta1, (double)t));
-                    s_coef[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)t));
-                    s_coef[2] = a.lr_decay_ln != 0.f ? expf(a.lr_decay_ln * fminf(step0, a.lr_decay_steps)) : 1.f;
-                }
-                __syncthreads();
                 const float bc1 = s_coef[0], bc2_sqrt = s_coef[1], lr_mult = s_coef[2];
                 const float inv = 1.0f / (scale * a.grad_div);
                 const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;

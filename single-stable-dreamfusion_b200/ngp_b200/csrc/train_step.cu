@@ -97,10 +97,16 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
     const float step0 = a.state[2];
     const bool skip = a.state[3] != 0.f;
     const float t = step0 + 1.f;
-    // same expressions as torch's fused Adam (bias corrections evaluated in double, then narrowed)
-    const float bc1 = (float)(1.0 - pow((double)a.beta1, (double)t));
-    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)a.beta2, (double)t));
-    const float lr_mult = a.lr_decay_ln != 0.f ? expf(a.lr_decay_ln * fminf(step0, a.lr_decay_steps)) : 1.f;
+    // same expressions as torch's fused Adam (bias corrections evaluated in double, then narrowed) - once per block: two
+    // double-precision pow() per THREAD made this kernel 35 us instead of ~12 (13 M instructions, fp64 is slow here)
+    __shared__ float s_coef[3];
+    if (threadIdx.x == 0) {
+        s_coef[0] = (float)(1.0 - pow((double)a.beta1, (double)t));
+        s_coef[1] = (float)sqrt(1.0 - pow((double)a.beta2, (double)t));
+        s_coef[2] = a.lr_decay_ln != 0.f ? expf(a.lr_decay_ln * fminf(step0, a.lr_decay_steps)) : 1.f;
+    }
+    __syncthreads();
+    const float bc1 = s_coef[0], bc2_sqrt = s_coef[1], lr_mult = s_coef[2];
     const float inv = 1.0f / (scale * a.grad_div);
     const float w1 = 1.f - a.beta1, w2 = 1.f - a.beta2;
 
