@@ -533,7 +533,9 @@ def run_b200_arm(args):
         roofline = {"kernel": dom, "unit": "GB/s", "avg_launch_ms": per_launch_ms, "launches_per_step": launches_per_step,
                     "samples_per_launch": points_per_launch,
                     "share_of_step": (tot_ms / max(args.profile_steps, 1)) / max(step_kernel_ms, 1e-9),
-                    "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "traffic_source": traffic,
+                    # (the capture's bytes per launch, scaled to this run's samples per launch)
+                    "traffic": (traffic["dram_bytes_per_launch"] * points_per_launch / max(traffic.get("samples_per_launch", 0.0), 1.0)
+                                if traffic else None), "traffic_source": traffic,
                     "l2_gather_peak_gbs": gathers_s * 4 / 1e9, "l2_red_lane_ops_peak_per_s": reds_s,
                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
                     "how": "CUDA events around each entry point over %d eager single-chain steps after the timed region, "
