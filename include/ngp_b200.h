@@ -403,6 +403,14 @@ int ngp_render_infer_loop(const float* rays_o, const float* rays_d, const float*
                           uint32_t Hres, uint32_t gridtype, int align_corners, const void* w1, const void* b1, const void* w2,
                           const void* b2, const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* weights_sum,
                           float* depth, float* image, void* workspace, uint64_t workspace_bytes, void* stream);
+/* The same loop with the field forward reading the embeddings through a quad table (ngp_grid_quad_table over the same fp16
+ * table, built by the caller before the launch; see ngp_field_forward_quads): bit-equal results. */
+int ngp_render_infer_loop_quads(const float* rays_o, const float* rays_d, const float* nears, const float* fars, uint32_t N, float bound,
+                          float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t* grid, float T_thresh,
+                          const float* noises, const void* table, const void* quads, const int* offsets, uint32_t L, uint32_t Cfeat, float S,
+                          uint32_t Hres, uint32_t gridtype, int align_corners, const void* w1, const void* b1, const void* w2,
+                          const void* b2, const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* weights_sum,
+                          float* depth, float* image, void* workspace, uint64_t workspace_bytes, void* stream);
 int ngp_render_infer_state(const void* workspace, int* state_host, void* stream);
 
 /* Ray generation on the device: nerf/utils.py:43-106 get_rays (the N = -1 full-image branch, as nerf/provider.py:227 calls

@@ -180,6 +180,7 @@ def main():
                 assert lib.ngp_field_set_option(2, groups) == 0 and lib.ngp_field_set_option(0, ctas) == 0
                 assert lib.ngp_field_set_option(1, carve) == 0
                 report("ngp_field_forward", {"groups": groups, "ctas_per_sm": ctas, "carveout": carve})
+                report("ngp_field_forward_quads", {"groups": groups, "ctas_per_sm": ctas, "carveout": carve})
         assert lib.ngp_field_set_option(2, 2) == 0 and lib.ngp_field_set_option(0, 0) == 0 and lib.ngp_field_set_option(1, -1) == 0
 
 

@@ -85,6 +85,8 @@ SIGNATURES = {
     "ngp_render_infer_workspace": (_u64, [_u32]),
     "ngp_render_infer_loop": (_i32, [_vp, _vp, _vp, _vp, _u32, _f32, _f32, _u32, _u32, _u32, _vp, _f32, _vp, _vp, _vp, _u32, _u32, _f32,
                                      _u32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _u64, _vp]),
+    "ngp_render_infer_loop_quads": (_i32, [_vp, _vp, _vp, _vp, _u32, _f32, _f32, _u32, _u32, _u32, _vp, _f32, _vp, _vp, _vp, _vp, _u32, _u32,
+                                           _f32, _u32, _u32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp, _u64, _vp]),
     "ngp_render_infer_state": (_i32, [_vp, C.POINTER(_i32), _vp]),
     "ngp_get_rays": (_i32, [_vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp]),
     "ngp_train_prologue_rays": (_i32, [_vp, _vp, _i32, _u32, _u32, _u32, _u32, _u32, _u32, _vp, _vp, _vp, _f32, _vp, _vp, _vp, _u32,

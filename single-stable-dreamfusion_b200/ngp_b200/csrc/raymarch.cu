@@ -2018,13 +2018,13 @@ inline InferLayout infer_layout(uint32_t N) {
 
 extern "C" uint64_t ngp_render_infer_workspace(uint32_t N) { return infer_layout(N).total; }
 
-extern "C" int ngp_render_infer_loop(const float* rays_o, const float* rays_d, const float* nears, const float* fars, uint32_t N,
-                                     float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
-                                     const uint8_t* grid, float T_thresh, const float* noises, const void* table,
-                                     const int* offsets, uint32_t L, uint32_t Cfeat, float S, uint32_t Hres, uint32_t gridtype,
-                                     int align_corners, const void* w1, const void* b1, const void* w2, const void* b2,
-                                     const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* weights_sum,
-                                     float* depth, float* image, void* workspace, uint64_t workspace_bytes, void* stream) {
+static int render_infer_loop_impl(const float* rays_o, const float* rays_d, const float* nears, const float* fars, uint32_t N,
+                                  float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                                  const uint8_t* grid, float T_thresh, const float* noises, const void* table, const void* quads,
+                                  const int* offsets, uint32_t L, uint32_t Cfeat, float S, uint32_t Hres, uint32_t gridtype,
+                                  int align_corners, const void* w1, const void* b1, const void* w2, const void* b2,
+                                  const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* weights_sum,
+                                  float* depth, float* image, void* workspace, uint64_t workspace_bytes, void* stream) {
     if (!rays_o || !rays_d || !nears || !fars || !grid || !table || !offsets || !w1 || !b1 || !w2 || !b2 || !w3 || !b3 ||
         !weights_sum || !depth || !image)
         return NGP_ERR_BAD_ARG;
@@ -2046,7 +2046,7 @@ extern "C" int ngp_render_infer_loop(const float* rays_o, const float* rays_d, c
     InferLoopKey key;
     memset(&key, 0, sizeof(key));
     const void* ptrs[] = {rays_o, rays_d, nears, fars, grid, noises, table, offsets, w1, b1, w2, b2, w3, b3, weights_sum, depth,
-                          image, workspace};
+                          image, workspace, quads};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) key.p[i] = ptrs[i];
     const uint32_t us[] = {N, max_steps, C, H, L, Cfeat, Hres, gridtype, (uint32_t)(align_corners != 0), 0u};
     for (size_t i = 0; i < 10; ++i) key.u[i] = us[i];
@@ -2103,9 +2103,12 @@ extern "C" int ngp_render_infer_loop(const float* rays_o, const float* rays_d, c
             const int g_march = N <= 16384u ? min(cdiv((uint64_t)N * 32, 128), num_sms() * 16) : g128;   // (warp-per-ray first pass)
             march::infer_march_kernel<<<g_march, 128, 0, cs>>>(st, N, alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
                                                             fars, xyzs, deltas, noises);
-            rc = ngp_field_forward(xyzs, (uint32_t)(align_up((uint64_t)N, 128)), &st->rows, table, offsets, L, Cfeat, S, Hres, gridtype,
-                                   align_corners, bound, w1, b1, w2, b2, w3, b3, hidden, out_dim, sigma, rgb, nullptr, nullptr, nullptr,
-                                   cs);
+            rc = quads ? ngp_field_forward_quads(xyzs, (uint32_t)(align_up((uint64_t)N, 128)), &st->rows, table, quads, offsets, L, Cfeat,
+                                                 S, Hres, gridtype, align_corners, bound, w1, b1, w2, b2, w3, b3, hidden, out_dim, sigma,
+                                                 rgb, nullptr, nullptr, nullptr, cs)
+                       : ngp_field_forward(xyzs, (uint32_t)(align_up((uint64_t)N, 128)), &st->rows, table, offsets, L, Cfeat, S, Hres,
+                                           gridtype, align_corners, bound, w1, b1, w2, b2, w3, b3, hidden, out_dim, sigma, rgb, nullptr,
+                                           nullptr, nullptr, cs);
             march::infer_composite_kernel<<<g128, 128, 0, cs>>>(st, N, T_thresh, alive, rays_t, sigma, rgb, deltas, weights_sum, depth,
                                                                 image);
             const int cblocks = cdiv(N, march::kCompactBlock);
@@ -2133,6 +2136,34 @@ extern "C" int ngp_render_infer_loop(const float* rays_o, const float* rays_d, c
     const cudaError_t le = cudaGraphLaunch(hit->exec, as_stream(stream));
     if (le != cudaSuccess) { cudaGetLastError(); return (int)le; }
     return launch_status();
+}
+
+extern "C" int ngp_render_infer_loop(const float* rays_o, const float* rays_d, const float* nears, const float* fars, uint32_t N,
+                                     float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                                     const uint8_t* grid, float T_thresh, const float* noises, const void* table,
+                                     const int* offsets, uint32_t L, uint32_t Cfeat, float S, uint32_t Hres, uint32_t gridtype,
+                                     int align_corners, const void* w1, const void* b1, const void* w2, const void* b2,
+                                     const void* w3, const void* b3, uint32_t hidden, uint32_t out_dim, float* weights_sum,
+                                     float* depth, float* image, void* workspace, uint64_t workspace_bytes, void* stream) {
+    return render_infer_loop_impl(rays_o, rays_d, nears, fars, N, bound, dt_gamma, max_steps, C, H, grid, T_thresh, noises, table,
+                                  nullptr, offsets, L, Cfeat, S, Hres, gridtype, align_corners, w1, b1, w2, b2, w3, b3, hidden, out_dim,
+                                  weights_sum, depth, image, workspace, workspace_bytes, stream);
+}
+
+// the same loop with the field reading the embeddings through a quad table (ngp_grid_quad_table, built by the caller from
+// the SAME fp16 table before the launch)
+extern "C" int ngp_render_infer_loop_quads(const float* rays_o, const float* rays_d, const float* nears, const float* fars,
+                                           uint32_t N, float bound, float dt_gamma, uint32_t max_steps, uint32_t C, uint32_t H,
+                                           const uint8_t* grid, float T_thresh, const float* noises, const void* table,
+                                           const void* quads, const int* offsets, uint32_t L, uint32_t Cfeat, float S,
+                                           uint32_t Hres, uint32_t gridtype, int align_corners, const void* w1, const void* b1,
+                                           const void* w2, const void* b2, const void* w3, const void* b3, uint32_t hidden,
+                                           uint32_t out_dim, float* weights_sum, float* depth, float* image, void* workspace,
+                                           uint64_t workspace_bytes, void* stream) {
+    if (!quads) return NGP_ERR_BAD_ARG;
+    return render_infer_loop_impl(rays_o, rays_d, nears, fars, N, bound, dt_gamma, max_steps, C, H, grid, T_thresh, noises, table,
+                                  quads, offsets, L, Cfeat, S, Hres, gridtype, align_corners, w1, b1, w2, b2, w3, b3, hidden, out_dim,
+                                  weights_sum, depth, image, workspace, workspace_bytes, stream);
 }
 
 // device int[8] view of the loop state after the last launch on this workspace: n_alive, n_step, step, cur, iters, ...

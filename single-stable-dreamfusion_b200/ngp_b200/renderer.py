@@ -265,10 +265,18 @@ class NeRFRenderer(nn.Module):
         hw = [cached_half(t) for t in (l0.weight, l0.bias, l1.weight, l1.bias, l2.weight, l2.bias)]
         table = cached_half(enc.embeddings)
         P = _cabi.ptr
-        rc = _cabi.call_rc("ngp_render_infer_loop", device, P(ws["rays_o"]), P(ws["rays_d"]), P(ws["nears"]), P(ws["fars"]), N,
+        L, S = enc.offsets.shape[0] - 1, float(np.log2(enc.per_level_scale))
+        # quad table of the current fp16 embeddings (csrc/field_mlp.cu: one or two 16-byte gathers per level instead of four
+        # to eight 4-byte ones), rebuilt per frame: 13 us next to a ~7 ms frame, and never stale
+        quads = ws.get("quads")
+        if quads is None or quads.shape[0] != table.shape[0]:
+            quads = ws["quads"] = torch.zeros(table.shape[0], 4, dtype=torch.int32, device=device)
+        _cabi.call("ngp_grid_quad_table", device, P(table), P(enc.offsets), L, table.shape[0], S, int(enc.base_resolution),
+                   int(enc.gridtype_id), int(bool(enc.align_corners)), P(quads))
+        rc = _cabi.call_rc("ngp_render_infer_loop_quads", device, P(ws["rays_o"]), P(ws["rays_d"]), P(ws["nears"]), P(ws["fars"]), N,
                            float(self.bound), float(dt_gamma), int(max_steps), int(self.cascade), int(self.grid_size),
-                           P(self.density_bitfield), float(T_thresh), P(ws["noises"]) if perturb else None, P(table),
-                           P(enc.offsets), enc.offsets.shape[0] - 1, 2, float(np.log2(enc.per_level_scale)),
+                           P(self.density_bitfield), float(T_thresh), P(ws["noises"]) if perturb else None, P(table), P(quads),
+                           P(enc.offsets), L, 2, S,
                            int(enc.base_resolution), int(enc.gridtype_id), int(bool(enc.align_corners)), *[P(t) for t in hw],
                            64, 4, P(ws["weights_sum"]), P(ws["depth"]), P(ws["image"]), P(ws["work"]), ws["work"].numel(),
                            launches=1)
