@@ -35,6 +35,7 @@ UNIT = "samples/s"
 VIEWS_PER_STEP = 8
 H = W = 64
 MAX_STEPS = 1024
+LOSS_LAG = 8   # e2e leg: the host consumes step k's loss while step k + LOSS_LAG is being enqueued
 
 
 def parse():
@@ -301,11 +302,14 @@ def run_b200_arm(args):
             loss = step_fn(host_batch(i) if e2e else dev_pool[i % n_pool])
             if e2e:
                 # device -> host read of the step's result, every step: the loss is copied to pinned host memory right
-                # behind the step and consumed two calls later (TrainStep.read_loss_async), --sync-loss: loss.item()
+                # behind the step and consumed LOSS_LAG calls later (TrainStep.read_loss_async), --sync-loss: loss.item().
+                # (A lag of 2 kept the host at most two steps ahead of the device: every scheduling hiccup of one of the 4-8
+                #  rank processes then stalled its GPU - and, through the gradient exchange, all of them: e2e was 13 % below
+                #  `value` at 4 GPUs.)
                 if args.sync_loss:
                     loss.item()
                 else:
-                    step_fn.read_loss_async(lag=2)
+                    step_fn.read_loss_async(lag=LOSS_LAG)
 
     # ---- warm-up ------------------------------------------------------------------------------------
     # the clock sampler (an nvidia-smi child process) is started BEFORE the warm-up: its start-up takes driver locks that
@@ -604,7 +608,7 @@ def run_b200_arm(args):
                     "ms_per_step": ms_e2e / args.steps,
                     "result_read": ("loss.item() after every step" if (args.sync_loss and not step_fn.overlap) else
                                     "every step copies its loss (4 bytes) to pinned host memory behind the step; the host reads "
-                                    "the value two calls later, when that copy has landed (no per-step device sync)")},
+                                    "the value %d calls later, when that copy has landed (no per-step device sync)" % LOSS_LAG)},
             "gpu_launches": launches * world,
             "host_enqueue_ms_per_step": host_ms,
             "clocks": clk,
