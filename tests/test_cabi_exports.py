@@ -60,3 +60,38 @@ def test_ops_fail_loudly_without_gpu():
     import raymarching
     with pytest.raises(Exception):
         raymarching.near_far_from_aabb(torch.zeros(4, 3), torch.ones(4, 3), torch.tensor([-1., -1, -1, 1, 1, 1]))
+
+
+def test_ctypes_signatures_match_the_header_argument_for_argument():
+    """Every prototype of include/ngp_b200.h against its ctypes signature in ngp_b200/_cabi.py: same number of arguments
+    and, position by position, the same kind (pointer / uint32_t / uint64_t / int / float).  A drifted signature would
+    otherwise only show up on a GPU, as a garbage argument."""
+    import ctypes as C
+    from ngp_b200 import _cabi
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    decls = re.findall(r"\b(int|uint64_t|const char\s*\*)\s+(ngp_[A-Za-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(decls) >= 60
+
+    def kind_of_c(param):
+        p = " ".join(param.split())
+        if "*" in p:
+            return "ptr"
+        for t in ("uint64_t", "uint32_t", "float", "int"):
+            if re.match(r"(const )?%s\b" % t, p):
+                return t
+        raise AssertionError("unparsed parameter: " + p)
+
+    def kind_of_ctypes(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_uint32: "uint32_t", C.c_uint64: "uint64_t", C.c_int: "int", C.c_float: "float"}[t]
+
+    for ret, name, params in decls:
+        res, args = _cabi.SIGNATURES[name]
+        params = params.strip()
+        plist = [] if params in ("", "void") else [p for p in params.split(",")]
+        assert len(plist) == len(args), "%s: header has %d arguments, ctypes %d" % (name, len(plist), len(args))
+        for i, (p, a) in enumerate(zip(plist, args)):
+            assert kind_of_c(p) == kind_of_ctypes(a), "%s argument %d: header `%s`, ctypes %s" % (name, i, p.strip(), a)
+        want = {"int": C.c_int, "uint64_t": C.c_uint64}.get(ret, C.c_char_p)
+        assert res is want, name
