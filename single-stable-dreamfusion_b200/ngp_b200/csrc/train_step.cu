@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
     const bool skip = a.state[3] != 0.f;
     const float t = step0 + 1.f;
     // same expressions as torch's fused Adam (bias corrections evaluated in double, then narrowed) - once per block: two
-    // double-precision pow() per THREAD made this kernel 35 us instead of ~12 (13 M instructions, fp64 is slow here)
+    // double-precision pow() per THREAD made this kernel 35 us instead of 23 (13 M instructions, fp64 is slow here)
     __shared__ float s_coef[3];
     if (threadIdx.x == 0) {
         s_coef[0] = (float)(1.0 - pow((double)a.beta1, (double)t));
